@@ -1,0 +1,226 @@
+/*
+ * rf_abi.h — C-ABI of librf_b200.so, the B200-native (sm_100a) mapping hot path of RemixFusion.
+ *
+ * The reference has no FFI for this path: it JIT-compiles CUDA-C strings with PyCUDA and launches them
+ * on raw device pointers, and it reaches tiny-cuda-nn through its torch binding.  Every entry point
+ * below names the reference launch / module call it replaces (file:line relative to the reference
+ * tree).  Conventions:
+ *
+ *   - extern "C", plain pointers and sizes, no torch types;
+ *   - pointers documented "device" are caller-owned device pointers (a torch tensor's data_ptr());
+ *     pointers documented "host" are small parameter blocks read synchronously during the call;
+ *   - nothing is allocated, nothing is retained after the call returns;
+ *   - the last argument is the cudaStream_t (as void*) the work is enqueued on; calls are asynchronous;
+ *   - return value: 0 = ok, <0 = bad argument (RF_E_*), >0 = cudaError_t of the failed launch;
+ *     rf_last_error() returns a thread-local human-readable string for the last non-zero return.
+ */
+#ifndef RF_ABI_H
+#define RF_ABI_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RF_ABI_VERSION 1
+
+#define RF_E_NULL      (-1)  /* required pointer is NULL                       */
+#define RF_E_RANGE     (-2)  /* size / slab / flag out of range                */
+#define RF_E_ALIGN     (-3)  /* pointer not aligned as the layout requires     */
+#define RF_E_UNSUPPORTED (-4)/* shape outside what the kernels are built for   */
+
+int         rf_version(void);
+const char* rf_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage 1a — local moving volume (tracker).  Replaces the PyCUDA launch of `integrate`
+ * model/Volume.py:729-756 (kernel model/Volume.py:196-336).
+ *
+ * Layout: three fp32 arrays of dx*dy*dz elements, index = z + y*dz + x*dy*dz (z fastest).
+ * packed_bgr is the folded colour image floor(B*65536 + G*256 + R) of model/Volume.py:728.
+ * origin is truncated toward zero to an integer exactly as the kernel does (model/Volume.py:230-232).
+ * x0,x1: x-slab [x0,x1) owned by the caller (multi-GPU sharding; 0,dx for the whole volume).  The
+ * array pointers always address the FULL volume's element 0 unless slab_local != 0, in which case
+ * they address the first element of slab x0 (a rank that only allocates its own slab).
+ * ---------------------------------------------------------------------------------------------- */
+int rf_tsdf_integrate_local(float* tsdf, float* weight, float* color,       /* device, in/out */
+                            int dx, int dy, int dz,
+                            const float origin[3],                           /* host */
+                            float voxel_size,
+                            const float K[9],                                /* host, row-major 3x3 */
+                            const float c2w[16],                             /* host, row-major 4x4 */
+                            const float* depth,                              /* device [H*W] metres */
+                            const float* packed_bgr,                         /* device [H*W] */
+                            int H, int W,
+                            float trunc_margin, float obs_weight,
+                            int weight_clamp, int reintegrate,
+                            const float old_bnd[6],                          /* host; may be NULL if !reintegrate */
+                            int x0, int x1, int slab_local,
+                            void* stream);
+
+/* model/Volume.py:723-728 — fold an RGB float image (values 0..255) into packed BGR, on device. */
+int rf_pack_bgr(const float* rgb_hw3 /*device [H*W*3]*/, float* packed /*device [H*W]*/, int n_pixels, void* stream);
+
+/* model/Volume.py:561-583 (`clean_tsdf`): tsdf=1, weight=0, colour=0 over n voxels. */
+int rf_tsdf_clear_local(float* tsdf, float* weight, float* color, int64_t n_voxels, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage 1b — global coarse volume "GBV" (mapper).  Replaces the PyCUDA launch of `map_integrate`
+ * mp_slam/mapper.py:843-872 (kernel mp_slam/mapper.py:37-158).
+ *
+ * Layout: trgb = tiny-cuda-nn Dense-grid params, [R^3][4] fp32 AoS (tsdf,r,g,b), voxel index
+ * v = x + y*R + z*R*R (x fastest); wgt = [R^3] fp32.  box = {x0,x1,y0,y1,z0,z1} (mapping.bound).
+ * rgb_hw3 is the interleaved float RGB image in [0,1].  z0,z1: z-slab [z0,z1) owned by the caller;
+ * slab_local as above.  c2w may live on the device (the reference passes a device tensor,
+ * mp_slam/mapper.py:849): set c2w_on_device != 0.
+ * ---------------------------------------------------------------------------------------------- */
+int rf_tsdf_integrate_global(float* trgb, float* wgt,                        /* device, in/out */
+                             int R,
+                             const float box[6],                             /* host */
+                             const float K[9],                               /* host */
+                             const float* c2w, int c2w_on_device,
+                             const float* depth,                             /* device [H*W] */
+                             const float* rgb_hw3,                           /* device [H*W*3] */
+                             int H, int W,
+                             float trunc_margin, float obs_weight,
+                             int z0, int z1, int slab_local,
+                             void* stream);
+
+/* mp_slam/mapper.py:161-183 + :267-282 (`clean_tsdf` / init_mapvolume): trgb[v] = (1,0,0,0). */
+int rf_tsdf_clear_global(float* trgb, int64_t n_voxels, void* stream);
+
+/* Count voxels a frame would touch (the metric's numerator): same predicate as the
+ * integrate kernels, no writes.  counts (device, uint64[2]) += {n_touched, n_band}. */
+int rf_tsdf_count_local(int dx, int dy, int dz, const float origin[3], float voxel_size,
+                        const float K[9], const float c2w[16], const float* depth, int H, int W,
+                        float trunc_margin, int reintegrate, const float old_bnd[6],
+                        int x0, int x1, unsigned long long* counts, void* stream);
+int rf_tsdf_count_global(int R, const float box[6], const float K[9], const float* c2w, int c2w_on_device,
+                         const float* depth, int H, int W, float trunc_margin,
+                         const float* trgb, const float* wgt, float obs_weight,
+                         int z0, int z1, unsigned long long* counts, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage 2 — encoders (what `tcnn.Encoding.forward/backward` did; model/encodings.py:33-51,65-76,
+ * model/scene_rep.py:60-93).  tiny-cuda-nn semantics: SURVEY.md Appendix B.
+ * ---------------------------------------------------------------------------------------------- */
+#define RF_MAX_LEVELS 16
+
+typedef struct rf_grid_desc {
+    int32_t  n_levels;                    /* <= RF_MAX_LEVELS */
+    int32_t  n_features;                  /* F: 1, 2 or 4 */
+    int32_t  is_hash;                     /* 1: HashGrid, 0: Dense */
+    int32_t  _pad;
+    float    scale[RF_MAX_LEVELS];        /* exp2f(l*log2f(s))*base - 1 */
+    uint32_t resolution[RF_MAX_LEVELS];   /* ceilf(scale)+1 */
+    uint32_t size[RF_MAX_LEVELS];         /* entries in the level (after hash cap / x8 round-up) */
+    uint32_t offset[RF_MAX_LEVELS + 1];   /* running sum of size[] (entries, not floats) */
+} rf_grid_desc;
+
+/* Fill a descriptor exactly as tiny-cuda-nn's GridEncoding constructor does (Appendix B1). */
+int rf_grid_desc_init(rf_grid_desc* d, int n_levels, int n_features, int is_hash,
+                      int log2_hashmap_size, int base_resolution, double per_level_scale);
+
+/* x: device [n,3] fp32 in normalised coords; params: device fp32 [F*offset[n_levels]];
+ * out: device [n, n_levels*F] fp32 row-major. */
+int rf_grid_encode_forward(const rf_grid_desc* d, const float* params, const float* x, int64_t n,
+                           float* out, void* stream);
+/* grad_params (device, same shape as params) += scatter of dout; dx (device [n,3]) written when non-NULL. */
+int rf_grid_encode_backward(const rf_grid_desc* d, const float* params, const float* x, int64_t n,
+                            const float* dout, float* grad_params, float* dx, void* stream);
+/* OneBlob, n_bins per coordinate, out [n, 3*n_bins]. */
+int rf_oneblob_forward(const float* x, int64_t n, int n_bins, float* out, void* stream);
+int rf_oneblob_backward(const float* x, int64_t n, int n_bins, const float* dout, float* dx, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage 2 — fused mixed-representation ray query + render (+ losses) and its backward.
+ * Replaces JointEncoding.render_rays/run_network/query_color_sdf/raw2outputs/sdf2weights
+ * (model/scene_rep.py:107-127,156-179,314-349,370-456), ColorSDFNet.forward (model/decoder.py:132-146)
+ * and, in training mode, the losses of JointEncoding.mapping (model/scene_rep.py:493-517,
+ * model/utils.py:170-256).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rf_ray_cfg {
+    /* sampling (model/scene_rep.py:417-441) */
+    float   range_d;        /* training.range_d */
+    int32_t n_range_d;      /* training.n_range_d */
+    int32_t n_samples_d;    /* training.n_samples_d */
+    float   near_, far_;    /* cam.near, cam.far */
+    int32_t perturb;        /* training.perturb > 0 */
+    /* query (model/scene_rep.py:329-345) */
+    float   c_trunc;        /* training.c_trunc */
+    float   trunc;          /* training.trunc */
+    int32_t clamp_mode;     /* 0: mapping (clamp +-1); 1: BA (clamp +-clamp_thr, decoder fed +-1) */
+    float   clamp_thr;      /* mapping.clamp */
+    /* render + losses */
+    float   sc_factor;      /* data.sc_factor */
+    float   depth_trunc;    /* cam.depth_trunc */
+    float   rgb_missing;    /* training.rgb_missing */
+    /* decoder shape (model/decoder.py) */
+    int32_t hidden;         /* decoder.hidden_dim == hidden_dim_color (32 or 64) */
+    int32_t n_bins;         /* pos.n_bins (16) */
+    int32_t geo_feat;       /* decoder.geo_feat_dim (15) */
+    int32_t mlp_precision;  /* 0: fp32 SIMT, 1: 3xTF32 tensor-core, 2: TF32 tensor-core */
+    int32_t _pad;
+    double  bbox[6];        /* float64 bounding box {x0,x1,y0,y1,z0,z1} (model/scene_rep.py:388) */
+} rf_ray_cfg;
+
+typedef struct rf_ray_params {
+    const float* hash_params;  /* device; HashGrid table */
+    const float* gbv_params;   /* device; Dense F=4 grid (the TSDF volume) */
+    const float* w_sdf0;       /* device [hidden, in_sdf]   nn.Linear weight, row-major [out,in] */
+    const float* w_sdf1;       /* device [1+geo, hidden] */
+    const float* w_col0;       /* device [hidden, in_col] */
+    const float* w_col1;       /* device [3, hidden] */
+} rf_ray_params;
+
+/* Forward.  rays_o, rays_d [N,3]; target_d [N]; u [N,S] jitter in [0,1) or NULL (then perturb must be 0);
+ * outputs: z_vals [N,S], raw [N,S,4], rgb_map [N,3], depth_map [N];
+ * loss_partials (device double[16], may be NULL): accumulates the sums the four losses are built from:
+ *   [0] sum (rgb*w - tgt*w)^2   [1] sum_valid (depth - d)^2   [2] n_valid
+ *   [3] sum (s*front - front)^2 [4] sum ((z+s*tr)*m - d*m)^2  [5] n_front (pre-mask) [6] n_sdf (pre-mask)
+ * target_rgb [N,3] required when loss_partials != NULL. */
+int rf_ray_query_forward(const rf_ray_cfg* cfg, const rf_grid_desc* hash, const rf_grid_desc* gbv,
+                         const rf_ray_params* p,
+                         const float* rays_o, const float* rays_d, const float* target_d,
+                         const float* target_rgb, const float* u, int64_t n_rays,
+                         float* z_vals, float* raw, float* rgb_map, float* depth_map,
+                         double* loss_partials, void* stream);
+
+typedef struct rf_ray_grads {
+    float* g_hash;     /* device, += ; same shape as hash_params (may be NULL) */
+    float* g_w_sdf0;   /* device, += */
+    float* g_w_sdf1;
+    float* g_w_col0;
+    float* g_w_col1;
+    float* g_rays_o;   /* device [N,3], written; NULL = mapping mode (no ray gradients) */
+    float* g_rays_d;   /* device [N,3], written; NULL likewise */
+} rf_ray_grads;
+
+/* Backward of the forward above (recomputes activations).  Upstream gradients:
+ *   d_rgb_map [N,3], d_depth_map [N], d_raw [N,S,4] (any may be NULL = zero);
+ * z_vals, raw as produced by the forward. */
+int rf_ray_query_backward(const rf_ray_cfg* cfg, const rf_grid_desc* hash, const rf_grid_desc* gbv,
+                          const rf_ray_params* p,
+                          const float* rays_o, const float* rays_d, int64_t n_rays,
+                          const float* z_vals, const float* raw,
+                          const float* d_rgb_map, const float* d_depth_map, const float* d_raw,
+                          const rf_ray_grads* g, void* stream);
+
+/* Point query (model/scene_rep.py:212-310 — query_sdf_res / query_color_residual / run_network(flat)):
+ * x [n,3] normalised coords -> raw [n,4] (rgb, sdf).  variant: 0 = query_color_sdf (cfg->clamp_mode),
+ * 1 = query_sdf_res (always +-1 clamp; rgb lanes hold geo garbage-free zeros), 2 = query_color_residual
+ * (decoder fed the unscaled GBV tsdf). */
+int rf_point_query_forward(const rf_ray_cfg* cfg, const rf_grid_desc* hash, const rf_grid_desc* gbv,
+                           const rf_ray_params* p, const float* x, int64_t n, int variant,
+                           float* raw, void* stream);
+
+/* Micro-benchmarks for the gather-bound roofline denominators: random 8-byte loads and
+ * random fp32 red.add over a table of table_bytes; returns elapsed ms in *ms (host). */
+int rf_microbench_gather(void* table, int64_t table_bytes, int64_t n_ops, int iters, float* ms, void* stream);
+int rf_microbench_atomic(void* table, int64_t table_bytes, int64_t n_ops, int iters, float* ms, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RF_ABI_H */

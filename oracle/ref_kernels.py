@@ -1,0 +1,126 @@
+"""TEST INFRASTRUCTURE ONLY.  Launch the literal reference TSDF kernels (cubins built by oracle/build_ref.py
+from the strings in /root/reference) on torch CUDA tensors through the CUDA driver API (cuda-python),
+reproducing the host wrappers of the reference launch for launch:
+
+  * moving_volume.integrate       model/Volume.py:713-757   (grid/block: model/Volume.py:110-123)
+  * Mapper.integrate_kf           mp_slam/mapper.py:823-872 (grid/block: mp_slam/mapper.py:239-251)
+  * Mapper.init_mapvolume         mp_slam/mapper.py:267-282
+
+Every scalar travels as float32 inside small device arrays exactly as PyCUDA's ``cuda.In`` would ship it.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_DIR = os.path.join(HERE, "_ref")
+
+
+def available() -> bool:
+    return (torch.cuda.is_available()
+            and os.path.exists(os.path.join(REF_DIR, "ref_local_volume.cubin"))
+            and os.path.exists(os.path.join(REF_DIR, "ref_global_volume.cubin")))
+
+
+def _check(res):
+    err = res[0]
+    if int(err) != 0:
+        raise RuntimeError(f"CUDA driver error {err}")
+    return res[1:] if len(res) > 2 else (res[1] if len(res) == 2 else None)
+
+
+class _Module:
+    def __init__(self, cubin: str):
+        from cuda.bindings import driver
+        self.drv = driver
+        torch.cuda.init()
+        torch.zeros(1, device="cuda")          # make sure the primary context is current
+        data = open(os.path.join(REF_DIR, cubin), "rb").read()
+        self.mod = _check(driver.cuModuleLoadData(data))
+        self.fn = {}
+
+    def get(self, name: str):
+        if name not in self.fn:
+            self.fn[name] = _check(self.drv.cuModuleGetFunction(self.mod, name.encode()))
+        return self.fn[name]
+
+    def launch(self, name, grid, block, ptrs):
+        """ptrs: list of device pointers (ints)."""
+        args = [ctypes.c_void_p(int(p)) for p in ptrs]
+        arr = (ctypes.c_void_p * len(args))(*[ctypes.addressof(a) for a in args])
+        stream = torch.cuda.current_stream().cuda_stream
+        _check(self.drv.cuLaunchKernel(self.get(name), grid[0], grid[1], grid[2], block[0], block[1], block[2],
+                                       0, stream, ctypes.addressof(arr), 0))
+
+
+_mods = {}
+
+
+def _mod(name):
+    if name not in _mods:
+        _mods[name] = _Module(name)
+    return _mods[name]
+
+
+def _launch_geometry(n_vox: int, max_threads=1024, max_grid=(2147483647, 65535, 65535)):
+    """model/Volume.py:110-123 == mp_slam/mapper.py:239-251."""
+    n_blocks = int(np.ceil(float(n_vox) / float(max_threads)))
+    gx = min(max_grid[0], int(np.floor(np.cbrt(n_blocks))))
+    gy = min(max_grid[1], int(np.floor(np.sqrt(n_blocks / gx))))
+    gz = min(max_grid[2], int(np.ceil(float(n_blocks) / float(gx * gy))))
+    n_loops = int(np.ceil(float(n_vox) / float(gx * gy * gz * max_threads)))
+    return (gx, gy, gz), n_loops
+
+
+def _dev(a) -> torch.Tensor:
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float32).reshape(-1))).cuda()
+
+
+def ref_integrate_local(tsdf, weight, color, vol_dim, vol_origin, voxel_size, K, c2w, depth, packed_bgr,
+                        trunc_margin, obs_weight=1.0, reintegrate_flag=0.0, weight_clamp=1.0, old_bnd=None):
+    """In place on the three CUDA fp32 tensors.  depth/packed_bgr: CUDA fp32 [H,W]."""
+    m = _mod("ref_local_volume.cubin")
+    H, W = depth.shape
+    grid, n_loops = _launch_geometry(int(np.prod(vol_dim)))
+    keep = [_dev(vol_dim), _dev(vol_origin), _dev(K), _dev(c2w),
+            _dev(old_bnd if old_bnd is not None else np.zeros(6))]
+    for loop in range(n_loops):
+        other = _dev([loop, voxel_size, H, W, trunc_margin, obs_weight, reintegrate_flag, weight_clamp])
+        keep.append(other)
+        m.launch("integrate", grid, (1024, 1, 1),
+                 [tsdf.data_ptr(), weight.data_ptr(), color.data_ptr(), keep[0].data_ptr(), keep[1].data_ptr(),
+                  keep[2].data_ptr(), keep[3].data_ptr(), other.data_ptr(), keep[4].data_ptr(),
+                  packed_bgr.data_ptr(), depth.data_ptr()])
+    torch.cuda.synchronize()
+
+
+def ref_integrate_global(trgb, wgt, R, box, K, c2w, depth, rgb, trunc_margin, obs_weight=1.0):
+    """In place on GBV params [R^3*4] and GBW params [R^3] (CUDA fp32).  rgb: CUDA fp32 [H,W,3] in [0,1]."""
+    m = _mod("ref_global_volume.cubin")
+    H, W = depth.shape
+    grid, n_loops = _launch_geometry(R ** 3)
+    voxel_size = 1.0 / R
+    keep = [_dev([R, R, R]), _dev(K), _dev(c2w)]
+    for loop in range(n_loops):
+        other = _dev([loop, voxel_size, H, W, trunc_margin, obs_weight,
+                      box[0], box[1], box[2], box[3], box[4], box[5]])
+        keep.append(other)
+        m.launch("integrate", grid, (1024, 1, 1),
+                 [trgb.data_ptr(), wgt.data_ptr(), keep[0].data_ptr(), keep[1].data_ptr(), keep[2].data_ptr(),
+                  other.data_ptr(), rgb.data_ptr(), depth.data_ptr()])
+    torch.cuda.synchronize()
+
+
+def ref_clear_global(trgb, R):
+    m = _mod("ref_global_volume.cubin")
+    grid, n_loops = _launch_geometry(R ** 3)
+    keep = [_dev([R, R, R])]
+    for loop in range(n_loops):
+        other = _dev([loop])
+        keep.append(other)
+        m.launch("clean_tsdf", grid, (1024, 1, 1), [trgb.data_ptr(), keep[0].data_ptr(), other.data_ptr()])
+    torch.cuda.synchronize()

@@ -1,0 +1,168 @@
+"""Local moving TSDF volume — host-side mirror of ``moving_volume`` (model/Volume.py:19-124, :713-757).
+
+Same constructor arguments, attribute names and ``integrate`` signature as the reference so that
+model/ROtracker.py:132,939 can call it unchanged; the work runs in librf_b200.so (``rf_tsdf_integrate_local``)
+instead of a PyCUDA JIT kernel.  Device memory is held in torch tensors (``tsdf_vol_gpu`` etc. keep the
+reference's names); the raw pointers stay valid for the object's lifetime.
+
+Scope: construction (``center`` bounds, model/Volume.py:1133-1149), ``integrate``, ``clean_volume``.  Volume
+re-centring (copy_volume / swap_rot_trans), point-cloud and mesh dumps are rows N2 / out of scope.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import abi
+
+
+class moving_volume:
+    """Moving volume of RGB-D images (reference: model/Volume.py:19)."""
+
+    def __init__(self, cfg, traj, init_pose, gpu_mode=True, start=0, device=None, x_slab=None):
+        self.config = cfg
+        v = cfg["volume"]
+        self.voxel_size = float(v["voxel_size"])
+        self.surface_trunc = cfg["training"]["trunc"]
+        self.trunc_margin = v["trunc"]
+        self.fix_x, self.fix_y, self.fix_z = v["x_config"]["fix"], v["y_config"]["fix"], v["z_config"]["fix"]
+        self.x_len, self.y_len, self.z_len = v["x_config"]["len"], v["y_config"]["len"], v["z_config"]["len"]
+        self.version = v["version"]
+        self.t_treshold = v.get("t_treshold", 1)
+        self.weight_clamp = v["weight_clamp"]
+        self.color_const = 256 * 256
+        if not gpu_mode or not torch.cuda.is_available():
+            raise abi.RfError("moving_volume: a CUDA device is required (the reference has no CPU path either, "
+                              "model/Volume.py:613-619)")
+        self.device = torch.device(device if device is not None else "cuda")
+
+        init_pose = np.asarray(init_pose, dtype=np.float64)
+        self.vol_bnds = np.asarray(self.initialize_vol_bnd(init_pose, traj, self.version))
+        assert self.vol_bnds.shape == (3, 2), "[!] `vol_bnds` should be of shape (3, 2)."
+        # model/Volume.py:67-71
+        self.vol_dim = np.ceil((self.vol_bnds[:, 1] - self.vol_bnds[:, 0]) / self.voxel_size).copy(order="C").astype(int)
+        self.vol_bnds[:, 1] = self.vol_bnds[:, 0] + self.vol_dim * self.voxel_size
+        self.vol_origin = self.vol_bnds[:, 0].copy(order="C").astype(np.float32)
+        self.start_id = 0
+        self.frame_to_Vrange = {}
+
+        dx, dy, dz = (int(d) for d in self.vol_dim)
+        if dx * dy * dz >= 2 ** 31:
+            raise abi.RfError("moving_volume: more than 2^31 voxels")
+        # x-slab owned by this process (multi-GPU sharding): arrays hold only the slab
+        self.x_slab = (0, dx) if x_slab is None else (int(x_slab[0]), int(x_slab[1]))
+        n_own = (self.x_slab[1] - self.x_slab[0]) * dy * dz
+        self.tsdf_vol_gpu = torch.ones(n_own, dtype=torch.float32, device=self.device)       # model/Volume.py:85
+        self.weight_vol_gpu = torch.zeros(n_own, dtype=torch.float32, device=self.device)    # :86
+        self.color_vol_gpu = torch.zeros(n_own, dtype=torch.float32, device=self.device)     # :87
+        self._frame = None
+
+    # ---- bounds (model/Volume.py:910-925, :1133-1149) ----------------------------------------------------
+    def initialize_vol_bnd(self, cam_pose_iter, traj, version):
+        if version == "center":
+            return self.center_volbnd(np.zeros((3, 2)), cam_pose_iter, traj)
+        raise NotImplementedError("volume.version != 'center' (angle-based bounds, model/Volume.py:1151-1201) "
+                                  "is volume bookkeeping outside the hot path")
+
+    def center_volbnd(self, vol_bnds, cam_pose_iter, tsdf_cam):
+        vol_bnds = np.zeros((3, 2))
+        if tsdf_cam is not None:
+            tsdf_cam.kfx, tsdf_cam.kfy, tsdf_cam.kfz = cam_pose_iter[0, 3], cam_pose_iter[1, 3], cam_pose_iter[2, 3]
+        center_cam = np.round(cam_pose_iter[:3, 3], 0)
+        for ax, ln in enumerate((self.x_len, self.y_len, self.z_len)):
+            vol_bnds[ax, 0] = center_cam[ax] - ln
+            vol_bnds[ax, 1] = center_cam[ax] + ln
+        return vol_bnds
+
+    # ---- hot path ---------------------------------------------------------------------------------------
+    def _stage(self, arr, key):
+        """Host numpy / CPU tensor -> device fp32 (pinned staging buffer, async copy); CUDA tensors pass through."""
+        if isinstance(arr, torch.Tensor) and arr.is_cuda:
+            return arr.to(torch.float32).contiguous()
+        a = arr.numpy() if isinstance(arr, torch.Tensor) else np.asarray(arr)
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        if self._frame is None:
+            self._frame = {}
+        slot = self._frame.get(key)
+        if slot is None or slot[0].shape != a.shape:
+            slot = (torch.empty(a.shape, dtype=torch.float32).pin_memory(),
+                    torch.empty(a.shape, dtype=torch.float32, device=self.device))
+            self._frame[key] = slot
+        slot[0].numpy()[...] = a
+        slot[1].copy_(slot[0], non_blocking=True)
+        return slot[1]
+
+    def integrate(self, color_im, depth_im, cam_intr, cam_pose, old_bnd, obs_weight=1., reintegrate_flag=0.0):
+        """Integrate an RGB-D frame into the TSDF volume (model/Volume.py:713-757).
+
+        color_im: (H, W, 3) RGB with channel values 0..255 (model/ROtracker.py:82,896); depth_im: (H, W) metres;
+        cam_intr: (3, 3); cam_pose: (4, 4) camera-to-world; old_bnd: (3, 2) or None.
+        """
+        depth = self._stage(depth_im, "depth")
+        im_h, im_w = depth.shape
+        rgb = self._stage(color_im, "rgb")
+        if rgb.shape != (im_h, im_w, 3):
+            raise abi.RfError(f"color_im shape {tuple(rgb.shape)} does not match depth {(im_h, im_w)}")
+        if self._frame is None:
+            self._frame = {}
+        packed = self._frame.get("packed")
+        if packed is None or packed.numel() != im_h * im_w:
+            packed = torch.empty(im_h * im_w, dtype=torch.float32, device=self.device)
+            self._frame["packed"] = packed
+        L = abi.lib()
+        st = abi.stream_ptr()
+        abi.check(L.rf_pack_bgr(abi.dptr(rgb), abi.dptr(packed), C.c_int(im_h * im_w), st), "rf_pack_bgr")
+        self.integrate_packed(depth, packed, cam_intr, cam_pose, old_bnd, obs_weight, reintegrate_flag)
+
+    def integrate_packed(self, depth, packed, cam_intr, cam_pose, old_bnd=None, obs_weight=1., reintegrate_flag=0.0):
+        """Same as integrate() with the frame already resident: depth [H,W], packed BGR [H*W] CUDA fp32."""
+        im_h, im_w = depth.shape
+        dx, dy, dz = (int(d) for d in self.vol_dim)
+        _o, o_p = abi.farr(self.vol_origin, 3)
+        _k, k_p = abi.farr(np.asarray(cam_intr, dtype=np.float64), 9)
+        _c, c_p = abi.farr(np.asarray(cam_pose.detach().cpu().numpy() if isinstance(cam_pose, torch.Tensor) else cam_pose,
+                                      dtype=np.float64), 16)
+        reint = 1 if float(reintegrate_flag) == 1.0 else 0
+        if old_bnd is not None:
+            _b, b_p = abi.farr(np.asarray(old_bnd, dtype=np.float64), 6)
+        else:
+            _b, b_p = None, C.POINTER(C.c_float)()
+        L = abi.lib()
+        rc = L.rf_tsdf_integrate_local(
+            abi.dptr(self.tsdf_vol_gpu), abi.dptr(self.weight_vol_gpu), abi.dptr(self.color_vol_gpu),
+            C.c_int(dx), C.c_int(dy), C.c_int(dz), o_p, C.c_float(self.voxel_size), k_p, c_p,
+            abi.dptr(depth), abi.dptr(packed), C.c_int(im_h), C.c_int(im_w),
+            C.c_float(self.trunc_margin), C.c_float(obs_weight),
+            C.c_int(1 if float(self.weight_clamp) == 1.0 else 0), C.c_int(reint), b_p,
+            C.c_int(self.x_slab[0]), C.c_int(self.x_slab[1]), C.c_int(1), abi.stream_ptr())
+        abi.check(rc, "rf_tsdf_integrate_local")
+
+    def count_touched(self, depth, cam_intr, cam_pose, old_bnd=None, reintegrate_flag=0.0):
+        """(n_touched, n_band) for this frame — the numerator of voxel-updates/s."""
+        im_h, im_w = depth.shape
+        dx, dy, dz = (int(d) for d in self.vol_dim)
+        _o, o_p = abi.farr(self.vol_origin, 3)
+        _k, k_p = abi.farr(np.asarray(cam_intr, dtype=np.float64), 9)
+        _c, c_p = abi.farr(np.asarray(cam_pose, dtype=np.float64), 16)
+        if old_bnd is not None:
+            _b, b_p = abi.farr(np.asarray(old_bnd, dtype=np.float64), 6)
+        else:
+            _b, b_p = None, C.POINTER(C.c_float)()
+        counts = torch.zeros(2, dtype=torch.int64, device=self.device)
+        rc = abi.lib().rf_tsdf_count_local(
+            C.c_int(dx), C.c_int(dy), C.c_int(dz), o_p, C.c_float(self.voxel_size), k_p, c_p,
+            abi.dptr(depth), C.c_int(im_h), C.c_int(im_w), C.c_float(self.trunc_margin),
+            C.c_int(1 if float(reintegrate_flag) == 1.0 else 0), b_p,
+            C.c_int(self.x_slab[0]), C.c_int(self.x_slab[1]), C.c_void_p(counts.data_ptr()), abi.stream_ptr())
+        abi.check(rc, "rf_tsdf_count_local")
+        c = counts.cpu()
+        return int(c[0]), int(c[1])
+
+    def clean_volume(self):
+        """Reset tsdf=1, weight=0, colour=0 (model/Volume.py:655-673)."""
+        rc = abi.lib().rf_tsdf_clear_local(abi.dptr(self.tsdf_vol_gpu), abi.dptr(self.weight_vol_gpu),
+                                           abi.dptr(self.color_vol_gpu), C.c_int64(self.tsdf_vol_gpu.numel()),
+                                           abi.stream_ptr())
+        abi.check(rc, "rf_tsdf_clear_local")
