@@ -160,8 +160,9 @@ typedef struct rf_ray_cfg {
     int32_t hidden;         /* decoder.hidden_dim == hidden_dim_color (32 or 64) */
     int32_t n_bins;         /* pos.n_bins (16) */
     int32_t geo_feat;       /* decoder.geo_feat_dim (15) */
-    int32_t mlp_precision;  /* 0: fp32 SIMT, 1: 3xTF32 tensor-core, 2: TF32 tensor-core */
+    int32_t mlp_precision;  /* 0: fp32 SIMT decoder (the accuracy anchor) */
     int32_t _pad;
+    int64_t n_rays_total;   /* rays in the whole batch when it is sharded over GPUs (loss means); 0 = n_rays */
     double  bbox[6];        /* float64 bounding box {x0,x1,y0,y1,z0,z1} (model/scene_rep.py:388) */
 } rf_ray_cfg;
 
@@ -174,22 +175,30 @@ typedef struct rf_ray_params {
     const float* w_col1;       /* device [3, hidden] */
 } rf_ray_params;
 
-/* Forward.  rays_o, rays_d [N,3]; target_d [N]; u [N,S] jitter in [0,1) or NULL (then perturb must be 0);
- * outputs: z_vals [N,S], raw [N,S,4], rgb_map [N,3], depth_map [N];
- * loss_partials (device double[16], may be NULL): accumulates the sums the four losses are built from:
+/* Depth sampling along rays (model/scene_rep.py:417-441).  target_d [N]; u [N,S] jitter in [0,1) (required when
+ * cfg->perturb, the reference draws it with torch.rand on the CPU generator, :441); z_tables (device,
+ * [2*n_range_d + n_samples_d]): linspace(-range_d, range_d, n_range_d), linspace(near, far, n_range_d),
+ * linspace(near, far, n_samples_d) exactly as torch.linspace produces them on the host; z_vals [N,S] out. */
+int rf_ray_sample_z(const rf_ray_cfg* cfg, const float* target_d, const float* u, const float* z_tables,
+                    int64_t n_rays, float* z_vals, void* stream);
+
+/* Forward.  rays_o, rays_d [N,3]; z_vals [N,S] (from rf_ray_sample_z);
+ * outputs: raw [N,S,4], rgb_map [N,3], depth_map [N];
+ * loss_partials (device double[8], may be NULL; caller zeroes it): accumulates the sums the four losses of
+ * JointEncoding.mapping are built from:
  *   [0] sum (rgb*w - tgt*w)^2   [1] sum_valid (depth - d)^2   [2] n_valid
  *   [3] sum (s*front - front)^2 [4] sum ((z+s*tr)*m - d*m)^2  [5] n_front (pre-mask) [6] n_sdf (pre-mask)
- * target_rgb [N,3] required when loss_partials != NULL. */
+ * target_d [N] and target_rgb [N,3] are required when loss_partials != NULL. */
 int rf_ray_query_forward(const rf_ray_cfg* cfg, const rf_grid_desc* hash, const rf_grid_desc* gbv,
                          const rf_ray_params* p,
                          const float* rays_o, const float* rays_d, const float* target_d,
-                         const float* target_rgb, const float* u, int64_t n_rays,
-                         float* z_vals, float* raw, float* rgb_map, float* depth_map,
+                         const float* target_rgb, const float* z_vals, int64_t n_rays,
+                         float* raw, float* rgb_map, float* depth_map,
                          double* loss_partials, void* stream);
 
 typedef struct rf_ray_grads {
     float* g_hash;     /* device, += ; same shape as hash_params (may be NULL) */
-    float* g_w_sdf0;   /* device, += */
+    float* g_w_sdf0;   /* device, += (each may be NULL) */
     float* g_w_sdf1;
     float* g_w_col0;
     float* g_w_col1;
@@ -197,15 +206,18 @@ typedef struct rf_ray_grads {
     float* g_rays_d;   /* device [N,3], written; NULL likewise */
 } rf_ray_grads;
 
-/* Backward of the forward above (recomputes activations).  Upstream gradients:
- *   d_rgb_map [N,3], d_depth_map [N], d_raw [N,S,4] (any may be NULL = zero);
- * z_vals, raw as produced by the forward. */
+/* Backward of the forward above (recomputes activations).  Upstream gradients (each may be NULL = zero):
+ *   d_rgb_map [N,3], d_depth_map [N], d_raw [N,S,4], and loss_grads (device float[4]: d/d rgb_loss, depth_loss,
+ *   sdf_loss, fs_loss) together with the forward's loss_partials (all-reduced over ranks when sharded).
+ * scratch: device, 16-byte aligned, >= 4*N*S floats (7*N*S when ray gradients are requested). */
 int rf_ray_query_backward(const rf_ray_cfg* cfg, const rf_grid_desc* hash, const rf_grid_desc* gbv,
                           const rf_ray_params* p,
-                          const float* rays_o, const float* rays_d, int64_t n_rays,
-                          const float* z_vals, const float* raw,
+                          const float* rays_o, const float* rays_d, const float* target_d,
+                          const float* target_rgb, int64_t n_rays,
+                          const float* z_vals, const float* raw, const float* rgb_map, const float* depth_map,
                           const float* d_rgb_map, const float* d_depth_map, const float* d_raw,
-                          const rf_ray_grads* g, void* stream);
+                          const float* loss_grads, const double* loss_partials,
+                          const rf_ray_grads* g, float* scratch, void* stream);
 
 /* Point query (model/scene_rep.py:212-310 — query_sdf_res / query_color_residual / run_network(flat)):
  * x [n,3] normalised coords -> raw [n,4] (rgb, sdf).  variant: 0 = query_color_sdf (cfg->clamp_mode),

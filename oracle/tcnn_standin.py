@@ -27,10 +27,13 @@ U32 = 0xFFFFFFFF
 def grid_levels(n_levels, n_features, is_hash, log2_hashmap_size, base_resolution, per_level_scale):
     """Appendix B1.  Returns lists scale (np.float32), resolution, size, offset (entries)."""
     pls = np.float32(per_level_scale)                      # JSON double narrowed to float by tcnn
-    log2s = np.float32(np.log2(pls))                       # std::log2(float)
+    # log2 / exp2 evaluated in double and rounded once to float: reproducible on any host (tcnn: std::log2(float) on
+    # the host and exp2f on the device, which may differ from this in the last bit — part of "parity unpinned")
+    log2s = np.float32(np.log2(np.float64(pls)))
     scale, res, size, offset = [], [], [], [0]
     for l in range(n_levels):
-        s = np.float32(np.exp2(np.float32(np.float32(l) * log2s)) * np.float32(base_resolution) - np.float32(1.0))
+        e = np.float32(np.exp2(np.float64(np.float32(l) * log2s)))
+        s = np.float32(e * np.float32(base_resolution) - np.float32(1.0))
         r = int(np.ceil(s)) + 1
         max_params = (2 ** 32 - 1) // 2
         n = max_params if float(np.float32(r) ** 3) > float(max_params) else r ** 3

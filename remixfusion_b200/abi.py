@@ -45,6 +45,7 @@ class RayCfg(C.Structure):
         ("sc_factor", C.c_float), ("depth_trunc", C.c_float), ("rgb_missing", C.c_float),
         ("hidden", C.c_int32), ("n_bins", C.c_int32), ("geo_feat", C.c_int32),
         ("mlp_precision", C.c_int32), ("_pad", C.c_int32),
+        ("n_rays_total", C.c_int64),
         ("bbox", C.c_double * 6),
     ]
 

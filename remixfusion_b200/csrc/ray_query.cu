@@ -1,0 +1,833 @@
+// ray_query.cu — Stage 2 of the mapping hot path: mixed-representation ray query, render, losses, backward.
+//
+// Replaces, fused, what the reference runs as ~40 ATen launches + 3 tiny-cuda-nn launches + 4 sgemms forward and
+// about twice that backward:
+//   JointEncoding.render_rays      model/scene_rep.py:407-456   -> ray_z_kernel (sampling) + sample_fwd_kernel + composite_fwd_kernel
+//   JointEncoding.run_network      model/scene_rep.py:370-402   -> fp64 normalisation inside the sample kernels
+//   JointEncoding.query_color_sdf  model/scene_rep.py:314-349   -> sample_fwd_kernel (hash + OneBlob + GBV trilerp + decoder)
+//   ColorSDFNet / SDFNet / ColorNet model/decoder.py:6-146      -> decoder inside the sample kernels
+//   raw2outputs / sdf2weights      model/scene_rep.py:107-179   -> composite_fwd_kernel
+//   mapping() losses               model/scene_rep.py:493-517, model/utils.py:170-256 -> loss partial sums in composite_fwd_kernel
+//   autograd backward (R8)                                       -> composite_bwd_kernel + sample_bwd_kernel + ray_grad_kernel
+//
+// Kernel plan (mlp_precision 0 = fp32 SIMT decoder, the accuracy anchor):
+//   * one thread per sample; decoder weights live transposed in shared memory ([in][out]) so that a thread streams its
+//     input features through `h[j] += x_k * Wt[k][j]` with broadcast 128-bit shared loads;
+//   * no activation ever goes to HBM: per sample the kernels read ray (28 B, L1-resident across the ray's samples),
+//     gather 16x8 hash entries (8 B) + 8 GBV voxels (16 B) and write raw (16 B); backward recomputes the forward;
+//   * table gradients are scattered with 8-byte vector reductions (RED.ADD.F32x2), decoder weight gradients are
+//     tile GEMMs over the 128 samples of a block accumulated in shared memory and flushed once per block.
+#include <math.h>
+#include <algorithm>
+#include "grid_encode.cuh"
+
+namespace rf {
+
+constexpr int kGeo = 15;            // decoder.geo_feat_dim
+constexpr int kNB = 16;             // pos.n_bins
+constexpr int kBlob = 3 * kNB;      // 48
+constexpr int kOut1 = 1 + kGeo;     // 16
+constexpr int kIn2 = kBlob + kGeo + 3;   // 66
+constexpr int kMaxS = 128;
+constexpr int kTile = 128;          // samples per block iteration == threads per block
+
+struct RayK {
+    int   n_range_d, n_samples_d, S, perturb;
+    float c_trunc, trunc, clamp_thr, sc_trunc, depth_trunc;
+    int   clamp_mode, rgb_all_ones, n_hash_out, in1;      // in1 = n_hash_out + 48 + 1
+    double b0[3], bl[3];                                   // bbox low corner and extent (float64, model/scene_rep.py:388)
+    long long n_rays, n_total;                             // local rays, and rays in the whole (multi-GPU) batch
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// z sampling — model/scene_rep.py:417-441.  One warp per ray.
+// tables: [n_range_d] offsets (linspace(-range_d, range_d)), [n_range_d] linspace(near, far, n_range_d),
+//         [n_samples_d] linspace(near, far, n_samples_d) — produced by torch.linspace on the host side so that the
+//         values are the ones the reference computes on the same machine.
+__global__ void ray_z_kernel(RayK k, const float* __restrict__ target_d, const float* __restrict__ u,
+                             const float* __restrict__ tables, float* __restrict__ z_vals) {
+    __shared__ float s_z[4][kMaxS];
+    __shared__ float s_a[4][kMaxS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    long long r = blockIdx.x * 4ll + warp;
+    if (r >= k.n_rays) return;
+    const int nA = k.n_range_d, nB = k.n_samples_d, S = k.S;
+    const float* tA = tables; const float* tAnf = tables + nA; const float* tB = tables + 2 * nA;
+    float d = target_d[r];
+    float* za = s_a[warp]; float* zs = s_z[warp];
+    for (int i = lane; i < nA; i += 32) za[i] = (d <= 0.f) ? tAnf[i] : __fadd_rn(tA[i], d);      // :422-424
+    __syncwarp();
+    if (nB > 0) {                                                                                 // :426-428 (cat + sort)
+        for (int i = lane; i < nA; i += 32) {
+            float v = za[i]; int c = 0;
+            for (int j = 0; j < nB; ++j) c += (tB[j] < v) ? 1 : 0;
+            zs[i + c] = v;
+        }
+        for (int j = lane; j < nB; j += 32) {
+            float v = tB[j]; int c = 0;
+            for (int i = 0; i < nA; ++i) c += (za[i] <= v) ? 1 : 0;
+            zs[j + c] = v;
+        }
+    } else {
+        for (int i = lane; i < nA; i += 32) zs[i] = za[i];
+    }
+    __syncwarp();
+    for (int s = lane; s < S; s += 32) {
+        float z = zs[s];
+        if (k.perturb) {                                                                          // :437-441
+            float lower = (s == 0) ? zs[0] : __fmul_rn(0.5f, __fadd_rn(zs[s], zs[s - 1]));
+            float upper = (s == S - 1) ? zs[S - 1] : __fmul_rn(0.5f, __fadd_rn(zs[s + 1], zs[s]));
+            z = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), u[r * S + s]));
+        }
+        z_vals[r * S + s] = z;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Per-sample building blocks
+// ------------------------------------------------------------------------------------------------------------
+template <int HID>
+__device__ __forceinline__ void axpy_row(float (&h)[HID], float a, const float* __restrict__ w) {
+#pragma unroll
+    for (int j = 0; j < HID; j += 4) {
+        float4 v = *reinterpret_cast<const float4*>(w + j);
+        h[j] = fmaf(a, v.x, h[j]); h[j + 1] = fmaf(a, v.y, h[j + 1]); h[j + 2] = fmaf(a, v.z, h[j + 2]); h[j + 3] = fmaf(a, v.w, h[j + 3]);
+    }
+}
+template <int HID>
+__device__ __forceinline__ float dot_row(const float (&h)[HID], const float* __restrict__ w) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int j = 0; j < HID; j += 4) {
+        float4 v = *reinterpret_cast<const float4*>(w + j);
+        a0 = fmaf(h[j], v.x, a0); a1 = fmaf(h[j + 1], v.y, a1); a2 = fmaf(h[j + 2], v.z, a2); a3 = fmaf(h[j + 3], v.w, a3);
+    }
+    return (a0 + a1) + (a2 + a3);
+}
+
+// sample position in normalised coordinates: pts = o + d*z (separate fp32 mul/add, :443), then float64
+// normalisation (:388) and the cast to fp32 tiny-cuda-nn applies at its boundary.
+__device__ __forceinline__ void sample_x(const RayK& k, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                         long long r, float z, float (&x)[3]) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float p = __fadd_rn(__ldg(rays_o + 3 * r + a), __fmul_rn(__ldg(rays_d + 3 * r + a), z));
+        x[a] = (float)(((double)p - k.b0[a]) / k.bl[a]);
+    }
+}
+
+__device__ __forceinline__ float2 hash_level_feat(const GridDev& g, const float* __restrict__ params, int l, const float (&x)[3]) {
+    unsigned cx, cy, cz; float fx, fy, fz;
+    pos_fract(x[0], g.scale[l], cx, fx); pos_fract(x[1], g.scale[l], cy, fy); pos_fract(x[2], g.scale[l], cz, fz);
+    const float2* tab = reinterpret_cast<const float2*>(params) + g.offset[l];
+    const unsigned size = g.size[l], res = g.res[l];
+    float2 v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        v[c] = __ldg(tab + grid_index(g.is_hash, size, res, cx + (c & 1), cy + ((c >> 1) & 1), cz + ((c >> 2) & 1)));
+    float f0 = 0.f, f1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        float w = corner_weight(c, fx, fy, fz);
+        f0 = fmaf(w, v[c].x, f0); f1 = fmaf(w, v[c].y, f1);
+    }
+    return make_float2(f0, f1);
+}
+
+__device__ __forceinline__ float4 gbv_feat(const GridDev& g, const float* __restrict__ params, const float (&x)[3]) {
+    unsigned cx, cy, cz; float fx, fy, fz;
+    pos_fract(x[0], g.scale[0], cx, fx); pos_fract(x[1], g.scale[0], cy, fy); pos_fract(x[2], g.scale[0], cz, fz);
+    const float4* tab = reinterpret_cast<const float4*>(params);
+    float4 v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        v[c] = __ldg(tab + grid_index(false, g.size[0], g.res[0], cx + (c & 1), cy + ((c >> 1) & 1), cz + ((c >> 2) & 1)));
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        float w = corner_weight(c, fx, fy, fz);
+        o.x = fmaf(w, v[c].x, o.x); o.y = fmaf(w, v[c].y, o.y); o.z = fmaf(w, v[c].z, o.z); o.w = fmaf(w, v[c].w, o.w);
+    }
+    return o;
+}
+
+// tsdf rescale and clamps — model/scene_rep.py:330-337 (and :230-233, :292-294 for the point-query variants)
+// variant 0: as cfg.clamp_mode; 1: query_sdf_res (always +-1); 2: query_color_residual (decoder fed raw g0, nothing added)
+__device__ __forceinline__ void tsdf_terms(const RayK& k, int variant, float g0, float& t_add, float& cin, float& dt_dg_add, float& dt_dg_cin) {
+    float t = __fdiv_rn(__fmul_rn(g0, k.c_trunc), k.trunc);
+    float s = k.c_trunc / k.trunc;
+    if (variant == 2) { t_add = 0.f; cin = g0; dt_dg_add = 0.f; dt_dg_cin = 1.f; return; }
+    if (variant == 0 && k.clamp_mode) {
+        float thr = k.clamp_thr;
+        t_add = fminf(fmaxf(t, -thr), thr);
+        cin = fminf(fmaxf(t_add, -1.f), 1.f);
+        dt_dg_add = (t >= -thr && t <= thr) ? s : 0.f;
+        dt_dg_cin = (t_add >= -1.f && t_add <= 1.f) ? dt_dg_add : 0.f;
+    } else {
+        t_add = fminf(fmaxf(t, -1.f), 1.f);
+        cin = t_add;
+        dt_dg_add = (t >= -1.f && t <= 1.f) ? s : 0.f;
+        dt_dg_cin = dt_dg_add;
+    }
+}
+
+struct Weights { const float* w_sdf0; const float* w_sdf1; const float* w_col0; const float* w_col1; };
+
+// shared-memory layout of the transposed decoder weights
+template <int HID>
+struct WSmem {
+    float* w0t;   // [in1][HID]
+    float* w1t;   // [HID][16]
+    float* w2t;   // [66][HID]
+    float* w3t;   // [HID][4]
+    __device__ static int floats(int in1) { return in1 * HID + HID * kOut1 + kIn2 * HID + HID * 4; }
+    __device__ void carve(float* base, int in1) { w0t = base; w1t = w0t + in1 * HID; w2t = w1t + HID * kOut1; w3t = w2t + kIn2 * HID; }
+    __device__ void load(const Weights& w, int in1) {
+        for (int i = threadIdx.x; i < HID * in1; i += blockDim.x) { int j = i / in1, kk = i - j * in1; w0t[kk * HID + j] = w.w_sdf0[i]; }
+        for (int i = threadIdx.x; i < kOut1 * HID; i += blockDim.x) { int o = i / HID, j = i - o * HID; w1t[j * kOut1 + o] = w.w_sdf1[i]; }
+        for (int i = threadIdx.x; i < HID * kIn2; i += blockDim.x) { int j = i / kIn2, kk = i - j * kIn2; w2t[kk * HID + j] = w.w_col0[i]; }
+        for (int i = threadIdx.x; i < HID * 4; i += blockDim.x) { int j = i >> 2, c = i & 3; w3t[i] = (c < 3) ? w.w_col1[c * HID + j] : 0.f; }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// Forward: one thread per sample.
+// FROM_X: positions given directly in normalised coordinates (point query) instead of rays + z.
+// ------------------------------------------------------------------------------------------------------------
+template <int HID, bool FROM_X>
+__global__ void __launch_bounds__(kTile) sample_fwd_kernel(RayK k, GridDev hg, GridDev gg, const float* __restrict__ hash_params,
+                                                           const float* __restrict__ gbv_params, Weights wts,
+                                                           const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                           const float* __restrict__ z_vals, const float* __restrict__ xin,
+                                                           long long P, int variant, float* __restrict__ raw) {
+    extern __shared__ __align__(16) float smem[];
+    WSmem<HID> W; W.carve(smem, k.in1); W.load(wts, k.in1);
+    __syncthreads();
+    const int L = hg.n_levels;
+    for (long long p = blockIdx.x * (long long)kTile + threadIdx.x; p < P; p += (long long)gridDim.x * kTile) {
+        float x[3];
+        if (FROM_X) { x[0] = xin[3 * p]; x[1] = xin[3 * p + 1]; x[2] = xin[3 * p + 2]; }
+        else sample_x(k, rays_o, rays_d, p / k.S, z_vals[p], x);
+        float h[HID];
+#pragma unroll
+        for (int j = 0; j < HID; ++j) h[j] = 0.f;
+        for (int l = 0; l < L; ++l) {                                       // model/scene_rep.py:325
+            float2 f = hash_level_feat(hg, hash_params, l, x);
+            axpy_row<HID>(h, f.x, W.w0t + (2 * l) * HID);
+            axpy_row<HID>(h, f.y, W.w0t + (2 * l + 1) * HID);
+        }
+        const int ob0 = k.n_hash_out;
+#pragma unroll 1
+        for (int c = 0; c < 3; ++c) {                                       // :327
+            float ob[kNB];
+            oneblob_coord<kNB>(x[c], ob);
+#pragma unroll
+            for (int b = 0; b < kNB; ++b) axpy_row<HID>(h, ob[b], W.w0t + (ob0 + c * kNB + b) * HID);
+        }
+        float4 g = gbv_feat(gg, gbv_params, x);                             // :329
+        float t_add, cin, d0, d1;
+        tsdf_terms(k, variant, g.x, t_add, cin, d0, d1);
+        axpy_row<HID>(h, cin, W.w0t + (ob0 + kBlob) * HID);
+        float o16[kOut1];
+#pragma unroll
+        for (int i = 0; i < kOut1; ++i) o16[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < HID; ++j) {                                     // model/decoder.py:105-110 (ReLU, Linear)
+            float a = fmaxf(h[j], 0.f);
+            const float4* wr = reinterpret_cast<const float4*>(W.w1t + j * kOut1);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float4 v = wr[q];
+                o16[4 * q] = fmaf(a, v.x, o16[4 * q]); o16[4 * q + 1] = fmaf(a, v.y, o16[4 * q + 1]);
+                o16[4 * q + 2] = fmaf(a, v.z, o16[4 * q + 2]); o16[4 * q + 3] = fmaf(a, v.w, o16[4 * q + 3]);
+            }
+        }
+        // colour net: input = [oneblob48, geo15, gbv_rgb3]  (model/decoder.py:141)
+#pragma unroll
+        for (int j = 0; j < HID; ++j) h[j] = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 3; ++c) {
+            float ob[kNB];
+            oneblob_coord<kNB>(x[c], ob);
+#pragma unroll
+            for (int b = 0; b < kNB; ++b) axpy_row<HID>(h, ob[b], W.w2t + (c * kNB + b) * HID);
+        }
+#pragma unroll
+        for (int i = 0; i < kGeo; ++i) axpy_row<HID>(h, o16[1 + i], W.w2t + (kBlob + i) * HID);
+        axpy_row<HID>(h, g.y, W.w2t + (kBlob + kGeo) * HID);
+        axpy_row<HID>(h, g.z, W.w2t + (kBlob + kGeo + 1) * HID);
+        axpy_row<HID>(h, g.w, W.w2t + (kBlob + kGeo + 2) * HID);
+        float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < HID; ++j) {
+            float a = fmaxf(h[j], 0.f);
+            float4 v = *reinterpret_cast<const float4*>(W.w3t + 4 * j);
+            r0 = fmaf(a, v.x, r0); r1 = fmaf(a, v.y, r1); r2 = fmaf(a, v.z, r2);
+        }
+        // :344-345 residual add
+        reinterpret_cast<float4*>(raw)[p] = make_float4(r0 + g.y, r1 + g.z, r2 + g.w, o16[0] + t_add);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Composite (sdf2weights + raw2outputs, model/scene_rep.py:107-127,156-179) and the loss partial sums
+// (model/scene_rep.py:493-517, model/utils.py:170-256).  One warp per ray.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float a) { return 1.0f / (1.0f + expf(-a)); }
+
+struct RayState { int first; float zthr; float denom; };
+
+// first sign change (argmax of the 0/1 mask => 0 if none), truncation threshold, normaliser
+__device__ __forceinline__ RayState ray_state(const RayK& k, const float4* __restrict__ raw_r, const float* __restrict__ z_r, int lane) {
+    const int S = k.S;
+    int first = 0x7fffffff;
+    for (int s = lane; s < S - 1; s += 32)
+        if (raw_r[s + 1].w * raw_r[s].w < 0.f) { first = s; break; }
+    for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+    if (first == 0x7fffffff) first = 0;
+    RayState st; st.first = first;
+    st.zthr = __fadd_rn(z_r[first], k.sc_trunc);
+    float sum = 0.f;
+    for (int s = lane; s < S; s += 32) {
+        float a = __fdiv_rn(raw_r[s].w, k.trunc);
+        float e = sigmoidf_(a) * sigmoidf_(-a);
+        sum += (z_r[s] < st.zthr) ? e : 0.f;
+    }
+    st.denom = warp_sum(sum) + 1e-8f;
+    return st;
+}
+
+__global__ void composite_fwd_kernel(RayK k, const float* __restrict__ raw, const float* __restrict__ z_vals,
+                                     const float* __restrict__ target_d, const float* __restrict__ target_rgb,
+                                     float* __restrict__ rgb_map, float* __restrict__ depth_map, double* __restrict__ partials) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    long long r = blockIdx.x * 4ll + warp;
+    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    if (r < k.n_rays) {
+        const int S = k.S;
+        const float4* raw_r = reinterpret_cast<const float4*>(raw) + r * S;
+        const float* z_r = z_vals + r * S;
+        RayState st = ray_state(k, raw_r, z_r, lane);
+        float c0 = 0.f, c1 = 0.f, c2 = 0.f, dm = 0.f;
+        float d = partials ? target_d[r] : 0.f;
+        bool valid = (d > 0.f) && (d < k.depth_trunc);
+        float fs = 0.f, sd = 0.f; int nf = 0, ns = 0;
+        for (int s = lane; s < S; s += 32) {
+            float4 v = raw_r[s]; float z = z_r[s];
+            float a = __fdiv_rn(v.w, k.trunc);
+            float w = (z < st.zthr) ? sigmoidf_(a) * sigmoidf_(-a) : 0.f;
+            w = w / st.denom;
+            c0 = fmaf(w, v.x, c0); c1 = fmaf(w, v.y, c1); c2 = fmaf(w, v.z, c2); dm = fmaf(w, z, dm);
+            if (partials) {
+                bool front = z < __fsub_rn(d, k.sc_trunc), back = z > __fadd_rn(d, k.sc_trunc);
+                bool sm = !front && !back && (d > 0.f);
+                nf += front ? 1 : 0; ns += sm ? 1 : 0;
+                if (valid && front) { float e = v.w - 1.0f; fs = fmaf(e, e, fs); }
+                if (valid && sm) { float e = __fadd_rn(z, __fmul_rn(v.w, k.sc_trunc)) - d; sd = fmaf(e, e, sd); }
+            }
+        }
+        c0 = warp_sum(c0); c1 = warp_sum(c1); c2 = warp_sum(c2); dm = warp_sum(dm);
+        if (lane == 0) { rgb_map[3 * r] = c0; rgb_map[3 * r + 1] = c1; rgb_map[3 * r + 2] = c2; depth_map[r] = dm; }
+        if (partials) {
+            fs = warp_sum(fs); sd = warp_sum(sd); nf = warp_sum(nf); ns = warp_sum(ns);
+            if (lane == 0) {
+                float wgt = (k.rgb_all_ones || valid) ? 1.f : 0.f;
+                float e0 = c0 * wgt - target_rgb[3 * r] * wgt, e1 = c1 * wgt - target_rgb[3 * r + 1] * wgt, e2 = c2 * wgt - target_rgb[3 * r + 2] * wgt;
+                acc[0] = (double)e0 * e0 + (double)e1 * e1 + (double)e2 * e2;
+                if (valid) { float e = dm - d; acc[1] = (double)e * e; acc[2] = 1.0; }
+                acc[3] = fs; acc[4] = sd; acc[5] = nf; acc[6] = ns;
+            }
+        }
+    }
+    if (partials) {
+        __shared__ double s_acc[4][7];
+        if (lane == 0) for (int i = 0; i < 7; ++i) s_acc[warp][i] = acc[i];
+        __syncthreads();
+        if (threadIdx.x < 7) {
+            double v = s_acc[0][threadIdx.x] + s_acc[1][threadIdx.x] + s_acc[2][threadIdx.x] + s_acc[3][threadIdx.x];
+            if (v != 0.0) atomicAdd(partials + threadIdx.x, v);
+        }
+    }
+}
+
+// Backward of composite + losses: writes the total gradient w.r.t. raw [N,S,4] into d_raw_out.
+// Upstream: d_rgb_map [N,3], d_depth_map [N], d_raw [N,S,4] (each may be NULL) and loss_grads (device float[4]:
+// d/d rgb_loss, depth_loss, sdf_loss, fs_loss; may be NULL) with the forward's `partials`.
+__global__ void composite_bwd_kernel(RayK k, const float* __restrict__ raw, const float* __restrict__ z_vals,
+                                     const float* __restrict__ rgb_map, const float* __restrict__ depth_map,
+                                     const float* __restrict__ target_d, const float* __restrict__ target_rgb,
+                                     const float* __restrict__ d_rgb_map, const float* __restrict__ d_depth_map,
+                                     const float* __restrict__ d_raw, const float* __restrict__ loss_grads,
+                                     const double* __restrict__ partials, float* __restrict__ d_raw_out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    long long r = blockIdx.x * 4ll + warp;
+    if (r >= k.n_rays) return;
+    const int S = k.S;
+    const float4* raw_r = reinterpret_cast<const float4*>(raw) + r * S;
+    const float* z_r = z_vals + r * S;
+    RayState st = ray_state(k, raw_r, z_r, lane);
+    float G0 = 0.f, G1 = 0.f, G2 = 0.f, GD = 0.f;
+    if (d_rgb_map) { G0 = d_rgb_map[3 * r]; G1 = d_rgb_map[3 * r + 1]; G2 = d_rgb_map[3 * r + 2]; }
+    if (d_depth_map) GD = d_depth_map[r];
+    float d = 0.f; bool valid = false; float cfs = 0.f, csd = 0.f;
+    if (loss_grads) {
+        d = target_d[r];
+        valid = (d > 0.f) && (d < k.depth_trunc);
+        const double NT = (double)k.n_total;
+        float wgt = (k.rgb_all_ones || valid) ? 1.f : 0.f;
+        float gl = loss_grads[0] * (float)(2.0 / (3.0 * NT));                          // mse over N*3 elements
+        G0 += gl * (rgb_map[3 * r] * wgt - target_rgb[3 * r] * wgt) * wgt;
+        G1 += gl * (rgb_map[3 * r + 1] * wgt - target_rgb[3 * r + 1] * wgt) * wgt;
+        G2 += gl * (rgb_map[3 * r + 2] * wgt - target_rgb[3 * r + 2] * wgt) * wgt;
+        double nv = partials[2];
+        if (valid && nv > 0) GD += loss_grads[1] * (float)(2.0 / nv) * (depth_map[r] - d);
+        double nf = partials[5], ns = partials[6], nn = nf + ns;                        // model/utils.py:190-196
+        double fs_w = 1.0 - nf / nn, sdf_w = 1.0 - ns / nn;
+        cfs = loss_grads[3] * (float)(fs_w * 2.0 / (NT * S));
+        csd = loss_grads[2] * (float)(sdf_w * 2.0 / (NT * S));
+    }
+    // pass 1: dot = sum_j dw_j * w_j
+    float dot = 0.f;
+    for (int s = lane; s < S; s += 32) {
+        float4 v = raw_r[s]; float z = z_r[s];
+        float a = __fdiv_rn(v.w, k.trunc);
+        float w = ((z < st.zthr) ? sigmoidf_(a) * sigmoidf_(-a) : 0.f) / st.denom;
+        float dw = G0 * v.x + G1 * v.y + G2 * v.z + GD * z;
+        dot = fmaf(dw, w, dot);
+    }
+    dot = warp_sum(dot);
+    float4* out_r = reinterpret_cast<float4*>(d_raw_out) + r * S;
+    const float4* up_r = d_raw ? reinterpret_cast<const float4*>(d_raw) + r * S : nullptr;
+    for (int s = lane; s < S; s += 32) {
+        float4 v = raw_r[s]; float z = z_r[s];
+        float a = __fdiv_rn(v.w, k.trunc);
+        float sg = sigmoidf_(a);
+        float e = (z < st.zthr) ? sg * sigmoidf_(-a) : 0.f;
+        float w = e / st.denom;
+        float dw = G0 * v.x + G1 * v.y + G2 * v.z + GD * z;
+        float de = (dw - dot) / st.denom;
+        float4 o;
+        o.x = w * G0; o.y = w * G1; o.z = w * G2;
+        o.w = de * e * (1.0f - 2.0f * sg) / k.trunc;
+        if (loss_grads) {
+            bool front = z < __fsub_rn(d, k.sc_trunc), back = z > __fadd_rn(d, k.sc_trunc);
+            bool sm = !front && !back && (d > 0.f);
+            if (valid && front) o.w += cfs * (v.w - 1.0f);
+            if (valid && sm) o.w += csd * (__fadd_rn(z, __fmul_rn(v.w, k.sc_trunc)) - d) * k.sc_trunc;
+        }
+        if (up_r) { float4 uu = up_r[s]; o.x += uu.x; o.y += uu.y; o.z += uu.z; o.w += uu.w; }
+        out_r[s] = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Sample backward: recompute the forward of a 128-sample tile, back-propagate through the decoder, scatter the
+// hash-table gradient, accumulate decoder weight gradients (tile GEMMs in shared memory), optional d/d position.
+// ------------------------------------------------------------------------------------------------------------
+// dW[n][k0..k0+KPT) += sum_m A[m][n] * B[m][k]   for the 128 rows of the tile; 128 threads.
+template <int NA, int KPT>
+__device__ __forceinline__ void tile_gemm_tn(float* __restrict__ dW, int ldw, const float* __restrict__ A, int lda,
+                                             const float* __restrict__ B, int ldb, int K) {
+    const int n = threadIdx.x % NA, k0 = (threadIdx.x / NA) * KPT;
+    if (k0 >= K) return;
+    float acc[KPT];
+#pragma unroll
+    for (int i = 0; i < KPT; ++i) acc[i] = 0.f;
+    for (int m = 0; m < kTile; ++m) {
+        float a = A[m * lda + n];
+        const float* b = B + m * ldb + k0;
+#pragma unroll
+        for (int i = 0; i < KPT; ++i) if (k0 + i < K) acc[i] = fmaf(a, b[i], acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < KPT; ++i) if (k0 + i < K) dW[n * ldw + k0 + i] += acc[i];
+}
+
+struct Grads { float* g_hash; float* g_w_sdf0; float* g_w_sdf1; float* g_w_col0; float* g_w_col1; };
+
+template <int HID, bool BA>
+__global__ void __launch_bounds__(kTile) sample_bwd_kernel(RayK k, GridDev hg, GridDev gg, const float* __restrict__ hash_params,
+                                                           const float* __restrict__ gbv_params, Weights wts,
+                                                           const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                           const float* __restrict__ z_vals, long long P,
+                                                           const float* __restrict__ d_raw_tot, Grads gr, float* __restrict__ d_pts) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int LDX1 = 84;                 // >= 81, multiple of 4
+    constexpr int LDX2 = 20;                 // geo15 + rgb3 (+2 pad)
+    constexpr int GROUPS = kTile / HID;      // k-groups of the weight-gradient GEMMs
+    const int in1 = k.in1;
+    WSmem<HID> W; W.carve(smem, in1);
+    float* dw0 = smem + WSmem<HID>::floats(in1);          // [HID][in1]   (nn.Linear layout [out][in])
+    float* dw1 = dw0 + HID * in1;                          // [16][HID]
+    float* dw2 = dw1 + kOut1 * HID;                        // [HID][66]
+    float* dw3 = dw2 + HID * kIn2;                         // [3][HID]
+    float* X1  = dw3 + 4 * HID;                            // [128][84]   sdf-net input row
+    float* H1r = X1 + kTile * LDX1;                        // [128][HID]  relu(hidden sdf)
+    float* Rg  = H1r + kTile * HID;                        // phase region
+    float* X2s = Rg;                                       // [128][20]   colour-net inputs 48..65
+    float* DH2 = X2s + kTile * LDX2;                       // [128][HID]
+    float* DO_ = Rg;                                       // [128][16]   (sdf phase overlays the colour phase)
+    float* DH1 = DO_ + kTile * kOut1;                      // [128][HID]
+    W.load(wts, in1);
+    for (int i = threadIdx.x; i < HID * in1 + kOut1 * HID + HID * kIn2 + 4 * HID; i += kTile) dw0[i] = 0.f;
+    __syncthreads();
+    const int L = hg.n_levels, ob0 = k.n_hash_out;
+    const int m = threadIdx.x;
+    float* x1 = X1 + m * LDX1;
+
+    for (long long base = blockIdx.x * (long long)kTile; base < P; base += (long long)gridDim.x * kTile) {
+        const long long p = base + m;
+        const bool live = p < P;
+        float x[3] = {0.f, 0.f, 0.f};
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        float t_add = 0.f, cin = 0.f, dg_add = 0.f, dg_cin = 0.f;
+        float4 dr = make_float4(0.f, 0.f, 0.f, 0.f);
+        float h[HID];
+#pragma unroll
+        for (int j = 0; j < HID; ++j) h[j] = 0.f;
+        if (live) {
+            sample_x(k, rays_o, rays_d, p / k.S, z_vals[p], x);
+            dr = reinterpret_cast<const float4*>(d_raw_tot)[p];
+            for (int l = 0; l < L; ++l) {
+                float2 f = hash_level_feat(hg, hash_params, l, x);
+                x1[2 * l] = f.x; x1[2 * l + 1] = f.y;
+                axpy_row<HID>(h, f.x, W.w0t + (2 * l) * HID);
+                axpy_row<HID>(h, f.y, W.w0t + (2 * l + 1) * HID);
+            }
+#pragma unroll 1
+            for (int c = 0; c < 3; ++c) {
+                float ob[kNB];
+                oneblob_coord<kNB>(x[c], ob);
+#pragma unroll
+                for (int b = 0; b < kNB; ++b) { x1[ob0 + c * kNB + b] = ob[b]; axpy_row<HID>(h, ob[b], W.w0t + (ob0 + c * kNB + b) * HID); }
+            }
+            g = gbv_feat(gg, gbv_params, x);
+            tsdf_terms(k, 0, g.x, t_add, cin, dg_add, dg_cin);
+            x1[ob0 + kBlob] = cin;
+            axpy_row<HID>(h, cin, W.w0t + (ob0 + kBlob) * HID);
+        } else {
+            for (int i = 0; i < in1; ++i) x1[i] = 0.f;
+        }
+        float o16[kOut1];
+#pragma unroll
+        for (int i = 0; i < kOut1; ++i) o16[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < HID; ++j) {
+            float a = fmaxf(h[j], 0.f);
+            H1r[m * HID + j] = a;
+            const float4* wr = reinterpret_cast<const float4*>(W.w1t + j * kOut1);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float4 v = wr[q];
+                o16[4 * q] = fmaf(a, v.x, o16[4 * q]); o16[4 * q + 1] = fmaf(a, v.y, o16[4 * q + 1]);
+                o16[4 * q + 2] = fmaf(a, v.z, o16[4 * q + 2]); o16[4 * q + 3] = fmaf(a, v.w, o16[4 * q + 3]);
+            }
+        }
+        // colour-net forward (hidden pre-activation in h)
+        float* x2 = X2s + m * LDX2;
+#pragma unroll
+        for (int i = 0; i < kGeo; ++i) x2[i] = o16[1 + i];
+        x2[kGeo] = g.y; x2[kGeo + 1] = g.z; x2[kGeo + 2] = g.w; x2[kGeo + 3] = 0.f; x2[kGeo + 4] = 0.f;
+#pragma unroll
+        for (int j = 0; j < HID; ++j) h[j] = 0.f;
+        for (int b = 0; b < kBlob; ++b) axpy_row<HID>(h, x1[ob0 + b], W.w2t + b * HID);
+#pragma unroll
+        for (int i = 0; i < kGeo + 3; ++i) axpy_row<HID>(h, x2[i], W.w2t + (kBlob + i) * HID);
+        // colour-net backward: dh2 = relu'(h2) * W3^T d_rgb ; dW3 via warp reduction
+#pragma unroll
+        for (int j = 0; j < HID; ++j) {
+            float4 v = *reinterpret_cast<const float4*>(W.w3t + 4 * j);
+            float a = fmaxf(h[j], 0.f);
+            float s0 = warp_sum(dr.x * a), s1 = warp_sum(dr.y * a), s2 = warp_sum(dr.z * a);
+            if ((threadIdx.x & 31) == 0) { atomicAdd(dw3 + j, s0); atomicAdd(dw3 + HID + j, s1); atomicAdd(dw3 + 2 * HID + j, s2); }
+            float dh = (h[j] > 0.f) ? fmaf(v.x, dr.x, fmaf(v.y, dr.y, v.z * dr.z)) : 0.f;
+            h[j] = dh;
+            DH2[m * HID + j] = dh;
+        }
+        // d colour-net inputs: geo (always), OneBlob + gbv rgb (BA only)
+        float dgeo[kGeo];
+#pragma unroll
+        for (int i = 0; i < kGeo; ++i) dgeo[i] = dot_row<HID>(h, W.w2t + (kBlob + i) * HID);
+        float dx[3] = {0.f, 0.f, 0.f};
+        float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);          // gradient w.r.t. the GBV features (tsdf, r, g, b)
+        float dob[BA ? kBlob : 1];
+        if constexpr (BA) {
+            for (int b = 0; b < kBlob; ++b) dob[b] = dot_row<HID>(h, W.w2t + b * HID);
+            dg.y = dot_row<HID>(h, W.w2t + (kBlob + kGeo) * HID) + dr.x;          // + residual add (:344)
+            dg.z = dot_row<HID>(h, W.w2t + (kBlob + kGeo + 1) * HID) + dr.y;
+            dg.w = dot_row<HID>(h, W.w2t + (kBlob + kGeo + 2) * HID) + dr.z;
+        }
+        __syncthreads();
+        // dW2[j][k] += DH2^T [X1(oneblob) | X2s]
+        tile_gemm_tn<HID, (kBlob + GROUPS - 1) / GROUPS>(dw2, kIn2, DH2, HID, X1 + ob0, LDX1, kBlob);
+        tile_gemm_tn<HID, (kGeo + 3 + GROUPS - 1) / GROUPS>(dw2 + kBlob, kIn2, DH2, HID, X2s, LDX2, kGeo + 3);
+        __syncthreads();
+        // sdf-net backward
+        float do16[kOut1];
+        do16[0] = dr.w;
+#pragma unroll
+        for (int i = 0; i < kGeo; ++i) do16[1 + i] = dgeo[i];
+#pragma unroll
+        for (int i = 0; i < kOut1; ++i) DO_[m * kOut1 + i] = do16[i];
+#pragma unroll
+        for (int j = 0; j < HID; ++j) {
+            const float4* wr = reinterpret_cast<const float4*>(W.w1t + j * kOut1);
+            float acc = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float4 v = wr[q];
+                acc = fmaf(v.x, do16[4 * q], acc); acc = fmaf(v.y, do16[4 * q + 1], acc);
+                acc = fmaf(v.z, do16[4 * q + 2], acc); acc = fmaf(v.w, do16[4 * q + 3], acc);
+            }
+            float dh = (H1r[m * HID + j] > 0.f) ? acc : 0.f;
+            h[j] = dh;
+            DH1[m * HID + j] = dh;
+        }
+        if (live) {
+            // hash-table gradient scatter (Appendix B5) and, in BA mode, input gradients (B6)
+            for (int l = 0; l < L; ++l) {
+                float d0 = dot_row<HID>(h, W.w0t + (2 * l) * HID), d1 = dot_row<HID>(h, W.w0t + (2 * l + 1) * HID);
+                unsigned cx, cy, cz; float fx, fy, fz;
+                pos_fract(x[0], hg.scale[l], cx, fx); pos_fract(x[1], hg.scale[l], cy, fy); pos_fract(x[2], hg.scale[l], cz, fz);
+                float gx = 0.f, gy = 0.f, gz = 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    unsigned idx = grid_index(hg.is_hash, hg.size[l], hg.res[l], cx + (c & 1), cy + ((c >> 1) & 1), cz + ((c >> 2) & 1));
+                    size_t e = (size_t)hg.offset[l] + idx;
+                    float w = corner_weight(c, fx, fy, fz);
+                    if (gr.g_hash) atomicAdd(reinterpret_cast<float2*>(gr.g_hash) + e, make_float2(w * d0, w * d1));
+                    if (BA) {
+                        float2 pv = __ldg(reinterpret_cast<const float2*>(hash_params) + e);
+                        float v = fmaf(d0, pv.x, d1 * pv.y);
+                        float wx = (c & 1) ? fx : 1.f - fx, wy = (c & 2) ? fy : 1.f - fy, wz = (c & 4) ? fz : 1.f - fz;
+                        gx += ((c & 1) ? v : -v) * wy * wz; gy += ((c & 2) ? v : -v) * wx * wz; gz += ((c & 4) ? v : -v) * wx * wy;
+                    }
+                }
+                if (BA) { float s = hg.scale[l]; dx[0] = fmaf(gx, s, dx[0]); dx[1] = fmaf(gy, s, dx[1]); dx[2] = fmaf(gz, s, dx[2]); }
+            }
+            if constexpr (BA) {
+                // OneBlob inputs of both nets
+                for (int b = 0; b < kBlob; ++b) dob[b] += dot_row<HID>(h, W.w0t + (ob0 + b) * HID);
+#pragma unroll 1
+                for (int c = 0; c < 3; ++c) {
+                    float gb[kNB];
+                    oneblob_coord_grad<kNB>(x[c], gb);
+                    float acc = 0.f;
+#pragma unroll
+                    for (int b = 0; b < kNB; ++b) acc = fmaf(gb[b], dob[c * kNB + b], acc);
+                    dx[c] += acc;
+                }
+                // tsdf channel: decoder input (cin) and the residual add (t_add)
+                float dcin = dot_row<HID>(h, W.w0t + (ob0 + kBlob) * HID);
+                dg.x = dcin * dg_cin + dr.w * dg_add;
+                // GBV trilinear input gradient
+                unsigned cx, cy, cz; float fx, fy, fz;
+                pos_fract(x[0], gg.scale[0], cx, fx); pos_fract(x[1], gg.scale[0], cy, fy); pos_fract(x[2], gg.scale[0], cz, fz);
+                float gx = 0.f, gy = 0.f, gz = 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    unsigned idx = grid_index(false, gg.size[0], gg.res[0], cx + (c & 1), cy + ((c >> 1) & 1), cz + ((c >> 2) & 1));
+                    float4 pv = __ldg(reinterpret_cast<const float4*>(gbv_params) + idx);
+                    float v = dg.x * pv.x + dg.y * pv.y + dg.z * pv.z + dg.w * pv.w;
+                    float wx = (c & 1) ? fx : 1.f - fx, wy = (c & 2) ? fy : 1.f - fy, wz = (c & 4) ? fz : 1.f - fz;
+                    gx += ((c & 1) ? v : -v) * wy * wz; gy += ((c & 2) ? v : -v) * wx * wz; gz += ((c & 4) ? v : -v) * wx * wy;
+                }
+                float s = gg.scale[0];
+                dx[0] = fmaf(gx, s, dx[0]); dx[1] = fmaf(gy, s, dx[1]); dx[2] = fmaf(gz, s, dx[2]);
+                // through the float64 normalisation (:388)
+                d_pts[3 * p]     = (float)((double)dx[0] / k.bl[0]);
+                d_pts[3 * p + 1] = (float)((double)dx[1] / k.bl[1]);
+                d_pts[3 * p + 2] = (float)((double)dx[2] / k.bl[2]);
+            }
+        }
+        __syncthreads();
+        // dW1[i][j] += DO^T H1r ; dW0[j][k] += DH1^T X1
+        tile_gemm_tn<kOut1, HID / (kTile / kOut1)>(dw1, HID, DO_, kOut1, H1r, HID, HID);
+        tile_gemm_tn<HID, (81 + GROUPS - 1) / GROUPS>(dw0, in1, DH1, HID, X1, LDX1, in1);
+        __syncthreads();
+    }
+    // flush decoder weight gradients
+    if (gr.g_w_sdf0) for (int i = threadIdx.x; i < HID * in1; i += kTile) atomicAdd(gr.g_w_sdf0 + i, dw0[i]);
+    if (gr.g_w_sdf1) for (int i = threadIdx.x; i < kOut1 * HID; i += kTile) atomicAdd(gr.g_w_sdf1 + i, dw1[i]);
+    if (gr.g_w_col0) for (int i = threadIdx.x; i < HID * kIn2; i += kTile) atomicAdd(gr.g_w_col0 + i, dw2[i]);
+    if (gr.g_w_col1) for (int i = threadIdx.x; i < 3 * HID; i += kTile) atomicAdd(gr.g_w_col1 + i, dw3[i]);
+}
+
+// dL/d rays_o = sum_s dL/d pts ; dL/d rays_d = sum_s z_s * dL/d pts   (pts = o + d*z, model/scene_rep.py:443)
+__global__ void ray_grad_kernel(RayK k, const float* __restrict__ d_pts, const float* __restrict__ z_vals,
+                                float* __restrict__ g_o, float* __restrict__ g_d) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    long long r = blockIdx.x * 4ll + warp;
+    if (r >= k.n_rays) return;
+    float o0 = 0, o1 = 0, o2 = 0, d0 = 0, d1 = 0, d2 = 0;
+    for (int s = lane; s < k.S; s += 32) {
+        long long p = r * k.S + s;
+        float z = z_vals[p], a = d_pts[3 * p], b = d_pts[3 * p + 1], c = d_pts[3 * p + 2];
+        o0 += a; o1 += b; o2 += c; d0 = fmaf(z, a, d0); d1 = fmaf(z, b, d1); d2 = fmaf(z, c, d2);
+    }
+    o0 = warp_sum(o0); o1 = warp_sum(o1); o2 = warp_sum(o2); d0 = warp_sum(d0); d1 = warp_sum(d1); d2 = warp_sum(d2);
+    if (lane == 0) {
+        if (g_o) { g_o[3 * r] = o0; g_o[3 * r + 1] = o1; g_o[3 * r + 2] = o2; }
+        if (g_d) { g_d[3 * r] = d0; g_d[3 * r + 1] = d1; g_d[3 * r + 2] = d2; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+static int make_rayk(RayK& k, const rf_ray_cfg* c, const rf_grid_desc* hash, const rf_grid_desc* gbv, long long n_rays, const char* who) {
+    RF_REQUIRE(c && hash && gbv, RF_E_NULL, "%s: NULL config/descriptor", who);
+    RF_REQUIRE(hash->n_features == 2 && hash->n_levels >= 1 && hash->n_levels <= RF_MAX_LEVELS, RF_E_UNSUPPORTED, "%s: hash grid must have F=2", who);
+    RF_REQUIRE(gbv->n_features == 4 && gbv->n_levels == 1 && !gbv->is_hash, RF_E_UNSUPPORTED, "%s: GBV must be a 1-level dense grid with F=4", who);
+    RF_REQUIRE(c->hidden == 32 || c->hidden == 64, RF_E_UNSUPPORTED, "%s: hidden width %d (32 and 64 are built)", who, c->hidden);
+    RF_REQUIRE(c->n_bins == kNB && c->geo_feat == kGeo, RF_E_UNSUPPORTED, "%s: n_bins %d / geo_feat_dim %d (16 / 15 are built)", who, c->n_bins, c->geo_feat);
+    RF_REQUIRE(c->mlp_precision == 0, RF_E_UNSUPPORTED, "%s: mlp_precision %d not built", who, c->mlp_precision);
+    RF_REQUIRE(c->n_range_d >= 1 && c->n_samples_d >= 0 && c->n_range_d <= kMaxS && c->n_range_d + c->n_samples_d <= kMaxS, RF_E_RANGE,
+               "%s: samples per ray %d+%d not in [1,%d]", who, c->n_range_d, c->n_samples_d, kMaxS);
+    RF_REQUIRE(n_rays >= 0 && n_rays < (1ll << 40), RF_E_RANGE, "%s: bad ray count", who);
+    RF_REQUIRE(c->trunc > 0.f, RF_E_RANGE, "%s: trunc must be positive", who);
+    k.n_range_d = c->n_range_d; k.n_samples_d = c->n_samples_d; k.S = c->n_range_d + c->n_samples_d; k.perturb = c->perturb ? 1 : 0;
+    k.c_trunc = c->c_trunc; k.trunc = c->trunc; k.clamp_thr = c->clamp_thr; k.clamp_mode = c->clamp_mode ? 1 : 0;
+    k.sc_trunc = (float)((double)c->sc_factor * (double)c->trunc);
+    k.depth_trunc = c->depth_trunc; k.rgb_all_ones = (c->rgb_missing != 0.f) ? 1 : 0;
+    k.n_hash_out = hash->n_levels * 2; k.in1 = k.n_hash_out + kBlob + 1;
+    for (int a = 0; a < 3; ++a) { k.b0[a] = c->bbox[2 * a]; k.bl[a] = c->bbox[2 * a + 1] - c->bbox[2 * a]; }
+    k.n_rays = n_rays; k.n_total = c->n_rays_total > 0 ? c->n_rays_total : n_rays;
+    return 0;
+}
+
+template <int HID> static size_t fwd_smem(int in1) { return sizeof(float) * (size_t)(in1 * HID + HID * kOut1 + kIn2 * HID + HID * 4); }
+template <int HID> static size_t bwd_smem(int in1) {
+    size_t w = in1 * HID + HID * kOut1 + kIn2 * HID + HID * 4;
+    size_t dw = HID * in1 + kOut1 * HID + HID * kIn2 + 4 * HID;
+    size_t tile = (size_t)kTile * (84 + HID + 20 + HID);
+    return sizeof(float) * (w + dw + tile);
+}
+
+template <int HID, bool FROM_X>
+static int launch_fwd(const RayK& k, const GridDev& hg, const GridDev& gg, const rf_ray_params* p, const float* rays_o, const float* rays_d,
+                      const float* z_vals, const float* xin, long long P, int variant, float* raw, cudaStream_t s) {
+    auto fn = sample_fwd_kernel<HID, FROM_X>;
+    size_t sm = fwd_smem<HID>(k.in1);
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return set_error((int)e, "cudaFuncSetAttribute(sample_fwd): %s", cudaGetErrorString(e));
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kTile, sm);
+    if (per_sm < 1) per_sm = 1;
+    long long tiles = (P + kTile - 1) / kTile;
+    int blocks = (int)std::min<long long>(tiles, (long long)num_sms() * per_sm);
+    Weights w{p->w_sdf0, p->w_sdf1, p->w_col0, p->w_col1};
+    fn<<<blocks, kTile, sm, s>>>(k, hg, gg, p->hash_params, p->gbv_params, w, rays_o, rays_d, z_vals, xin, P, variant, raw);
+    RF_CHECK_LAUNCH("sample_fwd_kernel");
+    return 0;
+}
+
+template <int HID, bool BA>
+static int launch_bwd(const RayK& k, const GridDev& hg, const GridDev& gg, const rf_ray_params* p, const float* rays_o, const float* rays_d,
+                      const float* z_vals, long long P, const float* d_raw_tot, const Grads& gr, float* d_pts, cudaStream_t s) {
+    auto fn = sample_bwd_kernel<HID, BA>;
+    size_t sm = bwd_smem<HID>(k.in1);
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return set_error((int)e, "cudaFuncSetAttribute(sample_bwd, %zu B): %s", sm, cudaGetErrorString(e));
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kTile, sm);
+    if (per_sm < 1) per_sm = 1;
+    long long tiles = (P + kTile - 1) / kTile;
+    int blocks = (int)std::min<long long>(tiles, (long long)num_sms() * per_sm);
+    Weights w{p->w_sdf0, p->w_sdf1, p->w_col0, p->w_col1};
+    fn<<<blocks, kTile, sm, s>>>(k, hg, gg, p->hash_params, p->gbv_params, w, rays_o, rays_d, z_vals, P, d_raw_tot, gr, d_pts);
+    RF_CHECK_LAUNCH("sample_bwd_kernel");
+    return 0;
+}
+
+}  // namespace rf
+
+using namespace rf;
+
+extern "C" int rf_ray_sample_z(const rf_ray_cfg* cfg, const float* target_d, const float* u, const float* z_tables,
+                               int64_t n_rays, float* z_vals, void* stream) {
+    RF_REQUIRE(cfg, RF_E_NULL, "rf_ray_sample_z: NULL cfg");
+    RF_REQUIRE(cfg->n_range_d >= 1 && cfg->n_samples_d >= 0 && cfg->n_range_d + cfg->n_samples_d <= kMaxS, RF_E_RANGE, "rf_ray_sample_z: bad sample counts");
+    if (n_rays == 0) return 0;
+    RF_REQUIRE(target_d && z_tables && z_vals, RF_E_NULL, "rf_ray_sample_z: NULL pointer");
+    RF_REQUIRE(!cfg->perturb || u, RF_E_NULL, "rf_ray_sample_z: perturb needs the jitter array u");
+    RayK k; memset(&k, 0, sizeof(k));
+    k.n_range_d = cfg->n_range_d; k.n_samples_d = cfg->n_samples_d; k.S = k.n_range_d + k.n_samples_d; k.perturb = cfg->perturb ? 1 : 0;
+    k.n_rays = n_rays;
+    ray_z_kernel<<<(unsigned)((n_rays + 3) / 4), 128, 0, (cudaStream_t)stream>>>(k, target_d, u, z_tables, z_vals);
+    RF_CHECK_LAUNCH("ray_z_kernel");
+    return 0;
+}
+
+extern "C" int rf_ray_query_forward(const rf_ray_cfg* cfg, const rf_grid_desc* hash, const rf_grid_desc* gbv, const rf_ray_params* p,
+                                    const float* rays_o, const float* rays_d, const float* target_d, const float* target_rgb,
+                                    const float* z_vals, int64_t n_rays,
+                                    float* raw, float* rgb_map, float* depth_map, double* loss_partials, void* stream) {
+    RayK k;
+    int rc = make_rayk(k, cfg, hash, gbv, n_rays, "rf_ray_query_forward"); if (rc) return rc;
+    if (n_rays == 0) return 0;
+    RF_REQUIRE(p && p->hash_params && p->gbv_params && p->w_sdf0 && p->w_sdf1 && p->w_col0 && p->w_col1, RF_E_NULL, "rf_ray_query_forward: NULL parameter pointer");
+    RF_REQUIRE(rays_o && rays_d && z_vals && raw && rgb_map && depth_map, RF_E_NULL, "rf_ray_query_forward: NULL pointer");
+    RF_REQUIRE(!loss_partials || (target_d && target_rgb), RF_E_NULL, "rf_ray_query_forward: losses need target_d and target_rgb");
+    RF_REQUIRE((((uintptr_t)raw | (uintptr_t)p->gbv_params) & 15) == 0 && ((uintptr_t)p->hash_params & 7) == 0, RF_E_ALIGN, "rf_ray_query_forward: raw/gbv need 16-byte, hash 8-byte alignment");
+    GridDev hg = to_dev(hash), gg = to_dev(gbv);
+    cudaStream_t s = (cudaStream_t)stream;
+    long long P = n_rays * k.S;
+    rc = (cfg->hidden == 64) ? launch_fwd<64, false>(k, hg, gg, p, rays_o, rays_d, z_vals, nullptr, P, 0, raw, s)
+                             : launch_fwd<32, false>(k, hg, gg, p, rays_o, rays_d, z_vals, nullptr, P, 0, raw, s);
+    if (rc) return rc;
+    composite_fwd_kernel<<<(unsigned)((n_rays + 3) / 4), 128, 0, s>>>(k, raw, z_vals, target_d, target_rgb, rgb_map, depth_map, loss_partials);
+    RF_CHECK_LAUNCH("composite_fwd_kernel");
+    return 0;
+}
+
+extern "C" int rf_ray_query_backward(const rf_ray_cfg* cfg, const rf_grid_desc* hash, const rf_grid_desc* gbv, const rf_ray_params* p,
+                                     const float* rays_o, const float* rays_d, const float* target_d, const float* target_rgb, int64_t n_rays,
+                                     const float* z_vals, const float* raw, const float* rgb_map, const float* depth_map,
+                                     const float* d_rgb_map, const float* d_depth_map, const float* d_raw,
+                                     const float* loss_grads, const double* loss_partials,
+                                     const rf_ray_grads* g, float* scratch, void* stream) {
+    RayK k;
+    int rc = make_rayk(k, cfg, hash, gbv, n_rays, "rf_ray_query_backward"); if (rc) return rc;
+    if (n_rays == 0) return 0;
+    RF_REQUIRE(p && p->hash_params && p->gbv_params && p->w_sdf0 && p->w_sdf1 && p->w_col0 && p->w_col1, RF_E_NULL, "rf_ray_query_backward: NULL parameter pointer");
+    RF_REQUIRE(rays_o && rays_d && z_vals && raw && g && scratch, RF_E_NULL, "rf_ray_query_backward: NULL pointer");
+    RF_REQUIRE(!loss_grads || (loss_partials && target_d && target_rgb && rgb_map && depth_map), RF_E_NULL, "rf_ray_query_backward: loss gradients need partials, targets and maps");
+    RF_REQUIRE(((uintptr_t)scratch & 15) == 0 && (!g->g_hash || ((uintptr_t)g->g_hash & 7) == 0), RF_E_ALIGN, "rf_ray_query_backward: scratch 16-byte / g_hash 8-byte alignment");
+    GridDev hg = to_dev(hash), gg = to_dev(gbv);
+    cudaStream_t s = (cudaStream_t)stream;
+    long long P = n_rays * k.S;
+    float* d_raw_tot = scratch;                 // [P,4]
+    float* d_pts = scratch + 4 * P;             // [P,3] (BA mode only)
+    composite_bwd_kernel<<<(unsigned)((n_rays + 3) / 4), 128, 0, s>>>(k, raw, z_vals, rgb_map, depth_map, target_d, target_rgb,
+                                                                       d_rgb_map, d_depth_map, d_raw, loss_grads, loss_partials, d_raw_tot);
+    RF_CHECK_LAUNCH("composite_bwd_kernel");
+    Grads gr{g->g_hash, g->g_w_sdf0, g->g_w_sdf1, g->g_w_col0, g->g_w_col1};
+    const bool ba = g->g_rays_o || g->g_rays_d;
+    if (cfg->hidden == 64) rc = ba ? launch_bwd<64, true>(k, hg, gg, p, rays_o, rays_d, z_vals, P, d_raw_tot, gr, d_pts, s)
+                                   : launch_bwd<64, false>(k, hg, gg, p, rays_o, rays_d, z_vals, P, d_raw_tot, gr, d_pts, s);
+    else rc = ba ? launch_bwd<32, true>(k, hg, gg, p, rays_o, rays_d, z_vals, P, d_raw_tot, gr, d_pts, s)
+                 : launch_bwd<32, false>(k, hg, gg, p, rays_o, rays_d, z_vals, P, d_raw_tot, gr, d_pts, s);
+    if (rc) return rc;
+    if (ba) {
+        ray_grad_kernel<<<(unsigned)((n_rays + 3) / 4), 128, 0, s>>>(k, d_pts, z_vals, g->g_rays_o, g->g_rays_d);
+        RF_CHECK_LAUNCH("ray_grad_kernel");
+    }
+    return 0;
+}
+
+extern "C" int rf_point_query_forward(const rf_ray_cfg* cfg, const rf_grid_desc* hash, const rf_grid_desc* gbv, const rf_ray_params* p,
+                                      const float* x, int64_t n, int variant, float* raw, void* stream) {
+    RayK k;
+    int rc = make_rayk(k, cfg, hash, gbv, 0, "rf_point_query_forward"); if (rc) return rc;
+    RF_REQUIRE(variant >= 0 && variant <= 2, RF_E_RANGE, "rf_point_query_forward: variant %d", variant);
+    RF_REQUIRE(n >= 0, RF_E_RANGE, "rf_point_query_forward: negative n");
+    if (n == 0) return 0;
+    RF_REQUIRE(p && p->hash_params && p->gbv_params && p->w_sdf0 && p->w_sdf1 && p->w_col0 && p->w_col1 && x && raw, RF_E_NULL, "rf_point_query_forward: NULL pointer");
+    RF_REQUIRE(((uintptr_t)raw & 15) == 0, RF_E_ALIGN, "rf_point_query_forward: raw must be 16-byte aligned");
+    GridDev hg = to_dev(hash), gg = to_dev(gbv);
+    cudaStream_t s = (cudaStream_t)stream;
+    k.S = 1;
+    return (cfg->hidden == 64) ? launch_fwd<64, true>(k, hg, gg, p, nullptr, nullptr, nullptr, x, n, variant, raw, s)
+                               : launch_fwd<32, true>(k, hg, gg, p, nullptr, nullptr, nullptr, x, n, variant, raw, s);
+}

@@ -1,0 +1,223 @@
+"""Stage-2 parity (GPU): the fused ray kernels behind ``JointEncoding`` vs (a) the golden vectors produced by the
+reference's own code (tests/golden/ray_golden.npz) and (b) the CPU oracle (oracle/ray_oracle.py) on fresh seeded
+inputs.  Bars (BASELINE.json north_star): hash indices bit-exact; rendered depth/colour and gradients within 1e-3
+relative.  The tolerances actually asserted are written next to each check."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import tcnn_standin
+from remixfusion_b200 import abi
+from remixfusion_b200.encodings import GridEncoding, OneBlobEncoding, get_encoder
+from remixfusion_b200.scene_rep import JointEncoding
+from tests import _ray_common as R
+
+pytestmark = pytest.mark.gpu
+G = np.load(R.GOLDEN)
+
+
+def _model_from_golden(name, cuda, cfg=None):
+    cfg = cfg or R.case_config(name)
+    bb = torch.from_numpy(np.array(cfg["mapping"]["bound"])).to(torch.float64)
+    m = JointEncoding(cfg, bb)
+    with torch.no_grad():
+        m.embed_res_fn.params.copy_(torch.from_numpy(G[f"{name}_hash_params"]))
+        m.GBV.params.copy_(torch.from_numpy(G["in_gbv"]))
+        s, c = m.decoder_res.sdf_net.model, m.decoder_res.color_net.model
+        s[0].weight.copy_(torch.from_numpy(G[f"{name}_w_sdf0"])); s[2].weight.copy_(torch.from_numpy(G[f"{name}_w_sdf1"]))
+        c[0].weight.copy_(torch.from_numpy(G[f"{name}_w_col0"])); c[2].weight.copy_(torch.from_numpy(G[f"{name}_w_col1"]))
+    return cfg, m
+
+
+def _close(got, ref, rtol, name, atol_frac=1e-4):
+    got = got.detach().cpu().numpy() if isinstance(got, torch.Tensor) else np.asarray(got)
+    scale = float(np.abs(ref).max()) if ref.size else 1.0
+    np.testing.assert_allclose(got, ref, rtol=rtol, atol=atol_frac * scale + 1e-12, err_msg=name)
+
+
+def _total(cfg, ret):
+    t = cfg["training"]
+    return (t["rgb_weight"] * ret["rgb_res_loss"] + t["depth_weight"] * ret["depth_res_loss"]
+            + t["sdf_weight"] * ret["sdf_res_loss"] + t["fs_weight"] * ret["fs_res_loss"])
+
+
+@pytest.mark.parametrize("name,clamp,ray_grads", [("A", False, False), ("B", True, True)])
+def test_mapping_matches_reference_golden(cuda, rf_lib, name, clamp, ray_grads):
+    cfg, m = _model_from_golden(name, cuda)
+    m.train()
+    ro = torch.from_numpy(G["in_rays_o"]).to(cuda).requires_grad_(ray_grads)
+    rd = torch.from_numpy(G["in_rays_d"]).to(cuda).requires_grad_(ray_grads)
+    tc = torch.from_numpy(G["in_target_rgb"]).to(cuda); td = torch.from_numpy(G["in_target_d"]).to(cuda)
+    ret = m.mapping(ro, rd, tc, td, clamp=clamp, u=torch.from_numpy(G[f"{name}_u"]))
+    for k in ("rgb_res_loss", "depth_res_loss", "sdf_res_loss", "fs_res_loss"):
+        _close(ret[k], G[f"{name}_{k}"], 2e-4, k)                   # losses: 2e-4 relative
+    _close(ret["rgb_res"], G[f"{name}_rgb_res"], 2e-4, "rgb_res")   # rendered colour: 2e-4 (bar 1e-3)
+    _close(ret["depth_res"], G[f"{name}_depth_res"], 2e-4, "depth_res")
+    loss = _total(cfg, ret)
+    loss.backward()
+    _close(loss, G[f"{name}_loss"], 2e-4, "loss")
+    s, c = m.decoder_res.sdf_net.model, m.decoder_res.color_net.model
+    got = {"g_hash": m.embed_res_fn.params.grad, "g_w_sdf0": s[0].weight.grad, "g_w_sdf1": s[2].weight.grad,
+           "g_w_col0": c[0].weight.grad, "g_w_col1": c[2].weight.grad}
+    if ray_grads:
+        got.update(g_rays_o=ro.grad, g_rays_d=rd.grad)
+    for k, v in got.items():
+        assert v is not None, k
+        _close(v, G[f"{name}_{k}"], 1e-3, k, atol_frac=2e-4)        # gradients: 1e-3 relative + 2e-4 of max |g| floor
+
+
+def test_eval_render_matches_reference_golden(cuda, rf_lib):
+    cfg, m = _model_from_golden("C", cuda)
+    m.eval()
+    ro = torch.from_numpy(G["in_rays_o"]).to(cuda); rd = torch.from_numpy(G["in_rays_d"]).to(cuda)
+    tc = torch.from_numpy(G["in_target_rgb"]).to(cuda); td = torch.from_numpy(G["in_target_d"]).to(cuda)
+    with torch.no_grad():
+        ret = m.mapping(ro, rd, tc, td)
+    assert np.array_equal(ret["z_vals"].cpu().numpy(), G["C_z_vals"])            # sample depths: bit-exact
+    _close(ret["raw"], G["C_raw"], 2e-4, "raw")
+    _close(ret["rgb_res_map"], G["C_rgb_res_map"], 2e-4, "rgb_res_map")
+    _close(ret["depth_res_map"], G["C_depth_res_map"], 2e-4, "depth_res_map")
+
+
+def test_z_sampling_bit_exact_with_jitter(cuda, rf_lib):
+    """z_vals for the jittered 48+11 sampling equal the reference's (golden A is rendered in eval mode with the same u)."""
+    cfg, m = _model_from_golden("A", cuda)
+    td = torch.from_numpy(G["in_target_d"]).to(cuda)
+    z = m.sample_z(td, td.shape[0], u=torch.from_numpy(G["A_u"]))
+    assert np.array_equal(z.cpu().numpy(), G["A_z_vals"])
+
+
+def test_hash_indices_bit_exact(cuda, rf_lib):
+    """Scatter 1.0 through the CUDA backward: the set of touched table entries (and their multiplicity pattern) must
+    equal the stand-in's corner indices, for in-box, out-of-box and negative coordinates."""
+    g = torch.Generator().manual_seed(0)
+    x = torch.cat([torch.rand(500, 3, generator=g), torch.rand(200, 3, generator=g) * 3 - 1,
+                   torch.tensor([[0., 0., 0.], [1., 1., 1.], [0.5, 0.999999, 1e-7]])])
+    for hash_size, res in ((10, 400), (14, 512), (19, 2048)):
+        pls = np.exp2(np.log2(res / 16) / 15)
+        enc = GridEncoding(16, 2, 16, pls, hash_size, True, cuda)
+        ref = tcnn_standin.GridStandIn(16, 2, True, hash_size, 16, pls)
+        assert list(enc.desc.resolution[:16]) == ref.res and list(enc.desc.offset[:17]) == ref.offset
+        idx = ref.level_indices(x)                                              # [N,16,8] absolute entries
+        expect = torch.zeros(ref.offset[-1], dtype=torch.bool)
+        expect[idx.reshape(-1)] = True
+        with torch.no_grad():
+            enc.params.fill_(1.0)
+        xc = x.to(cuda)
+        out = enc(xc)
+        out.sum().backward()
+        touched = (enc.params.grad.view(-1, 2).abs().sum(1) > 0).cpu()
+        # an entry whose 8 corner weights cancel to exactly zero cannot be told apart; require expect ⊇ touched and
+        # that every expected entry with a non-negligible weight is touched
+        assert not bool((touched & ~expect).any()), "CUDA touched entries the reference indices do not contain"
+        idxf, wf = [], []
+        for l in range(16):
+            i, w = tcnn_standin.grid_indices(x, ref.scale[l], ref.res[l], ref.size[l], True)
+            idxf.append(ref.offset[l] + i); wf.append(w)
+        idxf = torch.stack(idxf, 1).reshape(-1); wf = torch.stack(wf, 1).reshape(-1)
+        strong = torch.zeros(ref.offset[-1], dtype=torch.bool); strong[idxf[wf.abs() > 1e-6]] = True
+        assert not bool((strong & ~touched).any()), "reference indices missing from the CUDA scatter"
+
+
+def test_encoders_match_standin_fwd_bwd(cuda, rf_lib):
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(300, 3, generator=g) * 1.2 - 0.1
+    pls = np.exp2(np.log2(400 / 16) / 15)
+    for kind in ("hash", "dense"):
+        if kind == "hash":
+            enc = GridEncoding(16, 2, 16, pls, 12, True, cuda); ref = tcnn_standin.GridStandIn(16, 2, True, 12, 16, pls)
+        else:
+            enc = GridEncoding(1, 4, 24, 1, 0, False, cuda); ref = tcnn_standin.GridStandIn(1, 4, False, 0, 24, 1)
+        p = torch.rand(ref.params.shape, generator=g) - 0.5
+        with torch.no_grad():
+            enc.params.copy_(p); ref.params.copy_(p)
+        enc.params.requires_grad_(True)
+        xr = x.clone().requires_grad_(True); xc = x.to(cuda).requires_grad_(True)
+        wgt = torch.rand(300, ref.n_output_dims, generator=g)
+        (ref(xr) * wgt).sum().backward()
+        (enc(xc) * wgt.to(cuda)).sum().backward()
+        _close(enc(xc), ref(xr).detach().numpy(), 1e-5, kind + " fwd")
+        _close(enc.params.grad, ref.params.grad.numpy(), 1e-4, kind + " dparams")
+        _close(xc.grad, xr.grad.numpy(), 1e-3, kind + " dx", atol_frac=1e-3)
+    ob = OneBlobEncoding(16, cuda); obr = tcnn_standin.OneBlobStandIn(16)
+    xr = x.clone().requires_grad_(True); xc = x.to(cuda).requires_grad_(True)
+    wgt = torch.rand(300, 48, generator=g)
+    (obr(xr) * wgt).sum().backward(); (ob(xc) * wgt.to(cuda)).sum().backward()
+    _close(ob(xc), obr(xr).detach().numpy(), 1e-5, "oneblob fwd", atol_frac=1e-6)
+    _close(xc.grad, xr.grad.numpy(), 1e-3, "oneblob dx", atol_frac=1e-3)
+    e, od = get_encoder("HashGrid", log2_hashmap_size=10, desired_resolution=400)
+    assert od == 32 and e.params.numel() == e.desc.n_params
+
+
+@pytest.mark.parametrize("hidden,S_cfg", [(64, (48, 0)), (32, (21, 96))])
+def test_mapping_matches_cpu_oracle_fresh(cuda, rf_lib, hidden, S_cfg):
+    """Fresh seeded inputs, hidden 64 (BASELINE cfg 3) and ScanNet-style 21+96 sampling, vs oracle/ray_oracle.py."""
+    cfg = R.base_config(hash_size=11, R=32, hidden=hidden)
+    cfg["training"].update(n_range_d=S_cfg[0], n_samples_d=S_cfg[1], rgb_missing=0.0)
+    bb = torch.from_numpy(np.array(cfg["mapping"]["bound"])).to(torch.float64)
+    m = JointEncoding(cfg, bb)
+    g = torch.Generator().manual_seed(hidden)
+    h = R.hash_standin(cfg); gb = R.gbv_standin(cfg)
+    with torch.no_grad():
+        h.params.copy_((torch.rand(h.params.shape, generator=g) - 0.5) * 0.1)
+        gb.params.copy_(torch.from_numpy(G["in_gbv"]))
+        m.embed_res_fn.params.copy_(h.params); m.GBV.params.copy_(gb.params)
+    gb.params.requires_grad_(False)
+    ws = [w.detach().cpu().clone().requires_grad_(True) for w in m.decoder_res.fused_weights()]
+    from oracle.ray_oracle import RayOracle
+    orc = RayOracle(cfg, bb, h, gb, *ws)
+    n = 64
+    ro = torch.from_numpy(G["in_rays_o"][:n]); rd = torch.from_numpy(G["in_rays_d"][:n])
+    tc = torch.from_numpy(G["in_target_rgb"][:n]); td = torch.from_numpy(G["in_target_d"][:n])
+    u = torch.rand(n, sum(S_cfg), generator=g)
+    r_ref = orc.mapping(ro, rd, tc, td, u=u)
+    orc.total_loss(r_ref).backward()
+    m.train()
+    r = m.mapping(ro.to(cuda), rd.to(cuda), tc.to(cuda), td.to(cuda), u=u)
+    _total(cfg, r).backward()
+    for k in ("rgb_res_loss", "depth_res_loss", "sdf_res_loss", "fs_res_loss", "rgb_res", "depth_res"):
+        _close(r[k], r_ref[k].detach().numpy(), 2e-4, k)
+    _close(m.embed_res_fn.params.grad, h.params.grad.numpy(), 1e-3, "g_hash", atol_frac=2e-4)
+    for w_cuda, w_ref, nm in zip(m.decoder_res.fused_weights(), ws, ("sdf0", "sdf1", "col0", "col1")):
+        _close(w_cuda.grad, w_ref.grad.numpy(), 1e-3, "g_w_" + nm, atol_frac=2e-4)
+
+
+def test_point_queries_match_oracle(cuda, rf_lib):
+    cfg, m = _model_from_golden("A", cuda)
+    _, orc = R.oracle_from_golden(G, "A", requires_grad=False)
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(257, 3, generator=g)
+    with torch.no_grad():
+        raw = m.query_color_sdf(x.to(cuda))
+        _close(raw, orc.query_color_sdf(x).numpy(), 2e-4, "query_color_sdf")
+        ex = orc.GBV(x)
+        _close(m.query_sdf_ex(x.to(cuda)), ex[..., 0].numpy(), 1e-5, "query_sdf_ex")
+        _close(m.query_color_ex(x.to(cuda)), ex[..., 1:].numpy(), 1e-5, "query_color_ex")
+        t = torch.clamp(ex[..., 0] * 0.1 / 0.05, -1, 1)
+        sdf = (torch.relu(torch.cat([orc.embed_res_fn(x), orc.embedpos_fn(x), t[:, None]], -1) @ orc.w_sdf0.t()) @ orc.w_sdf1.t())[:, 0] + t
+        _close(m.query_sdf_res(x.to(cuda)), sdf.numpy(), 2e-4, "query_sdf_res")
+        col = orc.decoder(orc.embed_res_fn(x), orc.embedpos_fn(x), ex[..., :1], ex[..., 1:])[:, :3] + ex[..., 1:]
+        _close(m.query_color_residual(x.to(cuda)), col.numpy(), 2e-4, "query_color_residual")
+        pts = x.double() * (orc.bounding_box[:, 1] - orc.bounding_box[:, 0]) + orc.bounding_box[:, 0]
+        _close(m.run_network(pts.float().to(cuda)), orc.run_network(pts.float()).numpy(), 5e-4, "run_network", atol_frac=5e-4)
+    emb = m.query_sdf_res(x.to(cuda).reshape(1, 257, 3), embed=True)
+    assert emb.shape == (1, 257, 32) and emb.requires_grad
+
+
+def test_state_dict_layout(cuda, rf_lib):
+    """Checkpoint keys / shapes the reference writes (mp_slam/mapper.py:257-265)."""
+    cfg = R.base_config(hash_size=10, R=16)
+    m = JointEncoding(cfg, torch.from_numpy(np.array(cfg["mapping"]["bound"])).double())
+    sd = m.state_dict()
+    for k in ("GBV.params", "GBW.params", "embed_res_fn.params", "embedpos_fn.params",
+              "decoder_res.sdf_net.model.0.weight", "decoder_res.sdf_net.model.2.weight",
+              "decoder_res.color_net.model.0.weight", "decoder_res.color_net.model.2.weight",
+              "sdf_net_res.model.0.weight", "color_net_res.model.2.weight"):
+        assert k in sd, k
+    assert sd["GBV.params"].numel() == 4 * 16 ** 3 and sd["GBW.params"].numel() == 16 ** 3
+    assert sd["embedpos_fn.params"].numel() == 0
+    assert sd["decoder_res.sdf_net.model.0.weight"].shape == (32, 81)
+    assert sd["decoder_res.color_net.model.0.weight"].shape == (32, 66)
+    assert float(sd["GBW.params"].abs().sum()) == 0.0 and not m.GBV.params.requires_grad
