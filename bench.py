@@ -1,0 +1,587 @@
+#!/usr/bin/env python
+"""bench.py — the mapping hot path on BASELINE.json's config 2 (Replica-shaped 1200x680 sequence, 2 cm voxels).
+
+One *step* is one frame of the synthetic sequence pushed through the whole hot path:
+  1. TSDF fuse:   integrate the frame into the tracker's local moving volume (400 x 400 x 300 @ 2 cm) and into the
+                  mapper's global coarse volume (GBV, R = 200 over the Replica room0 bound);
+  2. mixed ray render, forward + backward: all 816 000 pixels of the frame as rays x (48 + 11) samples through
+                  JointEncoding.mapping (hash grid 16 x 2^16, OneBlob, GBV trilerp, 2 x 32 decoder, SDF compositing,
+                  the four mapping losses) and loss.backward() into the hash table and the decoder.
+Units per step = touched voxels (both volumes) + ray samples; metric = units / s (BASELINE.json: "TSDF
+voxel-updates/s + ray-samples/s (fwd+bwd)"), with the two parts also reported separately under "parts".
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N > 1 (torchrun): volumes are slab-sharded (x-slabs local, z-slabs GBV) with the frame broadcast from rank 0 over
+NCCL; every rank renders its own frame's rays (weak scaling) and the hash/decoder gradients are all-reduced.
+`--impl reference`: the reference's CPU path (oracle/: the C restatement of its TSDF kernels and the reference's own
+scene_rep semantics on a PyTorch stand-in for tiny-cuda-nn) on the box's host cores, bounded sample, scaled.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from remixfusion_b200 import configs, synth                      # noqa: E402
+
+METRIC = "TSDF voxel-updates/s + ray-samples/s (fwd+bwd)"
+UNIT = "voxel-updates+ray-samples/s"
+HBM_FALLBACK_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+N_POOL = 4                         # distinct frames of the 200-frame loop kept resident
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+def make_frames(cfg, n_pool, first=0, stride=1):
+    cam = cfg["cam"]
+    K = synth.intrinsics(cam["fx"], cam["fy"], cam["cx"], cam["cy"])
+    scene = synth.make_scene(cfg["mapping"]["bound"], 0)
+    poses = synth.loop_trajectory(scene, 200)
+    frames = []
+    for i in range(n_pool):
+        f = (first + i * stride) % 200
+        depth, rgb = synth.render_frame(scene, K, cam["H"], cam["W"], poses[f], seed=f)
+        frames.append((poses[f], depth, rgb))
+    return K, poses, frames
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        busy = sorted(sm)[len(sm) // 2:] if sm else []          # upper half = samples under load
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# =====================================================================================================================
+# reference arm / cpu_baseline: the reference's CPU path on the host cores
+# =====================================================================================================================
+def cpu_reference_step(cfg, K, frame, n_rays, threads, state=None):
+    """One bounded CPU step: full TSDF fuse (C oracle, all threads) + mapping fwd+bwd on `n_rays` rays (torch CPU
+    restatement of the reference's scene_rep + stand-in encoders).  Returns timings and unit counts."""
+    from oracle import tsdf_oracle as O
+    from oracle import ray_oracle as RC
+    from oracle.ray_oracle import RayOracle
+    c2w, depth, rgb = frame
+    cam = cfg["cam"]
+    if state is None:
+        state = {}
+        v = cfg["volume"]
+        center = np.round(c2w[:3, 3], 0)
+        lens = np.array([v["x_config"]["len"], v["y_config"]["len"], v["z_config"]["len"]], dtype=np.float64)
+        bnds = np.stack([center - lens, center + lens], 1)
+        dims = np.ceil((bnds[:, 1] - bnds[:, 0]) / v["voxel_size"]).astype(int)
+        n = int(dims.prod())
+        state.update(dims=dims, origin=bnds[:, 0].astype(np.float32), tsdf=np.ones(n, np.float32), w=np.zeros(n, np.float32),
+                     col=np.zeros(n, np.float32))
+        R = cfg["globalV"]["base_resolution"]
+        trgb = np.zeros(4 * R ** 3, np.float32); O.clear_global(trgb)
+        state.update(R=R, trgb=trgb, gw=np.zeros(R ** 3, np.float32))
+        torch.manual_seed(0)
+        h = RC.hash_standin(cfg); g = RC.gbv_standin(cfg)
+        hd = cfg["decoder"]["hidden_dim"]
+        ws = [torch.nn.Parameter((torch.rand(o, i) * 2 - 1) / np.sqrt(i)) for o, i in ((hd, 81), (16, hd), (hd, 66), (3, hd))]
+        bb = torch.from_numpy(np.array(cfg["mapping"]["bound"])).to(torch.float64)
+        state.update(oracle=RayOracle(cfg, bb, h, g, *ws), hash=h, gbv=g, ws=ws)
+    t0 = time.perf_counter()
+    packed = O.pack_bgr(np.floor(rgb * 255.0).astype(np.float32))
+    nt_l, _ = O.integrate_local(state["tsdf"], state["w"], state["col"], state["dims"], state["origin"], cfg["volume"]["voxel_size"],
+                                K, c2w, depth, packed, cfg["volume"]["trunc"], threads=threads)
+    box = [v for ax in cfg["mapping"]["bound"] for v in ax]
+    nt_g = O.integrate_global(state["trgb"], state["gw"], state["R"], box, K, c2w, depth, rgb, cfg["training"]["c_trunc"], threads=threads)
+    t_tsdf = time.perf_counter() - t0
+    # rays of this frame (mp_slam/mapper.py:337-344)
+    with torch.no_grad():
+        state["gbv"].params.copy_(torch.from_numpy(state["trgb"]))
+    state["gbv"].params.requires_grad_(False)
+    rng = np.random.default_rng(0)
+    pix = rng.choice(cam["H"] * cam["W"], n_rays, replace=False)
+    dirs = torch.from_numpy(synth.camera_dirs(K, cam["H"], cam["W"]).reshape(-1, 3)[pix])
+    c2w_t = torch.from_numpy(c2w.astype(np.float32))
+    rays_d = torch.sum(dirs[..., None, :] * c2w_t[:3, :3], -1)
+    rays_o = c2w_t[None, :3, -1].repeat(n_rays, 1)
+    tgt_d = torch.from_numpy(depth.reshape(-1)[pix])[:, None]
+    tgt_c = torch.from_numpy(rgb.reshape(-1, 3)[pix])
+    S = cfg["training"]["n_range_d"] + cfg["training"]["n_samples_d"]
+    t1 = time.perf_counter()
+    orc = state["oracle"]
+    for p in [state["hash"].params] + state["ws"]:
+        p.grad = None
+    ret = orc.mapping(rays_o, rays_d, tgt_c, tgt_d, u=torch.rand(n_rays, S))
+    orc.total_loss(ret).backward()
+    t_ray = time.perf_counter() - t1
+    return state, dict(t_tsdf=t_tsdf, t_ray=t_ray, touched=nt_l + nt_g, samples=n_rays * S)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cfg = configs.replica()
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    K, poses, frames = make_frames(cfg, 1)
+    cam = cfg["cam"]
+    S = cfg["training"]["n_range_d"] + cfg["training"]["n_samples_d"]
+    full_samples = cam["H"] * cam["W"] * S
+    n_rays = args.cpu_rays
+    state = None
+    for _ in range(max(args.warmup, 0) and 1):
+        state, _r = cpu_reference_step(cfg, K, frames[0], n_rays, threads, state)
+    ts = []
+    for _ in range(args.steps):
+        state, r = cpu_reference_step(cfg, K, frames[0], n_rays, threads, state)
+        ts.append(r)
+    t_tsdf = statistics.mean(x["t_tsdf"] for x in ts)
+    t_ray = statistics.mean(x["t_ray"] for x in ts)
+    touched = ts[-1]["touched"]
+    t_full = t_tsdf + t_ray * (full_samples / ts[-1]["samples"])            # ray part scaled linearly to the full frame
+    value = (touched + full_samples) / t_full
+    sample = (f"full TSDF fuse of one 1200x680 frame (400x400x300 local + 200^3 GBV, C oracle) + mapping fwd+bwd on {n_rays} "
+              f"rays x {S} (torch CPU restatement of the reference + stand-in encoders), ray time scaled x{full_samples / ts[-1]['samples']:.1f} to 816000 rays")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t_full * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic analytic scene (seeded)",
+            "config": workload_config(cfg, 1),
+            "parts": {"tsdf_voxel_updates_per_s": touched / t_tsdf, "ray_samples_per_s": ts[-1]["samples"] / t_ray},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(cfg, world):
+    cam, t = cfg["cam"], cfg["training"]
+    return {"workload": "BASELINE config 2: Replica-shaped 1200x680 frame -> TSDF fuse (local 400x400x300 @ 2 cm + GBV 200^3) "
+                        "+ full-frame mixed ray render fwd+bwd (816000 rays x 59 samples)",
+            "frame": f"{cam['W']}x{cam['H']}", "rays_per_gpu": cam["H"] * cam["W"], "samples_per_ray": t["n_range_d"] + t["n_samples_d"],
+            "hash": f"16 levels x 2^{cfg['grid']['hash_size']}", "hidden": cfg["decoder"]["hidden_dim"],
+            "l2": "inputs larger than L2 (576 MB local volume, 160 MB GBV, >2 GB ray buffers per step); no explicit flush",
+            "parallelism": f"dp{world}: x-slab/z-slab sharded volumes + frame broadcast; ray batch per rank + grad all-reduce"}
+
+
+# =====================================================================================================================
+# GPU arm
+# =====================================================================================================================
+def run_gpu(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from remixfusion_b200 import abi, dist as rdist
+    from remixfusion_b200.global_volume import MapVolume
+    from remixfusion_b200.scene_rep import JointEncoding
+    from remixfusion_b200.volume import moving_volume
+    abi.lib()                                                   # fail loudly if the CUDA library is missing
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    cfg = configs.replica(hidden=args.hidden, hash_size=args.hash_size)
+    cam = cfg["cam"]
+    H, W = cam["H"], cam["W"]
+    S = cfg["training"]["n_range_d"] + cfg["training"]["n_samples_d"]
+    group = dist.group.WORLD if world > 1 else None
+
+    # frames: the TSDF frame is rank 0's (broadcast); each rank renders rays of its own frame
+    K, poses, frames = make_frames(cfg, N_POOL, first=17 * rank, stride=50)
+    bb = torch.from_numpy(np.array(cfg["mapping"]["bound"])).to(torch.float64)
+    torch.manual_seed(0)
+    model = JointEncoding(cfg, bb, process_group=group).to(dev)
+    with torch.no_grad():
+        model.embed_res_fn.params.copy_((torch.rand_like(model.embed_res_fn.params) * 2 - 1) * 1e-2)
+    model.train()
+    params = [model.embed_res_fn.params] + list(model.decoder_res.fused_weights())
+
+    R = cfg["globalV"]["base_resolution"]
+    z_slab = rdist.slab(R, rank, world)
+    full_gbv = model.GBV                                        # replicated copy used by the ray query
+    if world > 1:
+        slab_model = type("M", (), {})()
+        slab_model.GBV = type("E", (), {})(); slab_model.GBW = type("E", (), {})()
+        slab_model.GBV.params = torch.zeros(4 * (z_slab[1] - z_slab[0]) * R * R, device=dev)
+        slab_model.GBW.params = torch.zeros((z_slab[1] - z_slab[0]) * R * R, device=dev)
+        mvol = MapVolume(cfg, slab_model, K, z_slab=z_slab)
+    else:
+        mvol = MapVolume(cfg, model, K)
+    mvol.init_mapvolume()
+    dx = int(np.ceil(2 * cfg["volume"]["x_config"]["len"] / cfg["volume"]["voxel_size"]))
+    x_slab = rdist.slab(dx, rank, world)
+    local = moving_volume(cfg, None, poses[0], device=dev, x_slab=x_slab if world > 1 else None)
+
+    # resident inputs
+    dirs = torch.from_numpy(synth.camera_dirs(K, H, W).reshape(-1, 3)).to(dev)
+    dev_frames = []
+    for c2w, depth, rgb in frames:
+        d = torch.from_numpy(depth).to(dev); c = torch.from_numpy(rgb).to(dev)
+        packed = torch.empty(H * W, device=dev)
+        abi.check(abi.lib().rf_pack_bgr(abi.dptr(torch.floor(c * 255.0).contiguous()), abi.dptr(packed), H * W, abi.stream_ptr()), "pack")
+        c2w_t = torch.from_numpy(c2w.astype(np.float32)).to(dev)
+        rays_d = torch.sum(dirs[..., None, :] * c2w_t[:3, :3], -1).contiguous()          # mp_slam/mapper.py:344
+        rays_o = c2w_t[None, :3, -1].repeat(H * W, 1).contiguous()
+        dev_frames.append(dict(c2w=c2w, c2w_t=c2w_t, depth=d, rgb=c, packed=packed, rays_o=rays_o, rays_d=rays_d,
+                               tgt_d=d.reshape(-1, 1).contiguous(), tgt_c=c.reshape(-1, 3).contiguous()))
+    # the frame every rank fuses is rank 0's
+    bc = [dict(depth=f["depth"].clone(), rgb=f["rgb"].clone(), packed=f["packed"].clone(), c2w=f["c2w"].copy()) for f in dev_frames]
+    if world > 1:
+        for f in bc:
+            rdist.broadcast_frame(f["depth"], f["rgb"], 0, group); dist.broadcast(f["packed"], 0, group=group)
+            pose = torch.from_numpy(f["c2w"]).to(dev); dist.broadcast(pose, 0, group=group); f["c2w"] = pose.cpu().numpy()
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    stage_ms = {"tsdf_local": 0.0, "tsdf_global": 0.0, "ray_fwd": 0.0, "ray_bwd": 0.0}
+    units = {"touched_local": 0, "touched_global": 0, "samples": 0}
+
+    def step(i, timed):
+        f = dev_frames[i % N_POOL]; b = bc[i % N_POOL]
+        e = [ev() for _ in range(5)] if timed else None
+        if world > 1:                                            # frame broadcast over NVLink (data path of the sharded fuse)
+            rdist.broadcast_frame(b["depth"], b["rgb"], 0, group)
+        if timed: e[0].record()
+        local.integrate_packed(b["depth"], b["packed"], K, b["c2w"], None, 1.0, 0.0)
+        if timed: e[1].record()
+        mvol.integrate_kf({"rgb": b["rgb"], "depth": b["depth"]}, torch.from_numpy(b["c2w"]).float(), 1.0)
+        if world > 1:                                            # replicate the GBV for the ray query (160 MB all-gather)
+            sizes = [4 * (rdist.slab(R, k, world)[1] - rdist.slab(R, k, world)[0]) * R * R for k in range(world)]
+            full_gbv.params.data.copy_(rdist.gather_slabs(mvol.model.GBV.params, sizes, group))
+        if timed: e[2].record()
+        for p in params:
+            p.grad = None
+        ret = model.mapping(f["rays_o"], f["rays_d"], f["tgt_c"], f["tgt_d"])
+        loss = configs.total_loss(cfg, ret)
+        if timed: e[3].record()
+        loss.backward()
+        if world > 1:
+            rdist.allreduce_grads(params, group)
+        if timed: e[4].record()
+        return e, loss
+
+    def count_units(i):
+        """(touched local, touched GBV) of this rank's slabs for frame i — same predicate as the integrate kernels."""
+        b = bc[i % N_POOL]
+        tl, _ = local.count_touched(b["depth"], K, b["c2w"])
+        tg = mvol.count_touched(b["depth"], torch.from_numpy(b["c2w"]).float())
+        return tl, tg
+
+    # ---- warm-up ------------------------------------------------------------------------------------------------
+    for i in range(args.warmup):
+        step(i, False)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+
+    # ---- unit counts (outside the timed region; same frames, same order) -------------------------------------------
+    per_frame_units = []
+    for i in range(N_POOL):
+        per_frame_units.append(count_units(i))
+
+    # ---- timed region ---------------------------------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_start, t_end = ev(), ev()
+    t_start.record()
+    evs = []
+    for i in range(args.steps):
+        e, loss = step(args.warmup + i, True)
+        evs.append(e)
+    t_end.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = t_start.elapsed_time(t_end)
+    for e in evs:
+        stage_ms["tsdf_local"] += e[0].elapsed_time(e[1]); stage_ms["tsdf_global"] += e[1].elapsed_time(e[2])
+        stage_ms["ray_fwd"] += e[2].elapsed_time(e[3]); stage_ms["ray_bwd"] += e[3].elapsed_time(e[4])
+    for i in range(args.steps):
+        tl, tg = per_frame_units[(args.warmup + i) % N_POOL]
+        units["touched_local"] += tl; units["touched_global"] += tg; units["samples"] += H * W * S
+
+    # ---- per-kernel timing of the dominant kernels (CUDA events on the launching stream, resident inputs) ------------
+    kern = time_kernels(model, cfg, dev_frames[0], dev, params)
+
+    # ---- e2e: public API with HOST buffers, H2D/D2H inside the timed region ----------------------------------------
+    e2e = run_e2e(args, cfg, K, frames, model, mvol, local, params, dev, rank, world, group, per_frame_units, S)
+
+    # ---- reduce over ranks ------------------------------------------------------------------------------------------
+    vec = torch.tensor([total_ms, e2e["ms"]], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([units["touched_local"], units["touched_global"], units["samples"]], dtype=torch.float64, device=dev)
+    e2e_units = torch.tensor([float(e2e["units"])], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(vec, op=dist.ReduceOp.MAX, group=group)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(e2e_units, op=dist.ReduceOp.SUM, group=group)
+    total_ms, e2e_ms = float(vec[0]), float(vec[1])
+    touched = float(cnt[0] + cnt[1]); samples = float(cnt[2])
+    if rank != 0:
+        return
+    secs = total_ms / 1e3
+    peak, peak_src = measured_peak()
+    P = H * W * S
+    dom = max(("ray_bwd", kern["sample_bwd_ms"]), ("ray_fwd", kern["sample_fwd_ms"]), key=lambda kv: kv[1])
+    alg = {"ray_bwd": 1024.0, "ray_fwd": 1152.0}[dom[0]]           # 1024 B atomics / 1152 B gathers per sample
+    achieved = alg * P / (dom[1] / 1e3) / 1e9
+    tl0, tg0 = per_frame_units[0]
+    hw_bytes = 8.0 * H * W
+    line = {
+        "metric": METRIC, "value": (touched + samples) / secs, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic analytic scene (seeded), random-init hash table / decoder",
+        "config": workload_config(cfg, world),
+        "parts": {
+            "tsdf_voxel_updates_per_s": touched / ((stage_ms["tsdf_local"] + stage_ms["tsdf_global"]) / 1e3) if touched else None,
+            "ray_samples_per_s_fwd_bwd": samples / world / ((stage_ms["ray_fwd"] + stage_ms["ray_bwd"]) / 1e3),
+            "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
+            "touched_local_per_frame": tl0, "touched_global_per_frame": tg0,
+        },
+        "roofline": {"bound": "hbm", "kernel": "sample_bwd_kernel" if dom[0] == "ray_bwd" else "sample_fwd_kernel",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_sample": alg, "launch_ms": dom[1]},
+        "roofline_parts": {
+            "ray_fwd_bwd_hbm_form": {"achieved": 2176.0 * P / ((kern["sample_fwd_ms"] + kern["sample_bwd_ms"]) / 1e3) / 1e9, "peak": peak,
+                                     "frac": 2176.0 * P / ((kern["sample_fwd_ms"] + kern["sample_bwd_ms"]) / 1e3) / 1e9 / peak,
+                                     "launch_ms": [kern["sample_fwd_ms"], kern["sample_bwd_ms"]]},
+            "tsdf_local": {"achieved": (16.0 * kern["touched_local"] + 8.0 * kern["band_local"] + hw_bytes) / (kern["tsdf_local_ms"] / 1e3) / 1e9,
+                           "peak": peak, "launch_ms": kern["tsdf_local_ms"],
+                           "frac": (16.0 * kern["touched_local"] + 8.0 * kern["band_local"] + hw_bytes) / (kern["tsdf_local_ms"] / 1e3) / 1e9 / peak,
+                           "swept_voxels_per_s": kern["swept_local"] / (kern["tsdf_local_ms"] / 1e3)},
+            "tsdf_global": {"achieved": (40.0 * kern["touched_global"] + 16.0 * H * W) / (kern["tsdf_global_ms"] / 1e3) / 1e9, "peak": peak,
+                            "frac": (40.0 * kern["touched_global"] + 16.0 * H * W) / (kern["tsdf_global_ms"] / 1e3) / 1e9 / peak,
+                            "launch_ms": kern["tsdf_global_ms"]},
+            "gather_peak_Gops": kern.get("gather_gops"), "atomic_peak_Gops": kern.get("atomic_gops"),
+        },
+        "e2e": {"value": float(e2e_units[0]) / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"], "steps": e2e["steps"],
+                "ms_per_step": e2e_ms / e2e["steps"]},
+        "gpu_launches": 7 * args.steps,
+        "clocks": clocks,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline(cfg, K, frames[0], H * W * S)
+    print(json.dumps(line), flush=True)
+
+
+def time_kernels(model, cfg, f, dev, params):
+    """Average launch duration of each hot kernel with CUDA events on the launching stream, inputs resident."""
+    import ctypes as C
+    from remixfusion_b200 import abi
+    from remixfusion_b200.global_volume import MapVolume
+    from remixfusion_b200.volume import moving_volume
+    out = {}
+    cam = cfg["cam"]; H, W = cam["H"], cam["W"]
+    Kmat = synth.intrinsics(cam["fx"], cam["fy"], cam["cx"], cam["cy"])
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def timeit(fn, iters=5):
+        fn(); torch.cuda.synchronize()
+        a, b = ev(), ev()
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record(); torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters
+
+    vol = moving_volume(cfg, None, f["c2w"], device=dev)
+    out["tsdf_local_ms"] = timeit(lambda: vol.integrate_packed(f["depth"], f["packed"], Kmat, f["c2w"], None, 1.0, 0.0))
+    tl, tb = vol.count_touched(f["depth"], Kmat, f["c2w"])
+    out.update(touched_local=tl, band_local=tb, swept_local=int(np.prod(vol.vol_dim)))
+    del vol
+    m2 = type("M", (), {})(); m2.GBV = type("E", (), {})(); m2.GBW = type("E", (), {})()
+    R = cfg["globalV"]["base_resolution"]
+    m2.GBV.params = torch.zeros(4 * R ** 3, device=dev); m2.GBW.params = torch.zeros(R ** 3, device=dev)
+    gv = MapVolume(cfg, m2, Kmat); gv.init_mapvolume()
+    pose = torch.from_numpy(f["c2w"]).float()
+    out["touched_global"] = gv.count_touched(f["depth"], pose)
+    out["tsdf_global_ms"] = timeit(lambda: gv.integrate_kf({"rgb": f["rgb"], "depth": f["depth"]}, pose, 1.0))
+    del gv, m2
+    # ray kernels through the C-ABI directly
+    n = H * W
+    S = cfg["training"]["n_range_d"] + cfg["training"]["n_samples_d"]
+    z = model.sample_z(f["tgt_d"], n)
+    meta = model._meta(True)
+    w = model.decoder_res.fused_weights()
+    p = abi.RayParams(abi.dptr(model.embed_res_fn.params.detach()), abi.dptr(model.GBV.params.detach()), abi.dptr(w[0].detach()),
+                      abi.dptr(w[1].detach()), abi.dptr(w[2].detach()), abi.dptr(w[3].detach()))
+    raw = torch.empty(n, S, 4, device=dev); rgbm = torch.empty(n, 3, device=dev); dm = torch.empty(n, device=dev)
+    part = torch.zeros(8, dtype=torch.float64, device=dev)
+    td = f["tgt_d"].reshape(-1).contiguous()
+    L = abi.lib()
+    cfgc = meta["cfg"]; cfgc.n_rays_total = n
+
+    def fwd():
+        part.zero_()
+        abi.check(L.rf_ray_query_forward(C.byref(cfgc), C.byref(meta["hash_desc"]), C.byref(meta["gbv_desc"]), C.byref(p), abi.dptr(f["rays_o"]),
+                                         abi.dptr(f["rays_d"]), abi.dptr(td), abi.dptr(f["tgt_c"]), abi.dptr(z), C.c_int64(n), abi.dptr(raw),
+                                         abi.dptr(rgbm), abi.dptr(dm), abi.dptr(part), abi.stream_ptr()), "fwd")
+    g_hash = torch.zeros_like(model.embed_res_fn.params); gws = [torch.zeros_like(x) for x in w]
+    grads = abi.RayGrads(abi.dptr(g_hash), abi.dptr(gws[0]), abi.dptr(gws[1]), abi.dptr(gws[2]), abi.dptr(gws[3]), None, None)
+    scratch = torch.empty(n * S * 4, device=dev)
+    lg = torch.tensor([5.0, 0.1, 1000.0, 10.0], device=dev)
+
+    def bwd():
+        abi.check(L.rf_ray_query_backward(C.byref(cfgc), C.byref(meta["hash_desc"]), C.byref(meta["gbv_desc"]), C.byref(p), abi.dptr(f["rays_o"]),
+                                          abi.dptr(f["rays_d"]), abi.dptr(td), abi.dptr(f["tgt_c"]), C.c_int64(n), abi.dptr(z), abi.dptr(raw),
+                                          abi.dptr(rgbm), abi.dptr(dm), None, None, None, abi.dptr(lg), abi.dptr(part), C.byref(grads),
+                                          abi.dptr(scratch), abi.stream_ptr()), "bwd")
+    out["sample_fwd_ms"] = timeit(fwd, 3)          # sample_fwd_kernel + composite_fwd_kernel (composite << 1 %)
+    out["sample_bwd_ms"] = timeit(bwd, 3)          # composite_bwd_kernel + sample_bwd_kernel
+    # gather / atomic peaks over a 40 MiB table (SURVEY §8d denominators)
+    tab = torch.zeros(40 * 1024 * 1024 // 4, device=dev)
+    ms = C.c_float(0)
+    nops = 1 << 30
+    if L.rf_microbench_gather(abi.dptr(tab), C.c_int64(tab.numel() * 4), C.c_int64(nops), 3, C.byref(ms), abi.stream_ptr()) == 0:
+        per = (nops + 148 * 8 * 256 - 1) // (148 * 8 * 256); per = (per + 7) // 8 * 8
+        out["gather_gops"] = per * 148 * 8 * 256 / (ms.value / 1e3) / 1e9
+    if L.rf_microbench_atomic(abi.dptr(tab), C.c_int64(tab.numel() * 4), C.c_int64(nops), 3, C.byref(ms), abi.stream_ptr()) == 0:
+        per = (nops + 148 * 8 * 256 - 1) // (148 * 8 * 256)
+        out["atomic_gops"] = per * 148 * 8 * 256 / (ms.value / 1e3) / 1e9
+    return out
+
+
+def run_e2e(args, cfg, K, frames, model, mvol, local, params, dev, rank, world, group, per_frame_units, S):
+    """Same step through the public API with HOST buffers: numpy frames into moving_volume.integrate / integrate_kf
+    (H2D inside), rays + targets from pinned host memory, loss read back to the host."""
+    import torch.distributed as dist
+    from remixfusion_b200 import dist as rdist
+    cam = cfg["cam"]; H, W = cam["H"], cam["W"]
+    dirs = synth.camera_dirs(K, H, W).reshape(-1, 3)
+    host = []
+    for c2w, depth, rgb in frames:
+        c2w32 = c2w.astype(np.float32)
+        rays_d = (dirs[:, None, :] * c2w32[None, :3, :3]).sum(-1).astype(np.float32)
+        rays_o = np.broadcast_to(c2w32[:3, 3], rays_d.shape).copy()
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        host.append(dict(c2w=c2w, depth=depth, rgb=rgb, rgb255=np.floor(rgb * 255.0).astype(np.float32),
+                         rays_o=pin(rays_o), rays_d=pin(rays_d), tgt_c=pin(rgb.reshape(-1, 3)), tgt_d=pin(depth.reshape(-1, 1)),
+                         rgb_t=pin(rgb), depth_t=pin(depth)))
+    h2d = 2 * (H * W * 4 + H * W * 12) + H * W * (12 + 12 + 12 + 4)
+    d2h = 4 * 4
+
+    def step(i):
+        f = host[i % len(host)]
+        local.integrate(f["rgb255"], f["depth"], K, f["c2w"], None, 1.0, 0.0)
+        mvol.integrate_kf({"rgb": f["rgb_t"], "depth": f["depth_t"]}, torch.from_numpy(f["c2w"]).float(), 1.0)
+        if world > 1:
+            R = cfg["globalV"]["base_resolution"]
+            sizes = [4 * (rdist.slab(R, k, world)[1] - rdist.slab(R, k, world)[0]) * R * R for k in range(world)]
+            model.GBV.params.data.copy_(rdist.gather_slabs(mvol.model.GBV.params, sizes, group))
+        for p in params:
+            p.grad = None
+        ro = f["rays_o"].to(dev, non_blocking=True); rd = f["rays_d"].to(dev, non_blocking=True)
+        tc = f["tgt_c"].to(dev, non_blocking=True); td = f["tgt_d"].to(dev, non_blocking=True)
+        ret = model.mapping(ro, rd, tc, td)
+        loss = configs.total_loss(cfg, ret)
+        loss.backward()
+        if world > 1:
+            rdist.allreduce_grads(params, group)
+        return torch.stack([ret["rgb_res_loss"], ret["depth_res_loss"], ret["sdf_res_loss"], ret["fs_res_loss"]]).cpu()
+
+    n_steps = max(2, min(args.steps, 4))
+    step(0); step(1)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(n_steps):
+        step(i)
+    b.record(); torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    units = 0
+    for i in range(n_steps):
+        tl, tg = per_frame_units[i % N_POOL]
+        units += tl + tg + H * W * S
+    return {"ms": a.elapsed_time(b), "steps": n_steps, "units": units, "h2d": h2d, "d2h": d2h}
+
+
+def cpu_baseline(cfg, K, frame, full_samples):
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    n_rays = 8192
+    state, _ = cpu_reference_step(cfg, K, frame, 2048, threads, None)       # warm-up (allocations, first-touch)
+    state, r = cpu_reference_step(cfg, K, frame, n_rays, threads, state)
+    t_full = r["t_tsdf"] + r["t_ray"] * (full_samples / r["samples"])
+    return {"value": (r["touched"] + full_samples) / t_full, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"full TSDF fuse of one 1200x680 frame (C oracle, {threads} threads: {r['t_tsdf']:.2f} s) + mapping fwd+bwd on "
+                      f"{n_rays} rays x {r['samples'] // n_rays} (torch CPU restatement of the reference + stand-in encoders: {r['t_ray']:.2f} s), "
+                      f"ray time scaled x{full_samples / r['samples']:.1f} to the full frame",
+            "tsdf_voxel_updates_per_s": r["touched"] / r["t_tsdf"], "ray_samples_per_s": r["samples"] / r["t_ray"]}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--hidden", type=int, default=None, help="decoder width (default: Replica yaml, 32)")
+    ap.add_argument("--hash-size", type=int, default=None, help="log2 hash-table size (default: Replica yaml, 16)")
+    ap.add_argument("--cpu-rays", type=int, default=8192, help="rays per CPU reference step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+    if world > 1:
+        from remixfusion_b200 import dist as rdist
+        rdist.init_from_env("nccl")
+    run_gpu(args, rank, world, local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

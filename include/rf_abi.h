@@ -99,7 +99,7 @@ int rf_tsdf_count_local(int dx, int dy, int dz, const float origin[3], float vox
 int rf_tsdf_count_global(int R, const float box[6], const float K[9], const float* c2w, int c2w_on_device,
                          const float* depth, int H, int W, float trunc_margin,
                          const float* trgb, const float* wgt, float obs_weight,
-                         int z0, int z1, unsigned long long* counts, void* stream);
+                         int z0, int z1, int slab_local, unsigned long long* counts, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Stage 2 — encoders (what `tcnn.Encoding.forward/backward` did; model/encodings.py:33-51,65-76,
@@ -228,7 +228,9 @@ int rf_point_query_forward(const rf_ray_cfg* cfg, const rf_grid_desc* hash, cons
                            float* raw, void* stream);
 
 /* Micro-benchmarks for the gather-bound roofline denominators: random 8-byte loads and
- * random fp32 red.add over a table of table_bytes; returns elapsed ms in *ms (host). */
+ * random fp32 red.add over a table of table_bytes.  Synchronous: runs `iters` launches after one warm-up and
+ * returns the mean ms per launch in *ms (host).  The number of operations actually issued per launch is n_ops
+ * rounded up to a multiple of (8 * SMs * 256 * 8) for gathers, (8 * SMs * 256) for atomics. */
 int rf_microbench_gather(void* table, int64_t table_bytes, int64_t n_ops, int iters, float* ms, void* stream);
 int rf_microbench_atomic(void* table, int64_t table_bytes, int64_t n_ops, int iters, float* ms, void* stream);
 

@@ -86,12 +86,10 @@ class MapVolume:
         _k, k_p = abi.farr(self.K, 9)
         _c, c_p = abi.farr(pose.detach().cpu().numpy() if isinstance(pose, torch.Tensor) else pose, 16)
         counts = torch.zeros(2, dtype=torch.int64, device=dev)
-        if self.slab_local:
-            raise abi.RfError("count_touched: not available on a slab-local volume")
         rc = abi.lib().rf_tsdf_count_global(
             C.c_int(R), b_p, k_p, c_p, C.c_int(0), abi.dptr(depth_im), C.c_int(im_h), C.c_int(im_w),
             C.c_float(self.trunc_margin), abi.dptr(self.model.GBV.params.data), abi.dptr(self.model.GBW.params.data),
-            C.c_float(obs_weight), C.c_int(self.z_slab[0]), C.c_int(self.z_slab[1]),
+            C.c_float(obs_weight), C.c_int(self.z_slab[0]), C.c_int(self.z_slab[1]), C.c_int(self.slab_local),
             C.c_void_p(counts.data_ptr()), abi.stream_ptr())
         abi.check(rc, "rf_tsdf_count_global")
         return int(counts.cpu()[0])

@@ -34,23 +34,7 @@ def case_config(name):
     return cfg
 
 
-def resolution_sdf(cfg):
-    """model/scene_rep.py:23-32"""
-    bb = np.array(cfg["mapping"]["bound"], dtype=np.float64)
-    dim_max = (bb[:, 1] - bb[:, 0]).max()
-    v = cfg["grid"]["voxel_sdf"]
-    return v if v > 10 else int(dim_max / v)
-
-
-def hash_standin(cfg):
-    res = resolution_sdf(cfg)
-    pls = np.exp2(np.log2(res / 16) / 15)                       # model/encodings.py:36
-    return tcnn_standin.GridStandIn(16, 2, True, cfg["grid"]["hash_size"], 16, pls)
-
-
-def gbv_standin(cfg):
-    g = cfg["globalV"]
-    return tcnn_standin.GridStandIn(g["n_levels"], g["n_features_per_level"], False, 0, g["base_resolution"], g["per_level_scale"])
+from oracle.ray_oracle import gbv_standin, hash_standin, resolution_sdf   # noqa: E402,F401
 
 
 def oracle_from_golden(G, name, requires_grad=True):

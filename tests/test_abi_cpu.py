@@ -1,0 +1,67 @@
+"""CPU suite: the C-ABI library builds for sm_100a, loads, and exports every symbol include/rf_abi.h declares
+(no compute calls without a GPU); host-side argument checks that need no device."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "rf_abi.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rf_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(rf_lib):
+    names = _declared()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(rf_lib, n), f"{n} declared in include/rf_abi.h but not exported by librf_b200.so"
+
+
+def test_version_and_error_string(rf_lib):
+    assert rf_lib.rf_version() == 1
+    rc = rf_lib.rf_tsdf_clear_global(C.c_void_p(0), C.c_int64(8), C.c_void_p(0))
+    assert rc == -1 and b"NULL" in rf_lib.rf_last_error()
+    rc = rf_lib.rf_tsdf_clear_local(C.c_void_p(8), C.c_void_p(8), C.c_void_p(8), C.c_int64(-1), C.c_void_p(0))
+    assert rc == -2
+
+
+def test_grid_desc_init_matches_tcnn_table(rf_lib):
+    import numpy as np
+    from oracle.tcnn_standin import grid_levels
+    from remixfusion_b200.encodings import make_grid_desc
+    for hs, res in ((16, 400), (19, 512), (21, 1750), (19, 5000), (12, 250)):
+        pls = np.exp2(np.log2(res / 16) / 15)                                   # model/encodings.py:36
+        s, r, n, o = grid_levels(16, 2, True, hs, 16, pls)
+        d = make_grid_desc(16, 2, True, hs, 16, pls)
+        assert [d.scale[i] for i in range(16)] == [float(v) for v in s]
+        assert list(d.resolution[:16]) == r and list(d.size[:16]) == n and list(d.offset[:17]) == o
+    d = make_grid_desc(1, 4, False, 0, 200, 1)                                   # GBV: model/scene_rep.py:60-74
+    assert d.scale[0] == 199.0 and d.resolution[0] == 200 and d.offset[1] == 8000000 and d.n_params == 32000000
+    from remixfusion_b200 import abi
+    bad = abi.GridDesc()
+    assert rf_lib.rf_grid_desc_init(C.byref(bad), 17, 2, 1, 19, 16, C.c_double(1.5)) == -2
+    assert rf_lib.rf_grid_desc_init(C.byref(bad), 16, 3, 1, 19, 16, C.c_double(1.5)) == -4
+
+
+def test_product_never_imports_oracle():
+    """The product path must not route through oracle/ (tier rule ③)."""
+    pkg = os.path.join(ROOT, "remixfusion_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f), errors="replace").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f"{f} imports oracle"
+                assert "liboracle" not in txt, f
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from remixfusion_b200 import abi
+    monkeypatch.setattr(abi, "_lib", None)
+    monkeypatch.setattr(abi, "LIB_PATH", "/nonexistent/librf_b200.so")
+    with pytest.raises(abi.RfError):
+        abi.lib()
