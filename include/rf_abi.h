@@ -234,6 +234,11 @@ int rf_point_query_forward(const rf_ray_cfg* cfg, const rf_grid_desc* hash, cons
 int rf_microbench_gather(void* table, int64_t table_bytes, int64_t n_ops, int iters, float* ms, void* stream);
 int rf_microbench_atomic(void* table, int64_t table_bytes, int64_t n_ops, int iters, float* ms, void* stream);
 
+/* Hardware self-test of the hand-written tcgen05 building blocks (csrc/umma.cuh): bf16x3 GEMM on one CTA.
+ * mode 0: D[128,N] = A[128,K] * B[N,K]^T; mode 1: D[f,j] = sum_m A[m,f] * B[m,j] (A [128,K], B [128,N]).
+ * Synchronous.  Returns 0, or 1001 if the MMA never completed. */
+int rf_umma_selftest(const float* A, const float* B, float* D, int K, int N, int mode, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
