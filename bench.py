@@ -52,6 +52,16 @@ def measured_peak():
     return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
 
 
+def measured_tensor_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, burst)"
+        except Exception:
+            pass
+    return 2250.0, "nominal dense bf16 (B200_PROFILING.md)"
+
+
 def make_frames(cfg, n_pool, first=0, stride=1):
     cam = cfg["cam"]
     K = synth.intrinsics(cam["fx"], cam["fy"], cam["cx"], cam["cy"])
@@ -365,9 +375,10 @@ def run_gpu(args, rank, world, local_rank):
     secs = total_ms / 1e3
     peak, peak_src = measured_peak()
     P = H * W * S
-    dom = max(("ray_bwd", kern["sample_bwd_ms"]), ("ray_fwd", kern["sample_fwd_ms"]), key=lambda kv: kv[1])
-    alg = {"ray_bwd": 1024.0, "ray_fwd": 1152.0}[dom[0]]           # 1024 B atomics / 1152 B gathers per sample
-    achieved = alg * P / (dom[1] / 1e3) / 1e9
+    tf_peak, tf_src = measured_tensor_peak()
+    peaks = (peak, peak_src, tf_peak, tf_src)
+    dom = max(kern["kernels_ms"].items(), key=lambda kv: kv[1])
+    roof = kernel_roofline(dom[0], dom[1], P, cfg["decoder"]["hidden_dim"], peaks)
     tl0, tg0 = per_frame_units[0]
     hw_bytes = 8.0 * H * W
     line = {
@@ -381,10 +392,9 @@ def run_gpu(args, rank, world, local_rank):
             "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
             "touched_local_per_frame": tl0, "touched_global_per_frame": tg0,
         },
-        "roofline": {"bound": "hbm", "kernel": "sample_bwd_kernel" if dom[0] == "ray_bwd" else "sample_fwd_kernel",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                     "peak_source": peak_src, "algorithmic_bytes_per_sample": alg, "launch_ms": dom[1]},
+        "roofline": roof,
         "roofline_parts": {
+            "kernels": {k: kernel_roofline(k, v, P, cfg["decoder"]["hidden_dim"], peaks) for k, v in kern["kernels_ms"].items()},
             "ray_fwd_bwd_hbm_form": {"achieved": 2176.0 * P / ((kern["sample_fwd_ms"] + kern["sample_bwd_ms"]) / 1e3) / 1e9, "peak": peak,
                                      "frac": 2176.0 * P / ((kern["sample_fwd_ms"] + kern["sample_bwd_ms"]) / 1e3) / 1e9 / peak,
                                      "launch_ms": [kern["sample_fwd_ms"], kern["sample_bwd_ms"]]},
@@ -399,12 +409,33 @@ def run_gpu(args, rank, world, local_rank):
         },
         "e2e": {"value": float(e2e_units[0]) / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"], "steps": e2e["steps"],
                 "ms_per_step": e2e_ms / e2e["steps"]},
-        "gpu_launches": 7 * args.steps,
+        "gpu_launches": (3 + len(kern["kernels_ms"])) * args.steps,     # 2 TSDF integrates + ray_z + the ray kernels above
         "clocks": clocks,
     }
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(cfg, K, frames[0], H * W * S)
     print(json.dumps(line), flush=True)
+
+
+PROF_NAMES = {3: "ray_pos_kernel", 4: "encode_walk_kernel", 5: "mlp_fwd_tc_kernel", 6: "composite_fwd_kernel",
+              7: "composite_bwd_kernel", 8: "mlp_bwd_tc_kernel", 9: "scatter_walk_kernel", 10: "sample_fwd_kernel",
+              11: "sample_bwd_kernel"}
+
+
+def kernel_roofline(name, ms, P, hidden, peaks):
+    """Roofline entry of one kernel.  Algorithmic work per sample: gathers 1152 B (16 levels x 8
+    corners x 8 B + 8 GBV corners x 16 B), table-gradient reductions 1024 B (16 x 8 x 2 x 4 B), decoder 2*166*h FLOP
+    forward and twice that backward."""
+    hbm, hbm_src, tf, tf_src = peaks
+    if name in ("mlp_fwd_tc_kernel", "mlp_bwd_tc_kernel"):
+        flop = 2.0 * 166 * hidden * (1 if name == "mlp_fwd_tc_kernel" else 2)
+        a = flop * P / (ms / 1e3) / 1e12
+        return {"bound": "tensor", "kernel": name, "achieved": a, "peak": tf, "unit": "TFLOP/s", "frac": a / tf, "traffic": None,
+                "peak_source": tf_src, "algorithmic_flop_per_sample": flop, "launch_ms": ms}
+    alg = {"encode_walk_kernel": 1152.0, "sample_fwd_kernel": 1152.0, "scatter_walk_kernel": 1024.0, "sample_bwd_kernel": 1024.0}.get(name, 40.0)
+    a = alg * P / (ms / 1e3) / 1e9
+    return {"bound": "hbm", "kernel": name, "achieved": a, "peak": hbm, "unit": "GB/s", "frac": a / hbm, "traffic": None,
+            "peak_source": hbm_src, "algorithmic_bytes_per_sample": alg, "launch_ms": ms}
 
 
 def time_kernels(model, cfg, f, dev, params):
@@ -453,24 +484,36 @@ def time_kernels(model, cfg, f, dev, params):
     td = f["tgt_d"].reshape(-1).contiguous()
     L = abi.lib()
     cfgc = meta["cfg"]; cfgc.n_rays_total = n
+    nws = int(L.rf_ray_workspace_floats(C.byref(cfgc), C.byref(meta["hash_desc"]), C.c_int64(n)))
+    ws = torch.empty(nws, device=dev) if nws > 0 else None
 
     def fwd():
         part.zero_()
         abi.check(L.rf_ray_query_forward(C.byref(cfgc), C.byref(meta["hash_desc"]), C.byref(meta["gbv_desc"]), C.byref(p), abi.dptr(f["rays_o"]),
                                          abi.dptr(f["rays_d"]), abi.dptr(td), abi.dptr(f["tgt_c"]), abi.dptr(z), C.c_int64(n), abi.dptr(raw),
-                                         abi.dptr(rgbm), abi.dptr(dm), abi.dptr(part), abi.stream_ptr()), "fwd")
+                                         abi.dptr(rgbm), abi.dptr(dm), abi.dptr(part), abi.dptr(ws), abi.stream_ptr()), "fwd")
     g_hash = torch.zeros_like(model.embed_res_fn.params); gws = [torch.zeros_like(x) for x in w]
     grads = abi.RayGrads(abi.dptr(g_hash), abi.dptr(gws[0]), abi.dptr(gws[1]), abi.dptr(gws[2]), abi.dptr(gws[3]), None, None)
-    scratch = torch.empty(n * S * 4, device=dev)
+    scratch = torch.empty(int(L.rf_ray_scratch_floats(C.byref(cfgc), C.byref(meta["hash_desc"]), C.c_int64(n), C.c_int(0))), device=dev)
     lg = torch.tensor([5.0, 0.1, 1000.0, 10.0], device=dev)
 
     def bwd():
         abi.check(L.rf_ray_query_backward(C.byref(cfgc), C.byref(meta["hash_desc"]), C.byref(meta["gbv_desc"]), C.byref(p), abi.dptr(f["rays_o"]),
                                           abi.dptr(f["rays_d"]), abi.dptr(td), abi.dptr(f["tgt_c"]), C.c_int64(n), abi.dptr(z), abi.dptr(raw),
                                           abi.dptr(rgbm), abi.dptr(dm), None, None, None, abi.dptr(lg), abi.dptr(part), C.byref(grads),
-                                          abi.dptr(scratch), abi.stream_ptr()), "bwd")
-    out["sample_fwd_ms"] = timeit(fwd, 3)          # sample_fwd_kernel + composite_fwd_kernel (composite << 1 %)
-    out["sample_bwd_ms"] = timeit(bwd, 3)          # composite_bwd_kernel + sample_bwd_kernel
+                                          abi.dptr(ws), abi.dptr(scratch), abi.stream_ptr()), "bwd")
+    out["sample_fwd_ms"] = timeit(fwd, 3)          # whole forward call: position + encode + decoder + composite
+    out["sample_bwd_ms"] = timeit(bwd, 3)          # whole backward call: composite bwd + decoder bwd + scatter
+    # per-kernel launch durations: CUDA events recorded by the library around each launch, on the launching stream
+    L.rf_profile_enable(1)
+    acc = np.zeros(16); reps = 3
+    for _ in range(reps):
+        fwd(); bwd()
+        buf = (C.c_float * 16)()
+        L.rf_profile_read(buf)
+        acc += np.maximum(np.array(buf[:], dtype=np.float64), 0.0)
+    L.rf_profile_enable(0)
+    out["kernels_ms"] = {PROF_NAMES[i]: acc[i] / reps for i in PROF_NAMES if acc[i] > 0}
     # gather / atomic peaks over a 40 MiB table (SURVEY §8d denominators)
     tab = torch.zeros(40 * 1024 * 1024 // 4, device=dev)
     ms = C.c_float(0)

@@ -160,7 +160,8 @@ typedef struct rf_ray_cfg {
     int32_t hidden;         /* decoder.hidden_dim == hidden_dim_color (32 or 64) */
     int32_t n_bins;         /* pos.n_bins (16) */
     int32_t geo_feat;       /* decoder.geo_feat_dim (15) */
-    int32_t mlp_precision;  /* 0: fp32 SIMT decoder (the accuracy anchor) */
+    int32_t mlp_precision;  /* 0: fp32 SIMT decoder (the accuracy anchor); 1: tcgen05 tensor-core decoder (bf16x3
+                             * products, fp32 accumulation; ~2^-16 relative per product) fed by feature planes */
     int32_t _pad;
     int64_t n_rays_total;   /* rays in the whole batch when it is sharded over GPUs (loss means); 0 = n_rays */
     double  bbox[6];        /* float64 bounding box {x0,x1,y0,y1,z0,z1} (model/scene_rep.py:388) */
@@ -194,7 +195,13 @@ int rf_ray_query_forward(const rf_ray_cfg* cfg, const rf_grid_desc* hash, const 
                          const float* rays_o, const float* rays_d, const float* target_d,
                          const float* target_rgb, const float* z_vals, int64_t n_rays,
                          float* raw, float* rgb_map, float* depth_map,
-                         double* loss_partials, void* stream);
+                         double* loss_partials, float* workspace, void* stream);
+
+/* Floats of `workspace` the forward needs (and the backward reads back): 0 for mlp_precision 0;
+ * (2*n_levels + 4 + 3) * N * S for mlp_precision 1 (hash feature planes, GBV features, normalised positions). */
+int64_t rf_ray_workspace_floats(const rf_ray_cfg* cfg, const rf_grid_desc* hash, int64_t n_rays);
+/* Floats of `scratch` the backward needs: 4*N*S (+ 2*n_levels*N*S for mlp_precision 1; 7*N*S with ray gradients). */
+int64_t rf_ray_scratch_floats(const rf_ray_cfg* cfg, const rf_grid_desc* hash, int64_t n_rays, int ray_grads);
 
 typedef struct rf_ray_grads {
     float* g_hash;     /* device, += ; same shape as hash_params (may be NULL) */
@@ -206,10 +213,10 @@ typedef struct rf_ray_grads {
     float* g_rays_d;   /* device [N,3], written; NULL likewise */
 } rf_ray_grads;
 
-/* Backward of the forward above (recomputes activations).  Upstream gradients (each may be NULL = zero):
+/* Backward of the forward above (recomputes activations; mlp_precision 1 re-reads the forward's workspace).  Upstream gradients (each may be NULL = zero):
  *   d_rgb_map [N,3], d_depth_map [N], d_raw [N,S,4], and loss_grads (device float[4]: d/d rgb_loss, depth_loss,
  *   sdf_loss, fs_loss) together with the forward's loss_partials (all-reduced over ranks when sharded).
- * scratch: device, 16-byte aligned, >= 4*N*S floats (7*N*S when ray gradients are requested). */
+ * workspace: the forward's (NULL for mlp_precision 0); scratch: device, 16-byte aligned, rf_ray_scratch_floats(). */
 int rf_ray_query_backward(const rf_ray_cfg* cfg, const rf_grid_desc* hash, const rf_grid_desc* gbv,
                           const rf_ray_params* p,
                           const float* rays_o, const float* rays_d, const float* target_d,
@@ -217,7 +224,7 @@ int rf_ray_query_backward(const rf_ray_cfg* cfg, const rf_grid_desc* hash, const
                           const float* z_vals, const float* raw, const float* rgb_map, const float* depth_map,
                           const float* d_rgb_map, const float* d_depth_map, const float* d_raw,
                           const float* loss_grads, const double* loss_partials,
-                          const rf_ray_grads* g, float* scratch, void* stream);
+                          const rf_ray_grads* g, const float* workspace, float* scratch, void* stream);
 
 /* Point query (model/scene_rep.py:212-310 — query_sdf_res / query_color_residual / run_network(flat)):
  * x [n,3] normalised coords -> raw [n,4] (rgb, sdf).  variant: 0 = query_color_sdf (cfg->clamp_mode),
@@ -233,6 +240,16 @@ int rf_point_query_forward(const rf_ray_cfg* cfg, const rf_grid_desc* hash, cons
  * rounded up to a multiple of (8 * SMs * 256 * 8) for gathers, (8 * SMs * 256) for atomics. */
 int rf_microbench_gather(void* table, int64_t table_bytes, int64_t n_ops, int iters, float* ms, void* stream);
 int rf_microbench_atomic(void* table, int64_t table_bytes, int64_t n_ops, int iters, float* ms, void* stream);
+
+/* Optional per-kernel timing for bench.py's live roofline numbers.  rf_profile_enable(1) makes the launchers
+ * bracket each hot kernel with CUDA events on the launching stream (the last launch of each slot is kept);
+ * rf_profile_read(ms) synchronises on those events and writes RF_PROF_SLOTS floats (ms, -1 = not launched). */
+#define RF_PROF_SLOTS 16
+enum { RF_PROF_TSDF_LOCAL = 0, RF_PROF_TSDF_GLOBAL = 1, RF_PROF_RAY_Z = 2, RF_PROF_RAY_POS = 3, RF_PROF_ENCODE = 4,
+       RF_PROF_MLP_FWD = 5, RF_PROF_COMPOSITE_FWD = 6, RF_PROF_COMPOSITE_BWD = 7, RF_PROF_MLP_BWD = 8,
+       RF_PROF_SCATTER = 9, RF_PROF_SAMPLE_FWD = 10, RF_PROF_SAMPLE_BWD = 11, RF_PROF_RAY_GRAD = 12 };
+int rf_profile_enable(int on);
+int rf_profile_read(float* ms);
 
 /* Hardware self-test of the hand-written tcgen05 building blocks (csrc/umma.cuh): bf16x3 GEMM on one CTA.
  * mode 0: D[128,N] = A[128,K] * B[N,K]^T; mode 1: D[f,j] = sum_m A[m,f] * B[m,j] (A [128,K], B [128,N]).

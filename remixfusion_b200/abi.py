@@ -74,6 +74,8 @@ def lib() -> C.CDLL:
         _lib = C.CDLL(LIB_PATH)
         _lib.rf_last_error.restype = C.c_char_p
         _lib.rf_version.restype = C.c_int
+        _lib.rf_ray_workspace_floats.restype = C.c_int64
+        _lib.rf_ray_scratch_floats.restype = C.c_int64
     return _lib
 
 

@@ -114,11 +114,12 @@ struct Weights { const float* w_sdf0; const float* w_sdf1; const float* w_col0; 
 
 struct Grads { float* g_hash; float* g_w_sdf0; float* g_w_sdf1; float* g_w_col0; float* g_w_col1; };
 
-// Launchers of the tensor-core path (ray_query_tc.cu); return 0 or an error code with rf_last_error set.
-int launch_fwd_tc(const RayK& k, const GridDev& hg, const GridDev& gg, const rf_ray_params* p, const float* rays_o, const float* rays_d,
-                  const float* z_vals, long long P, float* raw, float* feat, cudaStream_t s);
-int launch_bwd_tc(const RayK& k, const GridDev& hg, const GridDev& gg, const rf_ray_params* p, const float* rays_o, const float* rays_d,
-                  const float* z_vals, long long P, const float* feat, const float* d_raw_tot, const Grads& gr, cudaStream_t s);
-bool tc_supported(const RayK& k, int hidden, bool ba);
+// Tensor-core path (mlp_precision 1): ray_encode.cu (feature planes, table-gradient scatter) + ray_mlp_tc.cu (tcgen05
+// decoder).  Return 0 or an error code with rf_last_error set.
+bool tc_supported(const RayK& k, int hidden);
+int launch_fwd_tc(const RayK& k, int hidden, const GridDev& hg, const GridDev& gg, const rf_ray_params* p, const float* rays_o,
+                  const float* rays_d, const float* z_vals, long long P, float* raw, float* feat, cudaStream_t s);
+int launch_bwd_tc(const RayK& k, int hidden, const GridDev& hg, const rf_ray_params* p, long long P, const float* feat,
+                  const float* d_raw_tot, float* dfeat, const Grads& gr, cudaStream_t s);
 
 }  // namespace rf

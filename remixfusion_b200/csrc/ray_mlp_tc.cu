@@ -1,0 +1,605 @@
+// ray_mlp_tc.cu — the decoder of the mixed representation on the 5th-generation tensor cores (tcgen05, TMEM).
+//
+// Replaces ColorSDFNet.forward (model/decoder.py:132-146: SDFNet :59-110, ColorNet :6-53) and its autograd backward,
+// including the concatenations of JointEncoding.query_color_sdf (model/scene_rep.py:325-345), for 128-sample tiles:
+//
+//   forward   X1 = [hash32 | oneblob48 | tsdf]           H1 = relu(X1 W0^T)      O = H1 W1^T   (sdf, geo15)
+//             X2 = [oneblob48 | geo15 | gbv_rgb3]         H2 = relu(X2 W2^T)      rgb = H2 W3^T
+//             raw = (rgb + gbv_rgb, sdf + tsdf)                                   (:344-345)
+//   backward  recomputes the forward, then dH2 = (dRGB W3) . relu', dgeo = dH2 W2[:,geo], dO = [dsdf, dgeo],
+//             dH1 = (dO W1) . relu', dhash = dH1 W0[:,hash]; the four weight gradients X^T dH are accumulated in
+//             TMEM across all tiles a CTA processes and flushed once at the end.
+//
+// Numerics: every GEMM is a bf16x3 product (a_hi b_hi + a_hi b_lo + a_lo b_hi, fp32 accumulation in TMEM), i.e.
+// ~2^-16 relative per product — the "rendered colour / depth and gradients within 1e-3" bar with two orders of margin;
+// the fp32 SIMT kernels of ray_query.cu (mlp_precision 0) stay as the accuracy anchor.
+//
+// Structure: a CTA holds the decoder weights once (bf16 hi/lo, chunked no-swizzle layout of umma.cuh) and G
+// independent groups of 128 threads.  A group owns one tile at a time: thread m stages row m of the operands, one
+// elected thread issues the MMAs, everybody waits on the group's mbarrier and reads its own TMEM lane.  Groups run
+// out of phase, so one group's tensor-core latency is covered by another group's staging.  Inputs are the feature
+// planes written by ray_encode.cu (coalesced, streaming); no random access happens here.
+#include "ray_common.cuh"
+#include "umma.cuh"
+
+namespace rf {
+namespace {
+
+using namespace umma;
+
+constexpr int kChunkB = 2048;                  // bytes of one 8-column chunk of a 128-row operand
+constexpr int kXBlob = 4, kXTail = 10, kXCh = 14;   // X-order chunks: hash 0-3 | oneblob 4-9 | tail 10-13
+constexpr int kTailTsdf = 18;                  // tail = [geo15 | gbv_rgb3 | tsdf | 0 x13]
+constexpr int kKX = kXCh * 8;                  // 112
+
+template <int HID>
+struct WL {                                    // weight shared-memory layout (bytes); B operands, rows = out units
+    static constexpr int HC = HID / 8;
+    static constexpr int w0 = kXCh * HID * 16; // W0 [HID rows][112]  (X-order columns)
+    static constexpr int w1 = HC * 16 * 16;    // W1 [16 rows][HID]
+    static constexpr int w2 = 10 * HID * 16;   // W2 [HID rows][80]   (oneblob | tail)
+    static constexpr int w3 = HC * 16 * 16;    // W3 [16 rows][HID]   (rows 3..15 zero)
+    static constexpr int o_w0h = 0, o_w0l = w0, o_w1h = 2 * w0, o_w1l = o_w1h + w1, o_w2h = o_w1l + w1, o_w2l = o_w2h + w2,
+                         o_w3h = o_w2l + w2, o_w3l = o_w3h + w3;
+    static constexpr int total = 2 * (w0 + w1 + w2 + w3);
+};
+
+__device__ __forceinline__ void store_split(unsigned char* hi, unsigned char* lo, int rows, int r, int kx, float v) {
+    __nv_bfloat16 h, l; split_bf16(v, h, l);
+    uint32_t off = chunk_off(rows, r, kx >> 3) + (uint32_t)(kx & 7) * 2u;
+    *reinterpret_cast<__nv_bfloat16*>(hi + off) = h;
+    *reinterpret_cast<__nv_bfloat16*>(lo + off) = l;
+}
+
+// nn.Linear weights ([out][in], model/decoder.py:31-47,87-102) -> chunked bf16 hi/lo B operands
+template <int HID>
+__device__ void load_weights(unsigned char* w, const Weights& wt, int nthreads) {
+    using L = WL<HID>;
+    constexpr int in1 = 81;
+    for (int i = threadIdx.x; i < HID * kKX; i += nthreads) {
+        int j = i / kKX, kx = i - j * kKX;
+        float v = 0.f;
+        if (kx < 80) v = wt.w_sdf0[j * in1 + kx];
+        else if (kx == 80 + kTailTsdf) v = wt.w_sdf0[j * in1 + 80];
+        store_split(w + L::o_w0h, w + L::o_w0l, HID, j, kx, v);
+    }
+    for (int i = threadIdx.x; i < 16 * HID; i += nthreads) {
+        int r = i / HID, j = i - r * HID;
+        store_split(w + L::o_w1h, w + L::o_w1l, 16, r, j, wt.w_sdf1[r * HID + j]);
+        store_split(w + L::o_w3h, w + L::o_w3l, 16, r, j, (r < 3) ? wt.w_col1[r * HID + j] : 0.f);
+    }
+    for (int i = threadIdx.x; i < HID * 80; i += nthreads) {
+        int j = i / 80, kx = i - j * 80;
+        store_split(w + L::o_w2h, w + L::o_w2l, HID, j, kx, (kx < kIn2) ? wt.w_col0[j * kIn2 + kx] : 0.f);
+    }
+}
+
+__device__ __forceinline__ void grp_sync(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
+
+__device__ __forceinline__ void grp_wait(uint64_t* bar, uint32_t& phase) {
+    if (!mbar_wait(bar, phase)) __trap();          // a tensor-core pipeline that never completes must fail loudly
+    phase ^= 1u;
+    fence_after_sync();
+}
+
+// row m, chunk c of a 128-row operand <- 8 floats (hi and lo parts)
+__device__ __forceinline__ void stage8(unsigned char* hi, unsigned char* lo, int m, int c, const float* v) {
+    uint4 h, l; split8(v, h, l);
+    uint32_t off = chunk_off(128, m, c);
+    *reinterpret_cast<uint4*>(hi + off) = h;
+    *reinterpret_cast<uint4*>(lo + off) = l;
+}
+__device__ __forceinline__ void stage_zero(unsigned char* hi, unsigned char* lo, int m, int c) {
+    uint32_t off = chunk_off(128, m, c);
+    *reinterpret_cast<uint4*>(hi + off) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(lo + off) = make_uint4(0, 0, 0, 0);
+}
+
+__device__ __forceinline__ float cdf_u(float u) {
+    float u2 = u * u, u4 = u2 * u2;
+    return fminf(fmaxf((15.0f / 16.0f) * u * (1.0f - (2.0f / 3.0f) * u2 + (1.0f / 5.0f) * u4) + 0.5f, 0.0f), 1.0f);
+}
+// OneBlob of one coordinate (model/encodings.py:65-76; Appendix B7) into chunks c, c+1 of row m.  The quartic kernel
+// has support +-1/16, so only the bin holding x and its two neighbours are non-zero: inside [-0.9, 1.9] (where the
+// three periodic copies of Appendix B7 cover the support) the 16 bins are three values; elsewhere the general form.
+__device__ __forceinline__ void stage_oneblob(float x, unsigned char* hi, unsigned char* lo, int m, int c) {
+    if (x > -0.9f && x < 1.9f) {
+        stage_zero(hi, lo, m, c); stage_zero(hi, lo, m, c + 1);
+        float xw = x - floorf(x);
+        if (xw >= 1.0f) xw = 0.0f;
+        float t = xw * (float)kNB;
+        int b = (int)t;
+        float ub = (float)b - t;
+        float cb = cdf_u(ub), cb1 = cdf_u(ub + 1.0f);
+        const int km = (b - 1) & (kNB - 1), kp = (b + 1) & (kNB - 1);
+        __nv_bfloat16 h, l;
+        split_bf16(cb, h, l);
+        uint32_t o = chunk_off(128, m, c + (km >> 3)) + (uint32_t)(km & 7) * 2u;
+        *reinterpret_cast<__nv_bfloat16*>(hi + o) = h; *reinterpret_cast<__nv_bfloat16*>(lo + o) = l;
+        split_bf16(cb1 - cb, h, l);
+        o = chunk_off(128, m, c + (b >> 3)) + (uint32_t)(b & 7) * 2u;
+        *reinterpret_cast<__nv_bfloat16*>(hi + o) = h; *reinterpret_cast<__nv_bfloat16*>(lo + o) = l;
+        split_bf16(1.0f - cb1, h, l);
+        o = chunk_off(128, m, c + (kp >> 3)) + (uint32_t)(kp & 7) * 2u;
+        *reinterpret_cast<__nv_bfloat16*>(hi + o) = h; *reinterpret_cast<__nv_bfloat16*>(lo + o) = l;
+    } else {
+        float ob[kNB];
+        oneblob_coord<kNB>(x, ob);
+        stage8(hi, lo, m, c, ob); stage8(hi, lo, m, c + 1, ob + 8);
+    }
+}
+
+// ---- MMA issue helpers (one thread).  All operands are bf16 hi/lo pairs; each k-step issues the bf16x3 triple. ----
+// A [128 x K] K-major at consecutive chunks; B = weights [brows = N rows] K-major, chunks from the given address
+__device__ __forceinline__ void mma_kk(uint32_t d, uint32_t ah, uint32_t al, uint32_t bh, uint32_t bl, int brows, int nks,
+                                       uint32_t idesc, uint32_t& acc) {
+    for (int s = 0; s < nks; ++s) {
+        uint64_t dah = smem_desc(ah + 2 * s * kChunkB, kChunkB, 128), dal = smem_desc(al + 2 * s * kChunkB, kChunkB, 128);
+        uint64_t dbh = smem_desc(bh + 2 * s * brows * 16, brows * 16, 128), dbl = smem_desc(bl + 2 * s * brows * 16, brows * 16, 128);
+        mma_bf16(d, dah, dbh, idesc, acc); acc = 1;
+        mma_bf16(d, dah, dbl, idesc, 1);
+        mma_bf16(d, dal, dbh, idesc, 1);
+    }
+}
+// A [128 x K] K-major; B = weights stored [brows = K rows][chunks over N], used MN-major from chunk address bh/bl
+__device__ __forceinline__ void mma_km(uint32_t d, uint32_t ah, uint32_t al, uint32_t bh, uint32_t bl, int brows, int nks,
+                                       uint32_t idesc, uint32_t& acc) {
+    for (int s = 0; s < nks; ++s) {
+        uint64_t dah = smem_desc(ah + 2 * s * kChunkB, kChunkB, 128), dal = smem_desc(al + 2 * s * kChunkB, kChunkB, 128);
+        uint64_t dbh = smem_desc(bh + 2 * s * 128, 128, brows * 16), dbl = smem_desc(bl + 2 * s * 128, 128, brows * 16);
+        mma_bf16(d, dah, dbh, idesc, acc); acc = 1;
+        mma_bf16(d, dah, dbl, idesc, 1);
+        mma_bf16(d, dal, dbh, idesc, 1);
+    }
+}
+// D[f][j] (+)= sum over the 128 samples of A[m][f] B[m][j]: both operands [128 rows] used MN-major
+__device__ __forceinline__ void mma_mm(uint32_t d, uint32_t ah, uint32_t al, uint32_t bh, uint32_t bl, uint32_t idesc, uint32_t& acc) {
+    for (int s = 0; s < 8; ++s) {
+        uint64_t dah = smem_desc(ah + 2 * s * 128, 128, kChunkB), dal = smem_desc(al + 2 * s * 128, 128, kChunkB);
+        uint64_t dbh = smem_desc(bh + 2 * s * 128, 128, kChunkB), dbl = smem_desc(bl + 2 * s * 128, 128, kChunkB);
+        mma_bf16(d, dah, dbh, idesc, acc); acc = 1;
+        mma_bf16(d, dah, dbl, idesc, 1);
+        mma_bf16(d, dal, dbh, idesc, 1);
+    }
+}
+
+// hidden pre-activations of this thread's TMEM lane -> relu -> operand chunks; returns the relu mask
+template <int HID>
+__device__ __forceinline__ void relu_to_smem(uint32_t taddr, unsigned char* hi, unsigned char* lo, int m, uint32_t (&mask)[HID / 32]) {
+#pragma unroll
+    for (int q = 0; q < HID / 32; ++q) {
+        float v[32];
+        tmem_ld32(taddr + 32 * q, v);
+        uint32_t mk = 0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { if (v[i] > 0.f) mk |= (1u << i); v[i] = fmaxf(v[i], 0.f); }
+        mask[q] = mk;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) stage8(hi, lo, m, 4 * q + c, v + 8 * c);
+    }
+}
+// gradient w.r.t. the hidden pre-activation: TMEM lane . mask -> operand chunks
+template <int HID>
+__device__ __forceinline__ void masked_to_smem(uint32_t taddr, unsigned char* hi, unsigned char* lo, int m, const uint32_t (&mask)[HID / 32]) {
+#pragma unroll
+    for (int q = 0; q < HID / 32; ++q) {
+        float v[32];
+        tmem_ld32(taddr + 32 * q, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = ((mask[q] >> i) & 1u) ? v[i] : 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) stage8(hi, lo, m, 4 * q + c, v + 8 * c);
+    }
+}
+
+struct TileIn { float2 f[16]; float4 g; float x[3]; };
+
+__device__ __forceinline__ void load_tile(TileIn& t, const float* __restrict__ feat, long long P, long long p, bool live) {
+    if (live) {
+        const float2* fh = reinterpret_cast<const float2*>(feat);
+#pragma unroll
+        for (int l = 0; l < 16; ++l) t.f[l] = __ldg(fh + (long long)l * P + p);
+        t.g = __ldg(reinterpret_cast<const float4*>(feat + 32ll * P) + p);
+        const float* xn = feat + 36ll * P;
+        t.x[0] = __ldg(xn + p); t.x[1] = __ldg(xn + P + p); t.x[2] = __ldg(xn + 2 * P + p);
+    } else {
+#pragma unroll
+        for (int l = 0; l < 16; ++l) t.f[l] = make_float2(0.f, 0.f);
+        t.g = make_float4(0.f, 0.f, 0.f, 0.f);
+        t.x[0] = t.x[1] = t.x[2] = 0.5f;
+    }
+}
+
+// X row of thread m: hash chunks, OneBlob chunks, tail = [0 x15 | gbv rgb | decoder tsdf input | 0]
+__device__ __forceinline__ void stage_x(const TileIn& t, float cin, bool live, int m, unsigned char* hash_hi, unsigned char* hash_lo,
+                                        unsigned char* blob_hi, unsigned char* blob_lo, unsigned char* tail_hi, unsigned char* tail_lo) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float v[8] = {t.f[4 * c].x, t.f[4 * c].y, t.f[4 * c + 1].x, t.f[4 * c + 1].y, t.f[4 * c + 2].x, t.f[4 * c + 2].y, t.f[4 * c + 3].x, t.f[4 * c + 3].y};
+        stage8(hash_hi, hash_lo, m, c, v);
+    }
+    if (live) {
+#pragma unroll 1
+        for (int a = 0; a < 3; ++a) stage_oneblob(t.x[a], blob_hi, blob_lo, m, 2 * a);
+    } else {
+        for (int c = 0; c < 6; ++c) stage_zero(blob_hi, blob_lo, m, c);
+    }
+    stage_zero(tail_hi, tail_lo, m, 0);
+    float v1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, t.g.y};
+    float v2[8] = {t.g.z, t.g.w, cin, 0.f, 0.f, 0.f, 0.f, 0.f};
+    stage8(tail_hi, tail_lo, m, 1, v1);
+    stage8(tail_hi, tail_lo, m, 2, v2);
+    stage_zero(tail_hi, tail_lo, m, 3);
+}
+// geo features (decoder.py:108-110 output 1..15) into the tail once the SDF net has produced them
+__device__ __forceinline__ void stage_geo(const float (&o16)[16], float gy, int m, unsigned char* tail_hi, unsigned char* tail_lo) {
+    float v0[8], v1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v0[i] = o16[1 + i];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) v1[i] = o16[9 + i];
+    v1[7] = gy;
+    stage8(tail_hi, tail_lo, m, 0, v0);
+    stage8(tail_hi, tail_lo, m, 1, v1);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Forward
+// ------------------------------------------------------------------------------------------------------------
+template <int HID>
+struct FwdL {
+    static constexpr int HC = HID / 8;
+    // group region (chunks): [H hi HC | H lo HC] (hash hi at 0, hash lo at 4: dead once H1 is read) | blob hi 6 | tail hi 4 | blob lo 6 | tail lo 4
+    static constexpr int c_hash_hi = 0, c_hash_lo = 4, c_h_hi = 0, c_h_lo = HC;
+    static constexpr int c_blob_hi = 2 * HC, c_tail_hi = 2 * HC + 6, c_blob_lo = 2 * HC + 10, c_tail_lo = 2 * HC + 16;
+    static constexpr int chunks = 2 * HC + 20;
+    static constexpr int bytes = chunks * kChunkB;
+};
+
+template <int HID, int G>
+__global__ void __launch_bounds__(G * 128, 1) mlp_fwd_tc_kernel(RayK k, Weights wts, const float* __restrict__ feat, long long P,
+                                                                float* __restrict__ raw) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint64_t bars[G];
+    __shared__ uint32_t tmem_base_s;
+    using W = WL<HID>; using A = FwdL<HID>;
+    constexpr int HC = HID / 8;
+    constexpr uint32_t TCOLS = (G == 1) ? 128 : (G == 2) ? 256 : 512;
+    const int tid = threadIdx.x, g = tid >> 7, m = tid & 127, warp = tid >> 5;
+    unsigned char* wsm = smem + G * A::bytes;
+    unsigned char* act = smem + g * A::bytes;
+    if (warp == 0) tmem_alloc(&tmem_base_s, TCOLS);
+    if (tid == 0) { for (int i = 0; i < G; ++i) mbar_init(&bars[i], 1); fence_mbar_init(); }
+    load_weights<HID>(wsm, wts, G * 128);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tb = tmem_base_s + (uint32_t)g * 128u;                 // group's columns
+    const uint32_t tlane = tb + ((uint32_t)((warp & 3) * 32) << 16);       // this thread's lane quadrant
+    const uint32_t colH = 0, colO = 64;
+    uint64_t* bar = &bars[g];
+    uint32_t phase = 0;
+    unsigned char *hash_hi = act + A::c_hash_hi * kChunkB, *hash_lo = act + A::c_hash_lo * kChunkB;
+    unsigned char *h_hi = act + A::c_h_hi * kChunkB, *h_lo = act + A::c_h_lo * kChunkB;
+    unsigned char *blob_hi = act + A::c_blob_hi * kChunkB, *blob_lo = act + A::c_blob_lo * kChunkB;
+    unsigned char *tail_hi = act + A::c_tail_hi * kChunkB, *tail_lo = act + A::c_tail_lo * kChunkB;
+    const uint32_t w0h = smem_u32(wsm + W::o_w0h), w0l = smem_u32(wsm + W::o_w0l), w1h = smem_u32(wsm + W::o_w1h), w1l = smem_u32(wsm + W::o_w1l);
+    const uint32_t w2h = smem_u32(wsm + W::o_w2h), w2l = smem_u32(wsm + W::o_w2l), w3h = smem_u32(wsm + W::o_w3h), w3l = smem_u32(wsm + W::o_w3l);
+    constexpr uint32_t idH = idesc_bf16(HID, false, false), id16 = idesc_bf16(16, false, false);
+
+    for (long long tile = (long long)blockIdx.x * G + g; tile * kTile < P; tile += (long long)gridDim.x * G) {
+        const long long p = tile * kTile + m;
+        const bool live = p < P;
+        TileIn t; load_tile(t, feat, P, p, live);
+        float t_add, cin, d0, d1;
+        tsdf_terms(k, 0, t.g.x, t_add, cin, d0, d1);                                          // scene_rep.py:330-337
+        stage_x(t, cin, live, m, hash_hi, hash_lo, blob_hi, blob_lo, tail_hi, tail_lo);
+        fence_async_smem(); fence_before_sync(); grp_sync(g);
+        if (m == 0) {                                                                         // H1 = X1 W0^T
+            fence_after_sync();
+            uint32_t acc = 0;
+            mma_kk(tb + colH, smem_u32(hash_hi), smem_u32(hash_lo), w0h, w0l, HID, 2, idH, acc);
+            mma_kk(tb + colH, smem_u32(blob_hi), smem_u32(blob_lo), w0h + kXBlob * HID * 16, w0l + kXBlob * HID * 16, HID, 3, idH, acc);
+            mma_kk(tb + colH, smem_u32(tail_hi), smem_u32(tail_lo), w0h + kXTail * HID * 16, w0l + kXTail * HID * 16, HID, 2, idH, acc);
+            commit(bar);
+        }
+        grp_wait(bar, phase);
+        uint32_t mask[HID / 32];
+        relu_to_smem<HID>(tlane + colH, h_hi, h_lo, m, mask);                                 // decoder.py:105-107
+        fence_async_smem(); fence_before_sync(); grp_sync(g);
+        if (m == 0) {                                                                         // O = H1 W1^T
+            fence_after_sync();
+            uint32_t acc = 0;
+            mma_kk(tb + colO, smem_u32(h_hi), smem_u32(h_lo), w1h, w1l, 16, HC / 2, id16, acc);
+            commit(bar);
+        }
+        grp_wait(bar, phase);
+        float o16[16];
+        tmem_ld16(tlane + colO, o16);
+        const float sdf = o16[0] + t_add;                                                     // scene_rep.py:345
+        stage_geo(o16, t.g.y, m, tail_hi, tail_lo);
+        fence_async_smem(); fence_before_sync(); grp_sync(g);
+        if (m == 0) {                                                                         // H2 = X2 W2^T
+            fence_after_sync();
+            uint32_t acc = 0;
+            mma_kk(tb + colH, smem_u32(blob_hi), smem_u32(blob_lo), w2h, w2l, HID, 3, idH, acc);
+            mma_kk(tb + colH, smem_u32(tail_hi), smem_u32(tail_lo), w2h + 6 * HID * 16, w2l + 6 * HID * 16, HID, 2, idH, acc);
+            commit(bar);
+        }
+        grp_wait(bar, phase);
+        relu_to_smem<HID>(tlane + colH, h_hi, h_lo, m, mask);                                 // decoder.py:49-51
+        fence_async_smem(); fence_before_sync(); grp_sync(g);
+        if (m == 0) {                                                                         // rgb = H2 W3^T
+            fence_after_sync();
+            uint32_t acc = 0;
+            mma_kk(tb + colO, smem_u32(h_hi), smem_u32(h_lo), w3h, w3l, 16, HC / 2, id16, acc);
+            commit(bar);
+        }
+        grp_wait(bar, phase);
+        tmem_ld16(tlane + colO, o16);
+        if (live) reinterpret_cast<float4*>(raw)[p] = make_float4(o16[0] + t.g.y, o16[1] + t.g.z, o16[2] + t.g.w, sdf);   // :344-345
+        fence_before_sync();
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base_s, TCOLS);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Backward
+// ------------------------------------------------------------------------------------------------------------
+template <int HID>
+struct BwdL {
+    static constexpr int HC = HID / 8;
+    // group region (chunks): X hi [hash4|blob6|tail4] | X lo 14 | H1 hi,lo | H2 hi,lo | D hi 2 | D lo 2
+    static constexpr int c_x_hi = 0, c_x_lo = kXCh, c_h1_hi = 2 * kXCh, c_h1_lo = c_h1_hi + HC, c_h2_hi = c_h1_lo + HC, c_h2_lo = c_h2_hi + HC,
+                         c_d_hi = c_h2_lo + HC, c_d_lo = c_d_hi + 2;
+    static constexpr int chunks = c_d_lo + 2;
+    static constexpr int bytes = chunks * kChunkB;
+    // TMEM columns of a group: weight-gradient accumulators (transposed: lane = input feature, column = output unit), work
+    static constexpr int t_w0 = 0, t_w2 = HID, t_w1 = 2 * HID, t_w3 = 2 * HID + 16, t_a = 2 * HID + 32, t_b = 3 * HID + 32;
+    static constexpr int tcols = 256;
+};
+
+template <int HID, int G>
+__global__ void __launch_bounds__(G * 128, 1) mlp_bwd_tc_kernel(RayK k, Weights wts, const float* __restrict__ feat, long long P,
+                                                                const float* __restrict__ d_raw_tot, float* __restrict__ dfeat, Grads gr) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint64_t bars[G];
+    __shared__ uint32_t tmem_base_s;
+    using W = WL<HID>; using A = BwdL<HID>;
+    constexpr int HC = HID / 8;
+    constexpr uint32_t TCOLS = G * A::tcols;
+    const int tid = threadIdx.x, g = tid >> 7, m = tid & 127, warp = tid >> 5;
+    // weights sit after the group regions: the M = 128 MN-major reads of the narrow H / D operands run past their
+    // own chunks (rows of D that are never read back) and must stay inside the allocation
+    unsigned char* wsm = smem + G * A::bytes;
+    unsigned char* act = smem + g * A::bytes;
+    if (warp == 0) tmem_alloc(&tmem_base_s, TCOLS);
+    if (tid == 0) { for (int i = 0; i < G; ++i) mbar_init(&bars[i], 1); fence_mbar_init(); }
+    load_weights<HID>(wsm, wts, G * 128);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tb = tmem_base_s + (uint32_t)g * A::tcols;
+    const uint32_t tlane = tb + ((uint32_t)((warp & 3) * 32) << 16);
+    uint64_t* bar = &bars[g];
+    uint32_t phase = 0;
+    unsigned char *x_hi = act + A::c_x_hi * kChunkB, *x_lo = act + A::c_x_lo * kChunkB;
+    unsigned char *h1_hi = act + A::c_h1_hi * kChunkB, *h1_lo = act + A::c_h1_lo * kChunkB;
+    unsigned char *h2_hi = act + A::c_h2_hi * kChunkB, *h2_lo = act + A::c_h2_lo * kChunkB;
+    unsigned char *d_hi = act + A::c_d_hi * kChunkB, *d_lo = act + A::c_d_lo * kChunkB;
+    unsigned char *blob_hi = x_hi + kXBlob * kChunkB, *blob_lo = x_lo + kXBlob * kChunkB;
+    unsigned char *tail_hi = x_hi + kXTail * kChunkB, *tail_lo = x_lo + kXTail * kChunkB;
+    const uint32_t w0h = smem_u32(wsm + W::o_w0h), w0l = smem_u32(wsm + W::o_w0l), w1h = smem_u32(wsm + W::o_w1h), w1l = smem_u32(wsm + W::o_w1l);
+    const uint32_t w2h = smem_u32(wsm + W::o_w2h), w2l = smem_u32(wsm + W::o_w2l), w3h = smem_u32(wsm + W::o_w3h), w3l = smem_u32(wsm + W::o_w3l);
+    const uint32_t xh = smem_u32(x_hi), xl = smem_u32(x_lo), h1h = smem_u32(h1_hi), h1l = smem_u32(h1_lo), h2h = smem_u32(h2_hi), h2l = smem_u32(h2_lo);
+    const uint32_t dh = smem_u32(d_hi), dl = smem_u32(d_lo);
+    constexpr uint32_t idH = idesc_bf16(HID, false, false), id16 = idesc_bf16(16, false, false);
+    constexpr uint32_t idH_bm = idesc_bf16(HID, false, true), id16_bm = idesc_bf16(16, false, true), id32_bm = idesc_bf16(32, false, true);
+    constexpr uint32_t idH_mm = idesc_bf16(HID, true, true), id16_mm = idesc_bf16(16, true, true);
+    uint32_t wacc = 0;            // 0 until this group's weight-gradient accumulators hold a first tile
+
+    for (long long tile = (long long)blockIdx.x * G + g; tile * kTile < P; tile += (long long)gridDim.x * G) {
+        const long long p = tile * kTile + m;
+        const bool live = p < P;
+        TileIn t; load_tile(t, feat, P, p, live);
+        float4 dr = live ? __ldg(reinterpret_cast<const float4*>(d_raw_tot) + p) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float t_add, cin, d0, d1;
+        tsdf_terms(k, 0, t.g.x, t_add, cin, d0, d1);
+        stage_x(t, cin, live, m, x_hi, x_lo, blob_hi, blob_lo, tail_hi, tail_lo);
+        fence_async_smem(); fence_before_sync(); grp_sync(g);
+        if (m == 0) {                                                                         // H1 = X1 W0^T
+            fence_after_sync();
+            uint32_t acc = 0;
+            mma_kk(tb + A::t_a, xh, xl, w0h, w0l, HID, kXCh / 2, idH, acc);
+            commit(bar);
+        }
+        grp_wait(bar, phase);
+        uint32_t mask1[HID / 32], mask2[HID / 32];
+        relu_to_smem<HID>(tlane + A::t_a, h1_hi, h1_lo, m, mask1);
+        fence_async_smem(); fence_before_sync(); grp_sync(g);
+        if (m == 0) {                                                                         // O = H1 W1^T
+            fence_after_sync();
+            uint32_t acc = 0;
+            mma_kk(tb + A::t_b, h1h, h1l, w1h, w1l, 16, HC / 2, id16, acc);
+            commit(bar);
+        }
+        grp_wait(bar, phase);
+        float o16[16];
+        tmem_ld16(tlane + A::t_b, o16);
+        stage_geo(o16, t.g.y, m, tail_hi, tail_lo);
+        fence_async_smem(); fence_before_sync(); grp_sync(g);
+        if (m == 0) {                                                                         // H2 = X2 W2^T
+            fence_after_sync();
+            uint32_t acc = 0;
+            mma_kk(tb + A::t_a, xh + kXBlob * kChunkB, xl + kXBlob * kChunkB, w2h, w2l, HID, 5, idH, acc);
+            commit(bar);
+        }
+        grp_wait(bar, phase);
+        relu_to_smem<HID>(tlane + A::t_a, h2_hi, h2_lo, m, mask2);
+        {                                                                                     // dRGB (upstream of :344)
+            float v0[8] = {dr.x, dr.y, dr.z, 0.f, 0.f, 0.f, 0.f, 0.f};
+            stage8(d_hi, d_lo, m, 0, v0);
+            stage_zero(d_hi, d_lo, m, 1);
+        }
+        fence_async_smem(); fence_before_sync(); grp_sync(g);
+        if (m == 0) {
+            fence_after_sync();
+            uint32_t acc = 0;
+            mma_km(tb + A::t_a, dh, dl, w3h, w3l, 16, 1, idH_bm, acc);                        // dH2pre = dRGB W3
+            uint32_t a3 = wacc;
+            mma_mm(tb + A::t_w3, h2h, h2l, dh, dl, id16_mm, a3);                              // dW3^T += H2^T dRGB
+            commit(bar);
+        }
+        grp_wait(bar, phase);
+        masked_to_smem<HID>(tlane + A::t_a, h2_hi, h2_lo, m, mask2);                          // dH2 over H2
+        fence_async_smem(); fence_before_sync(); grp_sync(g);
+        if (m == 0) {
+            fence_after_sync();
+            uint32_t acc = 0;
+            mma_km(tb + A::t_b, h2h, h2l, w2h + 6 * HID * 16, w2l + 6 * HID * 16, HID, HC / 2, id16_bm, acc);   // d tail[0..15] = dH2 W2[:, 48..63]
+            uint32_t a2 = wacc;
+            mma_mm(tb + A::t_w2, xh + kXBlob * kChunkB, xl + kXBlob * kChunkB, h2h, h2l, idH_mm, a2);        // dW2^T += X2^T dH2
+            commit(bar);
+        }
+        grp_wait(bar, phase);
+        {
+            float dg[16];
+            tmem_ld16(tlane + A::t_b, dg);
+            float v0[8] = {dr.w, dg[0], dg[1], dg[2], dg[3], dg[4], dg[5], dg[6]};
+            float v1[8] = {dg[7], dg[8], dg[9], dg[10], dg[11], dg[12], dg[13], dg[14]};
+            stage8(d_hi, d_lo, m, 0, v0);                                                     // dO = [d sdf, d geo15]
+            stage8(d_hi, d_lo, m, 1, v1);
+        }
+        fence_async_smem(); fence_before_sync(); grp_sync(g);
+        if (m == 0) {
+            fence_after_sync();
+            uint32_t acc = 0;
+            mma_km(tb + A::t_a, dh, dl, w1h, w1l, 16, 1, idH_bm, acc);                        // dH1pre = dO W1
+            uint32_t a1 = wacc;
+            mma_mm(tb + A::t_w1, h1h, h1l, dh, dl, id16_mm, a1);                              // dW1^T += H1^T dO
+            commit(bar);
+        }
+        grp_wait(bar, phase);
+        masked_to_smem<HID>(tlane + A::t_a, h1_hi, h1_lo, m, mask1);                          // dH1 over H1
+        fence_async_smem(); fence_before_sync(); grp_sync(g);
+        if (m == 0) {
+            fence_after_sync();
+            uint32_t acc = 0;
+            mma_km(tb + A::t_a, h1h, h1l, w0h, w0l, HID, HC / 2, id32_bm, acc);               // d hash = dH1 W0[:, 0..31]
+            uint32_t a0 = wacc;
+            mma_mm(tb + A::t_w0, xh, xl, h1h, h1l, idH_mm, a0);                               // dW0^T += X1^T dH1
+            commit(bar);
+        }
+        wacc = 1;
+        grp_wait(bar, phase);
+        {
+            float dx[32];
+            tmem_ld32(tlane + A::t_a, dx);
+            if (live) {
+                float2* dj = reinterpret_cast<float2*>(dfeat);
+#pragma unroll
+                for (int l = 0; l < 16; ++l) dj[(long long)l * P + p] = make_float2(dx[2 * l], dx[2 * l + 1]);
+            }
+        }
+        fence_before_sync();
+    }
+    // flush the weight gradients of this group: lane = input feature (X order), column = output unit
+    if (wacc) {
+        fence_after_sync();
+        const int f = m;
+        int c0 = -1;                                          // column of w_sdf0 for X1 row f
+        if (f < 80) c0 = f; else if (f == 80 + kTailTsdf) c0 = 80;
+#pragma unroll
+        for (int q = 0; q < HID / 32; ++q) {
+            float v[32];
+            tmem_ld32(tlane + A::t_w0 + 32 * q, v);
+            if (gr.g_w_sdf0 && c0 >= 0) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) atomicAdd(gr.g_w_sdf0 + (32 * q + j) * 81 + c0, v[j]);
+            }
+            tmem_ld32(tlane + A::t_w2 + 32 * q, v);
+            if (gr.g_w_col0 && f < kIn2) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) atomicAdd(gr.g_w_col0 + (32 * q + j) * kIn2 + f, v[j]);
+            }
+        }
+        float v16[16];
+        tmem_ld16(tlane + A::t_w1, v16);
+        if (gr.g_w_sdf1 && f < HID) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) atomicAdd(gr.g_w_sdf1 + i * HID + f, v16[i]);
+        }
+        tmem_ld16(tlane + A::t_w3, v16);
+        if (gr.g_w_col1 && f < HID) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) atomicAdd(gr.g_w_col1 + i * HID + f, v16[i]);
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base_s, TCOLS);
+}
+
+template <int HID, int G> static size_t fwd_bytes() { return (size_t)G * FwdL<HID>::bytes + WL<HID>::total; }
+template <int HID, int G> static size_t bwd_bytes() { return (size_t)G * BwdL<HID>::bytes + WL<HID>::total; }
+
+template <int HID, int G>
+static int launch_fwd_g(const RayK& k, const Weights& w, const float* feat, long long P, float* raw, cudaStream_t s) {
+    auto fn = mlp_fwd_tc_kernel<HID, G>;
+    size_t sm = fwd_bytes<HID, G>();
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return set_error((int)e, "cudaFuncSetAttribute(mlp_fwd_tc, %zu B): %s", sm, cudaGetErrorString(e));
+    long long tiles = (P + kTile - 1) / kTile;
+    int blocks = (int)std::min<long long>((tiles + G - 1) / G, (long long)num_sms());
+    ProfScope ps(RF_PROF_MLP_FWD, s);
+    fn<<<blocks, G * 128, sm, s>>>(k, w, feat, P, raw);
+    RF_CHECK_LAUNCH("mlp_fwd_tc_kernel");
+    return 0;
+}
+template <int HID, int G>
+static int launch_bwd_g(const RayK& k, const Weights& w, const float* feat, long long P, const float* d_raw_tot, float* dfeat, const Grads& gr,
+                        cudaStream_t s) {
+    auto fn = mlp_bwd_tc_kernel<HID, G>;
+    size_t sm = bwd_bytes<HID, G>();
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return set_error((int)e, "cudaFuncSetAttribute(mlp_bwd_tc, %zu B): %s", sm, cudaGetErrorString(e));
+    long long tiles = (P + kTile - 1) / kTile;
+    int blocks = (int)std::min<long long>((tiles + G - 1) / G, (long long)num_sms());
+    ProfScope ps(RF_PROF_MLP_BWD, s);
+    fn<<<blocks, G * 128, sm, s>>>(k, w, feat, P, d_raw_tot, dfeat, gr);
+    RF_CHECK_LAUNCH("mlp_bwd_tc_kernel");
+    return 0;
+}
+
+}  // namespace
+
+int launch_encode(const RayK& k, const GridDev& hg, const GridDev& gg, const rf_ray_params* p, const float* rays_o, const float* rays_d,
+                  const float* z_vals, long long P, float* feat, cudaStream_t s);
+int launch_scatter(const RayK& k, const GridDev& hg, long long P, const float* feat, const float* dfeat, float* g_hash, cudaStream_t s);
+
+bool tc_supported(const RayK& k, int hidden) { return k.n_hash_out == 32 && (hidden == 32 || hidden == 64); }
+
+// workspace `feat`: (2L + 4 + 3) * P floats written here and read back by launch_bwd_tc
+int launch_fwd_tc(const RayK& k, int hidden, const GridDev& hg, const GridDev& gg, const rf_ray_params* p, const float* rays_o,
+                  const float* rays_d, const float* z_vals, long long P, float* raw, float* feat, cudaStream_t s) {
+    int rc = launch_encode(k, hg, gg, p, rays_o, rays_d, z_vals, P, feat, s);
+    if (rc) return rc;
+    Weights w{p->w_sdf0, p->w_sdf1, p->w_col0, p->w_col1};
+    return hidden == 64 ? launch_fwd_g<64, 2>(k, w, feat, P, raw, s) : launch_fwd_g<32, 3>(k, w, feat, P, raw, s);
+}
+
+// dfeat: 2L * P floats of scratch
+int launch_bwd_tc(const RayK& k, int hidden, const GridDev& hg, const rf_ray_params* p, long long P, const float* feat,
+                  const float* d_raw_tot, float* dfeat, const Grads& gr, cudaStream_t s) {
+    Weights w{p->w_sdf0, p->w_sdf1, p->w_col0, p->w_col1};
+    int rc = hidden == 64 ? launch_bwd_g<64, 1>(k, w, feat, P, d_raw_tot, dfeat, gr, s) : launch_bwd_g<32, 2>(k, w, feat, P, d_raw_tot, dfeat, gr, s);
+    if (rc) return rc;
+    if (gr.g_hash) rc = launch_scatter(k, hg, P, feat, dfeat, gr.g_hash, s);
+    return rc;
+}
+
+}  // namespace rf

@@ -574,7 +574,7 @@ static int make_rayk(RayK& k, const rf_ray_cfg* c, const rf_grid_desc* hash, con
     RF_REQUIRE(gbv->n_features == 4 && gbv->n_levels == 1 && !gbv->is_hash, RF_E_UNSUPPORTED, "%s: GBV must be a 1-level dense grid with F=4", who);
     RF_REQUIRE(c->hidden == 32 || c->hidden == 64, RF_E_UNSUPPORTED, "%s: hidden width %d (32 and 64 are built)", who, c->hidden);
     RF_REQUIRE(c->n_bins == kNB && c->geo_feat == kGeo, RF_E_UNSUPPORTED, "%s: n_bins %d / geo_feat_dim %d (16 / 15 are built)", who, c->n_bins, c->geo_feat);
-    RF_REQUIRE(c->mlp_precision == 0, RF_E_UNSUPPORTED, "%s: mlp_precision %d not built", who, c->mlp_precision);
+    RF_REQUIRE(c->mlp_precision == 0 || c->mlp_precision == 1, RF_E_UNSUPPORTED, "%s: mlp_precision %d not built (0: fp32 SIMT, 1: tcgen05 bf16x3)", who, c->mlp_precision);
     RF_REQUIRE(c->n_range_d >= 1 && c->n_samples_d >= 0 && c->n_range_d <= kMaxS && c->n_range_d + c->n_samples_d <= kMaxS, RF_E_RANGE,
                "%s: samples per ray %d+%d not in [1,%d]", who, c->n_range_d, c->n_samples_d, kMaxS);
     RF_REQUIRE(n_rays >= 0 && n_rays < (1ll << 40), RF_E_RANGE, "%s: bad ray count", who);
@@ -610,6 +610,7 @@ static int launch_fwd(const RayK& k, const GridDev& hg, const GridDev& gg, const
     long long tiles = (P + kTile - 1) / kTile;
     int blocks = (int)std::min<long long>(tiles, (long long)num_sms() * per_sm);
     Weights w{p->w_sdf0, p->w_sdf1, p->w_col0, p->w_col1};
+    ProfScope ps(RF_PROF_SAMPLE_FWD, s);
     fn<<<blocks, kTile, sm, s>>>(k, hg, gg, p->hash_params, p->gbv_params, w, rays_o, rays_d, z_vals, xin, P, variant, raw);
     RF_CHECK_LAUNCH("sample_fwd_kernel");
     return 0;
@@ -628,6 +629,7 @@ static int launch_bwd(const RayK& k, const GridDev& hg, const GridDev& gg, const
     long long tiles = (P + kTile - 1) / kTile;
     int blocks = (int)std::min<long long>(tiles, (long long)num_sms() * per_sm);
     Weights w{p->w_sdf0, p->w_sdf1, p->w_col0, p->w_col1};
+    ProfScope ps(RF_PROF_SAMPLE_BWD, s);
     fn<<<blocks, kTile, sm, s>>>(k, hg, gg, p->hash_params, p->gbv_params, w, rays_o, rays_d, z_vals, P, d_raw_tot, gr, d_pts);
     RF_CHECK_LAUNCH("sample_bwd_kernel");
     return 0;
@@ -647,7 +649,10 @@ extern "C" int rf_ray_sample_z(const rf_ray_cfg* cfg, const float* target_d, con
     RayK k; memset(&k, 0, sizeof(k));
     k.n_range_d = cfg->n_range_d; k.n_samples_d = cfg->n_samples_d; k.S = k.n_range_d + k.n_samples_d; k.perturb = cfg->perturb ? 1 : 0;
     k.n_rays = n_rays;
-    ray_z_kernel<<<(unsigned)((n_rays + 3) / 4), 128, 0, (cudaStream_t)stream>>>(k, target_d, u, z_tables, z_vals);
+    {
+        ProfScope ps(RF_PROF_RAY_Z, (cudaStream_t)stream);
+        ray_z_kernel<<<(unsigned)((n_rays + 3) / 4), 128, 0, (cudaStream_t)stream>>>(k, target_d, u, z_tables, z_vals);
+    }
     RF_CHECK_LAUNCH("ray_z_kernel");
     return 0;
 }
@@ -655,7 +660,7 @@ extern "C" int rf_ray_sample_z(const rf_ray_cfg* cfg, const float* target_d, con
 extern "C" int rf_ray_query_forward(const rf_ray_cfg* cfg, const rf_grid_desc* hash, const rf_grid_desc* gbv, const rf_ray_params* p,
                                     const float* rays_o, const float* rays_d, const float* target_d, const float* target_rgb,
                                     const float* z_vals, int64_t n_rays,
-                                    float* raw, float* rgb_map, float* depth_map, double* loss_partials, void* stream) {
+                                    float* raw, float* rgb_map, float* depth_map, double* loss_partials, float* workspace, void* stream) {
     RayK k;
     int rc = make_rayk(k, cfg, hash, gbv, n_rays, "rf_ray_query_forward"); if (rc) return rc;
     if (n_rays == 0) return 0;
@@ -666,10 +671,18 @@ extern "C" int rf_ray_query_forward(const rf_ray_cfg* cfg, const rf_grid_desc* h
     GridDev hg = to_dev(hash), gg = to_dev(gbv);
     cudaStream_t s = (cudaStream_t)stream;
     long long P = n_rays * k.S;
-    rc = (cfg->hidden == 64) ? launch_fwd<64, false>(k, hg, gg, p, rays_o, rays_d, z_vals, nullptr, P, 0, raw, s)
-                             : launch_fwd<32, false>(k, hg, gg, p, rays_o, rays_d, z_vals, nullptr, P, 0, raw, s);
+    if (cfg->mlp_precision == 1 && tc_supported(k, cfg->hidden)) {
+        RF_REQUIRE(workspace && ((uintptr_t)workspace & 15) == 0, RF_E_NULL, "rf_ray_query_forward: mlp_precision 1 needs a 16-byte aligned workspace of rf_ray_workspace_floats()");
+        rc = launch_fwd_tc(k, cfg->hidden, hg, gg, p, rays_o, rays_d, z_vals, P, raw, workspace, s);
+    } else {
+        rc = (cfg->hidden == 64) ? launch_fwd<64, false>(k, hg, gg, p, rays_o, rays_d, z_vals, nullptr, P, 0, raw, s)
+                                 : launch_fwd<32, false>(k, hg, gg, p, rays_o, rays_d, z_vals, nullptr, P, 0, raw, s);
+    }
     if (rc) return rc;
-    composite_fwd_kernel<<<(unsigned)((n_rays + 3) / 4), 128, 0, s>>>(k, raw, z_vals, target_d, target_rgb, rgb_map, depth_map, loss_partials);
+    {
+        ProfScope ps(RF_PROF_COMPOSITE_FWD, s);
+        composite_fwd_kernel<<<(unsigned)((n_rays + 3) / 4), 128, 0, s>>>(k, raw, z_vals, target_d, target_rgb, rgb_map, depth_map, loss_partials);
+    }
     RF_CHECK_LAUNCH("composite_fwd_kernel");
     return 0;
 }
@@ -679,7 +692,7 @@ extern "C" int rf_ray_query_backward(const rf_ray_cfg* cfg, const rf_grid_desc* 
                                      const float* z_vals, const float* raw, const float* rgb_map, const float* depth_map,
                                      const float* d_rgb_map, const float* d_depth_map, const float* d_raw,
                                      const float* loss_grads, const double* loss_partials,
-                                     const rf_ray_grads* g, float* scratch, void* stream) {
+                                     const rf_ray_grads* g, const float* workspace, float* scratch, void* stream) {
     RayK k;
     int rc = make_rayk(k, cfg, hash, gbv, n_rays, "rf_ray_query_backward"); if (rc) return rc;
     if (n_rays == 0) return 0;
@@ -692,11 +705,18 @@ extern "C" int rf_ray_query_backward(const rf_ray_cfg* cfg, const rf_grid_desc* 
     long long P = n_rays * k.S;
     float* d_raw_tot = scratch;                 // [P,4]
     float* d_pts = scratch + 4 * P;             // [P,3] (BA mode only)
-    composite_bwd_kernel<<<(unsigned)((n_rays + 3) / 4), 128, 0, s>>>(k, raw, z_vals, rgb_map, depth_map, target_d, target_rgb,
-                                                                       d_rgb_map, d_depth_map, d_raw, loss_grads, loss_partials, d_raw_tot);
+    {
+        ProfScope ps(RF_PROF_COMPOSITE_BWD, s);
+        composite_bwd_kernel<<<(unsigned)((n_rays + 3) / 4), 128, 0, s>>>(k, raw, z_vals, rgb_map, depth_map, target_d, target_rgb,
+                                                                           d_rgb_map, d_depth_map, d_raw, loss_grads, loss_partials, d_raw_tot);
+    }
     RF_CHECK_LAUNCH("composite_bwd_kernel");
     Grads gr{g->g_hash, g->g_w_sdf0, g->g_w_sdf1, g->g_w_col0, g->g_w_col1};
     const bool ba = g->g_rays_o || g->g_rays_d;
+    if (!ba && cfg->mlp_precision == 1 && tc_supported(k, cfg->hidden)) {
+        RF_REQUIRE(workspace, RF_E_NULL, "rf_ray_query_backward: mlp_precision 1 needs the forward's workspace");
+        return launch_bwd_tc(k, cfg->hidden, hg, p, P, workspace, d_raw_tot, scratch + 4 * P, gr, s);
+    }
     if (cfg->hidden == 64) rc = ba ? launch_bwd<64, true>(k, hg, gg, p, rays_o, rays_d, z_vals, P, d_raw_tot, gr, d_pts, s)
                                    : launch_bwd<64, false>(k, hg, gg, p, rays_o, rays_d, z_vals, P, d_raw_tot, gr, d_pts, s);
     else rc = ba ? launch_bwd<32, true>(k, hg, gg, p, rays_o, rays_d, z_vals, P, d_raw_tot, gr, d_pts, s)
@@ -707,6 +727,18 @@ extern "C" int rf_ray_query_backward(const rf_ray_cfg* cfg, const rf_grid_desc* 
         RF_CHECK_LAUNCH("ray_grad_kernel");
     }
     return 0;
+}
+
+extern "C" int64_t rf_ray_workspace_floats(const rf_ray_cfg* cfg, const rf_grid_desc* hash, int64_t n_rays) {
+    if (!cfg || !hash || cfg->mlp_precision != 1 || n_rays <= 0) return 0;
+    return (int64_t)(2 * hash->n_levels + 4 + 3) * n_rays * (cfg->n_range_d + cfg->n_samples_d);
+}
+
+extern "C" int64_t rf_ray_scratch_floats(const rf_ray_cfg* cfg, const rf_grid_desc* hash, int64_t n_rays, int ray_grads) {
+    if (!cfg || !hash || n_rays <= 0) return 0;
+    const int64_t P = n_rays * (cfg->n_range_d + cfg->n_samples_d);
+    if (ray_grads) return 7 * P;
+    return (cfg->mlp_precision == 1 ? 4 + 2 * hash->n_levels : 4) * P;
 }
 
 extern "C" int rf_point_query_forward(const rf_ray_cfg* cfg, const rf_grid_desc* hash, const rf_grid_desc* gbv, const rf_ray_params* p,

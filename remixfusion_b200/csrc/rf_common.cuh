@@ -25,6 +25,15 @@ int   set_error(int code, const char* fmt, ...);
             return rf::set_error((int)e__, "%s: %s", (what), cudaGetErrorString(e__)); \
     } while (0)
 
+// per-kernel event timing (rf_profile_enable / rf_profile_read)
+bool prof_enabled();
+void prof_mark(int slot, int which, cudaStream_t s);
+struct ProfScope {
+    int slot; cudaStream_t s;
+    ProfScope(int slot_, cudaStream_t s_) : slot(slot_), s(s_) { prof_mark(slot, 0, s); }
+    ~ProfScope() { prof_mark(slot, 1, s); }
+};
+
 static inline int num_sms() {
     static int n = 0;
     if (n == 0) {

@@ -1,6 +1,8 @@
 // umma_selftest.cu — hardware check of the tcgen05 building blocks in umma.cuh (descriptors, TMEM, commit/wait):
 //   mode 0:  D[128][N] = A[128][K] * B[N][K]^T      (both operands K-major)
 //   mode 1:  D[f][j]   = sum_m X[m][f] * Y[m][j]     (both operands MN-major: contraction over the 128 rows)
+//   mode 2:  D[128][N] = A[128][K] * W[K][N]         (A K-major; W stored with K rows and used MN-major: the form the
+//            decoder backward uses to multiply by a weight matrix kept in its forward layout), K in {16,32,64}
 // bf16x3 split (hi*hi + hi*lo + lo*hi), fp32 accumulation in TMEM.  One CTA of 128 threads.
 #include "rf_common.cuh"
 #include "umma.cuh"
@@ -15,8 +17,8 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const float* __restr
     const int tid = threadIdx.x, warp = tid >> 5;
     // mode 0: A [128 x K] (K/8 chunks, 128 rows), B [N x K] (K/8 chunks, N rows)
     // mode 1: X [128 x K] used as A MN-major (needs 16 feature chunks -> zero padded), Y [128 x N] (N/8 chunks, 128 rows)
-    const int a_chunks = (mode == 0) ? K / 8 : 16;
-    const int b_rows = (mode == 0) ? N : 128;
+    const int a_chunks = (mode == 1) ? 16 : K / 8;
+    const int b_rows = (mode == 0) ? N : (mode == 1) ? 128 : K;
     const int b_chunks = (mode == 0) ? K / 8 : N / 8;
     unsigned char* a_hi = smem;
     unsigned char* a_lo = a_hi + a_chunks * 128 * 16;
@@ -59,6 +61,15 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const float* __restr
                 umma::mma_bf16(tb, dah, dbl, id, 1);
                 umma::mma_bf16(tb, dal, dbh, id, 1);
             }
+        } else if (mode == 2) {
+            const uint32_t id = umma::idesc_bf16(N, false, true);
+            for (int s = 0; s < K / 16; ++s) {
+                uint64_t dah = umma::desc_kmajor(ah, 128, 2 * s), dal = umma::desc_kmajor(al, 128, 2 * s);
+                uint64_t dbh = umma::desc_mnmajor(bh, K, 0, 16 * s), dbl = umma::desc_mnmajor(bl, K, 0, 16 * s);
+                umma::mma_bf16(tb, dah, dbh, id, acc); acc = 1;
+                umma::mma_bf16(tb, dah, dbl, id, 1);
+                umma::mma_bf16(tb, dal, dbh, id, 1);
+            }
         } else {
             const uint32_t id = umma::idesc_bf16(N, true, true);
             for (int s = 0; s < 8; ++s) {
@@ -89,10 +100,10 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const float* __restr
 
 }  // namespace rf
 
-// A: [128,K] fp32, B: [N,K] (mode 0) or [128,N] (mode 1), D: [128,N]; returns 0 ok, 1 = MMA never completed (timeout)
+// A: [128,K] fp32, B: [N,K] (mode 0), [128,N] (mode 1) or [K,N] (mode 2), D: [128,N]; returns 0 ok, 1 = MMA never completed (timeout)
 extern "C" int rf_umma_selftest(const float* A, const float* B, float* D, int K, int N, int mode, void* stream) {
     RF_REQUIRE(A && B && D, RF_E_NULL, "rf_umma_selftest: NULL");
-    RF_REQUIRE(N >= 16 && N <= 64 && N % 16 == 0 && K >= 16 && K <= 128 && K % 16 == 0 && (mode == 0 || mode == 1), RF_E_RANGE, "rf_umma_selftest: bad shape");
+    RF_REQUIRE(N >= 16 && N <= 64 && N % 16 == 0 && K >= 16 && K <= 128 && K % 16 == 0 && mode >= 0 && mode <= 2, RF_E_RANGE, "rf_umma_selftest: bad shape");
     int* status; cudaMalloc(&status, sizeof(int)); cudaMemset(status, 0, sizeof(int));
     size_t sm = 2 * 16 * 128 * 16 + 2 * 16 * 128 * 16 + 1024;
     cudaFuncSetAttribute(rf::umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);

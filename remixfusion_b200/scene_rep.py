@@ -58,9 +58,13 @@ class _RayQueryFn(torch.autograd.Function):
             dist.all_reduce(cnt, group=group)
             n_total = int(cnt.item())
         cfg.n_rays_total = n_total
+        nws = int(abi.lib().rf_ray_workspace_floats(C.byref(cfg), C.byref(hdesc), C.c_int64(n)))
+        # feature planes of the tensor-core path: written by the forward, re-read by the backward
+        ws = torch.empty(nws, dtype=torch.float32, device=dev) if nws > 0 else None
         rc = abi.lib().rf_ray_query_forward(C.byref(cfg), C.byref(hdesc), C.byref(gdesc), C.byref(p), abi.dptr(ro), abi.dptr(rd),
                                             abi.dptr(td), abi.dptr(tc), abi.dptr(z_vals), C.c_int64(n), abi.dptr(raw),
-                                            abi.dptr(rgb_map), abi.dptr(depth_map), abi.dptr(partials), abi.stream_ptr())
+                                            abi.dptr(rgb_map), abi.dptr(depth_map), abi.dptr(partials), abi.dptr(ws),
+                                            abi.stream_ptr())
         abi.check(rc, "rf_ray_query_forward")
         losses = torch.zeros(4, dtype=torch.float32, device=dev)
         if with_losses:
@@ -77,6 +81,7 @@ class _RayQueryFn(torch.autograd.Function):
             ]).to(torch.float32)
         ctx.meta = meta
         ctx.n_total = n_total
+        ctx.ws = ws if any(ctx.needs_input_grad) else None
         ctx.save_for_backward(ro, rd, hash_params, w_sdf0, w_sdf1, w_col0, w_col1, gbv_params, z_vals, td, tc, raw,
                               rgb_map, depth_map, partials)
         return rgb_map, depth_map, raw, losses
@@ -97,7 +102,8 @@ class _RayQueryFn(torch.autograd.Function):
         ba = need[0] or need[1]
         g_o = torch.empty_like(ro) if ba else None
         g_d = torch.empty_like(rd) if ba else None
-        scratch = torch.empty(n * S * (7 if ba else 4), dtype=torch.float32, device=dev)
+        nsc = int(abi.lib().rf_ray_scratch_floats(C.byref(cfg), C.byref(hdesc), C.c_int64(n), C.c_int(1 if ba else 0)))
+        scratch = torch.empty(nsc, dtype=torch.float32, device=dev)
         grads = abi.RayGrads(abi.dptr(g_hash), abi.dptr(g_w[0]), abi.dptr(g_w[1]), abi.dptr(g_w[2]), abi.dptr(g_w[3]),
                              abi.dptr(g_o), abi.dptr(g_d))
         p = abi.RayParams(abi.dptr(hash_params.detach()), abi.dptr(gbv_params.detach()), abi.dptr(w_sdf0.detach()),
@@ -108,7 +114,7 @@ class _RayQueryFn(torch.autograd.Function):
             C.c_int64(n), abi.dptr(z_vals), abi.dptr(raw), abi.dptr(rgb_map), abi.dptr(depth_map),
             abi.dptr(f32(d_rgb_map)), abi.dptr(f32(d_depth_map)), abi.dptr(f32(d_raw)),
             abi.dptr(f32(d_losses) if use_loss else None), abi.dptr(partials if use_loss else None),
-            C.byref(grads), abi.dptr(scratch), abi.stream_ptr())
+            C.byref(grads), abi.dptr(ctx.ws), abi.dptr(scratch), abi.stream_ptr())
         abi.check(rc, "rf_ray_query_backward")
         return (g_o if need[0] else None, g_d if need[1] else None, g_hash, g_w[0], g_w[1], g_w[2], g_w[3],
                 None, None, None, None, None)
@@ -181,7 +187,8 @@ class JointEncoding(nn.Module):
             raise abi.RfError("fused decoder: built for num_layers = num_layers_color = 2 and equal hidden widths "
                               "(every shipped config; model/decoder.py defaults differ only in width)")
         cfg.hidden, cfg.n_bins, cfg.geo_feat = d["hidden_dim"], c["pos"]["n_bins"], d["geo_feat_dim"]
-        cfg.mlp_precision = int(c.get("b200", {}).get("mlp_precision", 0))
+        # 1 (default): tcgen05 tensor-core decoder fed by feature planes; 0: fp32 SIMT decoder (accuracy anchor)
+        cfg.mlp_precision = int(c.get("b200", {}).get("mlp_precision", 1))
         cfg.n_rays_total = 0
         bb = self.bounding_box.detach().cpu().numpy().astype(np.float64) if isinstance(self.bounding_box, torch.Tensor) \
             else np.asarray(self.bounding_box, dtype=np.float64)

@@ -18,8 +18,12 @@ pytestmark = pytest.mark.gpu
 G = np.load(R.GOLDEN)
 
 
-def _model_from_golden(name, cuda, cfg=None):
+PRECISIONS = [0, 1]     # 0: fp32 SIMT decoder; 1: tcgen05 bf16x3 decoder + run-length encode / scatter (the default)
+
+
+def _model_from_golden(name, cuda, cfg=None, prec=1):
     cfg = cfg or R.case_config(name)
+    cfg["b200"] = {"mlp_precision": prec}
     bb = torch.from_numpy(np.array(cfg["mapping"]["bound"])).to(torch.float64)
     m = JointEncoding(cfg, bb)
     with torch.no_grad():
@@ -37,15 +41,35 @@ def _close(got, ref, rtol, name, atol_frac=1e-4):
     np.testing.assert_allclose(got, ref, rtol=rtol, atol=atol_frac * scale + 1e-12, err_msg=name)
 
 
+def _close_grad(got, ref, name, prec, rtol=1e-3, atol_frac=2e-4):
+    """Gradient parity.  prec 0 (fp32 decoder): every element within rtol + atol_frac * max|g|.
+    prec 1 (bf16x3 tensor-core decoder, ~1e-6 absolute error on the hidden pre-activations): a pre-activation that the
+    oracle puts within that error of zero can land on the other side of the ReLU kink, which switches one hidden unit's
+    whole contribution for one sample (up to 128 table entries).  That is a property of comparing two finite-precision
+    evaluations of a piecewise-linear function, not of the kernel, so prec 1 asserts (a) relative L2 error <= 1e-3,
+    (b) at most 0.5 % of the elements outside the elementwise tolerance, (c) none of them off by more than 5 % of max|g|."""
+    got = got.detach().cpu().numpy() if isinstance(got, torch.Tensor) else np.asarray(got)
+    if prec == 0:
+        return _close(got, ref, rtol, name, atol_frac=atol_frac)
+    scale = float(np.abs(ref).max())
+    err = np.abs(got - ref)
+    bad = err > rtol * np.abs(ref) + atol_frac * scale + 1e-12
+    l2 = float(np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-30))
+    assert l2 <= 1e-3, f"{name}: relative L2 error {l2:.3e}"
+    assert bad.mean() <= 5e-3, f"{name}: {int(bad.sum())} of {bad.size} elements outside tolerance"
+    assert float(err.max()) <= 5e-2 * scale, f"{name}: max abs error {err.max():.3e} vs max |g| {scale:.3e}"
+
+
 def _total(cfg, ret):
     t = cfg["training"]
     return (t["rgb_weight"] * ret["rgb_res_loss"] + t["depth_weight"] * ret["depth_res_loss"]
             + t["sdf_weight"] * ret["sdf_res_loss"] + t["fs_weight"] * ret["fs_res_loss"])
 
 
+@pytest.mark.parametrize("prec", PRECISIONS)
 @pytest.mark.parametrize("name,clamp,ray_grads", [("A", False, False), ("B", True, True)])
-def test_mapping_matches_reference_golden(cuda, rf_lib, name, clamp, ray_grads):
-    cfg, m = _model_from_golden(name, cuda)
+def test_mapping_matches_reference_golden(cuda, rf_lib, name, clamp, ray_grads, prec):
+    cfg, m = _model_from_golden(name, cuda, prec=prec)
     m.train()
     ro = torch.from_numpy(G["in_rays_o"]).to(cuda).requires_grad_(ray_grads)
     rd = torch.from_numpy(G["in_rays_d"]).to(cuda).requires_grad_(ray_grads)
@@ -65,11 +89,12 @@ def test_mapping_matches_reference_golden(cuda, rf_lib, name, clamp, ray_grads):
         got.update(g_rays_o=ro.grad, g_rays_d=rd.grad)
     for k, v in got.items():
         assert v is not None, k
-        _close(v, G[f"{name}_{k}"], 1e-3, k, atol_frac=2e-4)        # gradients: 1e-3 relative + 2e-4 of max |g| floor
+        _close_grad(v, G[f"{name}_{k}"], k, prec)                   # gradients: 1e-3 relative + 2e-4 of max |g| floor
 
 
-def test_eval_render_matches_reference_golden(cuda, rf_lib):
-    cfg, m = _model_from_golden("C", cuda)
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_eval_render_matches_reference_golden(cuda, rf_lib, prec):
+    cfg, m = _model_from_golden("C", cuda, prec=prec)
     m.eval()
     ro = torch.from_numpy(G["in_rays_o"]).to(cuda); rd = torch.from_numpy(G["in_rays_d"]).to(cuda)
     tc = torch.from_numpy(G["in_target_rgb"]).to(cuda); td = torch.from_numpy(G["in_target_d"]).to(cuda)
@@ -151,10 +176,14 @@ def test_encoders_match_standin_fwd_bwd(cuda, rf_lib):
     assert od == 32 and e.params.numel() == e.desc.n_params
 
 
-@pytest.mark.parametrize("hidden,S_cfg", [(64, (48, 0)), (32, (21, 96))])
-def test_mapping_matches_cpu_oracle_fresh(cuda, rf_lib, hidden, S_cfg):
-    """Fresh seeded inputs, hidden 64 (BASELINE cfg 3) and ScanNet-style 21+96 sampling, vs oracle/ray_oracle.py."""
+@pytest.mark.parametrize("prec", PRECISIONS)
+@pytest.mark.parametrize("hidden,S_cfg,n", [(64, (48, 0), 64), (32, (21, 96), 64), (64, (48, 11), 1500), (32, (48, 11), 1500)])
+def test_mapping_matches_cpu_oracle_fresh(cuda, rf_lib, hidden, S_cfg, n, prec):
+    """Fresh seeded inputs, hidden 64 (BASELINE cfg 3) and ScanNet-style 21+96 sampling, vs oracle/ray_oracle.py.
+    The 1500-ray cases (88 500 samples = 692 tiles) make every CTA of the persistent tensor-core decoder loop over
+    several tiles (TMEM weight-gradient accumulation across tiles, ragged last tile)."""
     cfg = R.base_config(hash_size=11, R=32, hidden=hidden)
+    cfg["b200"] = {"mlp_precision": prec}
     cfg["training"].update(n_range_d=S_cfg[0], n_samples_d=S_cfg[1], rgb_missing=0.0)
     bb = torch.from_numpy(np.array(cfg["mapping"]["bound"])).to(torch.float64)
     m = JointEncoding(cfg, bb)
@@ -168,9 +197,15 @@ def test_mapping_matches_cpu_oracle_fresh(cuda, rf_lib, hidden, S_cfg):
     ws = [w.detach().cpu().clone().requires_grad_(True) for w in m.decoder_res.fused_weights()]
     from oracle.ray_oracle import RayOracle
     orc = RayOracle(cfg, bb, h, gb, *ws)
-    n = 64
-    ro = torch.from_numpy(G["in_rays_o"][:n]); rd = torch.from_numpy(G["in_rays_d"][:n])
-    tc = torch.from_numpy(G["in_target_rgb"][:n]); td = torch.from_numpy(G["in_target_d"][:n])
+    if n <= G["in_rays_o"].shape[0]:
+        ro = torch.from_numpy(G["in_rays_o"][:n]); rd = torch.from_numpy(G["in_rays_d"][:n])
+        tc = torch.from_numpy(G["in_target_rgb"][:n]); td = torch.from_numpy(G["in_target_d"][:n])
+    else:
+        b = torch.tensor(R.BOUND)
+        ro = b[:, 0] + (0.3 + 0.4 * torch.rand(n, 3, generator=g)) * (b[:, 1] - b[:, 0])
+        rd = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1)
+        tc = torch.rand(n, 3, generator=g)
+        td = (0.3 + 2.5 * torch.rand(n, 1, generator=g)) * (torch.rand(n, 1, generator=g) > 0.05)
     u = torch.rand(n, sum(S_cfg), generator=g)
     r_ref = orc.mapping(ro, rd, tc, td, u=u)
     orc.total_loss(r_ref).backward()
@@ -179,9 +214,9 @@ def test_mapping_matches_cpu_oracle_fresh(cuda, rf_lib, hidden, S_cfg):
     _total(cfg, r).backward()
     for k in ("rgb_res_loss", "depth_res_loss", "sdf_res_loss", "fs_res_loss", "rgb_res", "depth_res"):
         _close(r[k], r_ref[k].detach().numpy(), 2e-4, k)
-    _close(m.embed_res_fn.params.grad, h.params.grad.numpy(), 1e-3, "g_hash", atol_frac=2e-4)
+    _close_grad(m.embed_res_fn.params.grad, h.params.grad.numpy(), "g_hash", prec)
     for w_cuda, w_ref, nm in zip(m.decoder_res.fused_weights(), ws, ("sdf0", "sdf1", "col0", "col1")):
-        _close(w_cuda.grad, w_ref.grad.numpy(), 1e-3, "g_w_" + nm, atol_frac=2e-4)
+        _close_grad(w_cuda.grad, w_ref.grad.numpy(), "g_w_" + nm, prec)
 
 
 def test_point_queries_match_oracle(cuda, rf_lib):
