@@ -506,14 +506,16 @@ def time_kernels(model, cfg, f, dev, params):
     out["sample_bwd_ms"] = timeit(bwd, 3)          # whole backward call: composite bwd + decoder bwd + scatter
     # per-kernel launch durations: CUDA events recorded by the library around each launch, on the launching stream
     L.rf_profile_enable(1)
-    acc = np.zeros(16); reps = 3
+    acc = np.zeros(64); reps = 3
     for _ in range(reps):
         fwd(); bwd()
-        buf = (C.c_float * 16)()
+        buf = (C.c_float * 64)()
         L.rf_profile_read(buf)
         acc += np.maximum(np.array(buf[:], dtype=np.float64), 0.0)
     L.rf_profile_enable(0)
     out["kernels_ms"] = {PROF_NAMES[i]: acc[i] / reps for i in PROF_NAMES if acc[i] > 0}
+    if os.environ.get("RF_DEBUG_PER_LEVEL"):
+        print("per-level ms: scatter", [round(acc[16 + l] / reps, 3) for l in range(16)], "encode", [round(acc[40 + l] / reps, 3) for l in range(17)], file=sys.stderr)
     # gather / atomic peaks over a 40 MiB table (SURVEY §8d denominators)
     tab = torch.zeros(40 * 1024 * 1024 // 4, device=dev)
     ms = C.c_float(0)

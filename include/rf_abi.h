@@ -200,7 +200,8 @@ int rf_ray_query_forward(const rf_ray_cfg* cfg, const rf_grid_desc* hash, const 
 /* Floats of `workspace` the forward needs (and the backward reads back): 0 for mlp_precision 0;
  * (2*n_levels + 4 + 3) * N * S for mlp_precision 1 (hash feature planes, GBV features, normalised positions). */
 int64_t rf_ray_workspace_floats(const rf_ray_cfg* cfg, const rf_grid_desc* hash, int64_t n_rays);
-/* Floats of `scratch` the backward needs: 4*N*S (+ 2*n_levels*N*S for mlp_precision 1; 7*N*S with ray gradients). */
+/* Floats of `scratch` the backward needs: 4*N*S (mlp_precision 1: + 2*n_levels*N*S feature-gradient planes + the
+ * replicated gradient tables of the small levels; 7*N*S with ray gradients). */
 int64_t rf_ray_scratch_floats(const rf_ray_cfg* cfg, const rf_grid_desc* hash, int64_t n_rays, int ray_grads);
 
 typedef struct rf_ray_grads {
@@ -244,10 +245,11 @@ int rf_microbench_atomic(void* table, int64_t table_bytes, int64_t n_ops, int it
 /* Optional per-kernel timing for bench.py's live roofline numbers.  rf_profile_enable(1) makes the launchers
  * bracket each hot kernel with CUDA events on the launching stream (the last launch of each slot is kept);
  * rf_profile_read(ms) synchronises on those events and writes RF_PROF_SLOTS floats (ms, -1 = not launched). */
-#define RF_PROF_SLOTS 16
+#define RF_PROF_SLOTS 64
 enum { RF_PROF_TSDF_LOCAL = 0, RF_PROF_TSDF_GLOBAL = 1, RF_PROF_RAY_Z = 2, RF_PROF_RAY_POS = 3, RF_PROF_ENCODE = 4,
        RF_PROF_MLP_FWD = 5, RF_PROF_COMPOSITE_FWD = 6, RF_PROF_COMPOSITE_BWD = 7, RF_PROF_MLP_BWD = 8,
-       RF_PROF_SCATTER = 9, RF_PROF_SAMPLE_FWD = 10, RF_PROF_SAMPLE_BWD = 11, RF_PROF_RAY_GRAD = 12 };
+       RF_PROF_SCATTER = 9, RF_PROF_SAMPLE_FWD = 10, RF_PROF_SAMPLE_BWD = 11, RF_PROF_RAY_GRAD = 12,
+       RF_PROF_SCATTER_LEVEL0 = 16 /* +level, only with RF_DEBUG_PER_LEVEL=1 */, RF_PROF_ENCODE_LEVEL0 = 40 /* +level */ };
 int rf_profile_enable(int on);
 int rf_profile_read(float* ms);
 

@@ -45,6 +45,20 @@ __device__ __forceinline__ unsigned grid_index(bool is_hash, unsigned size, unsi
     return index % size;
 }
 
+// Same index, without the generic 32-bit modulo on the common paths: power-of-two sizes (every hashed level: T = 2^k)
+// reduce with a mask, and a dense index only needs the modulo when the sample lies outside the grid (A18).
+__device__ __forceinline__ unsigned grid_index_fast(bool is_hash, unsigned size, unsigned res, unsigned cx, unsigned cy, unsigned cz) {
+    const unsigned c[3] = {cx, cy, cz};
+    unsigned stride = 1, index = 0;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        if (stride <= size) { index += c[d] * stride; stride *= res; }
+    }
+    if (is_hash && size < stride) index = cx ^ (cy * 2654435761u) ^ (cz * 805459861u);
+    if ((size & (size - 1u)) == 0u) return index & (size - 1u);
+    return (index < size) ? index : index % size;
+}
+
 // Corner weight, Appendix B4 (weight = 1; for dim: weight *= frac or 1-frac).
 __device__ __forceinline__ float corner_weight(int corner, float fx, float fy, float fz) {
     float w = 1.0f;

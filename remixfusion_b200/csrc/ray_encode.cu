@@ -1,131 +1,186 @@
 // ray_encode.cu — the gather / scatter half of the Stage-2 tensor-core path (mlp_precision 1).
 //
-//   ray_pos_kernel      pts = o + d*z, float64 normalisation by the bounding box (model/scene_rep.py:443,388) -> xn [3][P]
+//   ray_pos_kernel      pts = o + d*z, float64 normalisation by the bounding box (model/scene_rep.py:443,388) -> xn planes
 //   encode_walk_kernel  hash levels + GBV trilinear features (tiny-cuda-nn grid forward, SURVEY Appendix B2-B4;
-//                       model/scene_rep.py:325,329) -> level-major feature planes
+//                       model/scene_rep.py:325,329) -> feature planes
 //   scatter_walk_kernel hash-table gradient (Appendix B5; autograd of model/scene_rep.py:325)
 //
-// Both grid kernels run one thread per (ray segment, level) that WALKS the samples of its segment in order: samples
-// along a ray are sorted in depth (model/scene_rep.py:428), so consecutive samples stay in the same grid cell for a
-// while on all but the finest levels.  The forward keeps the 8 corner values in registers until the cell changes
-// (one gather per cell run instead of one per sample); the backward accumulates the 8 corner gradients in registers
-// and issues its 8 vector reductions (RED.ADD.F32x2) only when the cell changes.  The per-sample arithmetic
-// (pos = fma(scale, x, 0.5), corner order, fma accumulation order) is the one grid_encode.cuh uses everywhere, so the
-// features are bit-identical to the thread-per-sample kernels.
+// Both grid kernels run one thread per (ray, level) that WALKS the samples of its ray in order.  Samples along a ray are
+// sorted in depth (model/scene_rep.py:428), so consecutive samples stay in the same grid cell for a while on all but
+// the finest levels: the forward keeps the 8 corner values in registers until the cell changes (one gather per cell
+// run instead of one per sample); the backward accumulates the 8 corner gradients in registers and issues its 8
+// vector reductions (RED.ADD.F32x2) only when the cell changes.  All planes are SAMPLE-MAJOR (index s * n_rays + r),
+// so the lanes of a warp (consecutive rays) read and write consecutive addresses at every step of the walk.  The
+// per-sample arithmetic (pos = fma(scale, x, 0.5), corner order, fma accumulation order) is the one grid_encode.cuh
+// uses everywhere, so the features are bit-identical to the thread-per-sample fp32 kernels.
 //
-// Workspace layout (floats), P = n_rays * S:   [0, 2L*P) hash features [L][P][2];  [2L*P, 2L*P + 4P) GBV [P][4];
-//                                              then xn [3][P].
+// Workspace layout (floats), P = n_rays * S:   [0, 2L*P) hash features [L][S][N][2];  [2L*P, 2L*P + 4P) GBV [S][N][4];
+//                                              then xn [3][S][N].
+#include <stdlib.h>
 #include "ray_common.cuh"
 
 namespace rf {
 
+// Plane index of sample s of ray r: sample-major, so that threads that each walk one ray touch consecutive addresses.
+//   q = s * n_rays + r
+// Positions: pts = o + d*z (:443), float64 normalisation (:388), written through a shared-memory transpose so that both
+// the [N][S] read of z_vals and the [S][N] write of the planes are full 128-byte segments.  Block = 32 rays.
 __global__ void __launch_bounds__(256) ray_pos_kernel(RayK k, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                                                       const float* __restrict__ z_vals, long long P, float* __restrict__ xn) {
-    long long p = blockIdx.x * 256ll + threadIdx.x;
-    if (p >= P) return;
-    float x[3];
-    sample_x(k, rays_o, rays_d, p / k.S, z_vals[p], x);
-    xn[p] = x[0]; xn[P + p] = x[1]; xn[2 * P + p] = x[2];
+    extern __shared__ float sx[];                       // [3][S][33]
+    const int S = k.S;
+    const long long r0 = blockIdx.x * 32ll;
+    const int nr = (int)min(32ll, k.n_rays - r0);
+    for (int i = threadIdx.x; i < nr * S; i += 256) {
+        const int rl = i / S, s = i - rl * S;
+        float x[3];
+        sample_x(k, rays_o, rays_d, r0 + rl, z_vals[r0 * S + i], x);
+        sx[s * 33 + rl] = x[0]; sx[(S + s) * 33 + rl] = x[1]; sx[(2 * S + s) * 33 + rl] = x[2];
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < 32 * S; j += 256) {
+        const int s = j >> 5, rl = j & 31;
+        if (rl < nr) {
+            const long long q = (long long)s * k.n_rays + r0 + rl;
+            xn[q] = sx[s * 33 + rl]; xn[P + q] = sx[(S + s) * 33 + rl]; xn[2 * P + q] = sx[(2 * S + s) * 33 + rl];
+        }
+    }
 }
 
-// unit u -> (ray, segment): lanes of a warp are consecutive rays at the same segment index
-struct WalkGeom { long long n_rays; int S, seg, nseg; };
+constexpr int kPF = 1;        // samples fetched ahead per walking thread (deeper prefetch measured slower: register pressure)
 
-__device__ __forceinline__ bool walk_unit(const WalkGeom& w, long long u, long long& p0, int& n) {
-    if (u >= w.n_rays * w.nseg) return false;
-    long long r = u % w.n_rays; int sg = (int)(u / w.n_rays);
-    int s0 = sg * w.seg;
-    n = min(w.seg, w.S - s0);
-    p0 = r * w.S + s0;
-    return n > 0;
-}
-
-// blockIdx.y = level (0..L-1 hash levels, L = GBV).
+// Features.  Thread = (ray, level), blockIdx.y + level0 = level (0..L-1 hash levels, L = GBV); lanes = consecutive rays.
 __global__ void __launch_bounds__(128) encode_walk_kernel(GridDev hg, GridDev gg, const float* __restrict__ hash_params,
                                                           const float* __restrict__ gbv_params, const float* __restrict__ xn,
-                                                          long long P, WalkGeom wg, float* __restrict__ feat) {
-    const int l = blockIdx.y, L = hg.n_levels;
-    long long p0; int n;
-    if (!walk_unit(wg, blockIdx.x * 128ll + threadIdx.x, p0, n)) return;
-    const float* xs = xn + p0; const float* ys = xn + P + p0; const float* zs = xn + 2 * P + p0;
+                                                          long long P, long long N, int S, int level0, float* __restrict__ feat) {
+    const int l = blockIdx.y + level0, L = hg.n_levels;
+    const long long r = blockIdx.x * 128ll + threadIdx.x;
+    if (r >= N) return;
+    const float* xs = xn + r; const float* ys = xn + P + r; const float* zs = xn + 2 * P + r;
     unsigned pcx = 0, pcy = 0, pcz = 0; bool have = false;
+    float xb[kPF], yb[kPF], zb[kPF];
+#pragma unroll
+    for (int u = 0; u < kPF; ++u) {
+        const long long o = (long long)min(u, S - 1) * N;
+        xb[u] = __ldg(xs + o); yb[u] = __ldg(ys + o); zb[u] = __ldg(zs + o);
+    }
     if (l < L) {
         const float scale = hg.scale[l];
         const unsigned size = hg.size[l], res = hg.res[l];
         const float2* tab = reinterpret_cast<const float2*>(hash_params) + hg.offset[l];
-        float2* out = reinterpret_cast<float2*>(feat) + (long long)l * P + p0;
+        float2* out = reinterpret_cast<float2*>(feat) + (long long)l * P + r;
         float2 v[8];
-        for (int i = 0; i < n; ++i) {
-            unsigned cx, cy, cz; float fx, fy, fz;
-            pos_fract(xs[i], scale, cx, fx); pos_fract(ys[i], scale, cy, fy); pos_fract(zs[i], scale, cz, fz);
-            if (!have || cx != pcx || cy != pcy || cz != pcz) {
+        for (int s0 = 0; s0 < S; s0 += kPF) {
+            float xc[kPF], yc[kPF], zc[kPF];
 #pragma unroll
-                for (int c = 0; c < 8; ++c)
-                    v[c] = __ldg(tab + grid_index(hg.is_hash, size, res, cx + (c & 1), cy + ((c >> 1) & 1), cz + ((c >> 2) & 1)));
-                pcx = cx; pcy = cy; pcz = cz; have = true;
-            }
-            float f0 = 0.f, f1 = 0.f;
+            for (int u = 0; u < kPF; ++u) { xc[u] = xb[u]; yc[u] = yb[u]; zc[u] = zb[u]; }
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                float w = corner_weight(c, fx, fy, fz);
-                f0 = fmaf(w, v[c].x, f0); f1 = fmaf(w, v[c].y, f1);
+            for (int u = 0; u < kPF; ++u) {
+                const long long o = (long long)min(s0 + kPF + u, S - 1) * N;
+                xb[u] = __ldg(xs + o); yb[u] = __ldg(ys + o); zb[u] = __ldg(zs + o);
             }
-            out[i] = make_float2(f0, f1);
+#pragma unroll
+            for (int u = 0; u < kPF; ++u) {
+                if (s0 + u < S) {
+                    unsigned cx, cy, cz; float fx, fy, fz;
+                    pos_fract(xc[u], scale, cx, fx); pos_fract(yc[u], scale, cy, fy); pos_fract(zc[u], scale, cz, fz);
+                    if (!have || cx != pcx || cy != pcy || cz != pcz) {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            v[c] = __ldg(tab + grid_index_fast(hg.is_hash, size, res, cx + (c & 1), cy + ((c >> 1) & 1), cz + ((c >> 2) & 1)));
+                        pcx = cx; pcy = cy; pcz = cz; have = true;
+                    }
+                    float f0 = 0.f, f1 = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        float w = corner_weight(c, fx, fy, fz);
+                        f0 = fmaf(w, v[c].x, f0); f1 = fmaf(w, v[c].y, f1);
+                    }
+                    out[(long long)(s0 + u) * N] = make_float2(f0, f1);
+                }
+            }
         }
     } else {
         const float scale = gg.scale[0];
         const unsigned size = gg.size[0], res = gg.res[0];
         const float4* tab = reinterpret_cast<const float4*>(gbv_params);
-        float4* out = reinterpret_cast<float4*>(feat + 2ll * L * P) + p0;
+        float4* out = reinterpret_cast<float4*>(feat + 2ll * L * P) + r;
         float4 v[8];
-        for (int i = 0; i < n; ++i) {
-            unsigned cx, cy, cz; float fx, fy, fz;
-            pos_fract(xs[i], scale, cx, fx); pos_fract(ys[i], scale, cy, fy); pos_fract(zs[i], scale, cz, fz);
-            if (!have || cx != pcx || cy != pcy || cz != pcz) {
+        for (int s0 = 0; s0 < S; s0 += kPF) {
+            float xc[kPF], yc[kPF], zc[kPF];
 #pragma unroll
-                for (int c = 0; c < 8; ++c)
-                    v[c] = __ldg(tab + grid_index(false, size, res, cx + (c & 1), cy + ((c >> 1) & 1), cz + ((c >> 2) & 1)));
-                pcx = cx; pcy = cy; pcz = cz; have = true;
-            }
-            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int u = 0; u < kPF; ++u) { xc[u] = xb[u]; yc[u] = yb[u]; zc[u] = zb[u]; }
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                float w = corner_weight(c, fx, fy, fz);
-                o.x = fmaf(w, v[c].x, o.x); o.y = fmaf(w, v[c].y, o.y); o.z = fmaf(w, v[c].z, o.z); o.w = fmaf(w, v[c].w, o.w);
+            for (int u = 0; u < kPF; ++u) {
+                const long long o = (long long)min(s0 + kPF + u, S - 1) * N;
+                xb[u] = __ldg(xs + o); yb[u] = __ldg(ys + o); zb[u] = __ldg(zs + o);
             }
-            out[i] = o;
+#pragma unroll
+            for (int u = 0; u < kPF; ++u) {
+                if (s0 + u < S) {
+                    unsigned cx, cy, cz; float fx, fy, fz;
+                    pos_fract(xc[u], scale, cx, fx); pos_fract(yc[u], scale, cy, fy); pos_fract(zc[u], scale, cz, fz);
+                    if (!have || cx != pcx || cy != pcy || cz != pcz) {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            v[c] = __ldg(tab + grid_index_fast(false, size, res, cx + (c & 1), cy + ((c >> 1) & 1), cz + ((c >> 2) & 1)));
+                        pcx = cx; pcy = cy; pcz = cz; have = true;
+                    }
+                    float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        float w = corner_weight(c, fx, fy, fz);
+                        o4.x = fmaf(w, v[c].x, o4.x); o4.y = fmaf(w, v[c].y, o4.y); o4.z = fmaf(w, v[c].z, o4.z); o4.w = fmaf(w, v[c].w, o4.w);
+                    }
+                    out[(long long)(s0 + u) * N] = o4;
+                }
+            }
         }
     }
 }
 
-// Table-gradient scatter.  dfeat [L][P][2].  blockIdx.y = level.
-__global__ void __launch_bounds__(128) scatter_walk_kernel(GridDev hg, const float* __restrict__ xn, const float* __restrict__ dfeat,
-                                                           long long P, WalkGeom wg, float* __restrict__ g_hash) {
-    const int l = blockIdx.y;
-    long long p0; int n;
-    if (!walk_unit(wg, blockIdx.x * 128ll + threadIdx.x, p0, n)) return;
-    const float* xs = xn + p0; const float* ys = xn + P + p0; const float* zs = xn + 2 * P + p0;
-    const float2* dj = reinterpret_cast<const float2*>(dfeat) + (long long)l * P + p0;
-    const float scale = hg.scale[l];
+// Table-gradient scatter, run-length reduced.  dfeat [L][P][2] (sample-major planes); thread = (ray, level): each lane
+// accumulates the 8 corner gradients of its current cell in registers and issues the 8 vector reductions
+// (RED.ADD.F32x2) when its cell changes.
+// Small (coarse) levels are the contended ones: every ray of the batch lands on the same few thousand entries, and
+// reductions onto one L2 line serialise.  Those levels accumulate into K private replicas of their gradient table
+// (replica = block index mod K, so that neighbouring blocks — neighbouring pixels — never share one) which
+// replica_reduce_kernel folds into the caller's table afterwards.
+struct ScatterRep {
+    unsigned k[RF_MAX_LEVELS];            // replicas per level (power of two; 1 = accumulate straight into g_hash)
+    unsigned base[RF_MAX_LEVELS];         // first entry of the level's replica block in the scratch (float2 units)
+};
+
+__global__ void __launch_bounds__(128) scatter_walk_kernel(GridDev hg, ScatterRep rep, const float* __restrict__ xn, const float* __restrict__ dfeat,
+                                                           long long P, long long N, int S, int level0, float* __restrict__ g_hash,
+                                                           float* __restrict__ g_rep) {
+    const int l = blockIdx.y + level0;
+    const long long r = blockIdx.x * 128ll + threadIdx.x;
+    if (r >= N) return;
     const unsigned size = hg.size[l], res = hg.res[l];
-    float2* gtab = reinterpret_cast<float2*>(g_hash) + hg.offset[l];
+    float2* gtab = (rep.k[l] > 1) ? reinterpret_cast<float2*>(g_rep) + rep.base[l] + (size_t)(blockIdx.x & (rep.k[l] - 1)) * size
+                                  : reinterpret_cast<float2*>(g_hash) + hg.offset[l];
+    const float* xs = xn + r; const float* ys = xn + P + r; const float* zs = xn + 2 * P + r;
+    const float2* dj = reinterpret_cast<const float2*>(dfeat) + (long long)l * P + r;
+    const float scale = hg.scale[l];
     unsigned pcx = 0, pcy = 0, pcz = 0; bool have = false;
     float2 acc[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) acc[c] = make_float2(0.f, 0.f);
-    for (int i = 0; i <= n; ++i) {
+    float xa = __ldg(xs), ya = __ldg(ys), za = __ldg(zs); float2 da = __ldg(dj);
+    for (int s = 0; s <= S; ++s) {
         unsigned cx = 0, cy = 0, cz = 0; float fx = 0.f, fy = 0.f, fz = 0.f;
-        float2 d = make_float2(0.f, 0.f);
-        const bool last = (i == n);
+        const float2 d = da;
+        const bool last = (s == S);
         if (!last) {
-            pos_fract(xs[i], scale, cx, fx); pos_fract(ys[i], scale, cy, fy); pos_fract(zs[i], scale, cz, fz);
-            d = dj[i];
+            pos_fract(xa, scale, cx, fx); pos_fract(ya, scale, cy, fy); pos_fract(za, scale, cz, fz);
+            if (s + 1 < S) { const long long o = (long long)(s + 1) * N; xa = __ldg(xs + o); ya = __ldg(ys + o); za = __ldg(zs + o); da = __ldg(dj + o); }
         }
         if (have && (last || cx != pcx || cy != pcy || cz != pcz)) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 if (acc[c].x != 0.f || acc[c].y != 0.f)
-                    atomicAdd(gtab + grid_index(hg.is_hash, size, res, pcx + (c & 1), pcy + ((c >> 1) & 1), pcz + ((c >> 2) & 1)), acc[c]);
+                    atomicAdd(gtab + grid_index_fast(hg.is_hash, size, res, pcx + (c & 1), pcy + ((c >> 1) & 1), pcz + ((c >> 2) & 1)), acc[c]);
                 acc[c] = make_float2(0.f, 0.f);
             }
         }
@@ -139,46 +194,89 @@ __global__ void __launch_bounds__(128) scatter_walk_kernel(GridDev hg, const flo
     }
 }
 
-static WalkGeom walk_geom(long long n_rays, int S) {
-    // Whole rays per thread when there are enough rays to fill the machine; otherwise cut rays into segments (odd
-    // length) so that small training batches (a few thousand rays) still expose enough parallelism.
-    WalkGeom w; w.n_rays = n_rays; w.S = S;
-    long long want = (long long)num_sms() * 2048 / 16;      // units per level for a full machine
-    int nseg = 1;
-    while (n_rays * nseg < want && S / (nseg + 1) >= 7) ++nseg;
-    int seg = (S + nseg - 1) / nseg;
-    if (nseg > 1 && (seg & 1) == 0) ++seg;
-    w.seg = seg; w.nseg = (S + seg - 1) / seg;
-    return w;
+// g_hash[level entries] += sum over the level's replicas.  blockIdx.y = level.
+__global__ void __launch_bounds__(256) replica_reduce_kernel(GridDev hg, ScatterRep rep, const float* __restrict__ g_rep, float* __restrict__ g_hash) {
+    const int l = blockIdx.y;
+    const unsigned K = rep.k[l], size = hg.size[l];
+    if (K <= 1) return;
+    const float2* src = reinterpret_cast<const float2*>(g_rep) + rep.base[l];
+    float2* dst = reinterpret_cast<float2*>(g_hash) + hg.offset[l];
+    for (unsigned e = blockIdx.x * 256u + threadIdx.x; e < size; e += gridDim.x * 256u) {
+        float2 a = make_float2(0.f, 0.f);
+        for (unsigned k = 0; k < K; ++k) { float2 v = __ldg(src + (size_t)k * size + e); a.x += v.x; a.y += v.y; }
+        float2 o = dst[e]; o.x += a.x; o.y += a.y; dst[e] = o;
+    }
 }
+
+// Replication plan: K = 2^20 / size rounded up to a power of two, clamped to [1, 32].  Returns the scratch entries used.
+static size_t scatter_plan(const GridDev& hg, ScatterRep& rep) {
+    static int budget = -1;
+    if (budget < 0) { const char* e = getenv("RF_SCATTER_REPLICA_ENTRIES"); budget = e ? atoi(e) : (1 << 20); }
+    size_t total = 0;
+    for (int l = 0; l < RF_MAX_LEVELS; ++l) {
+        rep.k[l] = 1; rep.base[l] = 0;
+        if (l >= hg.n_levels) continue;
+        unsigned k = 1;
+        while (k < 32 && (size_t)k * hg.size[l] < (size_t)budget) k <<= 1;
+        if (budget <= 0) k = 1;
+        rep.k[l] = k;
+        if (k > 1) { rep.base[l] = (unsigned)total; total += (size_t)k * hg.size[l]; }
+    }
+    return total;
+}
+size_t scatter_scratch_floats(const GridDev& hg) { ScatterRep rep; return 2 * scatter_plan(hg, rep); }
 
 int launch_encode(const RayK& k, const GridDev& hg, const GridDev& gg, const rf_ray_params* p, const float* rays_o, const float* rays_d,
                   const float* z_vals, long long P, float* feat, cudaStream_t s) {
     const int L = hg.n_levels;
     float* xn = feat + (2ll * L + 4) * P;
     {
+        static bool attr_done = false;
+        if (!attr_done) { cudaFuncSetAttribute(ray_pos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * kMaxS * 33 * (int)sizeof(float)); attr_done = true; }
         ProfScope ps(RF_PROF_RAY_POS, s);
-        ray_pos_kernel<<<(unsigned)((P + 255) / 256), 256, 0, s>>>(k, rays_o, rays_d, z_vals, P, xn);
+        ray_pos_kernel<<<(unsigned)((k.n_rays + 31) / 32), 256, 3 * k.S * 33 * sizeof(float), s>>>(k, rays_o, rays_d, z_vals, P, xn);
     }
     RF_CHECK_LAUNCH("ray_pos_kernel");
-    WalkGeom wg = walk_geom(k.n_rays, k.S);
-    long long units = wg.n_rays * wg.nseg;
-    dim3 grid((unsigned)((units + 127) / 128), (unsigned)(L + 1));
+    dim3 grid((unsigned)((k.n_rays + 127) / 128), (unsigned)(L + 1));
+    if (prof_enabled() && getenv("RF_DEBUG_PER_LEVEL")) {                 // per-level timing (diagnostics only)
+        for (int l = 0; l <= L; ++l) {
+            ProfScope pl(RF_PROF_ENCODE_LEVEL0 + l, s);
+            encode_walk_kernel<<<dim3(grid.x, 1), 128, 0, s>>>(hg, gg, p->hash_params, p->gbv_params, xn, P, k.n_rays, k.S, l, feat);
+        }
+        RF_CHECK_LAUNCH("encode_walk_kernel");
+        return 0;
+    }
     ProfScope ps(RF_PROF_ENCODE, s);
-    encode_walk_kernel<<<grid, 128, 0, s>>>(hg, gg, p->hash_params, p->gbv_params, xn, P, wg, feat);
+    encode_walk_kernel<<<grid, 128, 0, s>>>(hg, gg, p->hash_params, p->gbv_params, xn, P, k.n_rays, k.S, 0, feat);
     RF_CHECK_LAUNCH("encode_walk_kernel");
     return 0;
 }
 
-int launch_scatter(const RayK& k, const GridDev& hg, long long P, const float* feat, const float* dfeat, float* g_hash, cudaStream_t s) {
+// g_rep: scatter_scratch_floats() floats of scratch for the replicas (zeroed here)
+int launch_scatter(const RayK& k, const GridDev& hg, long long P, const float* feat, const float* dfeat, float* g_hash, float* g_rep, cudaStream_t s) {
     const int L = hg.n_levels;
     const float* xn = feat + (2ll * L + 4) * P;
-    WalkGeom wg = walk_geom(k.n_rays, k.S);
-    long long units = wg.n_rays * wg.nseg;
-    dim3 grid((unsigned)((units + 127) / 128), (unsigned)L);
-    ProfScope ps(RF_PROF_SCATTER, s);
-    scatter_walk_kernel<<<grid, 128, 0, s>>>(hg, xn, dfeat, P, wg, g_hash);
+    ScatterRep rep;
+    const size_t rep_entries = scatter_plan(hg, rep);
+    if (rep_entries) {
+        cudaError_t e = cudaMemsetAsync(g_rep, 0, rep_entries * sizeof(float2), s);
+        if (e != cudaSuccess) return set_error((int)e, "cudaMemsetAsync(scatter replicas): %s", cudaGetErrorString(e));
+    }
+    const unsigned gx = (unsigned)((k.n_rays + 127) / 128);
+    if (prof_enabled() && getenv("RF_DEBUG_PER_LEVEL")) {                 // per-level timing (diagnostics only)
+        for (int l = 0; l < L; ++l) {
+            ProfScope pl(RF_PROF_SCATTER_LEVEL0 + l, s);
+            scatter_walk_kernel<<<dim3(gx, 1), 128, 0, s>>>(hg, rep, xn, dfeat, P, k.n_rays, k.S, l, g_hash, g_rep);
+        }
+    } else {
+        ProfScope ps(RF_PROF_SCATTER, s);
+        scatter_walk_kernel<<<dim3(gx, L), 128, 0, s>>>(hg, rep, xn, dfeat, P, k.n_rays, k.S, 0, g_hash, g_rep);
+    }
     RF_CHECK_LAUNCH("scatter_walk_kernel");
+    if (rep_entries) {
+        replica_reduce_kernel<<<dim3(64, L), 256, 0, s>>>(hg, rep, g_rep, g_hash);
+        RF_CHECK_LAUNCH("replica_reduce_kernel");
+    }
     return 0;
 }
 

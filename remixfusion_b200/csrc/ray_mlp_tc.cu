@@ -18,7 +18,8 @@
 // independent groups of 128 threads.  A group owns one tile at a time: thread m stages row m of the operands, one
 // elected thread issues the MMAs, everybody waits on the group's mbarrier and reads its own TMEM lane.  Groups run
 // out of phase, so one group's tensor-core latency is covered by another group's staging.  Inputs are the feature
-// planes written by ray_encode.cu (coalesced, streaming); no random access happens here.
+// planes written by ray_encode.cu (sample-major: a tile is 128 consecutive rays at one sample index; coalesced,
+// streaming); no random access happens here.  Only raw / d_raw ([N][S][4], the reference's layout) are strided.
 #include "ray_common.cuh"
 #include "umma.cuh"
 
@@ -130,37 +131,35 @@ __device__ __forceinline__ void stage_oneblob(float x, unsigned char* hi, unsign
 }
 
 // ---- MMA issue helpers (one thread).  All operands are bf16 hi/lo pairs; each k-step issues the bf16x3 triple. ----
-// A [128 x K] K-major at consecutive chunks; B = weights [brows = N rows] K-major, chunks from the given address
-__device__ __forceinline__ void mma_kk(uint32_t d, uint32_t ah, uint32_t al, uint32_t bh, uint32_t bl, int brows, int nks,
-                                       uint32_t idesc, uint32_t& acc) {
-    for (int s = 0; s < nks; ++s) {
-        uint64_t dah = smem_desc(ah + 2 * s * kChunkB, kChunkB, 128), dal = smem_desc(al + 2 * s * kChunkB, kChunkB, 128);
-        uint64_t dbh = smem_desc(bh + 2 * s * brows * 16, brows * 16, 128), dbl = smem_desc(bl + 2 * s * brows * 16, brows * 16, 128);
+// The descriptors of consecutive k-steps differ only in the start-address field (bits 0..13, 16-byte units), so they are
+// built once and advanced with one 64-bit add per operand (shared memory is < 256 KB: no carry out of the field).
+template <int NKS>
+__device__ __forceinline__ void mma_steps(uint32_t d, uint64_t dah, uint64_t dal, uint64_t dbh, uint64_t dbl, uint32_t a_step, uint32_t b_step,
+                                          uint32_t idesc, uint32_t& acc) {
+#pragma unroll
+    for (int s = 0; s < NKS; ++s) {
         mma_bf16(d, dah, dbh, idesc, acc); acc = 1;
         mma_bf16(d, dah, dbl, idesc, 1);
         mma_bf16(d, dal, dbh, idesc, 1);
+        dah += a_step >> 4; dal += a_step >> 4; dbh += b_step >> 4; dbl += b_step >> 4;
     }
 }
+// A [128 x K] K-major at consecutive chunks; B = weights [brows = N rows] K-major, chunks from the given address
+template <int NKS>
+__device__ __forceinline__ void mma_kk(uint32_t d, uint32_t ah, uint32_t al, uint32_t bh, uint32_t bl, int brows, uint32_t idesc, uint32_t& acc) {
+    mma_steps<NKS>(d, smem_desc(ah, kChunkB, 128), smem_desc(al, kChunkB, 128), smem_desc(bh, brows * 16, 128), smem_desc(bl, brows * 16, 128),
+                   2 * kChunkB, 2 * brows * 16, idesc, acc);
+}
 // A [128 x K] K-major; B = weights stored [brows = K rows][chunks over N], used MN-major from chunk address bh/bl
-__device__ __forceinline__ void mma_km(uint32_t d, uint32_t ah, uint32_t al, uint32_t bh, uint32_t bl, int brows, int nks,
-                                       uint32_t idesc, uint32_t& acc) {
-    for (int s = 0; s < nks; ++s) {
-        uint64_t dah = smem_desc(ah + 2 * s * kChunkB, kChunkB, 128), dal = smem_desc(al + 2 * s * kChunkB, kChunkB, 128);
-        uint64_t dbh = smem_desc(bh + 2 * s * 128, 128, brows * 16), dbl = smem_desc(bl + 2 * s * 128, 128, brows * 16);
-        mma_bf16(d, dah, dbh, idesc, acc); acc = 1;
-        mma_bf16(d, dah, dbl, idesc, 1);
-        mma_bf16(d, dal, dbh, idesc, 1);
-    }
+template <int NKS>
+__device__ __forceinline__ void mma_km(uint32_t d, uint32_t ah, uint32_t al, uint32_t bh, uint32_t bl, int brows, uint32_t idesc, uint32_t& acc) {
+    mma_steps<NKS>(d, smem_desc(ah, kChunkB, 128), smem_desc(al, kChunkB, 128), smem_desc(bh, 128, brows * 16), smem_desc(bl, 128, brows * 16),
+                   2 * kChunkB, 2 * 128, idesc, acc);
 }
 // D[f][j] (+)= sum over the 128 samples of A[m][f] B[m][j]: both operands [128 rows] used MN-major
 __device__ __forceinline__ void mma_mm(uint32_t d, uint32_t ah, uint32_t al, uint32_t bh, uint32_t bl, uint32_t idesc, uint32_t& acc) {
-    for (int s = 0; s < 8; ++s) {
-        uint64_t dah = smem_desc(ah + 2 * s * 128, 128, kChunkB), dal = smem_desc(al + 2 * s * 128, 128, kChunkB);
-        uint64_t dbh = smem_desc(bh + 2 * s * 128, 128, kChunkB), dbl = smem_desc(bl + 2 * s * 128, 128, kChunkB);
-        mma_bf16(d, dah, dbh, idesc, acc); acc = 1;
-        mma_bf16(d, dah, dbl, idesc, 1);
-        mma_bf16(d, dal, dbh, idesc, 1);
-    }
+    mma_steps<8>(d, smem_desc(ah, 128, kChunkB), smem_desc(al, 128, kChunkB), smem_desc(bh, 128, kChunkB), smem_desc(bl, 128, kChunkB),
+                 2 * 128, 2 * 128, idesc, acc);
 }
 
 // hidden pre-activations of this thread's TMEM lane -> relu -> operand chunks; returns the relu mask
@@ -289,9 +288,10 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_fwd_tc_kernel(RayK k, Weights 
     constexpr uint32_t idH = idesc_bf16(HID, false, false), id16 = idesc_bf16(16, false, false);
 
     for (long long tile = (long long)blockIdx.x * G + g; tile * kTile < P; tile += (long long)gridDim.x * G) {
-        const long long p = tile * kTile + m;
-        const bool live = p < P;
-        TileIn t; load_tile(t, feat, P, p, live);
+        const long long q = tile * kTile + m;                                                 // plane index s * N + r
+        const bool live = q < P;
+        const long long p = live ? (q % k.n_rays) * k.S + q / k.n_rays : 0;                   // raw index r * S + s
+        TileIn t; load_tile(t, feat, P, q, live);
         float t_add, cin, d0, d1;
         tsdf_terms(k, 0, t.g.x, t_add, cin, d0, d1);                                          // scene_rep.py:330-337
         stage_x(t, cin, live, m, hash_hi, hash_lo, blob_hi, blob_lo, tail_hi, tail_lo);
@@ -299,9 +299,9 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_fwd_tc_kernel(RayK k, Weights 
         if (m == 0) {                                                                         // H1 = X1 W0^T
             fence_after_sync();
             uint32_t acc = 0;
-            mma_kk(tb + colH, smem_u32(hash_hi), smem_u32(hash_lo), w0h, w0l, HID, 2, idH, acc);
-            mma_kk(tb + colH, smem_u32(blob_hi), smem_u32(blob_lo), w0h + kXBlob * HID * 16, w0l + kXBlob * HID * 16, HID, 3, idH, acc);
-            mma_kk(tb + colH, smem_u32(tail_hi), smem_u32(tail_lo), w0h + kXTail * HID * 16, w0l + kXTail * HID * 16, HID, 2, idH, acc);
+            mma_kk<2>(tb + colH, smem_u32(hash_hi), smem_u32(hash_lo), w0h, w0l, HID, idH, acc);
+            mma_kk<3>(tb + colH, smem_u32(blob_hi), smem_u32(blob_lo), w0h + kXBlob * HID * 16, w0l + kXBlob * HID * 16, HID, idH, acc);
+            mma_kk<2>(tb + colH, smem_u32(tail_hi), smem_u32(tail_lo), w0h + kXTail * HID * 16, w0l + kXTail * HID * 16, HID, idH, acc);
             commit(bar);
         }
         grp_wait(bar, phase);
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_fwd_tc_kernel(RayK k, Weights 
         if (m == 0) {                                                                         // O = H1 W1^T
             fence_after_sync();
             uint32_t acc = 0;
-            mma_kk(tb + colO, smem_u32(h_hi), smem_u32(h_lo), w1h, w1l, 16, HC / 2, id16, acc);
+            mma_kk<HC / 2>(tb + colO, smem_u32(h_hi), smem_u32(h_lo), w1h, w1l, 16, id16, acc);
             commit(bar);
         }
         grp_wait(bar, phase);
@@ -323,8 +323,8 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_fwd_tc_kernel(RayK k, Weights 
         if (m == 0) {                                                                         // H2 = X2 W2^T
             fence_after_sync();
             uint32_t acc = 0;
-            mma_kk(tb + colH, smem_u32(blob_hi), smem_u32(blob_lo), w2h, w2l, HID, 3, idH, acc);
-            mma_kk(tb + colH, smem_u32(tail_hi), smem_u32(tail_lo), w2h + 6 * HID * 16, w2l + 6 * HID * 16, HID, 2, idH, acc);
+            mma_kk<3>(tb + colH, smem_u32(blob_hi), smem_u32(blob_lo), w2h, w2l, HID, idH, acc);
+            mma_kk<2>(tb + colH, smem_u32(tail_hi), smem_u32(tail_lo), w2h + 6 * HID * 16, w2l + 6 * HID * 16, HID, idH, acc);
             commit(bar);
         }
         grp_wait(bar, phase);
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_fwd_tc_kernel(RayK k, Weights 
         if (m == 0) {                                                                         // rgb = H2 W3^T
             fence_after_sync();
             uint32_t acc = 0;
-            mma_kk(tb + colO, smem_u32(h_hi), smem_u32(h_lo), w3h, w3l, 16, HC / 2, id16, acc);
+            mma_kk<HC / 2>(tb + colO, smem_u32(h_hi), smem_u32(h_lo), w3h, w3l, 16, id16, acc);
             commit(bar);
         }
         grp_wait(bar, phase);
@@ -403,9 +403,10 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_bwd_tc_kernel(RayK k, Weights 
     uint32_t wacc = 0;            // 0 until this group's weight-gradient accumulators hold a first tile
 
     for (long long tile = (long long)blockIdx.x * G + g; tile * kTile < P; tile += (long long)gridDim.x * G) {
-        const long long p = tile * kTile + m;
-        const bool live = p < P;
-        TileIn t; load_tile(t, feat, P, p, live);
+        const long long q = tile * kTile + m;                                                 // plane index s * N + r
+        const bool live = q < P;
+        const long long p = live ? (q % k.n_rays) * k.S + q / k.n_rays : 0;                   // raw index r * S + s
+        TileIn t; load_tile(t, feat, P, q, live);
         float4 dr = live ? __ldg(reinterpret_cast<const float4*>(d_raw_tot) + p) : make_float4(0.f, 0.f, 0.f, 0.f);
         float t_add, cin, d0, d1;
         tsdf_terms(k, 0, t.g.x, t_add, cin, d0, d1);
@@ -414,7 +415,7 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_bwd_tc_kernel(RayK k, Weights 
         if (m == 0) {                                                                         // H1 = X1 W0^T
             fence_after_sync();
             uint32_t acc = 0;
-            mma_kk(tb + A::t_a, xh, xl, w0h, w0l, HID, kXCh / 2, idH, acc);
+            mma_kk<kXCh / 2>(tb + A::t_a, xh, xl, w0h, w0l, HID, idH, acc);
             commit(bar);
         }
         grp_wait(bar, phase);
@@ -424,7 +425,7 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_bwd_tc_kernel(RayK k, Weights 
         if (m == 0) {                                                                         // O = H1 W1^T
             fence_after_sync();
             uint32_t acc = 0;
-            mma_kk(tb + A::t_b, h1h, h1l, w1h, w1l, 16, HC / 2, id16, acc);
+            mma_kk<HC / 2>(tb + A::t_b, h1h, h1l, w1h, w1l, 16, id16, acc);
             commit(bar);
         }
         grp_wait(bar, phase);
@@ -435,7 +436,7 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_bwd_tc_kernel(RayK k, Weights 
         if (m == 0) {                                                                         // H2 = X2 W2^T
             fence_after_sync();
             uint32_t acc = 0;
-            mma_kk(tb + A::t_a, xh + kXBlob * kChunkB, xl + kXBlob * kChunkB, w2h, w2l, HID, 5, idH, acc);
+            mma_kk<5>(tb + A::t_a, xh + kXBlob * kChunkB, xl + kXBlob * kChunkB, w2h, w2l, HID, idH, acc);
             commit(bar);
         }
         grp_wait(bar, phase);
@@ -449,7 +450,7 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_bwd_tc_kernel(RayK k, Weights 
         if (m == 0) {
             fence_after_sync();
             uint32_t acc = 0;
-            mma_km(tb + A::t_a, dh, dl, w3h, w3l, 16, 1, idH_bm, acc);                        // dH2pre = dRGB W3
+            mma_km<1>(tb + A::t_a, dh, dl, w3h, w3l, 16, idH_bm, acc);                        // dH2pre = dRGB W3
             uint32_t a3 = wacc;
             mma_mm(tb + A::t_w3, h2h, h2l, dh, dl, id16_mm, a3);                              // dW3^T += H2^T dRGB
             commit(bar);
@@ -460,7 +461,7 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_bwd_tc_kernel(RayK k, Weights 
         if (m == 0) {
             fence_after_sync();
             uint32_t acc = 0;
-            mma_km(tb + A::t_b, h2h, h2l, w2h + 6 * HID * 16, w2l + 6 * HID * 16, HID, HC / 2, id16_bm, acc);   // d tail[0..15] = dH2 W2[:, 48..63]
+            mma_km<HC / 2>(tb + A::t_b, h2h, h2l, w2h + 6 * HID * 16, w2l + 6 * HID * 16, HID, id16_bm, acc);   // d tail[0..15] = dH2 W2[:, 48..63]
             uint32_t a2 = wacc;
             mma_mm(tb + A::t_w2, xh + kXBlob * kChunkB, xl + kXBlob * kChunkB, h2h, h2l, idH_mm, a2);        // dW2^T += X2^T dH2
             commit(bar);
@@ -478,7 +479,7 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_bwd_tc_kernel(RayK k, Weights 
         if (m == 0) {
             fence_after_sync();
             uint32_t acc = 0;
-            mma_km(tb + A::t_a, dh, dl, w1h, w1l, 16, 1, idH_bm, acc);                        // dH1pre = dO W1
+            mma_km<1>(tb + A::t_a, dh, dl, w1h, w1l, 16, idH_bm, acc);                        // dH1pre = dO W1
             uint32_t a1 = wacc;
             mma_mm(tb + A::t_w1, h1h, h1l, dh, dl, id16_mm, a1);                              // dW1^T += H1^T dO
             commit(bar);
@@ -489,7 +490,7 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_bwd_tc_kernel(RayK k, Weights 
         if (m == 0) {
             fence_after_sync();
             uint32_t acc = 0;
-            mma_km(tb + A::t_a, h1h, h1l, w0h, w0l, HID, HC / 2, id32_bm, acc);               // d hash = dH1 W0[:, 0..31]
+            mma_km<HC / 2>(tb + A::t_a, h1h, h1l, w0h, w0l, HID, id32_bm, acc);               // d hash = dH1 W0[:, 0..31]
             uint32_t a0 = wacc;
             mma_mm(tb + A::t_w0, xh, xl, h1h, h1l, idH_mm, a0);                               // dW0^T += X1^T dH1
             commit(bar);
@@ -502,7 +503,7 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_bwd_tc_kernel(RayK k, Weights 
             if (live) {
                 float2* dj = reinterpret_cast<float2*>(dfeat);
 #pragma unroll
-                for (int l = 0; l < 16; ++l) dj[(long long)l * P + p] = make_float2(dx[2 * l], dx[2 * l + 1]);
+                for (int l = 0; l < 16; ++l) dj[(long long)l * P + q] = make_float2(dx[2 * l], dx[2 * l + 1]);
             }
         }
         fence_before_sync();
@@ -579,7 +580,7 @@ static int launch_bwd_g(const RayK& k, const Weights& w, const float* feat, long
 
 int launch_encode(const RayK& k, const GridDev& hg, const GridDev& gg, const rf_ray_params* p, const float* rays_o, const float* rays_d,
                   const float* z_vals, long long P, float* feat, cudaStream_t s);
-int launch_scatter(const RayK& k, const GridDev& hg, long long P, const float* feat, const float* dfeat, float* g_hash, cudaStream_t s);
+int launch_scatter(const RayK& k, const GridDev& hg, long long P, const float* feat, const float* dfeat, float* g_hash, float* g_rep, cudaStream_t s);
 
 bool tc_supported(const RayK& k, int hidden) { return k.n_hash_out == 32 && (hidden == 32 || hidden == 64); }
 
@@ -592,13 +593,13 @@ int launch_fwd_tc(const RayK& k, int hidden, const GridDev& hg, const GridDev& g
     return hidden == 64 ? launch_fwd_g<64, 2>(k, w, feat, P, raw, s) : launch_fwd_g<32, 3>(k, w, feat, P, raw, s);
 }
 
-// dfeat: 2L * P floats of scratch
+// dfeat: 2L * P floats of scratch, followed by scatter_scratch_floats() floats for the table replicas
 int launch_bwd_tc(const RayK& k, int hidden, const GridDev& hg, const rf_ray_params* p, long long P, const float* feat,
                   const float* d_raw_tot, float* dfeat, const Grads& gr, cudaStream_t s) {
     Weights w{p->w_sdf0, p->w_sdf1, p->w_col0, p->w_col1};
     int rc = hidden == 64 ? launch_bwd_g<64, 1>(k, w, feat, P, d_raw_tot, dfeat, gr, s) : launch_bwd_g<32, 2>(k, w, feat, P, d_raw_tot, dfeat, gr, s);
     if (rc) return rc;
-    if (gr.g_hash) rc = launch_scatter(k, hg, P, feat, dfeat, gr.g_hash, s);
+    if (gr.g_hash) rc = launch_scatter(k, hg, P, feat, dfeat, gr.g_hash, dfeat + 2ll * hg.n_levels * P, s);
     return rc;
 }
 

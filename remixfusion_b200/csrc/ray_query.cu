@@ -738,7 +738,9 @@ extern "C" int64_t rf_ray_scratch_floats(const rf_ray_cfg* cfg, const rf_grid_de
     if (!cfg || !hash || n_rays <= 0) return 0;
     const int64_t P = n_rays * (cfg->n_range_d + cfg->n_samples_d);
     if (ray_grads) return 7 * P;
-    return (cfg->mlp_precision == 1 ? 4 + 2 * hash->n_levels : 4) * P;
+    if (cfg->mlp_precision != 1) return 4 * P;
+    GridDev hg = to_dev(hash);
+    return (4 + 2 * hash->n_levels) * P + (int64_t)scatter_scratch_floats(hg);
 }
 
 extern "C" int rf_point_query_forward(const rf_ray_cfg* cfg, const rf_grid_desc* hash, const rf_grid_desc* gbv, const rf_ray_params* p,
