@@ -76,40 +76,60 @@ def make_frames(cfg, n_pool, first=0, stride=1):
 
 
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle-reason samples during the timed region.  In-process NVML polling (pynvml, 20 Hz): a spawned
+    `nvidia-smi -lms` costs tens of ms of driver stalls per query burst and would perturb the region it observes."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, gpu_index=0):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.rows, self.first, self.stop_flag, self.thread, self.h, self.nv = [], 0, False, None, None, None
+        self.gpu = gpu_index
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(self.gpu).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.nv = pynvml
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
         except Exception:
-            self.proc = None
+            self.nv = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((float(sm), float(mx), int(rs)))
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def mark(self):
+        """Rows before this call (warm-up) are not part of the timed region."""
+        self.first = len(self.rows)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-            except Exception:
-                continue
-            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
-                if len(r) > col and r[col].lower().startswith("active"):
-                    reasons.add(name)
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable"]}
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=1.0)
+        rows = self.rows[self.first:] or self.rows[-1:]
+        sm = [r[0] for r in rows]; mx = [r[1] for r in rows]
+        reasons = sorted({name for r in rows for name, bit in self.REASONS if r[2] & bit})
         busy = sorted(sm)[len(sm) // 2:] if sm else []          # upper half = samples under load
         return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm)}
 
 
 # =====================================================================================================================
@@ -300,6 +320,8 @@ def run_gpu(args, rank, world, local_rank):
         if timed: e[2].record()
         for p in params:
             p.grad = None
+        if timed and os.environ.get("RF_BENCH_DEBUG"):
+            dbg = torch.cuda.Event(enable_timing=True); dbg.record(); e.append(dbg)
         ret = model.mapping(f["rays_o"], f["rays_d"], f["tgt_c"], f["tgt_d"])
         loss = configs.total_loss(cfg, ret)
         if timed: e[3].record()
@@ -317,6 +339,10 @@ def run_gpu(args, rank, world, local_rank):
         return tl, tg
 
     # ---- warm-up ------------------------------------------------------------------------------------------------
+    # the clock sampler is spawned here: NVML start-up stalls the driver for tens of ms and must not land in the timed region
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for i in range(args.warmup):
         step(i, False)
     torch.cuda.synchronize()
@@ -329,12 +355,10 @@ def run_gpu(args, rank, world, local_rank):
         per_frame_units.append(count_units(i))
 
     # ---- timed region ---------------------------------------------------------------------------------------------
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    sampler.mark()
     t_start, t_end = ev(), ev()
     t_start.record()
     evs = []
@@ -348,6 +372,9 @@ def run_gpu(args, rank, world, local_rank):
     clocks = sampler.stop() if rank == 0 else None
     total_ms = t_start.elapsed_time(t_end)
     for e in evs:
+        if len(e) > 5:
+            print(f"[rank {rank}] e1->e2 {e[1].elapsed_time(e[2]):.2f} e2->dbg {e[2].elapsed_time(e[5]):.2f} dbg->e3 {e[5].elapsed_time(e[3]):.2f} "
+                  f"e3->e4 {e[3].elapsed_time(e[4]):.2f}", file=sys.stderr, flush=True)
         stage_ms["tsdf_local"] += e[0].elapsed_time(e[1]); stage_ms["tsdf_global"] += e[1].elapsed_time(e[2])
         stage_ms["ray_fwd"] += e[2].elapsed_time(e[3]); stage_ms["ray_bwd"] += e[3].elapsed_time(e[4])
     for i in range(args.steps):

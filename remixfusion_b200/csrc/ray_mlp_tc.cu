@@ -156,10 +156,28 @@ __device__ __forceinline__ void mma_km(uint32_t d, uint32_t ah, uint32_t al, uin
     mma_steps<NKS>(d, smem_desc(ah, kChunkB, 128), smem_desc(al, kChunkB, 128), smem_desc(bh, 128, brows * 16), smem_desc(bl, 128, brows * 16),
                    2 * kChunkB, 2 * 128, idesc, acc);
 }
-// D[f][j] (+)= sum over the 128 samples of A[m][f] B[m][j]: both operands [128 rows] used MN-major
-__device__ __forceinline__ void mma_mm(uint32_t d, uint32_t ah, uint32_t al, uint32_t bh, uint32_t bl, uint32_t idesc, uint32_t& acc) {
-    mma_steps<8>(d, smem_desc(ah, 128, kChunkB), smem_desc(al, 128, kChunkB), smem_desc(bh, 128, kChunkB), smem_desc(bl, 128, kChunkB),
-                 2 * 128, 2 * 128, idesc, acc);
+// Weight gradients D[f][j] (+)= sum over the 128 samples of A[m][f] B[m][j]: both operands [128 rows] used MN-major.
+// ONE MMA per k-step: `a` and `b` each address a hi block immediately
+// followed by its lo block.  M = 128 then spans [A_hi features | A_lo features | ...] and N spans [B_hi | B_lo], so
+// the accumulator holds hi*hi (rows < F, cols < n), hi*lo (rows < F, cols >= n) and lo*hi (rows >= F, cols < n) at once.
+__device__ __forceinline__ void mma_mm1(uint32_t d, uint32_t a, uint32_t b, uint32_t idesc, uint32_t& acc) {
+    uint64_t da = smem_desc(a, 128, kChunkB), db = smem_desc(b, 128, kChunkB);
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+        mma_bf16(d, da, db, idesc, acc); acc = 1;
+        da += (2 * 128) >> 4; db += (2 * 128) >> 4;
+    }
+}
+// X-based weight gradients: A = X (hi, lo separate), B = [dH_hi | dH_lo] contiguous: A_hi x [B_hi|B_lo] (N = 2n) and
+// A_lo x B_hi (N = n) accumulate hh + lh in columns [0,n) and hl in columns [n,2n).
+__device__ __forceinline__ void mma_mm2(uint32_t d, uint32_t ah, uint32_t al, uint32_t b, uint32_t idesc_2n, uint32_t idesc_n, uint32_t& acc) {
+    uint64_t dah = smem_desc(ah, 128, kChunkB), dal = smem_desc(al, 128, kChunkB), db = smem_desc(b, 128, kChunkB);
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+        mma_bf16(d, dah, db, idesc_2n, acc); acc = 1;
+        mma_bf16(d, dal, db, idesc_n, 1);
+        dah += (2 * 128) >> 4; dal += (2 * 128) >> 4; db += (2 * 128) >> 4;
+    }
 }
 
 // hidden pre-activations of this thread's TMEM lane -> relu -> operand chunks; returns the relu mask
@@ -207,6 +225,16 @@ __device__ __forceinline__ void load_tile(TileIn& t, const float* __restrict__ f
         t.g = make_float4(0.f, 0.f, 0.f, 0.f);
         t.x[0] = t.x[1] = t.x[2] = 0.5f;
     }
+}
+
+// Pull the next tile of this group towards L2 while the current one is processed: the 16 hash planes are 8 lines of
+// 128 B each per tile (one line per thread), GBV 16 lines, xn 3 x 4 lines.
+__device__ __forceinline__ void prefetch_tile(const float* __restrict__ feat, long long P, long long q0, int m) {
+    if (q0 >= P) return;
+    const long long last = P - 1;
+    prefetch_l2(feat + 2 * ((long long)(m >> 3) * P + min(q0 + 16 * (m & 7), last)));
+    if (m < 16) prefetch_l2(feat + 32ll * P + 4 * min(q0 + 8 * m, last));
+    else if (m < 28) prefetch_l2(feat + 36ll * P + (long long)((m - 16) >> 2) * P + min(q0 + 32 * ((m - 16) & 3), last));
 }
 
 // X row of thread m: hash chunks, OneBlob chunks, tail = [0 x15 | gbv rgb | decoder tsdf input | 0]
@@ -292,6 +320,7 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_fwd_tc_kernel(RayK k, Weights 
         const bool live = q < P;
         const long long p = live ? (q % k.n_rays) * k.S + q / k.n_rays : 0;                   // raw index r * S + s
         TileIn t; load_tile(t, feat, P, q, live);
+        prefetch_tile(feat, P, (tile + (long long)gridDim.x * G) * kTile, m);
         float t_add, cin, d0, d1;
         tsdf_terms(k, 0, t.g.x, t_add, cin, d0, d1);                                          // scene_rep.py:330-337
         stage_x(t, cin, live, m, hash_hi, hash_lo, blob_hi, blob_lo, tail_hi, tail_lo);
@@ -358,8 +387,9 @@ struct BwdL {
     static constexpr int chunks = c_d_lo + 2;
     static constexpr int bytes = chunks * kChunkB;
     // TMEM columns of a group: weight-gradient accumulators (transposed: lane = input feature, column = output unit), work
-    static constexpr int t_w0 = 0, t_w2 = HID, t_w1 = 2 * HID, t_w3 = 2 * HID + 16, t_a = 2 * HID + 32, t_b = 3 * HID + 32;
-    static constexpr int tcols = 256;
+    // dW0^T, dW2^T: 2*HID columns each (hh + lh | hl); dW1^T, dW3^T: 32 columns each (x hi | x lo), rows hi then lo
+    static constexpr int t_w0 = 0, t_w2 = 2 * HID, t_w1 = 4 * HID, t_w3 = 4 * HID + 32, t_a = 4 * HID + 64, t_b = 5 * HID + 64;
+    static constexpr int tcols = (HID == 32) ? 256 : 512;
 };
 
 template <int HID, int G>
@@ -399,7 +429,7 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_bwd_tc_kernel(RayK k, Weights 
     const uint32_t dh = smem_u32(d_hi), dl = smem_u32(d_lo);
     constexpr uint32_t idH = idesc_bf16(HID, false, false), id16 = idesc_bf16(16, false, false);
     constexpr uint32_t idH_bm = idesc_bf16(HID, false, true), id16_bm = idesc_bf16(16, false, true), id32_bm = idesc_bf16(32, false, true);
-    constexpr uint32_t idH_mm = idesc_bf16(HID, true, true), id16_mm = idesc_bf16(16, true, true);
+    constexpr uint32_t idH_mm = idesc_bf16(HID, true, true), id2H_mm = idesc_bf16(2 * HID, true, true), id32_mm = idesc_bf16(32, true, true);
     uint32_t wacc = 0;            // 0 until this group's weight-gradient accumulators hold a first tile
 
     for (long long tile = (long long)blockIdx.x * G + g; tile * kTile < P; tile += (long long)gridDim.x * G) {
@@ -407,6 +437,7 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_bwd_tc_kernel(RayK k, Weights 
         const bool live = q < P;
         const long long p = live ? (q % k.n_rays) * k.S + q / k.n_rays : 0;                   // raw index r * S + s
         TileIn t; load_tile(t, feat, P, q, live);
+        prefetch_tile(feat, P, (tile + (long long)gridDim.x * G) * kTile, m);
         float4 dr = live ? __ldg(reinterpret_cast<const float4*>(d_raw_tot) + p) : make_float4(0.f, 0.f, 0.f, 0.f);
         float t_add, cin, d0, d1;
         tsdf_terms(k, 0, t.g.x, t_add, cin, d0, d1);
@@ -452,7 +483,7 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_bwd_tc_kernel(RayK k, Weights 
             uint32_t acc = 0;
             mma_km<1>(tb + A::t_a, dh, dl, w3h, w3l, 16, idH_bm, acc);                        // dH2pre = dRGB W3
             uint32_t a3 = wacc;
-            mma_mm(tb + A::t_w3, h2h, h2l, dh, dl, id16_mm, a3);                              // dW3^T += H2^T dRGB
+            mma_mm1(tb + A::t_w3, h2h, dh, id32_mm, a3);                                      // dW3^T += H2^T dRGB
             commit(bar);
         }
         grp_wait(bar, phase);
@@ -463,7 +494,7 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_bwd_tc_kernel(RayK k, Weights 
             uint32_t acc = 0;
             mma_km<HC / 2>(tb + A::t_b, h2h, h2l, w2h + 6 * HID * 16, w2l + 6 * HID * 16, HID, id16_bm, acc);   // d tail[0..15] = dH2 W2[:, 48..63]
             uint32_t a2 = wacc;
-            mma_mm(tb + A::t_w2, xh + kXBlob * kChunkB, xl + kXBlob * kChunkB, h2h, h2l, idH_mm, a2);        // dW2^T += X2^T dH2
+            mma_mm2(tb + A::t_w2, xh + kXBlob * kChunkB, xl + kXBlob * kChunkB, h2h, id2H_mm, idH_mm, a2);   // dW2^T += X2^T dH2
             commit(bar);
         }
         grp_wait(bar, phase);
@@ -481,7 +512,7 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_bwd_tc_kernel(RayK k, Weights 
             uint32_t acc = 0;
             mma_km<1>(tb + A::t_a, dh, dl, w1h, w1l, 16, idH_bm, acc);                        // dH1pre = dO W1
             uint32_t a1 = wacc;
-            mma_mm(tb + A::t_w1, h1h, h1l, dh, dl, id16_mm, a1);                              // dW1^T += H1^T dO
+            mma_mm1(tb + A::t_w1, h1h, dh, id32_mm, a1);                                      // dW1^T += H1^T dO
             commit(bar);
         }
         grp_wait(bar, phase);
@@ -492,7 +523,7 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_bwd_tc_kernel(RayK k, Weights 
             uint32_t acc = 0;
             mma_km<HC / 2>(tb + A::t_a, h1h, h1l, w0h, w0l, HID, id32_bm, acc);               // d hash = dH1 W0[:, 0..31]
             uint32_t a0 = wacc;
-            mma_mm(tb + A::t_w0, xh, xl, h1h, h1l, idH_mm, a0);                               // dW0^T += X1^T dH1
+            mma_mm2(tb + A::t_w0, xh, xl, h1h, id2H_mm, idH_mm, a0);                          // dW0^T += X1^T dH1
             commit(bar);
         }
         wacc = 1;
@@ -508,36 +539,41 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_bwd_tc_kernel(RayK k, Weights 
         }
         fence_before_sync();
     }
-    // flush the weight gradients of this group: lane = input feature (X order), column = output unit
+    // flush the weight gradients of this group (TMEM lane = row of the accumulator, see BwdL)
     if (wacc) {
         fence_after_sync();
         const int f = m;
         int c0 = -1;                                          // column of w_sdf0 for X1 row f
         if (f < 80) c0 = f; else if (f == 80 + kTailTsdf) c0 = 80;
 #pragma unroll
-        for (int q = 0; q < HID / 32; ++q) {
-            float v[32];
+        for (int q = 0; q < HID / 32; ++q) {                  // X-based: value = (hh + lh)[j] + hl[j]
+            float v[32], u[32];
             tmem_ld32(tlane + A::t_w0 + 32 * q, v);
+            tmem_ld32(tlane + A::t_w0 + HID + 32 * q, u);
             if (gr.g_w_sdf0 && c0 >= 0) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) atomicAdd(gr.g_w_sdf0 + (32 * q + j) * 81 + c0, v[j]);
+                for (int j = 0; j < 32; ++j) atomicAdd(gr.g_w_sdf0 + (32 * q + j) * 81 + c0, v[j] + u[j]);
             }
             tmem_ld32(tlane + A::t_w2 + 32 * q, v);
+            tmem_ld32(tlane + A::t_w2 + HID + 32 * q, u);
             if (gr.g_w_col0 && f < kIn2) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) atomicAdd(gr.g_w_col0 + (32 * q + j) * kIn2 + f, v[j]);
+                for (int j = 0; j < 32; ++j) atomicAdd(gr.g_w_col0 + (32 * q + j) * kIn2 + f, v[j] + u[j]);
             }
         }
-        float v16[16];
-        tmem_ld16(tlane + A::t_w1, v16);
-        if (gr.g_w_sdf1 && f < HID) {
+        // H-based: rows [0,HID) = hi features (columns: x hi | x lo), rows [HID,2HID) = lo features (column block x hi)
+        float v32[32];
+        tmem_ld32(tlane + A::t_w1, v32);
+        if (gr.g_w_sdf1 && f < 2 * HID) {
+            const int j = (f < HID) ? f : f - HID;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) atomicAdd(gr.g_w_sdf1 + i * HID + f, v16[i]);
+            for (int i = 0; i < 16; ++i) atomicAdd(gr.g_w_sdf1 + i * HID + j, (f < HID) ? v32[i] + v32[16 + i] : v32[i]);
         }
-        tmem_ld16(tlane + A::t_w3, v16);
-        if (gr.g_w_col1 && f < HID) {
+        tmem_ld32(tlane + A::t_w3, v32);
+        if (gr.g_w_col1 && f < 2 * HID) {
+            const int j = (f < HID) ? f : f - HID;
 #pragma unroll
-            for (int i = 0; i < 3; ++i) atomicAdd(gr.g_w_col1 + i * HID + f, v16[i]);
+            for (int i = 0; i < 3; ++i) atomicAdd(gr.g_w_col1 + i * HID + j, (f < HID) ? v32[i] + v32[16 + i] : v32[i]);
         }
     }
     fence_before_sync();
