@@ -57,7 +57,14 @@ int rf_tsdf_integrate_local(float* tsdf, float* weight, float* color,       /* d
                             int weight_clamp, int reintegrate,
                             const float old_bnd[6],                          /* host; may be NULL if !reintegrate */
                             int x0, int x1, int slab_local,
+                            const float* rcp_lambda,                         /* device [H*W] from rf_tsdf_pixel_lambda, or NULL */
                             void* stream);
+
+/* The per-pixel factor 1/sqrt(vx^2 + vy^2 + 1), vx = (px - cx)/fx, vy = (py - cy)/fy, of the projective SDF
+ * (model/Volume.py:280-283, mp_slam/mapper.py:108-111).  It depends on the intrinsics only, so a caller computes it
+ * once per camera and passes it to every integrate; the kernels then load it next to the depth instead of spending two
+ * IEEE divides, a square root and a reciprocal per projected voxel.  Same operations in the same order: bit-identical. */
+int rf_tsdf_pixel_lambda(const float K[9], int H, int W, float* rcp_lambda /*device [H*W]*/, void* stream);
 
 /* model/Volume.py:723-728 — fold an RGB float image (values 0..255) into packed BGR, on device. */
 int rf_pack_bgr(const float* rgb_hw3 /*device [H*W*3]*/, float* packed /*device [H*W]*/, int n_pixels, void* stream);
@@ -85,6 +92,7 @@ int rf_tsdf_integrate_global(float* trgb, float* wgt,                        /* 
                              int H, int W,
                              float trunc_margin, float obs_weight,
                              int z0, int z1, int slab_local,
+                             const float* rcp_lambda,                        /* device [H*W] or NULL (see above) */
                              void* stream);
 
 /* mp_slam/mapper.py:161-183 + :267-282 (`clean_tsdf` / init_mapvolume): trgb[v] = (1,0,0,0). */

@@ -100,6 +100,24 @@ def dptr(t) -> C.c_void_p:
     return C.c_void_p(t.data_ptr())
 
 
+_pixel_lambda_cache = {}
+
+
+def pixel_lambda(K, H, W, device):
+    """Cached per-camera 1/lambda image for the TSDF kernels (rf_tsdf_pixel_lambda): depends on the intrinsics only."""
+    Kf = np.ascontiguousarray(np.asarray(K, dtype=np.float32).reshape(-1))
+    key = (Kf.tobytes(), int(H), int(W), str(device))
+    t = _pixel_lambda_cache.get(key)
+    if t is None:
+        t = torch.empty(int(H) * int(W), dtype=torch.float32, device=device)
+        check(lib().rf_tsdf_pixel_lambda(Kf.ctypes.data_as(C.POINTER(C.c_float)), C.c_int(int(H)), C.c_int(int(W)), dptr(t),
+                                         stream_ptr()), "rf_tsdf_pixel_lambda")
+        if len(_pixel_lambda_cache) > 8:
+            _pixel_lambda_cache.clear()
+        _pixel_lambda_cache[key] = t
+    return t
+
+
 def farr(values, n=None):
     a = np.ascontiguousarray(np.asarray(values, dtype=np.float32).reshape(-1))
     if n is not None and a.size != n:

@@ -141,7 +141,7 @@ __device__ __forceinline__ void mma_steps(uint32_t d, uint64_t dah, uint64_t dal
         mma_bf16(d, dah, dbh, idesc, acc); acc = 1;
         mma_bf16(d, dah, dbl, idesc, 1);
         mma_bf16(d, dal, dbh, idesc, 1);
-        dah += a_step >> 4; dal += a_step >> 4; dbh += b_step >> 4; dbl += b_step >> 4;
+        dah = desc_advance(dah, a_step); dal = desc_advance(dal, a_step); dbh = desc_advance(dbh, b_step); dbl = desc_advance(dbl, b_step);
     }
 }
 // A [128 x K] K-major at consecutive chunks; B = weights [brows = N rows] K-major, chunks from the given address
@@ -165,7 +165,7 @@ __device__ __forceinline__ void mma_mm1(uint32_t d, uint32_t a, uint32_t b, uint
 #pragma unroll
     for (int s = 0; s < 8; ++s) {
         mma_bf16(d, da, db, idesc, acc); acc = 1;
-        da += (2 * 128) >> 4; db += (2 * 128) >> 4;
+        da = desc_advance(da, 2 * 128); db = desc_advance(db, 2 * 128);
     }
 }
 // X-based weight gradients: A = X (hi, lo separate), B = [dH_hi | dH_lo] contiguous: A_hi x [B_hi|B_lo] (N = 2n) and
@@ -176,7 +176,7 @@ __device__ __forceinline__ void mma_mm2(uint32_t d, uint32_t ah, uint32_t al, ui
     for (int s = 0; s < 8; ++s) {
         mma_bf16(d, dah, db, idesc_2n, acc); acc = 1;
         mma_bf16(d, dal, db, idesc_n, 1);
-        dah += (2 * 128) >> 4; dal += (2 * 128) >> 4; db += (2 * 128) >> 4;
+        dah = desc_advance(dah, 2 * 128); dal = desc_advance(dal, 2 * 128); db = desc_advance(db, 2 * 128);
     }
 }
 
@@ -210,6 +210,24 @@ __device__ __forceinline__ void masked_to_smem(uint32_t taddr, unsigned char* hi
 }
 
 struct TileIn { float2 f[16]; float4 g; float x[3]; };
+
+// Plane index q = s * N + r of the first row of a group's current tile, kept as (s, r) and advanced by a fixed number of
+// rows per iteration: no 64-bit division per thread per tile.
+struct TilePos {
+    long long N; int S;
+    long long s, r;            // of row 0 of the tile
+    long long ds, dr;          // advance per iteration
+    __device__ void init(long long n_rays, int S_, long long q0, long long step) {
+        N = n_rays; S = S_; s = q0 / N; r = q0 - s * N; ds = step / N; dr = step - ds * N;
+    }
+    __device__ void next() { s += ds; r += dr; if (r >= N) { r -= N; ++s; } }
+    // raw index r * S + s of row m (m < 128; N may be smaller than 128)
+    __device__ long long raw_index(int m) const {
+        long long rr = r + m, ss = s;
+        while (rr >= N) { rr -= N; ++ss; }
+        return rr * S + ss;
+    }
+};
 
 __device__ __forceinline__ void load_tile(TileIn& t, const float* __restrict__ feat, long long P, long long p, bool live) {
     if (live) {
@@ -315,10 +333,11 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_fwd_tc_kernel(RayK k, Weights 
     const uint32_t w2h = smem_u32(wsm + W::o_w2h), w2l = smem_u32(wsm + W::o_w2l), w3h = smem_u32(wsm + W::o_w3h), w3l = smem_u32(wsm + W::o_w3l);
     constexpr uint32_t idH = idesc_bf16(HID, false, false), id16 = idesc_bf16(16, false, false);
 
-    for (long long tile = (long long)blockIdx.x * G + g; tile * kTile < P; tile += (long long)gridDim.x * G) {
+    TilePos tp; tp.init(k.n_rays, k.S, ((long long)blockIdx.x * G + g) * kTile, (long long)gridDim.x * G * kTile);
+    for (long long tile = (long long)blockIdx.x * G + g; tile * kTile < P; tile += (long long)gridDim.x * G, tp.next()) {
         const long long q = tile * kTile + m;                                                 // plane index s * N + r
         const bool live = q < P;
-        const long long p = live ? (q % k.n_rays) * k.S + q / k.n_rays : 0;                   // raw index r * S + s
+        const long long p = live ? tp.raw_index(m) : 0;                                       // raw index r * S + s
         TileIn t; load_tile(t, feat, P, q, live);
         prefetch_tile(feat, P, (tile + (long long)gridDim.x * G) * kTile, m);
         float t_add, cin, d0, d1;
@@ -432,10 +451,11 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_bwd_tc_kernel(RayK k, Weights 
     constexpr uint32_t idH_mm = idesc_bf16(HID, true, true), id2H_mm = idesc_bf16(2 * HID, true, true), id32_mm = idesc_bf16(32, true, true);
     uint32_t wacc = 0;            // 0 until this group's weight-gradient accumulators hold a first tile
 
-    for (long long tile = (long long)blockIdx.x * G + g; tile * kTile < P; tile += (long long)gridDim.x * G) {
+    TilePos tp; tp.init(k.n_rays, k.S, ((long long)blockIdx.x * G + g) * kTile, (long long)gridDim.x * G * kTile);
+    for (long long tile = (long long)blockIdx.x * G + g; tile * kTile < P; tile += (long long)gridDim.x * G, tp.next()) {
         const long long q = tile * kTile + m;                                                 // plane index s * N + r
         const bool live = q < P;
-        const long long p = live ? (q % k.n_rays) * k.S + q / k.n_rays : 0;                   // raw index r * S + s
+        const long long p = live ? tp.raw_index(m) : 0;                                       // raw index r * S + s
         TileIn t; load_tile(t, feat, P, q, live);
         prefetch_tile(feat, P, (tile + (long long)gridDim.x * G) * kTile, m);
         float4 dr = live ? __ldg(reinterpret_cast<const float4*>(d_raw_tot) + p) : make_float4(0.f, 0.f, 0.f, 0.f);

@@ -61,6 +61,11 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int n, bool a_mn_major, bool b
            ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
+// advance the start-address field of a descriptor by `bytes` (low word only: the field never carries out, smem < 256 KB)
+__device__ __forceinline__ uint64_t desc_advance(uint64_t d, uint32_t bytes) {
+    return (d & 0xFFFFFFFF00000000ull) | (uint64_t)((uint32_t)d + (bytes >> 4));
+}
+
 // D[tmem] (+)= A * B^T ; one thread issues
 __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"

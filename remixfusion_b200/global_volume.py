@@ -73,7 +73,8 @@ class MapVolume:
             abi.dptr(self.model.GBV.params.data), abi.dptr(self.model.GBW.params.data), C.c_int(R), b_p, k_p,
             c_p, C.c_int(on_dev), abi.dptr(depth_im), abi.dptr(color_im), C.c_int(im_h), C.c_int(im_w),
             C.c_float(self.trunc_margin), C.c_float(obs_weight),
-            C.c_int(self.z_slab[0]), C.c_int(self.z_slab[1]), C.c_int(self.slab_local), abi.stream_ptr())
+            C.c_int(self.z_slab[0]), C.c_int(self.z_slab[1]), C.c_int(self.slab_local),
+            abi.dptr(abi.pixel_lambda(_k, im_h, im_w, dev)), abi.stream_ptr())
         abi.check(rc, "rf_tsdf_integrate_global")
 
     def count_touched(self, depth_im, pose, obs_weight=1.0):

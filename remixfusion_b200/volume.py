@@ -136,7 +136,8 @@ class moving_volume:
             abi.dptr(depth), abi.dptr(packed), C.c_int(im_h), C.c_int(im_w),
             C.c_float(self.trunc_margin), C.c_float(obs_weight),
             C.c_int(1 if float(self.weight_clamp) == 1.0 else 0), C.c_int(reint), b_p,
-            C.c_int(self.x_slab[0]), C.c_int(self.x_slab[1]), C.c_int(1), abi.stream_ptr())
+            C.c_int(self.x_slab[0]), C.c_int(self.x_slab[1]), C.c_int(1),
+            abi.dptr(abi.pixel_lambda(_k, im_h, im_w, depth.device)), abi.stream_ptr())
         abi.check(rc, "rf_tsdf_integrate_local")
 
     def count_touched(self, depth, cam_intr, cam_pose, old_bnd=None, reintegrate_flag=0.0):

@@ -234,3 +234,27 @@ def test_abi_errors(cuda, rf_lib):
     t = torch.zeros(16, device=cuda)
     rc = rf_lib.rf_tsdf_clear_global(C.c_void_p(t.data_ptr() + 4), C.c_int64(1), C.c_void_p(0))
     assert rc == -3
+
+
+def test_pixel_lambda_image_is_bit_identical_to_inline(cuda, rf_lib, monkeypatch):
+    """The hoisted per-pixel 1/lambda image (rf_tsdf_pixel_lambda) and the inline per-voxel evaluation (NULL image) must
+    give the same bits: same operations, same order (model/Volume.py:280-283)."""
+    from remixfusion_b200 import abi
+    cam = T.small_cam(2)
+    K, c2w, depth, rgb = T.frame(cam, [[-3, 3], [-3, 3], [-2, 2]], eye=(0.2, -0.3, 0.1), target=(2.0, 1.0, 0.0), seed=5)
+    rgb255 = np.floor(rgb * 255.0).astype(np.float32)
+    outs = []
+    for use_image in (True, False):
+        if not use_image:
+            monkeypatch.setattr(abi, "pixel_lambda", lambda *a, **k: None)
+        mv = moving_volume(_cfg(0.04, (3, 3, 2)), None, np.eye(4), device=cuda)
+        mv.integrate(rgb255, depth, K, c2w, None)
+        m = _Model(48, cuda)
+        gv = MapVolume({"globalV": {"base_resolution": 48}, "mapping": {"bound": [[-3, 3], [-3, 3], [-2, 2]]},
+                        "training": {"c_trunc": 0.1}}, m, K)
+        gv.init_mapvolume()
+        gv.integrate_kf({"rgb": torch.from_numpy(rgb), "depth": torch.from_numpy(depth)}, torch.from_numpy(c2w).float(), 1.0)
+        outs.append([t.cpu().numpy() for t in (mv.tsdf_vol_gpu, mv.weight_vol_gpu, mv.color_vol_gpu, m.GBV.params, m.GBW.params)])
+    assert float(np.abs(outs[0][1]).sum()) > 0 and float(np.abs(outs[0][4]).sum()) > 0
+    for a, b in zip(*outs):
+        assert np.array_equal(_bits(a), _bits(b))
