@@ -433,6 +433,8 @@ def run_gpu(args, rank, world, local_rank):
                             "frac": (40.0 * kern["touched_global"] + 16.0 * H * W) / (kern["tsdf_global_ms"] / 1e3) / 1e9 / peak,
                             "launch_ms": kern["tsdf_global_ms"]},
             "gather_peak_Gops": kern.get("gather_gops"), "atomic_peak_Gops": kern.get("atomic_gops"),
+            # SURVEY §8d gather-bound roofline: t_roof = P*136/G_peak + P*256/A_peak (peaks measured above); frac = t_roof / t_measured
+            "ray_fwd_bwd_gather_form": gather_form(P, kern),
         },
         "e2e": {"value": float(e2e_units[0]) / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"], "steps": e2e["steps"],
                 "ms_per_step": e2e_ms / e2e["steps"]},
@@ -442,6 +444,15 @@ def run_gpu(args, rank, world, local_rank):
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(cfg, K, frames[0], H * W * S)
     print(json.dumps(line), flush=True)
+
+
+def gather_form(P, kern):
+    g, a = kern.get("gather_gops"), kern.get("atomic_gops")
+    if not g or not a:
+        return None
+    t_roof = (P * 136.0 / (g * 1e9) + P * 256.0 / (a * 1e9)) * 1e3
+    t_meas = kern["sample_fwd_ms"] + kern["sample_bwd_ms"]
+    return {"t_roof_ms": t_roof, "t_measured_ms": t_meas, "frac": t_roof / t_meas}
 
 
 PROF_NAMES = {3: "ray_pos_kernel", 4: "encode_walk_kernel", 5: "mlp_fwd_tc_kernel", 6: "composite_fwd_kernel",
