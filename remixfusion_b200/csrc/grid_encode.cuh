@@ -59,6 +59,41 @@ __device__ __forceinline__ unsigned grid_index_fast(bool is_hash, unsigned size,
     return (index < size) ? index : index % size;
 }
 
+// The 8 corner indices of one cell at once (same arithmetic as grid_index, Appendix B3, shared between the corners):
+// hashed levels reuse cy*P1, cz*P2 (and (c+1)*P = c*P + P in uint32), dense levels add constant offsets to one base
+// index; a power-of-two size reduces with a mask, any other size only pays the modulo when the index is out of range.
+struct CornerIndexer {
+    unsigned size, mask, s2, s3;
+    bool hashed, pow2;
+    __device__ __forceinline__ void init(bool is_hash, unsigned size_, unsigned res) {
+        size = size_; s2 = 0; s3 = 0;
+        unsigned stride = res;                                   // after dimension 0 (stride 1 <= size always)
+        if (stride <= size) { s2 = stride; stride *= res; if (stride <= size) { s3 = stride; stride *= res; } }
+        hashed = is_hash && size < stride;
+        pow2 = (size & (size - 1u)) == 0u; mask = size - 1u;
+    }
+    __device__ __forceinline__ void cell(unsigned cx, unsigned cy, unsigned cz, unsigned (&idx)[8]) const {
+        if (hashed) {
+            const unsigned a[2] = {cx, cx + 1u};
+            const unsigned b0 = cy * 2654435761u, c0 = cz * 805459861u;
+            const unsigned b[2] = {b0, b0 + 2654435761u}, c[2] = {c0, c0 + 805459861u};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) idx[k] = a[k & 1] ^ b[(k >> 1) & 1] ^ c[(k >> 2) & 1];
+        } else {
+            const unsigned base = cx + cy * s2 + cz * s3;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) idx[k] = base + (unsigned)(k & 1) + ((k & 2) ? s2 : 0u) + ((k & 4) ? s3 : 0u);
+        }
+        if (pow2) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) idx[k] &= mask;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) if (idx[k] >= size) idx[k] %= size;
+        }
+    }
+};
+
 // Corner weight, Appendix B4 (weight = 1; for dim: weight *= frac or 1-frac).
 __device__ __forceinline__ float corner_weight(int corner, float fx, float fy, float fz) {
     float w = 1.0f;

@@ -47,8 +47,6 @@ __global__ void __launch_bounds__(256) ray_pos_kernel(RayK k, const float* __res
     }
 }
 
-constexpr int kPF = 1;        // samples fetched ahead per walking thread (deeper prefetch measured slower: register pressure)
-
 // Features.  Thread = (ray, level), blockIdx.y + level0 = level (0..L-1 hash levels, L = GBV); lanes = consecutive rays.
 __global__ void __launch_bounds__(128) encode_walk_kernel(GridDev hg, GridDev gg, const float* __restrict__ hash_params,
                                                           const float* __restrict__ gbv_params, const float* __restrict__ xn,
@@ -58,90 +56,67 @@ __global__ void __launch_bounds__(128) encode_walk_kernel(GridDev hg, GridDev gg
     if (r >= N) return;
     const float* xs = xn + r; const float* ys = xn + P + r; const float* zs = xn + 2 * P + r;
     unsigned pcx = 0, pcy = 0, pcz = 0; bool have = false;
-    float xb[kPF], yb[kPF], zb[kPF];
-#pragma unroll
-    for (int u = 0; u < kPF; ++u) {
-        const long long o = (long long)min(u, S - 1) * N;
-        xb[u] = __ldg(xs + o); yb[u] = __ldg(ys + o); zb[u] = __ldg(zs + o);
-    }
+    float xa = __ldg(xs), ya = __ldg(ys), za = __ldg(zs);
+    CornerIndexer ci;
+    unsigned idx[8];
     if (l < L) {
         const float scale = hg.scale[l];
-        const unsigned size = hg.size[l], res = hg.res[l];
+        ci.init(hg.is_hash != 0, hg.size[l], hg.res[l]);
         const float2* tab = reinterpret_cast<const float2*>(hash_params) + hg.offset[l];
         float2* out = reinterpret_cast<float2*>(feat) + (long long)l * P + r;
         float2 v[8];
-        for (int s0 = 0; s0 < S; s0 += kPF) {
-            float xc[kPF], yc[kPF], zc[kPF];
+        for (int s = 0; s < S; ++s) {
+            const float x = xa, y = ya, z = za;
+            if (s + 1 < S) { xs += N; ys += N; zs += N; xa = __ldg(xs); ya = __ldg(ys); za = __ldg(zs); }
+            unsigned cx, cy, cz; float fx, fy, fz;
+            pos_fract(x, scale, cx, fx); pos_fract(y, scale, cy, fy); pos_fract(z, scale, cz, fz);
+            if (!have || cx != pcx || cy != pcy || cz != pcz) {
+                ci.cell(cx, cy, cz, idx);
 #pragma unroll
-            for (int u = 0; u < kPF; ++u) { xc[u] = xb[u]; yc[u] = yb[u]; zc[u] = zb[u]; }
-#pragma unroll
-            for (int u = 0; u < kPF; ++u) {
-                const long long o = (long long)min(s0 + kPF + u, S - 1) * N;
-                xb[u] = __ldg(xs + o); yb[u] = __ldg(ys + o); zb[u] = __ldg(zs + o);
+                for (int c = 0; c < 8; ++c) v[c] = __ldg(tab + idx[c]);
+                pcx = cx; pcy = cy; pcz = cz; have = true;
             }
+            float f0 = 0.f, f1 = 0.f;
 #pragma unroll
-            for (int u = 0; u < kPF; ++u) {
-                if (s0 + u < S) {
-                    unsigned cx, cy, cz; float fx, fy, fz;
-                    pos_fract(xc[u], scale, cx, fx); pos_fract(yc[u], scale, cy, fy); pos_fract(zc[u], scale, cz, fz);
-                    if (!have || cx != pcx || cy != pcy || cz != pcz) {
-#pragma unroll
-                        for (int c = 0; c < 8; ++c)
-                            v[c] = __ldg(tab + grid_index_fast(hg.is_hash, size, res, cx + (c & 1), cy + ((c >> 1) & 1), cz + ((c >> 2) & 1)));
-                        pcx = cx; pcy = cy; pcz = cz; have = true;
-                    }
-                    float f0 = 0.f, f1 = 0.f;
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        float w = corner_weight(c, fx, fy, fz);
-                        f0 = fmaf(w, v[c].x, f0); f1 = fmaf(w, v[c].y, f1);
-                    }
-                    out[(long long)(s0 + u) * N] = make_float2(f0, f1);
-                }
+            for (int c = 0; c < 8; ++c) {
+                float w = corner_weight(c, fx, fy, fz);
+                f0 = fmaf(w, v[c].x, f0); f1 = fmaf(w, v[c].y, f1);
             }
+            *out = make_float2(f0, f1);
+            out += N;
         }
     } else {
         const float scale = gg.scale[0];
-        const unsigned size = gg.size[0], res = gg.res[0];
+        ci.init(false, gg.size[0], gg.res[0]);
         const float4* tab = reinterpret_cast<const float4*>(gbv_params);
         float4* out = reinterpret_cast<float4*>(feat + 2ll * L * P) + r;
         float4 v[8];
-        for (int s0 = 0; s0 < S; s0 += kPF) {
-            float xc[kPF], yc[kPF], zc[kPF];
+        for (int s = 0; s < S; ++s) {
+            const float x = xa, y = ya, z = za;
+            if (s + 1 < S) { xs += N; ys += N; zs += N; xa = __ldg(xs); ya = __ldg(ys); za = __ldg(zs); }
+            unsigned cx, cy, cz; float fx, fy, fz;
+            pos_fract(x, scale, cx, fx); pos_fract(y, scale, cy, fy); pos_fract(z, scale, cz, fz);
+            if (!have || cx != pcx || cy != pcy || cz != pcz) {
+                ci.cell(cx, cy, cz, idx);
 #pragma unroll
-            for (int u = 0; u < kPF; ++u) { xc[u] = xb[u]; yc[u] = yb[u]; zc[u] = zb[u]; }
-#pragma unroll
-            for (int u = 0; u < kPF; ++u) {
-                const long long o = (long long)min(s0 + kPF + u, S - 1) * N;
-                xb[u] = __ldg(xs + o); yb[u] = __ldg(ys + o); zb[u] = __ldg(zs + o);
+                for (int c = 0; c < 8; ++c) v[c] = __ldg(tab + idx[c]);
+                pcx = cx; pcy = cy; pcz = cz; have = true;
             }
+            float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int u = 0; u < kPF; ++u) {
-                if (s0 + u < S) {
-                    unsigned cx, cy, cz; float fx, fy, fz;
-                    pos_fract(xc[u], scale, cx, fx); pos_fract(yc[u], scale, cy, fy); pos_fract(zc[u], scale, cz, fz);
-                    if (!have || cx != pcx || cy != pcy || cz != pcz) {
-#pragma unroll
-                        for (int c = 0; c < 8; ++c)
-                            v[c] = __ldg(tab + grid_index_fast(false, size, res, cx + (c & 1), cy + ((c >> 1) & 1), cz + ((c >> 2) & 1)));
-                        pcx = cx; pcy = cy; pcz = cz; have = true;
-                    }
-                    float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        float w = corner_weight(c, fx, fy, fz);
-                        o4.x = fmaf(w, v[c].x, o4.x); o4.y = fmaf(w, v[c].y, o4.y); o4.z = fmaf(w, v[c].z, o4.z); o4.w = fmaf(w, v[c].w, o4.w);
-                    }
-                    out[(long long)(s0 + u) * N] = o4;
-                }
+            for (int c = 0; c < 8; ++c) {
+                float w = corner_weight(c, fx, fy, fz);
+                o4.x = fmaf(w, v[c].x, o4.x); o4.y = fmaf(w, v[c].y, o4.y); o4.z = fmaf(w, v[c].z, o4.z); o4.w = fmaf(w, v[c].w, o4.w);
             }
+            *out = o4;
+            out += N;
         }
     }
 }
 
 // Table-gradient scatter, run-length reduced.  dfeat [L][P][2] (sample-major planes); thread = (ray, level): each lane
 // accumulates the 8 corner gradients of its current cell in registers and issues the 8 vector reductions
-// (RED.ADD.F32x2) when its cell changes.
+// (RED.ADD.F32x2) when its cell changes; runs whose gradients are all zero (samples past the truncation mask) issue none.
 // Small (coarse) levels are the contended ones: every ray of the batch lands on the same few thousand entries, and
 // reductions onto one L2 line serialise.  Those levels accumulate into K private replicas of their gradient table
 // (replica = block index mod K, so that neighbouring blocks — neighbouring pixels — never share one) which
@@ -157,13 +132,14 @@ __global__ void __launch_bounds__(128) scatter_walk_kernel(GridDev hg, ScatterRe
     const int l = blockIdx.y + level0;
     const long long r = blockIdx.x * 128ll + threadIdx.x;
     if (r >= N) return;
-    const unsigned size = hg.size[l], res = hg.res[l];
+    const unsigned size = hg.size[l];
     float2* gtab = (rep.k[l] > 1) ? reinterpret_cast<float2*>(g_rep) + rep.base[l] + (size_t)(blockIdx.x & (rep.k[l] - 1)) * size
                                   : reinterpret_cast<float2*>(g_hash) + hg.offset[l];
     const float* xs = xn + r; const float* ys = xn + P + r; const float* zs = xn + 2 * P + r;
     const float2* dj = reinterpret_cast<const float2*>(dfeat) + (long long)l * P + r;
     const float scale = hg.scale[l];
-    unsigned pcx = 0, pcy = 0, pcz = 0; bool have = false;
+    CornerIndexer ci; ci.init(hg.is_hash != 0, size, hg.res[l]);
+    unsigned pcx = 0, pcy = 0, pcz = 0; bool have = false, nz = false;
     float2 acc[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) acc[c] = make_float2(0.f, 0.f);
@@ -174,18 +150,22 @@ __global__ void __launch_bounds__(128) scatter_walk_kernel(GridDev hg, ScatterRe
         const bool last = (s == S);
         if (!last) {
             pos_fract(xa, scale, cx, fx); pos_fract(ya, scale, cy, fy); pos_fract(za, scale, cz, fz);
-            if (s + 1 < S) { const long long o = (long long)(s + 1) * N; xa = __ldg(xs + o); ya = __ldg(ys + o); za = __ldg(zs + o); da = __ldg(dj + o); }
+            if (s + 1 < S) { xs += N; ys += N; zs += N; dj += N; xa = __ldg(xs); ya = __ldg(ys); za = __ldg(zs); da = __ldg(dj); }
         }
         if (have && (last || cx != pcx || cy != pcy || cz != pcz)) {
+            if (nz) {
+                unsigned idx[8];
+                ci.cell(pcx, pcy, pcz, idx);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                if (acc[c].x != 0.f || acc[c].y != 0.f)
-                    atomicAdd(gtab + grid_index_fast(hg.is_hash, size, res, pcx + (c & 1), pcy + ((c >> 1) & 1), pcz + ((c >> 2) & 1)), acc[c]);
-                acc[c] = make_float2(0.f, 0.f);
+                for (int c = 0; c < 8; ++c) atomicAdd(gtab + idx[c], acc[c]);
             }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[c] = make_float2(0.f, 0.f);
+            nz = false;
         }
         if (last) break;
         pcx = cx; pcy = cy; pcz = cz; have = true;
+        nz = nz || d.x != 0.f || d.y != 0.f;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             float w = corner_weight(c, fx, fy, fz);

@@ -256,3 +256,53 @@ def test_state_dict_layout(cuda, rf_lib):
     assert sd["decoder_res.sdf_net.model.0.weight"].shape == (32, 81)
     assert sd["decoder_res.color_net.model.0.weight"].shape == (32, 66)
     assert float(sd["GBW.params"].abs().sum()) == 0.0 and not m.GBV.params.requires_grad
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+@pytest.mark.parametrize("n,S_cfg", [(2, (48, 11)), (5, (2, 0)), (37, (2, 3)), (130, (4, 0))])
+def test_ragged_batches_match_cpu_oracle(cuda, rf_lib, n, S_cfg, prec):
+    """Edge shapes of the batch: two rays (the reference itself cannot run one: its `.squeeze()` drops the batch axis), two samples per ray (one is an empty argmax in the reference), fewer rays than a 128-sample tile (a tile then spans
+    several sample indices of the sample-major planes), a ray count just over one tile."""
+    cfg = R.base_config(hash_size=10, R=32, hidden=32)
+    cfg["b200"] = {"mlp_precision": prec}
+    cfg["training"].update(n_range_d=S_cfg[0], n_samples_d=S_cfg[1])
+    bb = torch.from_numpy(np.array(cfg["mapping"]["bound"])).to(torch.float64)
+    m = JointEncoding(cfg, bb)
+    g = torch.Generator().manual_seed(100 + n)
+    h = R.hash_standin(cfg); gb = R.gbv_standin(cfg)
+    with torch.no_grad():
+        h.params.copy_((torch.rand(h.params.shape, generator=g) - 0.5) * 0.1)
+        gb.params.copy_(torch.from_numpy(G["in_gbv"]))
+        m.embed_res_fn.params.copy_(h.params); m.GBV.params.copy_(gb.params)
+    gb.params.requires_grad_(False)
+    ws = [w.detach().cpu().clone().requires_grad_(True) for w in m.decoder_res.fused_weights()]
+    from oracle.ray_oracle import RayOracle
+    orc = RayOracle(cfg, bb, h, gb, *ws)
+    b = torch.tensor(R.BOUND)
+    ro = b[:, 0] + (0.3 + 0.4 * torch.rand(n, 3, generator=g)) * (b[:, 1] - b[:, 0])
+    rd = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1)
+    tc = torch.rand(n, 3, generator=g)
+    td = 0.3 + 2.5 * torch.rand(n, 1, generator=g)
+    u = torch.rand(n, sum(S_cfg), generator=g)
+    r_ref = orc.mapping(ro, rd, tc, td, u=u)
+    orc.total_loss(r_ref).backward()
+    m.train()
+    r = m.mapping(ro.to(cuda), rd.to(cuda), tc.to(cuda), td.to(cuda), u=u)
+    _total(cfg, r).backward()
+    for k in ("rgb_res_loss", "depth_res_loss", "sdf_res_loss", "fs_res_loss", "rgb_res", "depth_res"):
+        ref = r_ref[k].detach().numpy()
+        if np.all(np.isfinite(ref)):
+            _close(r[k], ref, 2e-4, k)
+    _close_grad(m.embed_res_fn.params.grad, h.params.grad.numpy(), "g_hash", prec)
+    for w_cuda, w_ref, nm in zip(m.decoder_res.fused_weights(), ws, ("sdf0", "sdf1", "col0", "col1")):
+        _close_grad(w_cuda.grad, w_ref.grad.numpy(), "g_w_" + nm, prec)
+
+
+def test_empty_batch_is_a_no_op(cuda, rf_lib):
+    cfg = R.base_config(hash_size=10, R=16, hidden=32)
+    m = JointEncoding(cfg, torch.from_numpy(np.array(cfg["mapping"]["bound"])).double())
+    m.eval()
+    z = torch.zeros(0, 3, device=cuda)
+    with torch.no_grad():
+        ret = m.mapping(z, z, z, torch.zeros(0, 1, device=cuda))
+    assert ret["rgb_res_map"].shape == (0, 3) and ret["raw"].shape[0] == 0
