@@ -289,17 +289,55 @@ __device__ __forceinline__ void stage_geo(const float (&o16)[16], float gy, int 
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Forward
+// Forward.  The decoder kernels are bound by shared-memory bandwidth (tensor-core operand reads + staging stores), so
+// the forward keeps every A operand it can in TENSOR MEMORY: a thread writes its row of the hash features, of the
+// tail and of the hidden activations as bf16 pairs with tcgen05.st and the MMAs read them with the TS form
+// (tcgen05.mma [d], [a_tmem], b_desc).  Only the OneBlob block stays in shared memory (three scalars per coordinate at
+// data-dependent columns).  TMEM columns of a group: accumulator [0,HID) (H, then O/rgb aliased on [0,16)),
+// hash hi/lo 16+16, tail hi/lo 16+16, hidden hi/lo HID/2 + HID/2.
 // ------------------------------------------------------------------------------------------------------------
 template <int HID>
 struct FwdL {
-    static constexpr int HC = HID / 8;
-    // group region (chunks): [H hi HC | H lo HC] (hash hi at 0, hash lo at 4: dead once H1 is read) | blob hi 6 | tail hi 4 | blob lo 6 | tail lo 4
-    static constexpr int c_hash_hi = 0, c_hash_lo = 4, c_h_hi = 0, c_h_lo = HC;
-    static constexpr int c_blob_hi = 2 * HC, c_tail_hi = 2 * HC + 6, c_blob_lo = 2 * HC + 10, c_tail_lo = 2 * HC + 16;
-    static constexpr int chunks = 2 * HC + 20;
+    static constexpr int c_blob_hi = 0, c_blob_lo = 6, chunks = 12;     // shared memory per group: OneBlob hi / lo
     static constexpr int bytes = chunks * kChunkB;
+    static constexpr int t_acc = 0, t_hash_hi = HID, t_hash_lo = HID + 16, t_tail_hi = HID + 32, t_tail_lo = HID + 48,
+                         t_h_hi = HID + 64, t_h_lo = HID + 64 + HID / 2, tcols = 2 * HID + 64;
 };
+
+// A from TMEM (hi at column ah, lo at column al, 8 columns per k-step); B = weights K-major
+template <int NKS>
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t ah, uint32_t al, uint32_t bh, uint32_t bl, int brows, uint32_t idesc, uint32_t& acc) {
+    uint64_t dbh = smem_desc(bh, brows * 16, 128), dbl = smem_desc(bl, brows * 16, 128);
+#pragma unroll
+    for (int s = 0; s < NKS; ++s) {
+        mma_bf16_ts(d, ah + 8 * s, dbh, idesc, acc); acc = 1;
+        mma_bf16_ts(d, ah + 8 * s, dbl, idesc, 1);
+        mma_bf16_ts(d, al + 8 * s, dbh, idesc, 1);
+        dbh = desc_advance(dbh, 2 * brows * 16); dbl = desc_advance(dbl, 2 * brows * 16);
+    }
+}
+// 8 floats -> bf16 hi / lo pairs -> 4 TMEM columns each (chunk c of an operand whose hi / lo blocks start at th / tl)
+__device__ __forceinline__ void tstage8(uint32_t th, uint32_t tl, int c, const float* v) {
+    uint4 h, l; split8(v, h, l);
+    tmem_st4(th + 4 * c, h);
+    tmem_st4(tl + 4 * c, l);
+}
+__device__ __forceinline__ void tstage_zero(uint32_t th, uint32_t tl, int c) {
+    tmem_st4(th + 4 * c, make_uint4(0, 0, 0, 0));
+    tmem_st4(tl + 4 * c, make_uint4(0, 0, 0, 0));
+}
+template <int HID>
+__device__ __forceinline__ void relu_to_tmem(uint32_t tacc, uint32_t th, uint32_t tl) {
+#pragma unroll
+    for (int q = 0; q < HID / 32; ++q) {
+        float v[32];
+        tmem_ld32(tacc + 32 * q, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tstage8(th, tl, 4 * q + c, v + 8 * c);
+    }
+}
 
 template <int HID, int G>
 __global__ void __launch_bounds__(G * 128, 1) mlp_fwd_tc_kernel(RayK k, Weights wts, const float* __restrict__ feat, long long P,
@@ -309,7 +347,8 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_fwd_tc_kernel(RayK k, Weights 
     __shared__ uint32_t tmem_base_s;
     using W = WL<HID>; using A = FwdL<HID>;
     constexpr int HC = HID / 8;
-    constexpr uint32_t TCOLS = (G == 1) ? 128 : (G == 2) ? 256 : 512;
+    constexpr uint32_t TCOLS = (G * A::tcols <= 128) ? 128 : (G * A::tcols <= 256) ? 256 : 512;
+    static_assert(G * A::tcols <= 512, "TMEM columns");
     const int tid = threadIdx.x, g = tid >> 7, m = tid & 127, warp = tid >> 5;
     unsigned char* wsm = smem + G * A::bytes;
     unsigned char* act = smem + g * A::bytes;
@@ -320,15 +359,11 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_fwd_tc_kernel(RayK k, Weights 
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-    const uint32_t tb = tmem_base_s + (uint32_t)g * 128u;                 // group's columns
+    const uint32_t tb = tmem_base_s + (uint32_t)g * A::tcols;              // group's columns (lane 0: MMA operand addresses)
     const uint32_t tlane = tb + ((uint32_t)((warp & 3) * 32) << 16);       // this thread's lane quadrant
-    const uint32_t colH = 0, colO = 64;
     uint64_t* bar = &bars[g];
     uint32_t phase = 0;
-    unsigned char *hash_hi = act + A::c_hash_hi * kChunkB, *hash_lo = act + A::c_hash_lo * kChunkB;
-    unsigned char *h_hi = act + A::c_h_hi * kChunkB, *h_lo = act + A::c_h_lo * kChunkB;
     unsigned char *blob_hi = act + A::c_blob_hi * kChunkB, *blob_lo = act + A::c_blob_lo * kChunkB;
-    unsigned char *tail_hi = act + A::c_tail_hi * kChunkB, *tail_lo = act + A::c_tail_lo * kChunkB;
     const uint32_t w0h = smem_u32(wsm + W::o_w0h), w0l = smem_u32(wsm + W::o_w0l), w1h = smem_u32(wsm + W::o_w1h), w1l = smem_u32(wsm + W::o_w1l);
     const uint32_t w2h = smem_u32(wsm + W::o_w2h), w2l = smem_u32(wsm + W::o_w2l), w3h = smem_u32(wsm + W::o_w3h), w3l = smem_u32(wsm + W::o_w3l);
     constexpr uint32_t idH = idesc_bf16(HID, false, false), id16 = idesc_bf16(16, false, false);
@@ -342,50 +377,81 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_fwd_tc_kernel(RayK k, Weights 
         prefetch_tile(feat, P, (tile + (long long)gridDim.x * G) * kTile, m);
         float t_add, cin, d0, d1;
         tsdf_terms(k, 0, t.g.x, t_add, cin, d0, d1);                                          // scene_rep.py:330-337
-        stage_x(t, cin, live, m, hash_hi, hash_lo, blob_hi, blob_lo, tail_hi, tail_lo);
+        // X row: hash -> TMEM, OneBlob -> shared memory, tail = [0 x15 | gbv rgb | decoder tsdf input | 0] -> TMEM
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float v[8] = {t.f[4 * c].x, t.f[4 * c].y, t.f[4 * c + 1].x, t.f[4 * c + 1].y, t.f[4 * c + 2].x, t.f[4 * c + 2].y, t.f[4 * c + 3].x, t.f[4 * c + 3].y};
+            tstage8(tlane + A::t_hash_hi, tlane + A::t_hash_lo, c, v);
+        }
+        if (live) {
+#pragma unroll 1
+            for (int a = 0; a < 3; ++a) stage_oneblob(t.x[a], blob_hi, blob_lo, m, 2 * a);
+        } else {
+            for (int c = 0; c < 6; ++c) stage_zero(blob_hi, blob_lo, m, c);
+        }
+        {
+            float v1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, t.g.y};
+            float v2[8] = {t.g.z, t.g.w, cin, 0.f, 0.f, 0.f, 0.f, 0.f};
+            tstage_zero(tlane + A::t_tail_hi, tlane + A::t_tail_lo, 0);
+            tstage8(tlane + A::t_tail_hi, tlane + A::t_tail_lo, 1, v1);
+            tstage8(tlane + A::t_tail_hi, tlane + A::t_tail_lo, 2, v2);
+            tstage_zero(tlane + A::t_tail_hi, tlane + A::t_tail_lo, 3);
+        }
+        tmem_st_wait();
         fence_async_smem(); fence_before_sync(); grp_sync(g);
         if (m == 0) {                                                                         // H1 = X1 W0^T
             fence_after_sync();
             uint32_t acc = 0;
-            mma_kk<2>(tb + colH, smem_u32(hash_hi), smem_u32(hash_lo), w0h, w0l, HID, idH, acc);
-            mma_kk<3>(tb + colH, smem_u32(blob_hi), smem_u32(blob_lo), w0h + kXBlob * HID * 16, w0l + kXBlob * HID * 16, HID, idH, acc);
-            mma_kk<2>(tb + colH, smem_u32(tail_hi), smem_u32(tail_lo), w0h + kXTail * HID * 16, w0l + kXTail * HID * 16, HID, idH, acc);
+            mma_ts<2>(tb + A::t_acc, tb + A::t_hash_hi, tb + A::t_hash_lo, w0h, w0l, HID, idH, acc);
+            mma_kk<3>(tb + A::t_acc, smem_u32(blob_hi), smem_u32(blob_lo), w0h + kXBlob * HID * 16, w0l + kXBlob * HID * 16, HID, idH, acc);
+            mma_ts<2>(tb + A::t_acc, tb + A::t_tail_hi, tb + A::t_tail_lo, w0h + kXTail * HID * 16, w0l + kXTail * HID * 16, HID, idH, acc);
             commit(bar);
         }
         grp_wait(bar, phase);
-        uint32_t mask[HID / 32];
-        relu_to_smem<HID>(tlane + colH, h_hi, h_lo, m, mask);                                 // decoder.py:105-107
-        fence_async_smem(); fence_before_sync(); grp_sync(g);
+        relu_to_tmem<HID>(tlane + A::t_acc, tlane + A::t_h_hi, tlane + A::t_h_lo);            // decoder.py:105-107
+        tmem_st_wait();
+        fence_before_sync(); grp_sync(g);
         if (m == 0) {                                                                         // O = H1 W1^T
             fence_after_sync();
             uint32_t acc = 0;
-            mma_kk<HC / 2>(tb + colO, smem_u32(h_hi), smem_u32(h_lo), w1h, w1l, 16, id16, acc);
+            mma_ts<HC / 2>(tb + A::t_acc, tb + A::t_h_hi, tb + A::t_h_lo, w1h, w1l, 16, id16, acc);
             commit(bar);
         }
         grp_wait(bar, phase);
         float o16[16];
-        tmem_ld16(tlane + colO, o16);
+        tmem_ld16(tlane + A::t_acc, o16);
         const float sdf = o16[0] + t_add;                                                     // scene_rep.py:345
-        stage_geo(o16, t.g.y, m, tail_hi, tail_lo);
-        fence_async_smem(); fence_before_sync(); grp_sync(g);
+        {                                                                                     // geo15 into the tail
+            float v0[8], v1[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v0[i] = o16[1 + i];
+#pragma unroll
+            for (int i = 0; i < 7; ++i) v1[i] = o16[9 + i];
+            v1[7] = t.g.y;
+            tstage8(tlane + A::t_tail_hi, tlane + A::t_tail_lo, 0, v0);
+            tstage8(tlane + A::t_tail_hi, tlane + A::t_tail_lo, 1, v1);
+        }
+        tmem_st_wait();
+        fence_before_sync(); grp_sync(g);
         if (m == 0) {                                                                         // H2 = X2 W2^T
             fence_after_sync();
             uint32_t acc = 0;
-            mma_kk<3>(tb + colH, smem_u32(blob_hi), smem_u32(blob_lo), w2h, w2l, HID, idH, acc);
-            mma_kk<2>(tb + colH, smem_u32(tail_hi), smem_u32(tail_lo), w2h + 6 * HID * 16, w2l + 6 * HID * 16, HID, idH, acc);
+            mma_kk<3>(tb + A::t_acc, smem_u32(blob_hi), smem_u32(blob_lo), w2h, w2l, HID, idH, acc);
+            mma_ts<2>(tb + A::t_acc, tb + A::t_tail_hi, tb + A::t_tail_lo, w2h + 6 * HID * 16, w2l + 6 * HID * 16, HID, idH, acc);
             commit(bar);
         }
         grp_wait(bar, phase);
-        relu_to_smem<HID>(tlane + colH, h_hi, h_lo, m, mask);                                 // decoder.py:49-51
-        fence_async_smem(); fence_before_sync(); grp_sync(g);
+        relu_to_tmem<HID>(tlane + A::t_acc, tlane + A::t_h_hi, tlane + A::t_h_lo);            // decoder.py:49-51
+        tmem_st_wait();
+        fence_before_sync(); grp_sync(g);
         if (m == 0) {                                                                         // rgb = H2 W3^T
             fence_after_sync();
             uint32_t acc = 0;
-            mma_kk<HC / 2>(tb + colO, smem_u32(h_hi), smem_u32(h_lo), w3h, w3l, 16, id16, acc);
+            mma_ts<HC / 2>(tb + A::t_acc, tb + A::t_h_hi, tb + A::t_h_lo, w3h, w3l, 16, id16, acc);
             commit(bar);
         }
         grp_wait(bar, phase);
-        tmem_ld16(tlane + colO, o16);
+        tmem_ld16(tlane + A::t_acc, o16);
         if (live) reinterpret_cast<float4*>(raw)[p] = make_float4(o16[0] + t.g.y, o16[1] + t.g.z, o16[2] + t.g.w, sdf);   // :344-345
         fence_before_sync();
     }
@@ -646,7 +712,7 @@ int launch_fwd_tc(const RayK& k, int hidden, const GridDev& hg, const GridDev& g
     int rc = launch_encode(k, hg, gg, p, rays_o, rays_d, z_vals, P, feat, s);
     if (rc) return rc;
     Weights w{p->w_sdf0, p->w_sdf1, p->w_col0, p->w_col1};
-    return hidden == 64 ? launch_fwd_g<64, 2>(k, w, feat, P, raw, s) : launch_fwd_g<32, 3>(k, w, feat, P, raw, s);
+    return hidden == 64 ? launch_fwd_g<64, 2>(k, w, feat, P, raw, s) : launch_fwd_g<32, 4>(k, w, feat, P, raw, s);
 }
 
 // dfeat: 2L * P floats of scratch, followed by scatter_scratch_floats() floats for the table replicas
