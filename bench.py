@@ -406,6 +406,10 @@ def run_gpu(args, rank, world, local_rank):
     peaks = (peak, peak_src, tf_peak, tf_src)
     dom = max(kern["kernels_ms"].items(), key=lambda kv: kv[1])
     roof = kernel_roofline(dom[0], dom[1], P, cfg["decoder"]["hidden_dim"], peaks)
+    traffic, traffic_src = ncu_traffic()
+    if dom[0] in traffic and cfg["decoder"]["hidden_dim"] == 32 and cfg["grid"]["hash_size"] == 16:
+        roof["traffic"] = traffic[dom[0]]
+        roof["traffic_source"] = f"profiles/{traffic_src} (ncu --set full, same workload)"
     tl0, tg0 = per_frame_units[0]
     hw_bytes = 8.0 * H * W
     line = {
@@ -458,6 +462,32 @@ def gather_form(P, kern):
 PROF_NAMES = {3: "ray_pos_kernel", 4: "encode_walk_kernel", 5: "mlp_fwd_tc_kernel", 6: "composite_fwd_kernel",
               7: "composite_bwd_kernel", 8: "mlp_bwd_tc_kernel", 9: "scatter_walk_kernel", 10: "sample_fwd_kernel",
               11: "sample_bwd_kernel"}
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of each kernel (dram__bytes_read.sum + dram__bytes_write.sum) from the newest committed
+    `ncu --set full` summary under profiles/ — taken on this same workload (bench config 2), one capture per kernel."""
+    import csv
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_full_summary.csv")))
+    if not files:
+        return {}, None
+    rows = list(csv.reader(open(files[-1])))
+    names = rows[0][2:]
+    val = {r[0]: r for r in rows[1:]}
+    out = {}
+    try:
+        rd, wr = val["dram__bytes_read.sum"], val["dram__bytes_write.sum"]
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        for i, n in enumerate(names):
+            key = next((k for k in PROF_NAMES.values() if k.replace("_kernel", "") in n or n.startswith(k[:12])), None)
+            if key is None and "mlp_fwd" in n: key = "mlp_fwd_tc_kernel"
+            if key is None and "mlp_bwd" in n: key = "mlp_bwd_tc_kernel"
+            if key:
+                out[key] = float(rd[2 + i]) * scale.get(rd[1], 1.0) + float(wr[2 + i]) * scale.get(wr[1], 1.0)
+    except Exception:
+        return {}, None
+    return out, os.path.basename(files[-1])
 
 
 def kernel_roofline(name, ms, P, hidden, peaks):
