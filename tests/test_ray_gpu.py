@@ -41,15 +41,16 @@ def _close(got, ref, rtol, name, atol_frac=1e-4):
     np.testing.assert_allclose(got, ref, rtol=rtol, atol=atol_frac * scale + 1e-12, err_msg=name)
 
 
-def _close_grad(got, ref, name, prec, rtol=1e-3, atol_frac=2e-4):
+def _close_grad(got, ref, name, prec, rtol=1e-3, atol_frac=2e-4, kink_aware=False):
     """Gradient parity.  prec 0 (fp32 decoder): every element within rtol + atol_frac * max|g|.
     prec 1 (bf16x3 tensor-core decoder, ~1e-6 absolute error on the hidden pre-activations): a pre-activation that the
     oracle puts within that error of zero can land on the other side of the ReLU kink, which switches one hidden unit's
     whole contribution for one sample (up to 128 table entries).  That is a property of comparing two finite-precision
-    evaluations of a piecewise-linear function, not of the kernel, so prec 1 asserts (a) relative L2 error <= 1e-3,
+    evaluations of a piecewise-linear function, not of the kernel (with millions of pre-activations per batch even two
+    fp32 evaluations disagree on a few: kink_aware=True for the large batches), so this mode asserts (a) relative L2 error <= 1e-3,
     (b) at most 0.5 % of the elements outside the elementwise tolerance, (c) none of them off by more than 5 % of max|g|."""
     got = got.detach().cpu().numpy() if isinstance(got, torch.Tensor) else np.asarray(got)
-    if prec == 0:
+    if prec == 0 and not kink_aware:
         return _close(got, ref, rtol, name, atol_frac=atol_frac)
     scale = float(np.abs(ref).max())
     err = np.abs(got - ref)
@@ -186,6 +187,7 @@ def test_mapping_matches_cpu_oracle_fresh(cuda, rf_lib, hidden, S_cfg, n, prec):
     cfg["b200"] = {"mlp_precision": prec}
     cfg["training"].update(n_range_d=S_cfg[0], n_samples_d=S_cfg[1], rgb_missing=0.0)
     bb = torch.from_numpy(np.array(cfg["mapping"]["bound"])).to(torch.float64)
+    torch.manual_seed(1000 + hidden + n)                    # decoder init (nn.Linear default) is part of the test vector
     m = JointEncoding(cfg, bb)
     g = torch.Generator().manual_seed(hidden)
     h = R.hash_standin(cfg); gb = R.gbv_standin(cfg)
@@ -214,9 +216,10 @@ def test_mapping_matches_cpu_oracle_fresh(cuda, rf_lib, hidden, S_cfg, n, prec):
     _total(cfg, r).backward()
     for k in ("rgb_res_loss", "depth_res_loss", "sdf_res_loss", "fs_res_loss", "rgb_res", "depth_res"):
         _close(r[k], r_ref[k].detach().numpy(), 2e-4, k)
-    _close_grad(m.embed_res_fn.params.grad, h.params.grad.numpy(), "g_hash", prec)
+    big = n > 1000                                          # millions of hidden pre-activations: see _close_grad
+    _close_grad(m.embed_res_fn.params.grad, h.params.grad.numpy(), "g_hash", prec, kink_aware=big)
     for w_cuda, w_ref, nm in zip(m.decoder_res.fused_weights(), ws, ("sdf0", "sdf1", "col0", "col1")):
-        _close_grad(w_cuda.grad, w_ref.grad.numpy(), "g_w_" + nm, prec)
+        _close_grad(w_cuda.grad, w_ref.grad.numpy(), "g_w_" + nm, prec, kink_aware=big)
 
 
 def test_point_queries_match_oracle(cuda, rf_lib):
@@ -267,6 +270,7 @@ def test_ragged_batches_match_cpu_oracle(cuda, rf_lib, n, S_cfg, prec):
     cfg["b200"] = {"mlp_precision": prec}
     cfg["training"].update(n_range_d=S_cfg[0], n_samples_d=S_cfg[1])
     bb = torch.from_numpy(np.array(cfg["mapping"]["bound"])).to(torch.float64)
+    torch.manual_seed(2000 + n)
     m = JointEncoding(cfg, bb)
     g = torch.Generator().manual_seed(100 + n)
     h = R.hash_standin(cfg); gb = R.gbv_standin(cfg)
