@@ -91,8 +91,9 @@ class _OneBlobFn(torch.autograd.Function):
         if not ctx.needs_input_grad[0]:
             return None, None
         dx = torch.empty_like(x32)
+        dout32 = dout.contiguous().to(torch.float32)          # keep the copy referenced until the kernel is enqueued
         abi.check(abi.lib().rf_oneblob_backward(abi.dptr(x32), C.c_int64(x32.shape[0]), C.c_int(ctx.n_bins),
-                                                abi.dptr(dout.contiguous().to(torch.float32)), abi.dptr(dx), abi.stream_ptr()),
+                                                abi.dptr(dout32), abi.dptr(dx), abi.stream_ptr()),
                   "rf_oneblob_backward")
         return dx.to(ctx.x_dtype), None
 

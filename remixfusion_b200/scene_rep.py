@@ -109,11 +109,14 @@ class _RayQueryFn(torch.autograd.Function):
         p = abi.RayParams(abi.dptr(hash_params.detach()), abi.dptr(gbv_params.detach()), abi.dptr(w_sdf0.detach()),
                           abi.dptr(w_sdf1.detach()), abi.dptr(w_col0.detach()), abi.dptr(w_col1.detach()))
         use_loss = d_losses is not None and partials is not None
+        # contiguous fp32 copies of the upstream gradients must stay referenced until the kernels are enqueued: a temporary
+        # dropped right after dptr() hands its block back to the caching allocator, and the next temporary may reuse it
+        up = [f32(d_rgb_map), f32(d_depth_map), f32(d_raw), f32(d_losses) if use_loss else None]
         rc = abi.lib().rf_ray_query_backward(
             C.byref(cfg), C.byref(hdesc), C.byref(gdesc), C.byref(p), abi.dptr(ro), abi.dptr(rd), abi.dptr(td), abi.dptr(tc),
             C.c_int64(n), abi.dptr(z_vals), abi.dptr(raw), abi.dptr(rgb_map), abi.dptr(depth_map),
-            abi.dptr(f32(d_rgb_map)), abi.dptr(f32(d_depth_map)), abi.dptr(f32(d_raw)),
-            abi.dptr(f32(d_losses) if use_loss else None), abi.dptr(partials if use_loss else None),
+            abi.dptr(up[0]), abi.dptr(up[1]), abi.dptr(up[2]),
+            abi.dptr(up[3]), abi.dptr(partials if use_loss else None),
             C.byref(grads), abi.dptr(ctx.ws), abi.dptr(scratch), abi.stream_ptr())
         abi.check(rc, "rf_ray_query_backward")
         return (g_o if need[0] else None, g_d if need[1] else None, g_hash, g_w[0], g_w[1], g_w[2], g_w[3],
