@@ -32,6 +32,7 @@ constexpr int kChunkB = 2048;                  // bytes of one 8-column chunk of
 constexpr int kXBlob = 4, kXTail = 10, kXCh = 14;   // X-order chunks: hash 0-3 | oneblob 4-9 | tail 10-13
 constexpr int kTailTsdf = 18;                  // tail = [geo15 | gbv_rgb3 | tsdf | 0 x13]
 constexpr int kKX = kXCh * 8;                  // 112
+constexpr int kFlushTiles = 256;               // weight-gradient accumulators are flushed every this many tiles
 
 template <int HID>
 struct WL {                                    // weight shared-memory layout (bytes); B operands, rows = out units
@@ -484,6 +485,48 @@ struct BwdL {
     static constexpr int tcols = (HID == 32) ? 256 : 512;
 };
 
+// Weight gradients of a group: TMEM accumulators (lane = row, see BwdL) -> global, with atomics.
+template <int HID>
+__device__ __forceinline__ void flush_wgrads(uint32_t tlane, const Grads& gr, int m) {
+    using A = BwdL<HID>;
+    {
+        fence_after_sync();
+        const int f = m;
+        int c0 = -1;                                          // column of w_sdf0 for X1 row f
+        if (f < 80) c0 = f; else if (f == 80 + kTailTsdf) c0 = 80;
+#pragma unroll
+        for (int q = 0; q < HID / 32; ++q) {                  // X-based: value = (hh + lh)[j] + hl[j]
+            float v[32], u[32];
+            tmem_ld32(tlane + A::t_w0 + 32 * q, v);
+            tmem_ld32(tlane + A::t_w0 + HID + 32 * q, u);
+            if (gr.g_w_sdf0 && c0 >= 0) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) atomicAdd(gr.g_w_sdf0 + (32 * q + j) * 81 + c0, v[j] + u[j]);
+            }
+            tmem_ld32(tlane + A::t_w2 + 32 * q, v);
+            tmem_ld32(tlane + A::t_w2 + HID + 32 * q, u);
+            if (gr.g_w_col0 && f < kIn2) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) atomicAdd(gr.g_w_col0 + (32 * q + j) * kIn2 + f, v[j] + u[j]);
+            }
+        }
+        // H-based: rows [0,HID) = hi features (columns: x hi | x lo), rows [HID,2HID) = lo features (column block x hi)
+        float v32[32];
+        tmem_ld32(tlane + A::t_w1, v32);
+        if (gr.g_w_sdf1 && f < 2 * HID) {
+            const int j = (f < HID) ? f : f - HID;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) atomicAdd(gr.g_w_sdf1 + i * HID + j, (f < HID) ? v32[i] + v32[16 + i] : v32[i]);
+        }
+        tmem_ld32(tlane + A::t_w3, v32);
+        if (gr.g_w_col1 && f < 2 * HID) {
+            const int j = (f < HID) ? f : f - HID;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) atomicAdd(gr.g_w_col1 + i * HID + j, (f < HID) ? v32[i] + v32[16 + i] : v32[i]);
+        }
+    }
+}
+
 template <int HID, int G>
 __global__ void __launch_bounds__(G * 128, 1) mlp_bwd_tc_kernel(RayK k, Weights wts, const float* __restrict__ feat, long long P,
                                                                 const float* __restrict__ d_raw_tot, float* __restrict__ dfeat, Grads gr) {
@@ -523,6 +566,7 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_bwd_tc_kernel(RayK k, Weights 
     constexpr uint32_t idH_bm = idesc_bf16(HID, false, true), id16_bm = idesc_bf16(16, false, true), id32_bm = idesc_bf16(32, false, true);
     constexpr uint32_t idH_mm = idesc_bf16(HID, true, true), id2H_mm = idesc_bf16(2 * HID, true, true), id32_mm = idesc_bf16(32, true, true);
     uint32_t wacc = 0;            // 0 until this group's weight-gradient accumulators hold a first tile
+    int since_flush = 0;
 
     // inputs software-pipelined through their own registers, as in the forward
     const long long tstep = (long long)gridDim.x * G;
@@ -644,45 +688,12 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_bwd_tc_kernel(RayK k, Weights 
                 for (int l = 0; l < 16; ++l) dj[(long long)l * P + q] = make_float2(dx[2 * l], dx[2 * l + 1]);
             }
         }
+        // fp32 accumulation in TMEM over thousands of tiles drifts (2e-4 relative on 2^20 rays at one group per SM):
+        // hand the partial sums over every kFlushTiles tiles and restart the accumulators
+        if (++since_flush == kFlushTiles) { flush_wgrads<HID>(tlane, gr, m); wacc = 0; since_flush = 0; }
         fence_before_sync();
     }
-    // flush the weight gradients of this group (TMEM lane = row of the accumulator, see BwdL)
-    if (wacc) {
-        fence_after_sync();
-        const int f = m;
-        int c0 = -1;                                          // column of w_sdf0 for X1 row f
-        if (f < 80) c0 = f; else if (f == 80 + kTailTsdf) c0 = 80;
-#pragma unroll
-        for (int q = 0; q < HID / 32; ++q) {                  // X-based: value = (hh + lh)[j] + hl[j]
-            float v[32], u[32];
-            tmem_ld32(tlane + A::t_w0 + 32 * q, v);
-            tmem_ld32(tlane + A::t_w0 + HID + 32 * q, u);
-            if (gr.g_w_sdf0 && c0 >= 0) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) atomicAdd(gr.g_w_sdf0 + (32 * q + j) * 81 + c0, v[j] + u[j]);
-            }
-            tmem_ld32(tlane + A::t_w2 + 32 * q, v);
-            tmem_ld32(tlane + A::t_w2 + HID + 32 * q, u);
-            if (gr.g_w_col0 && f < kIn2) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) atomicAdd(gr.g_w_col0 + (32 * q + j) * kIn2 + f, v[j] + u[j]);
-            }
-        }
-        // H-based: rows [0,HID) = hi features (columns: x hi | x lo), rows [HID,2HID) = lo features (column block x hi)
-        float v32[32];
-        tmem_ld32(tlane + A::t_w1, v32);
-        if (gr.g_w_sdf1 && f < 2 * HID) {
-            const int j = (f < HID) ? f : f - HID;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) atomicAdd(gr.g_w_sdf1 + i * HID + j, (f < HID) ? v32[i] + v32[16 + i] : v32[i]);
-        }
-        tmem_ld32(tlane + A::t_w3, v32);
-        if (gr.g_w_col1 && f < 2 * HID) {
-            const int j = (f < HID) ? f : f - HID;
-#pragma unroll
-            for (int i = 0; i < 3; ++i) atomicAdd(gr.g_w_col1 + i * HID + j, (f < HID) ? v32[i] + v32[16 + i] : v32[i]);
-        }
-    }
+    if (wacc) flush_wgrads<HID>(tlane, gr, m);
     fence_before_sync();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base_s, TCOLS);

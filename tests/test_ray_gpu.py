@@ -312,15 +312,18 @@ def test_empty_batch_is_a_no_op(cuda, rf_lib):
     assert ret["rgb_res_map"].shape == (0, 3) and ret["raw"].shape[0] == 0
 
 
-def test_full_size_properties(cuda, rf_lib):
-    """BASELINE config 2 at full size (one 1200x680 frame = 816 000 rays x 59 samples = 48.1 M samples; no oracle can
-    run this), checked through size-independent properties:
+@pytest.mark.parametrize("shape", ["cfg2", "cfg3"])
+def test_full_size_properties(cuda, rf_lib, shape):
+    """BASELINE config 2 at full size (one 1200x680 frame = 816 000 rays x 59 samples = 48.1 M samples) and config 3
+    (2^20 rays x 48 samples, hash 16 x 2^19 at resolution 512, hidden 64); no oracle can run these, so they are checked
+    through size-independent properties:
       * per-ray outputs do not depend on what else is in the batch: rendering the two halves separately gives the SAME
         BITS as rendering all rays at once (different tile / plane composition, same per-row arithmetic);
       * gradients are additive over a split of the batch (fp32 reduction order differs: rel-L2 <= 1e-4);
       * rendered depth is a sub-convex combination of the ray's sample depths and every output is finite."""
     from remixfusion_b200 import configs, synth
-    cfg = configs.replica()
+    cfg = configs.replica() if shape == "cfg2" else configs.replica(hidden=64, hash_size=19, n_range_d=48, n_samples_d=0,
+                                                                    voxel_sdf=8.0 / 512)
     cfg["training"]["perturb"] = 0
     cam = cfg["cam"]; H, W = cam["H"], cam["W"]
     K = synth.intrinsics(cam["fx"], cam["fy"], cam["cx"], cam["cy"])
@@ -338,7 +341,10 @@ def test_full_size_properties(cuda, rf_lib):
     rays_d = torch.sum(dirs[..., None, :] * c2w_t[:3, :3], -1).contiguous()
     rays_o = c2w_t[None, :3, -1].repeat(H * W, 1).contiguous()
     td = torch.from_numpy(depth).to(cuda).reshape(-1, 1).contiguous()
-    n = H * W
+    if shape == "cfg3":                                    # 2^20 rays drawn from the frame's pixels (with repetition)
+        pick = torch.randint(0, H * W, (1 << 20,), generator=torch.Generator().manual_seed(5)).to(cuda)
+        rays_o, rays_d, td = rays_o[pick].contiguous(), rays_d[pick].contiguous(), td[pick].contiguous()
+    n = rays_o.shape[0]
     half = n // 2 + 13                                    # not a multiple of the tile size
     params = [m.embed_res_fn.params] + list(m.decoder_res.fused_weights())
 
