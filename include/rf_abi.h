@@ -241,7 +241,10 @@ int rf_ray_query_backward(const rf_ray_cfg* cfg, const rf_grid_desc* hash, const
  * (decoder fed the unscaled GBV tsdf). */
 int rf_point_query_forward(const rf_ray_cfg* cfg, const rf_grid_desc* hash, const rf_grid_desc* gbv,
                            const rf_ray_params* p, const float* x, int64_t n, int variant,
-                           float* raw, void* stream);
+                           float* raw, float* workspace, void* stream);
+/* Floats of `workspace` for the call above: 0 for mlp_precision 0, (2*n_levels + 4 + 3) * n for mlp_precision 1
+ * (the same feature planes as the ray query, one sample per "ray"). */
+int64_t rf_point_workspace_floats(const rf_ray_cfg* cfg, const rf_grid_desc* hash, int64_t n);
 
 /* Micro-benchmarks for the gather-bound roofline denominators: random 8-byte loads and
  * random fp32 red.add over a table of table_bytes.  Synchronous: runs `iters` launches after one warm-up and

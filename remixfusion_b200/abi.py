@@ -76,6 +76,7 @@ def lib() -> C.CDLL:
         _lib.rf_version.restype = C.c_int
         _lib.rf_ray_workspace_floats.restype = C.c_int64
         _lib.rf_ray_scratch_floats.restype = C.c_int64
+        _lib.rf_point_workspace_floats.restype = C.c_int64
     return _lib
 
 

@@ -120,6 +120,8 @@ bool tc_supported(const RayK& k, int hidden);
 size_t scatter_scratch_floats(const GridDev& hg);
 int launch_fwd_tc(const RayK& k, int hidden, const GridDev& hg, const GridDev& gg, const rf_ray_params* p, const float* rays_o,
                   const float* rays_d, const float* z_vals, long long P, float* raw, float* feat, cudaStream_t s);
+int launch_points_tc(RayK k, int hidden, const GridDev& hg, const GridDev& gg, const rf_ray_params* p, const float* x, long long n,
+                     int variant, float* raw, float* feat, cudaStream_t s);
 int launch_bwd_tc(const RayK& k, int hidden, const GridDev& hg, const rf_ray_params* p, long long P, const float* feat,
                   const float* d_raw_tot, float* dfeat, const Grads& gr, cudaStream_t s);
 

@@ -47,6 +47,13 @@ __global__ void __launch_bounds__(256) ray_pos_kernel(RayK k, const float* __res
     }
 }
 
+// Point queries (model/scene_rep.py:212-310): positions are given, already normalised: [n][3] -> planes [3][n].
+__global__ void __launch_bounds__(256) point_pos_kernel(const float* __restrict__ x, long long n, float* __restrict__ xn) {
+    const long long i = blockIdx.x * 256ll + threadIdx.x;
+    if (i >= n) return;
+    xn[i] = x[3 * i]; xn[n + i] = x[3 * i + 1]; xn[2 * n + i] = x[3 * i + 2];
+}
+
 // Features.  Thread = (ray, level), blockIdx.y + level0 = level (0..L-1 hash levels, L = GBV); lanes = consecutive rays.
 __global__ void __launch_bounds__(128) encode_walk_kernel(GridDev hg, GridDev gg, const float* __restrict__ hash_params,
                                                           const float* __restrict__ gbv_params, const float* __restrict__ xn,
@@ -205,6 +212,19 @@ static size_t scatter_plan(const GridDev& hg, ScatterRep& rep) {
     return total;
 }
 size_t scatter_scratch_floats(const GridDev& hg) { ScatterRep rep; return 2 * scatter_plan(hg, rep); }
+
+// point queries: n "rays" of one sample each (planes degenerate to [n]; the walk is one step long)
+int launch_encode_points(const GridDev& hg, const GridDev& gg, const rf_ray_params* p, const float* x, long long n, float* feat, cudaStream_t s) {
+    const int L = hg.n_levels;
+    float* xn = feat + (2ll * L + 4) * n;
+    point_pos_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, n, xn);
+    RF_CHECK_LAUNCH("point_pos_kernel");
+    dim3 grid((unsigned)((n + 127) / 128), (unsigned)(L + 1));
+    ProfScope ps(RF_PROF_ENCODE, s);
+    encode_walk_kernel<<<grid, 128, 0, s>>>(hg, gg, p->hash_params, p->gbv_params, xn, n, n, 1, 0, feat);
+    RF_CHECK_LAUNCH("encode_walk_kernel");
+    return 0;
+}
 
 int launch_encode(const RayK& k, const GridDev& hg, const GridDev& gg, const rf_ray_params* p, const float* rays_o, const float* rays_d,
                   const float* z_vals, long long P, float* feat, cudaStream_t s) {

@@ -342,7 +342,7 @@ __device__ __forceinline__ void relu_to_tmem(uint32_t tacc, uint32_t th, uint32_
 
 template <int HID, int G>
 __global__ void __launch_bounds__(G * 128, 1) mlp_fwd_tc_kernel(RayK k, Weights wts, const float* __restrict__ feat, long long P,
-                                                                float* __restrict__ raw) {
+                                                                int variant, float* __restrict__ raw) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint64_t bars[G];
     __shared__ uint32_t tmem_base_s;
@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_fwd_tc_kernel(RayK k, Weights 
         prefetch_tile(feat, P, (tile + 2 * tstep) * kTile, m);
         const float4 gb = t.g;                                                                // GBV features of this tile
         float t_add, cin, d0, d1;
-        tsdf_terms(k, 0, gb.x, t_add, cin, d0, d1);                                           // scene_rep.py:330-337
+        tsdf_terms(k, variant, gb.x, t_add, cin, d0, d1);                                     // scene_rep.py:330-337 (:230-233, :292-294)
         // X row: hash -> TMEM, OneBlob -> shared memory, tail = [0 x15 | gbv rgb | decoder tsdf input | 0] -> TMEM
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -703,7 +703,7 @@ template <int HID, int G> static size_t fwd_bytes() { return (size_t)G * FwdL<HI
 template <int HID, int G> static size_t bwd_bytes() { return (size_t)G * BwdL<HID>::bytes + WL<HID>::total; }
 
 template <int HID, int G>
-static int launch_fwd_g(const RayK& k, const Weights& w, const float* feat, long long P, float* raw, cudaStream_t s) {
+static int launch_fwd_g(const RayK& k, const Weights& w, const float* feat, long long P, int variant, float* raw, cudaStream_t s) {
     auto fn = mlp_fwd_tc_kernel<HID, G>;
     size_t sm = fwd_bytes<HID, G>();
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
@@ -711,7 +711,7 @@ static int launch_fwd_g(const RayK& k, const Weights& w, const float* feat, long
     long long tiles = (P + kTile - 1) / kTile;
     int blocks = (int)std::min<long long>((tiles + G - 1) / G, (long long)num_sms());
     ProfScope ps(RF_PROF_MLP_FWD, s);
-    fn<<<blocks, G * 128, sm, s>>>(k, w, feat, P, raw);
+    fn<<<blocks, G * 128, sm, s>>>(k, w, feat, P, variant, raw);
     RF_CHECK_LAUNCH("mlp_fwd_tc_kernel");
     return 0;
 }
@@ -735,6 +735,7 @@ static int launch_bwd_g(const RayK& k, const Weights& w, const float* feat, long
 int launch_encode(const RayK& k, const GridDev& hg, const GridDev& gg, const rf_ray_params* p, const float* rays_o, const float* rays_d,
                   const float* z_vals, long long P, float* feat, cudaStream_t s);
 int launch_scatter(const RayK& k, const GridDev& hg, long long P, const float* feat, const float* dfeat, float* g_hash, float* g_rep, cudaStream_t s);
+int launch_encode_points(const GridDev& hg, const GridDev& gg, const rf_ray_params* p, const float* x, long long n, float* feat, cudaStream_t s);
 
 bool tc_supported(const RayK& k, int hidden) { return k.n_hash_out == 32 && (hidden == 32 || hidden == 64); }
 
@@ -744,7 +745,17 @@ int launch_fwd_tc(const RayK& k, int hidden, const GridDev& hg, const GridDev& g
     int rc = launch_encode(k, hg, gg, p, rays_o, rays_d, z_vals, P, feat, s);
     if (rc) return rc;
     Weights w{p->w_sdf0, p->w_sdf1, p->w_col0, p->w_col1};
-    return hidden == 64 ? launch_fwd_g<64, 2>(k, w, feat, P, raw, s) : launch_fwd_g<32, 4>(k, w, feat, P, raw, s);
+    return hidden == 64 ? launch_fwd_g<64, 2>(k, w, feat, P, 0, raw, s) : launch_fwd_g<32, 4>(k, w, feat, P, 0, raw, s);
+}
+
+// point queries through the same kernels: n points = n rays of one sample; variant selects the tsdf handling
+int launch_points_tc(RayK k, int hidden, const GridDev& hg, const GridDev& gg, const rf_ray_params* p, const float* x, long long n,
+                     int variant, float* raw, float* feat, cudaStream_t s) {
+    k.n_rays = n; k.S = 1;
+    int rc = launch_encode_points(hg, gg, p, x, n, feat, s);
+    if (rc) return rc;
+    Weights w{p->w_sdf0, p->w_sdf1, p->w_col0, p->w_col1};
+    return hidden == 64 ? launch_fwd_g<64, 2>(k, w, feat, n, variant, raw, s) : launch_fwd_g<32, 4>(k, w, feat, n, variant, raw, s);
 }
 
 // dfeat: 2L * P floats of scratch, followed by scatter_scratch_floats() floats for the table replicas

@@ -734,6 +734,11 @@ extern "C" int64_t rf_ray_workspace_floats(const rf_ray_cfg* cfg, const rf_grid_
     return (int64_t)(2 * hash->n_levels + 4 + 3) * n_rays * (cfg->n_range_d + cfg->n_samples_d);
 }
 
+extern "C" int64_t rf_point_workspace_floats(const rf_ray_cfg* cfg, const rf_grid_desc* hash, int64_t n) {
+    if (!cfg || !hash || cfg->mlp_precision != 1 || n <= 0) return 0;
+    return (int64_t)(2 * hash->n_levels + 4 + 3) * n;
+}
+
 extern "C" int64_t rf_ray_scratch_floats(const rf_ray_cfg* cfg, const rf_grid_desc* hash, int64_t n_rays, int ray_grads) {
     if (!cfg || !hash || n_rays <= 0) return 0;
     const int64_t P = n_rays * (cfg->n_range_d + cfg->n_samples_d);
@@ -744,7 +749,7 @@ extern "C" int64_t rf_ray_scratch_floats(const rf_ray_cfg* cfg, const rf_grid_de
 }
 
 extern "C" int rf_point_query_forward(const rf_ray_cfg* cfg, const rf_grid_desc* hash, const rf_grid_desc* gbv, const rf_ray_params* p,
-                                      const float* x, int64_t n, int variant, float* raw, void* stream) {
+                                      const float* x, int64_t n, int variant, float* raw, float* workspace, void* stream) {
     RayK k;
     int rc = make_rayk(k, cfg, hash, gbv, 0, "rf_point_query_forward"); if (rc) return rc;
     RF_REQUIRE(variant >= 0 && variant <= 2, RF_E_RANGE, "rf_point_query_forward: variant %d", variant);
@@ -755,6 +760,10 @@ extern "C" int rf_point_query_forward(const rf_ray_cfg* cfg, const rf_grid_desc*
     GridDev hg = to_dev(hash), gg = to_dev(gbv);
     cudaStream_t s = (cudaStream_t)stream;
     k.S = 1;
+    if (cfg->mlp_precision == 1 && tc_supported(k, cfg->hidden)) {
+        RF_REQUIRE(workspace && ((uintptr_t)workspace & 15) == 0, RF_E_NULL, "rf_point_query_forward: mlp_precision 1 needs a 16-byte aligned workspace of rf_point_workspace_floats()");
+        return launch_points_tc(k, cfg->hidden, hg, gg, p, x, n, variant, raw, workspace, s);
+    }
     return (cfg->hidden == 64) ? launch_fwd<64, true>(k, hg, gg, p, nullptr, nullptr, nullptr, x, n, variant, raw, s)
                                : launch_fwd<32, true>(k, hg, gg, p, nullptr, nullptr, nullptr, x, n, variant, raw, s);
 }

@@ -273,8 +273,11 @@ class JointEncoding(nn.Module):
         p = abi.RayParams(abi.dptr(self.embed_res_fn.params.detach()), abi.dptr(self.GBV.params.detach()),
                           abi.dptr(w[0].detach()), abi.dptr(w[1].detach()), abi.dptr(w[2].detach()), abi.dptr(w[3].detach()))
         cfg = self._ray_cfg()
+        nws = int(abi.lib().rf_point_workspace_floats(C.byref(cfg), C.byref(self.embed_res_fn.desc), C.c_int64(n)))
+        ws = torch.empty(nws, dtype=torch.float32, device=x.device) if nws > 0 else None
         rc = abi.lib().rf_point_query_forward(C.byref(cfg), C.byref(self.embed_res_fn.desc), C.byref(self.GBV.desc), C.byref(p),
-                                              abi.dptr(x), C.c_int64(n), C.c_int(variant), abi.dptr(raw), abi.stream_ptr())
+                                              abi.dptr(x), C.c_int64(n), C.c_int(variant), abi.dptr(raw), abi.dptr(ws),
+                                              abi.stream_ptr())
         abi.check(rc, "rf_point_query_forward")
         return raw
 

@@ -222,8 +222,9 @@ def test_mapping_matches_cpu_oracle_fresh(cuda, rf_lib, hidden, S_cfg, n, prec):
         _close_grad(w_cuda.grad, w_ref.grad.numpy(), "g_w_" + nm, prec, kink_aware=big)
 
 
-def test_point_queries_match_oracle(cuda, rf_lib):
-    cfg, m = _model_from_golden("A", cuda)
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_point_queries_match_oracle(cuda, rf_lib, prec):
+    cfg, m = _model_from_golden("A", cuda, prec=prec)
     _, orc = R.oracle_from_golden(G, "A", requires_grad=False)
     g = torch.Generator().manual_seed(3)
     x = torch.rand(257, 3, generator=g)
