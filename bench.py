@@ -436,6 +436,9 @@ def run_gpu(args, rank, world, local_rank):
             "tsdf_global": {"achieved": (40.0 * kern["touched_global"] + 16.0 * H * W) / (kern["tsdf_global_ms"] / 1e3) / 1e9, "peak": peak,
                             "frac": (40.0 * kern["touched_global"] + 16.0 * H * W) / (kern["tsdf_global_ms"] / 1e3) / 1e9 / peak,
                             "launch_ms": kern["tsdf_global_ms"]},
+            "tsdf_recenter": {"achieved": 24.0 * kern["swept_local"] / (kern["tsdf_recenter_ms"] / 1e3) / 1e9, "peak": peak,
+                              "frac": 24.0 * kern["swept_local"] / (kern["tsdf_recenter_ms"] / 1e3) / 1e9 / peak,
+                              "launch_ms": kern["tsdf_recenter_ms"], "algorithmic_bytes_per_voxel": 24.0},
             "gather_peak_Gops": kern.get("gather_gops"), "atomic_peak_Gops": kern.get("atomic_gops"),
             # SURVEY §8d gather-bound roofline: t_roof = P*136/G_peak + P*256/A_peak (peaks measured above); frac = t_roof / t_measured
             "ray_fwd_bwd_gather_form": gather_form(P, kern),
@@ -530,6 +533,16 @@ def time_kernels(model, cfg, f, dev, params):
     out["tsdf_local_ms"] = timeit(lambda: vol.integrate_packed(f["depth"], f["packed"], Kmat, f["c2w"], None, 1.0, 0.0))
     tl, tb = vol.count_touched(f["depth"], Kmat, f["c2w"])
     out.update(touched_local=tl, band_local=tb, swept_local=int(np.prod(vol.vol_dim)))
+    # N2: re-centring of the moving volume by one metre along x (ping-pong arrays: 12 B read + 12 B written per voxel)
+    Lb = abi.lib(); Lb.rf_profile_enable(1)
+    b0 = vol.vol_bnds.copy(); acc_r = 0.0
+    for i in range(6):
+        b1 = b0 + (np.array([[1.0], [0.0], [0.0]]) if i % 2 == 0 else 0.0)
+        vol.update_tsdf_swap_rot_trans(b1.copy(), vol.vol_bnds.copy())
+        buf = (C.c_float * 64)(); Lb.rf_profile_read(buf)
+        if i >= 2: acc_r += buf[13]
+    Lb.rf_profile_enable(0)
+    out["tsdf_recenter_ms"] = acc_r / 4
     del vol
     m2 = type("M", (), {})(); m2.GBV = type("E", (), {})(); m2.GBW = type("E", (), {})()
     R = cfg["globalV"]["base_resolution"]

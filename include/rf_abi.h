@@ -60,6 +60,17 @@ int rf_tsdf_integrate_local(float* tsdf, float* weight, float* color,       /* d
                             const float* rcp_lambda,                         /* device [H*W] from rf_tsdf_pixel_lambda, or NULL */
                             void* stream);
 
+/* N2 — re-centring of the moving volume when the camera leaves it.  Replaces `copy_volume` +
+ * `swap_rot_trans` (model/Volume.py:585-610, :128-194; host :796-858, :883-908): every voxel of the NEW volume
+ * (dims dx,dy,dz at `origin`) takes the value of the nearest OLD voxel at the same world position, or (1,0,0) outside
+ * the old volume.  The caller keeps two sets of arrays and swaps them (no backup copy: 24 instead of 48 B/voxel);
+ * new and old arrays must not alias.  `origin` / `old_origin` are the float bounds the reference passes (not truncated). */
+int rf_tsdf_recenter(float* tsdf, float* weight, float* color,                       /* device, written: new volume */
+                     const float* old_tsdf, const float* old_weight, const float* old_color,
+                     int dx, int dy, int dz, const float origin[3],
+                     int odx, int ody, int odz, const float old_origin[3],
+                     float voxel_size, void* stream);
+
 /* The per-pixel factor 1/sqrt(vx^2 + vy^2 + 1), vx = (px - cx)/fx, vy = (py - cy)/fy, of the projective SDF
  * (model/Volume.py:280-283, mp_slam/mapper.py:108-111).  It depends on the intrinsics only, so a caller computes it
  * once per camera and passes it to every integrate; the kernels then load it next to the depth instead of spending two
@@ -268,7 +279,7 @@ int rf_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, i
 #define RF_PROF_SLOTS 64
 enum { RF_PROF_TSDF_LOCAL = 0, RF_PROF_TSDF_GLOBAL = 1, RF_PROF_RAY_Z = 2, RF_PROF_RAY_POS = 3, RF_PROF_ENCODE = 4,
        RF_PROF_MLP_FWD = 5, RF_PROF_COMPOSITE_FWD = 6, RF_PROF_COMPOSITE_BWD = 7, RF_PROF_MLP_BWD = 8,
-       RF_PROF_SCATTER = 9, RF_PROF_SAMPLE_FWD = 10, RF_PROF_SAMPLE_BWD = 11, RF_PROF_RAY_GRAD = 12,
+       RF_PROF_SCATTER = 9, RF_PROF_SAMPLE_FWD = 10, RF_PROF_SAMPLE_BWD = 11, RF_PROF_RAY_GRAD = 12, RF_PROF_TSDF_RECENTER = 13,
        RF_PROF_SCATTER_LEVEL0 = 16 /* +level, only with RF_DEBUG_PER_LEVEL=1 */, RF_PROF_ENCODE_LEVEL0 = 40 /* +level */ };
 int rf_profile_enable(int on);
 int rf_profile_read(float* ms);

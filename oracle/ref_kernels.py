@@ -98,6 +98,21 @@ def ref_integrate_local(tsdf, weight, color, vol_dim, vol_origin, voxel_size, K,
     torch.cuda.synchronize()
 
 
+def ref_recenter(new, old, vol_dim, vol_origin, old_vol_dim, old_origin, voxel_size):
+    """model/Volume.py:796-858: launch the reference `swap_rot_trans` (new <- old).  new / old: lists of three CUDA fp32
+    tensors (tsdf, weight, color); the reference's `old` is its backup copy of the volume (copy_volume, :883-908)."""
+    m = _mod("ref_local_volume.cubin")
+    grid, n_loops = _launch_geometry(int(np.prod(vol_dim)))
+    keep = [_dev(vol_dim), _dev(vol_origin), _dev(old_origin), _dev(old_vol_dim)]
+    for loop in range(n_loops):
+        other = _dev([loop, voxel_size])
+        keep.append(other)
+        m.launch("swap_rot_trans", grid, (1024, 1, 1),
+                 [new[0].data_ptr(), old[0].data_ptr(), new[1].data_ptr(), old[1].data_ptr(), new[2].data_ptr(), old[2].data_ptr(),
+                  keep[0].data_ptr(), keep[1].data_ptr(), keep[2].data_ptr(), keep[3].data_ptr(), other.data_ptr()])
+    torch.cuda.synchronize()
+
+
 def ref_integrate_global(trgb, wgt, R, box, K, c2w, depth, rgb, trunc_margin, obs_weight=1.0):
     """In place on GBV params [R^3*4] and GBW params [R^3] (CUDA fp32).  rgb: CUDA fp32 [H,W,3] in [0,1]."""
     m = _mod("ref_global_volume.cubin")

@@ -112,3 +112,24 @@ def clear_global(trgb):
 def clear_local(tsdf, weight, color):
     lib().oracle_clear_local(tsdf.ctypes.data_as(C.POINTER(C.c_float)), weight.ctypes.data_as(C.POINTER(C.c_float)),
                              color.ctypes.data_as(C.POINTER(C.c_float)), C.c_int64(tsdf.size))
+
+
+def recenter(old_tsdf, old_weight, old_color, old_dim, old_origin, new_dim, new_origin, voxel_size, threads=8):
+    """model/Volume.py:128-194 (swap_rot_trans) on numpy fp32 arrays: returns the three new arrays."""
+    L = lib()
+    n = int(np.prod(new_dim))
+    out = [np.empty(n, np.float32) for _ in range(3)]
+    olds = [np.ascontiguousarray(a, np.float32) for a in (old_tsdf, old_weight, old_color)]
+    dim = np.ascontiguousarray(new_dim, np.int32); odim = np.ascontiguousarray(old_dim, np.int32)
+    org = np.ascontiguousarray(new_origin, np.float32); oorg = np.ascontiguousarray(old_origin, np.float32)
+    P = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+
+    def run(lo, hi):
+        L.oracle_recenter(P(out[0], C.c_float), P(out[1], C.c_float), P(out[2], C.c_float),
+                          P(olds[0], C.c_float), P(olds[1], C.c_float), P(olds[2], C.c_float),
+                          P(dim, C.c_int32), P(org, C.c_float), P(odim, C.c_int32), P(oorg, C.c_float),
+                          C.c_float(voxel_size), C.c_int64(lo), C.c_int64(hi))
+    cuts = np.linspace(0, n, max(1, min(threads * 4, n)) + 1).astype(np.int64)
+    with ThreadPoolExecutor(max_workers=max(1, threads)) as ex:          # ctypes releases the GIL during the call
+        list(ex.map(lambda ab: run(int(ab[0]), int(ab[1])), zip(cuts[:-1], cuts[1:])))
+    return out

@@ -5,8 +5,8 @@ model/ROtracker.py:132,939 can call it unchanged; the work runs in librf_b200.so
 instead of a PyCUDA JIT kernel.  Device memory is held in torch tensors (``tsdf_vol_gpu`` etc. keep the
 reference's names); the raw pointers stay valid for the object's lifetime.
 
-Scope: construction (``center`` bounds, model/Volume.py:1133-1149), ``integrate``, ``clean_volume``.  Volume
-re-centring (copy_volume / swap_rot_trans), point-cloud and mesh dumps are rows N2 / out of scope.
+Scope: construction (``center`` bounds, model/Volume.py:1133-1149), ``integrate``, ``clean_volume`` and the volume
+re-centring ``copy_volume`` / ``update_tsdf_swap_rot_trans`` (N2).  Point-cloud and mesh dumps are out of scope.
 """
 from __future__ import annotations
 
@@ -75,6 +75,48 @@ class moving_volume:
             vol_bnds[ax, 0] = center_cam[ax] - ln
             vol_bnds[ax, 1] = center_cam[ax] + ln
         return vol_bnds
+
+    # ---- re-centring (N2): model/Volume.py:883-908 copy_volume, :796-858 update_tsdf_swap_rot_trans ----------------
+    def copy_volume(self):
+        """The reference copies the live arrays into backup arrays here and gathers from the backup in
+        ``update_tsdf_swap_rot_trans``.  This implementation ping-pongs between two sets of arrays instead, so there is
+        nothing to copy: the live arrays ARE the source of the next swap (half the memory traffic)."""
+        return None
+
+    def update_tsdf_swap_rot_trans(self, vol_bnds, old_bnds):
+        """Move the volume to ``vol_bnds``: every voxel takes the value of the nearest voxel of the old volume
+        (bounds ``old_bnds``) at the same world position, or the cleared value (model/Volume.py:796-858, kernel :128-194)."""
+        if self.x_slab != (0, int(self.vol_dim[0])):
+            raise abi.RfError("re-centring a slab-sharded moving volume is not built (the tracker's volume is single-GPU)")
+        old_dims = tuple(int(d) for d in self.vol_dim)
+        self.vol_bnds = np.asarray(vol_bnds, dtype=np.float64)
+        self.vol_dim = np.ceil((self.vol_bnds[:, 1] - self.vol_bnds[:, 0]) / self.voxel_size).copy(order="C").astype(int)
+        self.vol_bnds[:, 1] = self.vol_bnds[:, 0] + self.vol_dim * self.voxel_size
+        self.vol_origin = self.vol_bnds[:, 0].copy(order="C").astype(np.float32)
+        old_bnds = np.asarray(old_bnds, dtype=np.float64)
+        old_origin = old_bnds[:, 0].copy(order="C").astype(np.float32)
+        old_vol_dim = np.ceil((old_bnds[:, 1] - old_bnds[:, 0]) / self.voxel_size).astype(int)
+        if tuple(int(d) for d in old_vol_dim) != old_dims:
+            raise abi.RfError(f"old_bnds describe {tuple(old_vol_dim)} voxels but the volume holds {old_dims}")
+        dx, dy, dz = (int(d) for d in self.vol_dim)
+        n = dx * dy * dz
+        if n >= 2 ** 31:
+            raise abi.RfError("moving_volume: more than 2^31 voxels")
+        back = getattr(self, "_back", None)
+        if back is None or back[0].numel() != n:
+            back = [torch.empty(n, dtype=torch.float32, device=self.device) for _ in range(3)]
+        _o, o_p = abi.farr(self.vol_origin, 3)
+        _oo, oo_p = abi.farr(old_origin, 3)
+        rc = abi.lib().rf_tsdf_recenter(abi.dptr(back[0]), abi.dptr(back[1]), abi.dptr(back[2]),
+                                        abi.dptr(self.tsdf_vol_gpu), abi.dptr(self.weight_vol_gpu), abi.dptr(self.color_vol_gpu),
+                                        C.c_int(dx), C.c_int(dy), C.c_int(dz), o_p,
+                                        C.c_int(old_dims[0]), C.c_int(old_dims[1]), C.c_int(old_dims[2]), oo_p,
+                                        C.c_float(self.voxel_size), abi.stream_ptr())
+        abi.check(rc, "rf_tsdf_recenter")
+        live = [self.tsdf_vol_gpu, self.weight_vol_gpu, self.color_vol_gpu]
+        self.tsdf_vol_gpu, self.weight_vol_gpu, self.color_vol_gpu = back
+        self._back = live if live[0].numel() == n else None
+        self.x_slab = (0, dx)
 
     # ---- hot path ---------------------------------------------------------------------------------------
     def _stage(self, arr, key):
