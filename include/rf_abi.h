@@ -267,11 +267,13 @@ int rf_microbench_atomic(void* table, int64_t table_bytes, int64_t n_ops, int it
 /* ------------------------------------------------------------------------------------------------
  * N1 — the optimiser step after each backward: torch.optim.Adam as mp_slam/slam.py:271-286 sets it up
  * (betas 0.9/0.99; decoder weight_decay 1e-6; table eps 1e-15), dense torch semantics, one pass; zero_grad != 0 also
- * clears the gradient (mp_slam/mapper.py:423).  All arrays: device fp32 [n], 16-byte aligned.  step = 1 for the first call.
+ * clears the gradient (mp_slam/mapper.py:423).  All arrays: device fp32 [n], 16-byte aligned.  step = 1 for the first call;
+ * step_dev (device float, may be NULL) overrides it with a step count read by the kernel, so that the call can be
+ * captured in a CUDA graph and replayed (torch's `capturable` Adam keeps the same device-side float step).
  * ---------------------------------------------------------------------------------------------- */
 int rf_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                  double lr, double beta1, double beta2, double eps, double weight_decay,
-                 int64_t step, int zero_grad, void* stream);
+                 int64_t step, const float* step_dev, int zero_grad, void* stream);
 
 /* Optional per-kernel timing for bench.py's live roofline numbers.  rf_profile_enable(1) makes the launchers
  * bracket each hot kernel with CUDA events on the launching stream (the last launch of each slot is kept);

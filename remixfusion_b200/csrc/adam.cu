@@ -16,6 +16,7 @@
 namespace rf {
 
 struct AdamK { float w1, beta2, w2, wd, eps, step_size, inv_bc2_sqrt_div; int zero_grad; };
+struct AdamDyn { double lr, beta1, beta2; const float* step; };      // step count read on the device (CUDA-graph capture)
 
 __device__ __forceinline__ void adam_one(float& p, float& g, float& m, float& v, const AdamK& k) {
     float gg = (k.wd != 0.f) ? __fadd_rn(g, __fmul_rn(k.wd, p)) : g;
@@ -27,7 +28,12 @@ __device__ __forceinline__ void adam_one(float& p, float& g, float& m, float& v,
 }
 
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                                                   long long n, AdamK k) {
+                                                   long long n, AdamK k, AdamDyn dyn) {
+    if (dyn.step) {                                        // same float64 scalars the host path derives, from the device step count
+        const double t = (double)__ldg(dyn.step);
+        const double bc1 = 1.0 - pow(dyn.beta1, t), bc2 = 1.0 - pow(dyn.beta2, t);
+        k.step_size = (float)(dyn.lr / bc1); k.inv_bc2_sqrt_div = (float)sqrt(bc2);
+    }
     const long long n4 = n >> 2;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -50,8 +56,9 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float*
 using namespace rf;
 
 extern "C" int rf_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
-                            double beta2, double eps, double weight_decay, int64_t step, int zero_grad, void* stream) {
-    RF_REQUIRE(n >= 0 && step >= 1, RF_E_RANGE, "rf_adam_step: n >= 0 and step >= 1 required");
+                            double beta2, double eps, double weight_decay, int64_t step, const float* step_dev, int zero_grad, void* stream) {
+    RF_REQUIRE(n >= 0 && (step >= 1 || step_dev), RF_E_RANGE, "rf_adam_step: n >= 0 and step >= 1 (or a device step count) required");
+    if (step < 1) step = 1;
     if (n == 0) return 0;
     RF_REQUIRE(param && grad && exp_avg && exp_avg_sq, RF_E_NULL, "rf_adam_step: NULL pointer");
     RF_REQUIRE((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0, RF_E_ALIGN, "rf_adam_step: 16-byte alignment");
@@ -62,7 +69,8 @@ extern "C" int rf_adam_step(float* param, float* grad, float* exp_avg, float* ex
     k.eps = (float)eps; k.step_size = (float)(lr / bc1); k.inv_bc2_sqrt_div = (float)sqrt(bc2); k.zero_grad = zero_grad ? 1 : 0;
     long long n4 = (n + 3) / 4;
     int blocks = (int)std::min<long long>((n4 + 255) / 256, (long long)num_sms() * 8);
-    adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, (long long)n, k);
+    AdamDyn dyn{lr, beta1, beta2, step_dev};
+    adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, (long long)n, k, dyn);
     RF_CHECK_LAUNCH("adam_kernel");
     return 0;
 }

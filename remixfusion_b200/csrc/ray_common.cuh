@@ -117,7 +117,7 @@ struct Grads { float* g_hash; float* g_w_sdf0; float* g_w_sdf1; float* g_w_col0;
 // Tensor-core path (mlp_precision 1): ray_encode.cu (feature planes, table-gradient scatter) + ray_mlp_tc.cu (tcgen05
 // decoder).  Return 0 or an error code with rf_last_error set.
 bool tc_supported(const RayK& k, int hidden);
-size_t scatter_scratch_floats(const GridDev& hg);
+size_t scatter_scratch_floats(const GridDev& hg, long long n_rays);
 int launch_fwd_tc(const RayK& k, int hidden, const GridDev& hg, const GridDev& gg, const rf_ray_params* p, const float* rays_o,
                   const float* rays_d, const float* z_vals, long long P, float* raw, float* feat, cudaStream_t s);
 int launch_points_tc(RayK k, int hidden, const GridDev& hg, const GridDev& gg, const rf_ray_params* p, const float* x, long long n,

@@ -17,6 +17,7 @@
 // Workspace layout (floats), P = n_rays * S:   [0, 2L*P) hash features [L][S][N][2];  [2L*P, 2L*P + 4P) GBV [S][N][4];
 //                                              then xn [3][S][N].
 #include <stdlib.h>
+#include <algorithm>
 #include "ray_common.cuh"
 
 namespace rf {
@@ -196,9 +197,12 @@ __global__ void __launch_bounds__(256) replica_reduce_kernel(GridDev hg, Scatter
 }
 
 // Replication plan: K = 2^20 / size rounded up to a power of two, clamped to [1, 32].  Returns the scratch entries used.
-static size_t scatter_plan(const GridDev& hg, ScatterRep& rep) {
-    static int budget = -1;
-    if (budget < 0) { const char* e = getenv("RF_SCATTER_REPLICA_ENTRIES"); budget = e ? atoi(e) : (1 << 20); }
+static size_t scatter_plan(const GridDev& hg, long long n_rays, ScatterRep& rep) {
+    static int budget0 = -1;
+    if (budget0 < 0) { const char* e = getenv("RF_SCATTER_REPLICA_ENTRIES"); budget0 = e ? atoi(e) : (1 << 20); }
+    // contention grows with the batch: small batches (a few thousand rays, the reference's training batches) get few or
+    // no replicas, so that zeroing and folding them does not become their fixed cost
+    const long long budget = std::min<long long>(budget0, 16 * n_rays);
     size_t total = 0;
     for (int l = 0; l < RF_MAX_LEVELS; ++l) {
         rep.k[l] = 1; rep.base[l] = 0;
@@ -211,7 +215,7 @@ static size_t scatter_plan(const GridDev& hg, ScatterRep& rep) {
     }
     return total;
 }
-size_t scatter_scratch_floats(const GridDev& hg) { ScatterRep rep; return 2 * scatter_plan(hg, rep); }
+size_t scatter_scratch_floats(const GridDev& hg, long long n_rays) { ScatterRep rep; return 2 * scatter_plan(hg, n_rays, rep); }
 
 // point queries: n "rays" of one sample each (planes degenerate to [n]; the walk is one step long)
 int launch_encode_points(const GridDev& hg, const GridDev& gg, const rf_ray_params* p, const float* x, long long n, float* feat, cudaStream_t s) {
@@ -257,7 +261,7 @@ int launch_scatter(const RayK& k, const GridDev& hg, long long P, const float* f
     const int L = hg.n_levels;
     const float* xn = feat + (2ll * L + 4) * P;
     ScatterRep rep;
-    const size_t rep_entries = scatter_plan(hg, rep);
+    const size_t rep_entries = scatter_plan(hg, k.n_rays, rep);
     if (rep_entries) {
         cudaError_t e = cudaMemsetAsync(g_rep, 0, rep_entries * sizeof(float2), s);
         if (e != cudaSuccess) return set_error((int)e, "cudaMemsetAsync(scatter replicas): %s", cudaGetErrorString(e));

@@ -745,7 +745,7 @@ extern "C" int64_t rf_ray_scratch_floats(const rf_ray_cfg* cfg, const rf_grid_de
     if (ray_grads) return 7 * P;
     if (cfg->mlp_precision != 1) return 4 * P;
     GridDev hg = to_dev(hash);
-    return (4 + 2 * hash->n_levels) * P + (int64_t)scatter_scratch_floats(hg);
+    return (4 + 2 * hash->n_levels) * P + (int64_t)scatter_scratch_floats(hg, (long long)n_rays);
 }
 
 extern "C" int rf_point_query_forward(const rf_ray_cfg* cfg, const rf_grid_desc* hash, const rf_grid_desc* gbv, const rf_ray_params* p,

@@ -223,7 +223,9 @@ class JointEncoding(nn.Module):
         S = t["n_range_d"] + t["n_samples_d"]
         cfg = self._ray_cfg()
         if cfg.perturb and u is None:
-            u = torch.rand(n_rays, S).to(dev) if n_rays * S <= (1 << 20) else torch.rand(n_rays, S, device=dev)
+            # a pageable host-to-device copy cannot be captured in a CUDA graph: draw on the device while capturing
+            on_host = n_rays * S <= (1 << 20) and not (dev.type == "cuda" and torch.cuda.is_current_stream_capturing())
+            u = torch.rand(n_rays, S).to(dev) if on_host else torch.rand(n_rays, S, device=dev)
         if u is not None:
             u = u.to(dev, torch.float32).contiguous()
         z_vals = torch.empty(n_rays, S, dtype=torch.float32, device=dev)
