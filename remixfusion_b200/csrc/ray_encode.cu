@@ -58,11 +58,17 @@ __global__ void __launch_bounds__(256) point_pos_kernel(const float* __restrict_
 // Features.  Thread = (ray, level), blockIdx.y + level0 = level (0..L-1 hash levels, L = GBV); lanes = consecutive rays.
 __global__ void __launch_bounds__(128) encode_walk_kernel(GridDev hg, GridDev gg, const float* __restrict__ hash_params,
                                                           const float* __restrict__ gbv_params, const float* __restrict__ xn,
-                                                          long long P, long long N, int S, int level0, float* __restrict__ feat) {
+                                                          long long P, long long N, int S, int seg, int level0, float* __restrict__ feat) {
     const int l = blockIdx.y + level0, L = hg.n_levels;
-    const long long r = blockIdx.x * 128ll + threadIdx.x;
-    if (r >= N) return;
-    const float* xs = xn + r; const float* ys = xn + P + r; const float* zs = xn + 2 * P + r;
+    // unit = (ray, segment of `seg` samples): lanes are consecutive rays of one segment.  Large batches use one segment
+    // (the whole ray); small ones are cut so that the dependent walk is short and the grid fills the machine.
+    const long long unit = blockIdx.x * 128ll + threadIdx.x;
+    const long long r = unit % N;
+    const int s_begin = (int)(unit / N) * seg;
+    if (s_begin >= S) return;
+    const int s_end = min(S, s_begin + seg);
+    const long long first = (long long)s_begin * N + r;
+    const float* xs = xn + first; const float* ys = xn + P + first; const float* zs = xn + 2 * P + first;
     unsigned pcx = 0, pcy = 0, pcz = 0; bool have = false;
     float xa = __ldg(xs), ya = __ldg(ys), za = __ldg(zs);
     CornerIndexer ci;
@@ -71,11 +77,11 @@ __global__ void __launch_bounds__(128) encode_walk_kernel(GridDev hg, GridDev gg
         const float scale = hg.scale[l];
         ci.init(hg.is_hash != 0, hg.size[l], hg.res[l]);
         const float2* tab = reinterpret_cast<const float2*>(hash_params) + hg.offset[l];
-        float2* out = reinterpret_cast<float2*>(feat) + (long long)l * P + r;
+        float2* out = reinterpret_cast<float2*>(feat) + (long long)l * P + first;
         float2 v[8];
-        for (int s = 0; s < S; ++s) {
+        for (int s = s_begin; s < s_end; ++s) {
             const float x = xa, y = ya, z = za;
-            if (s + 1 < S) { xs += N; ys += N; zs += N; xa = __ldg(xs); ya = __ldg(ys); za = __ldg(zs); }
+            if (s + 1 < s_end) { xs += N; ys += N; zs += N; xa = __ldg(xs); ya = __ldg(ys); za = __ldg(zs); }
             unsigned cx, cy, cz; float fx, fy, fz;
             pos_fract(x, scale, cx, fx); pos_fract(y, scale, cy, fy); pos_fract(z, scale, cz, fz);
             if (!have || cx != pcx || cy != pcy || cz != pcz) {
@@ -97,11 +103,11 @@ __global__ void __launch_bounds__(128) encode_walk_kernel(GridDev hg, GridDev gg
         const float scale = gg.scale[0];
         ci.init(false, gg.size[0], gg.res[0]);
         const float4* tab = reinterpret_cast<const float4*>(gbv_params);
-        float4* out = reinterpret_cast<float4*>(feat + 2ll * L * P) + r;
+        float4* out = reinterpret_cast<float4*>(feat + 2ll * L * P) + first;
         float4 v[8];
-        for (int s = 0; s < S; ++s) {
+        for (int s = s_begin; s < s_end; ++s) {
             const float x = xa, y = ya, z = za;
-            if (s + 1 < S) { xs += N; ys += N; zs += N; xa = __ldg(xs); ya = __ldg(ys); za = __ldg(zs); }
+            if (s + 1 < s_end) { xs += N; ys += N; zs += N; xa = __ldg(xs); ya = __ldg(ys); za = __ldg(zs); }
             unsigned cx, cy, cz; float fx, fy, fz;
             pos_fract(x, scale, cx, fx); pos_fract(y, scale, cy, fy); pos_fract(z, scale, cz, fz);
             if (!have || cx != pcx || cy != pcy || cz != pcz) {
@@ -135,16 +141,20 @@ struct ScatterRep {
 };
 
 __global__ void __launch_bounds__(128) scatter_walk_kernel(GridDev hg, ScatterRep rep, const float* __restrict__ xn, const float* __restrict__ dfeat,
-                                                           long long P, long long N, int S, int level0, float* __restrict__ g_hash,
+                                                           long long P, long long N, int S, int seg, int level0, float* __restrict__ g_hash,
                                                            float* __restrict__ g_rep) {
     const int l = blockIdx.y + level0;
-    const long long r = blockIdx.x * 128ll + threadIdx.x;
-    if (r >= N) return;
+    const long long unit = blockIdx.x * 128ll + threadIdx.x;                // (ray, segment), as in encode_walk_kernel
+    const long long r = unit % N;
+    const int s_begin = (int)(unit / N) * seg;
+    if (s_begin >= S) return;
+    const int s_end = min(S, s_begin + seg);
+    const long long first = (long long)s_begin * N + r;
     const unsigned size = hg.size[l];
     float2* gtab = (rep.k[l] > 1) ? reinterpret_cast<float2*>(g_rep) + rep.base[l] + (size_t)(blockIdx.x & (rep.k[l] - 1)) * size
                                   : reinterpret_cast<float2*>(g_hash) + hg.offset[l];
-    const float* xs = xn + r; const float* ys = xn + P + r; const float* zs = xn + 2 * P + r;
-    const float2* dj = reinterpret_cast<const float2*>(dfeat) + (long long)l * P + r;
+    const float* xs = xn + first; const float* ys = xn + P + first; const float* zs = xn + 2 * P + first;
+    const float2* dj = reinterpret_cast<const float2*>(dfeat) + (long long)l * P + first;
     const float scale = hg.scale[l];
     CornerIndexer ci; ci.init(hg.is_hash != 0, size, hg.res[l]);
     unsigned pcx = 0, pcy = 0, pcz = 0; bool have = false, nz = false;
@@ -152,13 +162,13 @@ __global__ void __launch_bounds__(128) scatter_walk_kernel(GridDev hg, ScatterRe
 #pragma unroll
     for (int c = 0; c < 8; ++c) acc[c] = make_float2(0.f, 0.f);
     float xa = __ldg(xs), ya = __ldg(ys), za = __ldg(zs); float2 da = __ldg(dj);
-    for (int s = 0; s <= S; ++s) {
+    for (int s = s_begin; s <= s_end; ++s) {
         unsigned cx = 0, cy = 0, cz = 0; float fx = 0.f, fy = 0.f, fz = 0.f;
         const float2 d = da;
-        const bool last = (s == S);
+        const bool last = (s == s_end);
         if (!last) {
             pos_fract(xa, scale, cx, fx); pos_fract(ya, scale, cy, fy); pos_fract(za, scale, cz, fz);
-            if (s + 1 < S) { xs += N; ys += N; zs += N; dj += N; xa = __ldg(xs); ya = __ldg(ys); za = __ldg(zs); da = __ldg(dj); }
+            if (s + 1 < s_end) { xs += N; ys += N; zs += N; dj += N; xa = __ldg(xs); ya = __ldg(ys); za = __ldg(zs); da = __ldg(dj); }
         }
         if (have && (last || cx != pcx || cy != pcy || cz != pcz)) {
             if (nz) {
@@ -217,6 +227,14 @@ static size_t scatter_plan(const GridDev& hg, long long n_rays, ScatterRep& rep)
 }
 size_t scatter_scratch_floats(const GridDev& hg, long long n_rays) { ScatterRep rep; return 2 * scatter_plan(hg, n_rays, rep); }
 
+// samples per walking thread: the whole ray for big batches; for small ones segments of >= 8 samples such that a level
+// launch has ~32 k threads
+static int walk_segment(long long n_rays, int S) {
+    long long nseg = std::min<long long>((32768 + n_rays - 1) / std::max<long long>(n_rays, 1), std::max(1, S / 8));
+    if (nseg < 1) nseg = 1;
+    return (int)((S + nseg - 1) / nseg);
+}
+
 // point queries: n "rays" of one sample each (planes degenerate to [n]; the walk is one step long)
 int launch_encode_points(const GridDev& hg, const GridDev& gg, const rf_ray_params* p, const float* x, long long n, float* feat, cudaStream_t s) {
     const int L = hg.n_levels;
@@ -225,7 +243,7 @@ int launch_encode_points(const GridDev& hg, const GridDev& gg, const rf_ray_para
     RF_CHECK_LAUNCH("point_pos_kernel");
     dim3 grid((unsigned)((n + 127) / 128), (unsigned)(L + 1));
     ProfScope ps(RF_PROF_ENCODE, s);
-    encode_walk_kernel<<<grid, 128, 0, s>>>(hg, gg, p->hash_params, p->gbv_params, xn, n, n, 1, 0, feat);
+    encode_walk_kernel<<<grid, 128, 0, s>>>(hg, gg, p->hash_params, p->gbv_params, xn, n, n, 1, 1, 0, feat);
     RF_CHECK_LAUNCH("encode_walk_kernel");
     return 0;
 }
@@ -241,17 +259,19 @@ int launch_encode(const RayK& k, const GridDev& hg, const GridDev& gg, const rf_
         ray_pos_kernel<<<(unsigned)((k.n_rays + 31) / 32), 256, 3 * k.S * 33 * sizeof(float), s>>>(k, rays_o, rays_d, z_vals, P, xn);
     }
     RF_CHECK_LAUNCH("ray_pos_kernel");
-    dim3 grid((unsigned)((k.n_rays + 127) / 128), (unsigned)(L + 1));
+    const int seg = walk_segment(k.n_rays, k.S);
+    const long long units = k.n_rays * ((k.S + seg - 1) / seg);
+    dim3 grid((unsigned)((units + 127) / 128), (unsigned)(L + 1));
     if (prof_enabled() && getenv("RF_DEBUG_PER_LEVEL")) {                 // per-level timing (diagnostics only)
         for (int l = 0; l <= L; ++l) {
             ProfScope pl(RF_PROF_ENCODE_LEVEL0 + l, s);
-            encode_walk_kernel<<<dim3(grid.x, 1), 128, 0, s>>>(hg, gg, p->hash_params, p->gbv_params, xn, P, k.n_rays, k.S, l, feat);
+            encode_walk_kernel<<<dim3(grid.x, 1), 128, 0, s>>>(hg, gg, p->hash_params, p->gbv_params, xn, P, k.n_rays, k.S, seg, l, feat);
         }
         RF_CHECK_LAUNCH("encode_walk_kernel");
         return 0;
     }
     ProfScope ps(RF_PROF_ENCODE, s);
-    encode_walk_kernel<<<grid, 128, 0, s>>>(hg, gg, p->hash_params, p->gbv_params, xn, P, k.n_rays, k.S, 0, feat);
+    encode_walk_kernel<<<grid, 128, 0, s>>>(hg, gg, p->hash_params, p->gbv_params, xn, P, k.n_rays, k.S, seg, 0, feat);
     RF_CHECK_LAUNCH("encode_walk_kernel");
     return 0;
 }
@@ -266,15 +286,17 @@ int launch_scatter(const RayK& k, const GridDev& hg, long long P, const float* f
         cudaError_t e = cudaMemsetAsync(g_rep, 0, rep_entries * sizeof(float2), s);
         if (e != cudaSuccess) return set_error((int)e, "cudaMemsetAsync(scatter replicas): %s", cudaGetErrorString(e));
     }
-    const unsigned gx = (unsigned)((k.n_rays + 127) / 128);
+    const int seg = walk_segment(k.n_rays, k.S);
+    const long long units = k.n_rays * ((k.S + seg - 1) / seg);
+    const unsigned gx = (unsigned)((units + 127) / 128);
     if (prof_enabled() && getenv("RF_DEBUG_PER_LEVEL")) {                 // per-level timing (diagnostics only)
         for (int l = 0; l < L; ++l) {
             ProfScope pl(RF_PROF_SCATTER_LEVEL0 + l, s);
-            scatter_walk_kernel<<<dim3(gx, 1), 128, 0, s>>>(hg, rep, xn, dfeat, P, k.n_rays, k.S, l, g_hash, g_rep);
+            scatter_walk_kernel<<<dim3(gx, 1), 128, 0, s>>>(hg, rep, xn, dfeat, P, k.n_rays, k.S, seg, l, g_hash, g_rep);
         }
     } else {
         ProfScope ps(RF_PROF_SCATTER, s);
-        scatter_walk_kernel<<<dim3(gx, L), 128, 0, s>>>(hg, rep, xn, dfeat, P, k.n_rays, k.S, 0, g_hash, g_rep);
+        scatter_walk_kernel<<<dim3(gx, L), 128, 0, s>>>(hg, rep, xn, dfeat, P, k.n_rays, k.S, seg, 0, g_hash, g_rep);
     }
     RF_CHECK_LAUNCH("scatter_walk_kernel");
     if (rep_entries) {
