@@ -260,7 +260,7 @@ def run_gpu(args, rank, world, local_rank):
     K, poses, frames = make_frames(cfg, N_POOL, first=17 * rank, stride=50)
     bb = torch.from_numpy(np.array(cfg["mapping"]["bound"])).to(torch.float64)
     torch.manual_seed(0)
-    model = JointEncoding(cfg, bb, process_group=group).to(dev)
+    model = JointEncoding(cfg, bb, process_group=group, equal_shards=True).to(dev)      # every rank renders one full frame
     with torch.no_grad():
         model.embed_res_fn.params.copy_((torch.rand_like(model.embed_res_fn.params) * 2 - 1) * 1e-2)
     model.train()

@@ -54,9 +54,12 @@ class _RayQueryFn(torch.autograd.Function):
         n_total = n
         if group is not None:
             import torch.distributed as dist
-            cnt = torch.tensor([n], dtype=torch.int64, device=dev)
-            dist.all_reduce(cnt, group=group)
-            n_total = int(cnt.item())
+            if meta.get("equal_shards", False):
+                n_total = n * dist.get_world_size(group)
+            else:
+                cnt = torch.tensor([n], dtype=torch.int64, device=dev)
+                dist.all_reduce(cnt, group=group)
+                n_total = int(cnt.item())
         cfg.n_rays_total = n_total
         nws = int(abi.lib().rf_ray_workspace_floats(C.byref(cfg), C.byref(hdesc), C.c_int64(n)))
         # feature planes of the tensor-core path: written by the forward, re-read by the backward
@@ -124,12 +127,15 @@ class _RayQueryFn(torch.autograd.Function):
 
 
 class JointEncoding(nn.Module):
-    def __init__(self, config, bound_box, num_kf=None, rba_factory=None, process_group=None):
+    def __init__(self, config, bound_box, num_kf=None, rba_factory=None, process_group=None, equal_shards=False):
         super().__init__()
         self.config = config
         self.bounding_box = bound_box                # float64 tensor [3,2] in the reference (run.py:90)
         self.num_kf = num_kf
         self.process_group = process_group           # ray batches sharded over ranks: loss sums are all-reduced
+        # every rank passes the same number of rays to mapping(): the global ray count is then n * world_size and needs
+        # neither a collective nor the host synchronisation of reading it back
+        self.equal_shards = bool(equal_shards)
         self.get_resolution()
         self.get_encoding(config)
         self.get_decoder(config, rba_factory)
@@ -213,7 +219,7 @@ class JointEncoding(nn.Module):
 
     def _meta(self, with_losses):
         return {"cfg": self._ray_cfg(), "hash_desc": self.embed_res_fn.desc, "gbv_desc": self.GBV.desc,
-                "with_losses": with_losses, "group": self.process_group}
+                "with_losses": with_losses, "group": self.process_group, "equal_shards": self.equal_shards}
 
     def sample_z(self, target_d, n_rays, u=None):
         """z_vals [N,S] (model/scene_rep.py:417-441).  `u` injects the jitter (tests); otherwise it is drawn like the
