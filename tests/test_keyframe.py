@@ -7,7 +7,7 @@ import os
 import numpy as np
 import torch
 
-from remixfusion_b200.keyframe import KeyFrameDatabase
+from remixfusion_b200.ray_store import KeyFrameDatabase, _distinct
 
 G = np.load(os.path.join(os.path.dirname(__file__), "golden", "keyframe_golden.npz"))
 
@@ -25,7 +25,7 @@ def _run(device):
     # device-side draws: distinct, in range, right count
     rays2, fids2 = db.sample_global_rays(BS)
     assert rays2.shape == (BS, 7) and fids2.shape == (BS,)
-    idx = db._draw(3 * KEEP, BS)
+    idx = _distinct(3 * KEEP, BS, db.device)
     assert len(torch.unique(idx)) == BS and int(idx.min()) >= 0 and int(idx.max()) < 3 * KEEP
     return db
 
