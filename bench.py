@@ -341,7 +341,7 @@ def run_gpu(args, rank, world, local_rank):
     # ---- warm-up ------------------------------------------------------------------------------------------------
     # the clock sampler is spawned here: NVML start-up stalls the driver for tens of ms and must not land in the timed region
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("RF_BENCH_NO_SAMPLER"):
         sampler.start()
     for i in range(args.warmup):
         step(i, False)
@@ -362,10 +362,15 @@ def run_gpu(args, rank, world, local_rank):
     t_start, t_end = ev(), ev()
     t_start.record()
     evs = []
+    host_t = []
     for i in range(args.steps):
+        h0 = time.perf_counter()
         e, loss = step(args.warmup + i, True)
+        host_t.append((time.perf_counter() - h0) * 1e3)
         evs.append(e)
     t_end.record()
+    if os.environ.get("RF_BENCH_DEBUG"):
+        print(f"[rank {rank}] host ms per step: " + " ".join(f"{x:.2f}" for x in host_t), file=sys.stderr, flush=True)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

@@ -22,6 +22,7 @@
 // streaming); no random access happens here.  Only raw / d_raw ([N][S][4], the reference's layout) are strided.
 #include "ray_common.cuh"
 #include "umma.cuh"
+#include <stdlib.h>
 
 namespace rf {
 namespace {
@@ -699,6 +700,297 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_bwd_tc_kernel(RayK k, Weights 
     if (warp == 0) tmem_dealloc(tmem_base_s, TCOLS);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Backward, two threads per tile row.  Same MMAs, layouts and TMEM map as mlp_bwd_tc_kernel; a group is 256 threads and
+// thread (m, h) handles half h of everything row m stages or reads back (hash levels 8h..8h+7, hidden units
+// [h HID/2, (h+1) HID/2), one of the two D chunks, ...), so the serial SIMT stretch between two tensor-core phases is
+// half as long and a CTA runs 16 warps (hidden 32) instead of 8.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void grp_sync2(int g) { asm volatile("bar.sync %0, 256;" ::"r"(g + 1) : "memory"); }
+
+template <int NC>      // NC (16 | 32) accumulator columns of this lane -> relu -> chunks c0.. ; returns the relu mask
+__device__ __forceinline__ uint32_t relu_half(uint32_t taddr, unsigned char* hi, unsigned char* lo, int m, int c0) {
+    uint32_t mk = 0;
+#pragma unroll
+    for (int q = 0; q < NC / 16; ++q) {
+        float v[16];
+        tmem_ld16(taddr + 16 * q, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { if (v[i] > 0.f) mk |= (1u << (16 * q + i)); v[i] = fmaxf(v[i], 0.f); }
+        stage8(hi, lo, m, c0 + 2 * q, v); stage8(hi, lo, m, c0 + 2 * q + 1, v + 8);
+    }
+    return mk;
+}
+template <int NC>
+__device__ __forceinline__ void masked_half(uint32_t taddr, unsigned char* hi, unsigned char* lo, int m, int c0, uint32_t mask) {
+#pragma unroll
+    for (int q = 0; q < NC / 16; ++q) {
+        float v[16];
+        tmem_ld16(taddr + 16 * q, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = ((mask >> (16 * q + i)) & 1u) ? v[i] : 0.f;
+        stage8(hi, lo, m, c0 + 2 * q, v); stage8(hi, lo, m, c0 + 2 * q + 1, v + 8);
+    }
+}
+
+struct TileHalf { float2 f[8]; float4 g; float x0, x1; };   // h = 0: levels 0-7, x, y; h = 1: levels 8-15, z, GBV texel
+
+__device__ __forceinline__ void load_half(TileHalf& t, const float* __restrict__ feat, long long P, long long p, bool live, int h) {
+    t.g = make_float4(0.f, 0.f, 0.f, 0.f); t.x0 = t.x1 = 0.5f;
+    if (live) {
+        const float2* fh = reinterpret_cast<const float2*>(feat) + (long long)(8 * h) * P;
+#pragma unroll
+        for (int l = 0; l < 8; ++l) t.f[l] = __ldg(fh + (long long)l * P + p);
+        const float* xn = feat + 36ll * P;
+        if (h == 0) { t.x0 = __ldg(xn + p); t.x1 = __ldg(xn + P + p); }
+        else { t.x0 = __ldg(xn + 2 * P + p); t.g = __ldg(reinterpret_cast<const float4*>(feat + 32ll * P) + p); }
+    } else {
+#pragma unroll
+        for (int l = 0; l < 8; ++l) t.f[l] = make_float2(0.f, 0.f);
+    }
+}
+
+// Weight gradients of a group, split between the two threads of a lane: h = 0 flushes dW0^T and dW1^T, h = 1 dW2^T and dW3^T.
+template <int HID>
+__device__ __forceinline__ void flush_wgrads2(uint32_t tlane, const Grads& gr, int f, int h) {
+    using A = BwdL<HID>;
+    fence_after_sync();
+    float* gx = h ? gr.g_w_col0 : gr.g_w_sdf0;
+    const int ld = h ? kIn2 : 81;
+    int c0 = -1;                                              // column of the first-layer weight for X row f
+    if (h == 0) { if (f < 80) c0 = f; else if (f == 80 + kTailTsdf) c0 = 80; }
+    else if (f < kIn2) c0 = f;
+    const uint32_t tx = tlane + (h ? A::t_w2 : A::t_w0);
+#pragma unroll 1
+    for (int q = 0; q < HID / 16; ++q) {                      // X-based: value = (hh + lh)[j] + hl[j]
+        float v[16], u[16];
+        tmem_ld16(tx + 16 * q, v);
+        tmem_ld16(tx + HID + 16 * q, u);
+        if (gx && c0 >= 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) atomicAdd(gx + (16 * q + j) * ld + c0, v[j] + u[j]);
+        }
+    }
+    // H-based: rows [0,HID) = hi features (columns: x hi | x lo), rows [HID,2HID) = lo features (column block x hi)
+    float v32[32];
+    tmem_ld32(tlane + (h ? A::t_w3 : A::t_w1), v32);
+    float* gh = h ? gr.g_w_col1 : gr.g_w_sdf1;
+    const int rows = h ? 3 : 16;
+    if (gh && f < 2 * HID) {
+        const int j = (f < HID) ? f : f - HID;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) if (i < rows) atomicAdd(gh + i * HID + j, (f < HID) ? v32[i] + v32[16 + i] : v32[i]);
+    }
+}
+
+template <int HID, int G>
+__global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights wts, const float* __restrict__ feat, long long P,
+                                                                 const float* __restrict__ d_raw_tot, float* __restrict__ dfeat, Grads gr) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint64_t bars[G];
+    __shared__ uint32_t tmem_base_s;
+    using W = WL<HID>; using A = BwdL<HID>;
+    constexpr int HC = HID / 8, NH = HID / 2;
+    constexpr uint32_t TCOLS = G * A::tcols;
+    const int tid = threadIdx.x, g = tid >> 8, m = tid & 127, h = (tid >> 7) & 1, warp = tid >> 5;
+    unsigned char* wsm = smem + G * A::bytes;                  // after the group regions (see mlp_bwd_tc_kernel)
+    unsigned char* act = smem + g * A::bytes;
+    if (warp == 0) tmem_alloc(&tmem_base_s, TCOLS);
+    if (tid == 0) { for (int i = 0; i < G; ++i) mbar_init(&bars[i], 1); fence_mbar_init(); }
+    load_weights<HID>(wsm, wts, G * 256);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tb = tmem_base_s + (uint32_t)g * A::tcols;
+    const uint32_t tlane = tb + ((uint32_t)((warp & 3) * 32) << 16);
+    const bool issuer = (tid & 255) == 0;
+    uint64_t* bar = &bars[g];
+    uint32_t phase = 0;
+    unsigned char *x_hi = act + A::c_x_hi * kChunkB, *x_lo = act + A::c_x_lo * kChunkB;
+    unsigned char *h1_hi = act + A::c_h1_hi * kChunkB, *h1_lo = act + A::c_h1_lo * kChunkB;
+    unsigned char *h2_hi = act + A::c_h2_hi * kChunkB, *h2_lo = act + A::c_h2_lo * kChunkB;
+    unsigned char *d_hi = act + A::c_d_hi * kChunkB, *d_lo = act + A::c_d_lo * kChunkB;
+    unsigned char *blob_hi = x_hi + kXBlob * kChunkB, *blob_lo = x_lo + kXBlob * kChunkB;
+    unsigned char *tail_hi = x_hi + kXTail * kChunkB, *tail_lo = x_lo + kXTail * kChunkB;
+    const uint32_t w0h = smem_u32(wsm + W::o_w0h), w0l = smem_u32(wsm + W::o_w0l), w1h = smem_u32(wsm + W::o_w1h), w1l = smem_u32(wsm + W::o_w1l);
+    const uint32_t w2h = smem_u32(wsm + W::o_w2h), w2l = smem_u32(wsm + W::o_w2l), w3h = smem_u32(wsm + W::o_w3h), w3l = smem_u32(wsm + W::o_w3l);
+    const uint32_t xh = smem_u32(x_hi), xl = smem_u32(x_lo), h1h = smem_u32(h1_hi), h1l = smem_u32(h1_lo), h2h = smem_u32(h2_hi), h2l = smem_u32(h2_lo);
+    const uint32_t dh = smem_u32(d_hi), dl = smem_u32(d_lo);
+    constexpr uint32_t idH = idesc_bf16(HID, false, false), id16 = idesc_bf16(16, false, false);
+    constexpr uint32_t idH_bm = idesc_bf16(HID, false, true), id16_bm = idesc_bf16(16, false, true), id32_bm = idesc_bf16(32, false, true);
+    constexpr uint32_t idH_mm = idesc_bf16(HID, true, true), id2H_mm = idesc_bf16(2 * HID, true, true), id32_mm = idesc_bf16(32, true, true);
+    uint32_t wacc = 0;
+    int since_flush = 0;
+
+    const long long tstep = (long long)gridDim.x * G;
+    TilePos tp; tp.init(k.n_rays, k.S, ((long long)blockIdx.x * G + g) * kTile, tstep * kTile);
+    TileHalf t;
+    float4 dr_next = make_float4(0.f, 0.f, 0.f, 0.f);
+    {
+        const long long q0 = ((long long)blockIdx.x * G + g) * kTile + m;
+        load_half(t, feat, P, q0, q0 < P, h);
+        if (h && q0 < P) dr_next = __ldg(reinterpret_cast<const float4*>(d_raw_tot) + tp.raw_index(m));
+    }
+    for (long long tile = (long long)blockIdx.x * G + g; tile * kTile < P; tile += tstep, tp.next()) {
+        const long long q = tile * kTile + m;                                                 // plane index s * N + r
+        const bool live = q < P;
+        if (h == 0) prefetch_tile(feat, P, (tile + 2 * tstep) * kTile, m);
+        const float4 dr = dr_next;                                                            // h = 1 only
+        const float gy = t.g.y;
+        {                                                                                     // X row m, half h
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                float v[8] = {t.f[4 * c].x, t.f[4 * c].y, t.f[4 * c + 1].x, t.f[4 * c + 1].y, t.f[4 * c + 2].x, t.f[4 * c + 2].y, t.f[4 * c + 3].x, t.f[4 * c + 3].y};
+                stage8(x_hi, x_lo, m, 2 * h + c, v);
+            }
+            if (h == 0) {
+                if (live) { stage_oneblob(t.x0, blob_hi, blob_lo, m, 0); stage_oneblob(t.x1, blob_hi, blob_lo, m, 2); }
+                else { for (int c = 0; c < 4; ++c) stage_zero(blob_hi, blob_lo, m, c); }
+            } else {
+                if (live) stage_oneblob(t.x0, blob_hi, blob_lo, m, 4);
+                else { stage_zero(blob_hi, blob_lo, m, 4); stage_zero(blob_hi, blob_lo, m, 5); }
+                float t_add, cin, d0, d1;
+                tsdf_terms(k, 0, t.g.x, t_add, cin, d0, d1);
+                stage_zero(tail_hi, tail_lo, m, 0);
+                float v1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, t.g.y};
+                float v2[8] = {t.g.z, t.g.w, cin, 0.f, 0.f, 0.f, 0.f, 0.f};
+                stage8(tail_hi, tail_lo, m, 1, v1);
+                stage8(tail_hi, tail_lo, m, 2, v2);
+                stage_zero(tail_hi, tail_lo, m, 3);
+            }
+        }
+        {                                                                                     // next tile's inputs
+            const long long qn = (tile + tstep) * kTile + m;
+            load_half(t, feat, P, qn, qn < P, h);
+            if (h) {
+                TilePos tn = tp; tn.next();
+                dr_next = (qn < P) ? __ldg(reinterpret_cast<const float4*>(d_raw_tot) + tn.raw_index(m)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        fence_async_smem(); fence_before_sync(); grp_sync2(g);
+        if (issuer) {                                                                         // H1 = X1 W0^T
+            fence_after_sync();
+            uint32_t acc = 0;
+            mma_kk<kXCh / 2>(tb + A::t_a, xh, xl, w0h, w0l, HID, idH, acc);
+            commit(bar);
+        }
+        grp_wait(bar, phase);
+        const uint32_t mask1 = relu_half<NH>(tlane + A::t_a + NH * h, h1_hi, h1_lo, m, (HC / 2) * h);
+        fence_async_smem(); fence_before_sync(); grp_sync2(g);
+        if (issuer) {                                                                         // O = H1 W1^T
+            fence_after_sync();
+            uint32_t acc = 0;
+            mma_kk<HC / 2>(tb + A::t_b, h1h, h1l, w1h, w1l, 16, id16, acc);
+            commit(bar);
+        }
+        grp_wait(bar, phase);
+        {                                                                                     // geo -> tail chunk h
+            float o8[8];
+            if (h == 0) {
+                float o16[16];
+                tmem_ld16(tlane + A::t_b, o16);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o8[i] = o16[1 + i];
+            } else {
+                float o16[16];
+                tmem_ld16(tlane + A::t_b, o16);
+#pragma unroll
+                for (int i = 0; i < 7; ++i) o8[i] = o16[9 + i];
+                o8[7] = gy;
+            }
+            stage8(tail_hi, tail_lo, m, h, o8);
+        }
+        fence_async_smem(); fence_before_sync(); grp_sync2(g);
+        if (issuer) {                                                                         // H2 = X2 W2^T
+            fence_after_sync();
+            uint32_t acc = 0;
+            mma_kk<5>(tb + A::t_a, xh + kXBlob * kChunkB, xl + kXBlob * kChunkB, w2h, w2l, HID, idH, acc);
+            commit(bar);
+        }
+        grp_wait(bar, phase);
+        const uint32_t mask2 = relu_half<NH>(tlane + A::t_a + NH * h, h2_hi, h2_lo, m, (HC / 2) * h);
+        if (h) {                                                                              // dRGB (upstream of :344)
+            float v0[8] = {dr.x, dr.y, dr.z, 0.f, 0.f, 0.f, 0.f, 0.f};
+            stage8(d_hi, d_lo, m, 0, v0);
+        } else {
+            stage_zero(d_hi, d_lo, m, 1);
+        }
+        fence_async_smem(); fence_before_sync(); grp_sync2(g);
+        if (issuer) {
+            fence_after_sync();
+            uint32_t acc = 0;
+            mma_km<1>(tb + A::t_a, dh, dl, w3h, w3l, 16, idH_bm, acc);                        // dH2pre = dRGB W3
+            uint32_t a3 = wacc;
+            mma_mm1(tb + A::t_w3, h2h, dh, id32_mm, a3);                                      // dW3^T += H2^T dRGB
+            commit(bar);
+        }
+        grp_wait(bar, phase);
+        masked_half<NH>(tlane + A::t_a + NH * h, h2_hi, h2_lo, m, (HC / 2) * h, mask2);       // dH2 over H2
+        fence_async_smem(); fence_before_sync(); grp_sync2(g);
+        if (issuer) {
+            fence_after_sync();
+            uint32_t acc = 0;
+            mma_km<HC / 2>(tb + A::t_b, h2h, h2l, w2h + 6 * HID * 16, w2l + 6 * HID * 16, HID, id16_bm, acc);   // d tail[0..15] = dH2 W2[:, 48..63]
+            uint32_t a2 = wacc;
+            mma_mm2(tb + A::t_w2, xh + kXBlob * kChunkB, xl + kXBlob * kChunkB, h2h, id2H_mm, idH_mm, a2);   // dW2^T += X2^T dH2
+            commit(bar);
+        }
+        grp_wait(bar, phase);
+        {                                                                                     // dO = [d sdf, d geo15], chunk 1 - h
+            float dg[16], v[8];
+            tmem_ld16(tlane + A::t_b, dg);
+            if (h) {
+                v[0] = dr.w;
+#pragma unroll
+                for (int i = 0; i < 7; ++i) v[1 + i] = dg[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = dg[7 + i];
+            }
+            stage8(d_hi, d_lo, m, 1 - h, v);
+        }
+        fence_async_smem(); fence_before_sync(); grp_sync2(g);
+        if (issuer) {
+            fence_after_sync();
+            uint32_t acc = 0;
+            mma_km<1>(tb + A::t_a, dh, dl, w1h, w1l, 16, idH_bm, acc);                        // dH1pre = dO W1
+            uint32_t a1 = wacc;
+            mma_mm1(tb + A::t_w1, h1h, dh, id32_mm, a1);                                      // dW1^T += H1^T dO
+            commit(bar);
+        }
+        grp_wait(bar, phase);
+        masked_half<NH>(tlane + A::t_a + NH * h, h1_hi, h1_lo, m, (HC / 2) * h, mask1);       // dH1 over H1
+        fence_async_smem(); fence_before_sync(); grp_sync2(g);
+        if (issuer) {
+            fence_after_sync();
+            uint32_t acc = 0;
+            mma_km<HC / 2>(tb + A::t_a, h1h, h1l, w0h, w0l, HID, id32_bm, acc);               // d hash = dH1 W0[:, 0..31]
+            uint32_t a0 = wacc;
+            mma_mm2(tb + A::t_w0, xh, xl, h1h, id2H_mm, idH_mm, a0);                          // dW0^T += X1^T dH1
+            commit(bar);
+        }
+        wacc = 1;
+        grp_wait(bar, phase);
+        {
+            float dx[16];
+            tmem_ld16(tlane + A::t_a + 16 * h, dx);
+            if (live) {
+                float2* dj = reinterpret_cast<float2*>(dfeat) + (long long)(8 * h) * P;
+#pragma unroll
+                for (int l = 0; l < 8; ++l) dj[(long long)l * P + q] = make_float2(dx[2 * l], dx[2 * l + 1]);
+            }
+        }
+        if (++since_flush == kFlushTiles) { flush_wgrads2<HID>(tlane, gr, m, h); wacc = 0; since_flush = 0; }
+        fence_before_sync();
+    }
+    if (wacc) flush_wgrads2<HID>(tlane, gr, m, h);
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base_s, TCOLS);
+}
+
 template <int HID, int G> static size_t fwd_bytes() { return (size_t)G * FwdL<HID>::bytes + WL<HID>::total; }
 template <int HID, int G> static size_t bwd_bytes() { return (size_t)G * BwdL<HID>::bytes + WL<HID>::total; }
 
@@ -718,14 +1010,15 @@ static int launch_fwd_g(const RayK& k, const Weights& w, const float* feat, long
 template <int HID, int G>
 static int launch_bwd_g(const RayK& k, const Weights& w, const float* feat, long long P, const float* d_raw_tot, float* dfeat, const Grads& gr,
                         cudaStream_t s) {
-    auto fn = mlp_bwd_tc_kernel<HID, G>;
+    static const int tpr = [] { const char* e = getenv("RF_MLP_BWD_TPR"); return e ? atoi(e) : 2; }();
+    auto fn = (tpr == 2) ? mlp_bwd_tc2_kernel<HID, G> : mlp_bwd_tc_kernel<HID, G>;
     size_t sm = bwd_bytes<HID, G>();
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return set_error((int)e, "cudaFuncSetAttribute(mlp_bwd_tc, %zu B): %s", sm, cudaGetErrorString(e));
     long long tiles = (P + kTile - 1) / kTile;
     int blocks = (int)std::min<long long>((tiles + G - 1) / G, (long long)num_sms());
     ProfScope ps(RF_PROF_MLP_BWD, s);
-    fn<<<blocks, G * 128, sm, s>>>(k, w, feat, P, d_raw_tot, dfeat, gr);
+    fn<<<blocks, G * (tpr == 2 ? 256 : 128), sm, s>>>(k, w, feat, P, d_raw_tot, dfeat, gr);
     RF_CHECK_LAUNCH("mlp_bwd_tc_kernel");
     return 0;
 }
