@@ -709,8 +709,31 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_bwd_tc_kernel(RayK k, Weights 
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void grp_sync2(int g) { asm volatile("bar.sync %0, 256;" ::"r"(g + 1) : "memory"); }
 
+// row m, chunk c of a narrow operand that is read both ways: MN-major from shared memory (weight gradients) and as the
+// K-major A operand of the next GEMM from tensor memory (hi block at th, lo block at tl, 4 columns per chunk)
+__device__ __forceinline__ void stage8_both(unsigned char* hi, unsigned char* lo, int m, int c, const float* v, uint32_t th, uint32_t tl) {
+    uint4 h, l; split8(v, h, l);
+    uint32_t off = chunk_off(128, m, c);
+    *reinterpret_cast<uint4*>(hi + off) = h;
+    *reinterpret_cast<uint4*>(lo + off) = l;
+    tmem_st4(th + 4 * c, h);
+    tmem_st4(tl + 4 * c, l);
+}
+// A from TMEM; B = weights stored [brows = K rows][chunks over N], used MN-major (cf. mma_km)
+template <int NKS>
+__device__ __forceinline__ void mma_ts_m(uint32_t d, uint32_t ah, uint32_t al, uint32_t bh, uint32_t bl, int brows, uint32_t idesc, uint32_t& acc) {
+    uint64_t dbh = smem_desc(bh, 128, brows * 16), dbl = smem_desc(bl, 128, brows * 16);
+#pragma unroll
+    for (int s = 0; s < NKS; ++s) {
+        mma_bf16_ts(d, ah + 8 * s, dbh, idesc, acc); acc = 1;
+        mma_bf16_ts(d, ah + 8 * s, dbl, idesc, 1);
+        mma_bf16_ts(d, al + 8 * s, dbh, idesc, 1);
+        dbh = desc_advance(dbh, 2 * 128); dbl = desc_advance(dbl, 2 * 128);
+    }
+}
+
 template <int NC>      // NC (16 | 32) accumulator columns of this lane -> relu -> chunks c0.. ; returns the relu mask
-__device__ __forceinline__ uint32_t relu_half(uint32_t taddr, unsigned char* hi, unsigned char* lo, int m, int c0) {
+__device__ __forceinline__ uint32_t relu_half(uint32_t taddr, unsigned char* hi, unsigned char* lo, int m, int c0, uint32_t th, uint32_t tl) {
     uint32_t mk = 0;
 #pragma unroll
     for (int q = 0; q < NC / 16; ++q) {
@@ -718,19 +741,19 @@ __device__ __forceinline__ uint32_t relu_half(uint32_t taddr, unsigned char* hi,
         tmem_ld16(taddr + 16 * q, v);
 #pragma unroll
         for (int i = 0; i < 16; ++i) { if (v[i] > 0.f) mk |= (1u << (16 * q + i)); v[i] = fmaxf(v[i], 0.f); }
-        stage8(hi, lo, m, c0 + 2 * q, v); stage8(hi, lo, m, c0 + 2 * q + 1, v + 8);
+        stage8_both(hi, lo, m, c0 + 2 * q, v, th, tl); stage8_both(hi, lo, m, c0 + 2 * q + 1, v + 8, th, tl);
     }
     return mk;
 }
 template <int NC>
-__device__ __forceinline__ void masked_half(uint32_t taddr, unsigned char* hi, unsigned char* lo, int m, int c0, uint32_t mask) {
+__device__ __forceinline__ void masked_half(uint32_t taddr, unsigned char* hi, unsigned char* lo, int m, int c0, uint32_t mask, uint32_t th, uint32_t tl) {
 #pragma unroll
     for (int q = 0; q < NC / 16; ++q) {
         float v[16];
         tmem_ld16(taddr + 16 * q, v);
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = ((mask >> (16 * q + i)) & 1u) ? v[i] : 0.f;
-        stage8(hi, lo, m, c0 + 2 * q, v); stage8(hi, lo, m, c0 + 2 * q + 1, v + 8);
+        stage8_both(hi, lo, m, c0 + 2 * q, v, th, tl); stage8_both(hi, lo, m, c0 + 2 * q + 1, v + 8, th, tl);
     }
 }
 
@@ -793,6 +816,11 @@ __global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights
     using W = WL<HID>; using A = BwdL<HID>;
     constexpr int HC = HID / 8, NH = HID / 2;
     constexpr uint32_t TCOLS = G * A::tcols;
+    // work columns: t_a as in BwdL; the 16-column results (O, d geo) alias the first columns of t_a at hidden 32 (its
+    // content is consumed by then), which frees HID columns for the operand slot: [hi HID/2 | lo HID/2] of the narrow
+    // operand the next GEMM reads K-major (H1, dRGB, dH2, dO, dH1 in turn)
+    constexpr uint32_t T_A = A::t_a, T_B = (HID == 32) ? A::t_a : A::t_b, T_S = (HID == 32) ? A::t_a + 32 : A::t_b + 16;
+    static_assert(T_S + HID <= A::tcols, "operand slot exceeds the group's TMEM columns");
     const int tid = threadIdx.x, g = tid >> 8, m = tid & 127, h = (tid >> 7) & 1, warp = tid >> 5;
     unsigned char* wsm = smem + G * A::bytes;                  // after the group regions (see mlp_bwd_tc_kernel)
     unsigned char* act = smem + g * A::bytes;
@@ -805,6 +833,7 @@ __global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights
     fence_after_sync();
     const uint32_t tb = tmem_base_s + (uint32_t)g * A::tcols;
     const uint32_t tlane = tb + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t ts_hi = tlane + T_S, ts_lo = tlane + T_S + NH;
     const bool issuer = (tid & 255) == 0;
     uint64_t* bar = &bars[g];
     uint32_t phase = 0;
@@ -873,16 +902,16 @@ __global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights
         if (issuer) {                                                                         // H1 = X1 W0^T
             fence_after_sync();
             uint32_t acc = 0;
-            mma_kk<kXCh / 2>(tb + A::t_a, xh, xl, w0h, w0l, HID, idH, acc);
+            mma_kk<kXCh / 2>(tb + T_A, xh, xl, w0h, w0l, HID, idH, acc);
             commit(bar);
         }
         grp_wait(bar, phase);
-        const uint32_t mask1 = relu_half<NH>(tlane + A::t_a + NH * h, h1_hi, h1_lo, m, (HC / 2) * h);
-        fence_async_smem(); fence_before_sync(); grp_sync2(g);
+        const uint32_t mask1 = relu_half<NH>(tlane + T_A + NH * h, h1_hi, h1_lo, m, (HC / 2) * h, ts_hi, ts_lo);
+        tmem_st_wait(); fence_async_smem(); fence_before_sync(); grp_sync2(g);
         if (issuer) {                                                                         // O = H1 W1^T
             fence_after_sync();
             uint32_t acc = 0;
-            mma_kk<HC / 2>(tb + A::t_b, h1h, h1l, w1h, w1l, 16, id16, acc);
+            mma_ts<HC / 2>(tb + T_B, tb + T_S, tb + T_S + NH, w1h, w1l, 16, id16, acc);
             commit(bar);
         }
         grp_wait(bar, phase);
@@ -890,12 +919,12 @@ __global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights
             float o8[8];
             if (h == 0) {
                 float o16[16];
-                tmem_ld16(tlane + A::t_b, o16);
+                tmem_ld16(tlane + T_B, o16);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) o8[i] = o16[1 + i];
             } else {
                 float o16[16];
-                tmem_ld16(tlane + A::t_b, o16);
+                tmem_ld16(tlane + T_B, o16);
 #pragma unroll
                 for (int i = 0; i < 7; ++i) o8[i] = o16[9 + i];
                 o8[7] = gy;
@@ -906,33 +935,46 @@ __global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights
         if (issuer) {                                                                         // H2 = X2 W2^T
             fence_after_sync();
             uint32_t acc = 0;
-            mma_kk<5>(tb + A::t_a, xh + kXBlob * kChunkB, xl + kXBlob * kChunkB, w2h, w2l, HID, idH, acc);
+            mma_kk<5>(tb + T_A, xh + kXBlob * kChunkB, xl + kXBlob * kChunkB, w2h, w2l, HID, idH, acc);
             commit(bar);
         }
         grp_wait(bar, phase);
-        const uint32_t mask2 = relu_half<NH>(tlane + A::t_a + NH * h, h2_hi, h2_lo, m, (HC / 2) * h);
+        uint32_t mask2;
+        {                                                                                     // H2 -> shared memory only (no GEMM reads it K-major)
+            uint32_t mk = 0;
+#pragma unroll
+            for (int qq = 0; qq < NH / 16; ++qq) {
+                float v[16];
+                tmem_ld16(tlane + T_A + NH * h + 16 * qq, v);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { if (v[i] > 0.f) mk |= (1u << (16 * qq + i)); v[i] = fmaxf(v[i], 0.f); }
+                stage8(h2_hi, h2_lo, m, (HC / 2) * h + 2 * qq, v); stage8(h2_hi, h2_lo, m, (HC / 2) * h + 2 * qq + 1, v + 8);
+            }
+            mask2 = mk;
+        }
         if (h) {                                                                              // dRGB (upstream of :344)
             float v0[8] = {dr.x, dr.y, dr.z, 0.f, 0.f, 0.f, 0.f, 0.f};
-            stage8(d_hi, d_lo, m, 0, v0);
+            stage8_both(d_hi, d_lo, m, 0, v0, ts_hi, ts_lo);
         } else {
             stage_zero(d_hi, d_lo, m, 1);
+            tmem_st4(ts_hi + 4, make_uint4(0, 0, 0, 0)); tmem_st4(ts_lo + 4, make_uint4(0, 0, 0, 0));
         }
-        fence_async_smem(); fence_before_sync(); grp_sync2(g);
+        tmem_st_wait(); fence_async_smem(); fence_before_sync(); grp_sync2(g);
         if (issuer) {
             fence_after_sync();
             uint32_t acc = 0;
-            mma_km<1>(tb + A::t_a, dh, dl, w3h, w3l, 16, idH_bm, acc);                        // dH2pre = dRGB W3
+            mma_ts_m<1>(tb + T_A, tb + T_S, tb + T_S + NH, w3h, w3l, 16, idH_bm, acc);        // dH2pre = dRGB W3
             uint32_t a3 = wacc;
             mma_mm1(tb + A::t_w3, h2h, dh, id32_mm, a3);                                      // dW3^T += H2^T dRGB
             commit(bar);
         }
         grp_wait(bar, phase);
-        masked_half<NH>(tlane + A::t_a + NH * h, h2_hi, h2_lo, m, (HC / 2) * h, mask2);       // dH2 over H2
-        fence_async_smem(); fence_before_sync(); grp_sync2(g);
+        masked_half<NH>(tlane + T_A + NH * h, h2_hi, h2_lo, m, (HC / 2) * h, mask2, ts_hi, ts_lo);   // dH2 over H2
+        tmem_st_wait(); fence_async_smem(); fence_before_sync(); grp_sync2(g);
         if (issuer) {
             fence_after_sync();
             uint32_t acc = 0;
-            mma_km<HC / 2>(tb + A::t_b, h2h, h2l, w2h + 6 * HID * 16, w2l + 6 * HID * 16, HID, id16_bm, acc);   // d tail[0..15] = dH2 W2[:, 48..63]
+            mma_ts_m<HC / 2>(tb + T_B, tb + T_S, tb + T_S + NH, w2h + 6 * HID * 16, w2l + 6 * HID * 16, HID, id16_bm, acc);   // d tail[0..15] = dH2 W2[:, 48..63]
             uint32_t a2 = wacc;
             mma_mm2(tb + A::t_w2, xh + kXBlob * kChunkB, xl + kXBlob * kChunkB, h2h, id2H_mm, idH_mm, a2);   // dW2^T += X2^T dH2
             commit(bar);
@@ -940,7 +982,7 @@ __global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights
         grp_wait(bar, phase);
         {                                                                                     // dO = [d sdf, d geo15], chunk 1 - h
             float dg[16], v[8];
-            tmem_ld16(tlane + A::t_b, dg);
+            tmem_ld16(tlane + T_B, dg);
             if (h) {
                 v[0] = dr.w;
 #pragma unroll
@@ -949,24 +991,24 @@ __global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = dg[7 + i];
             }
-            stage8(d_hi, d_lo, m, 1 - h, v);
+            stage8_both(d_hi, d_lo, m, 1 - h, v, ts_hi, ts_lo);
         }
-        fence_async_smem(); fence_before_sync(); grp_sync2(g);
+        tmem_st_wait(); fence_async_smem(); fence_before_sync(); grp_sync2(g);
         if (issuer) {
             fence_after_sync();
             uint32_t acc = 0;
-            mma_km<1>(tb + A::t_a, dh, dl, w1h, w1l, 16, idH_bm, acc);                        // dH1pre = dO W1
+            mma_ts_m<1>(tb + T_A, tb + T_S, tb + T_S + NH, w1h, w1l, 16, idH_bm, acc);        // dH1pre = dO W1
             uint32_t a1 = wacc;
             mma_mm1(tb + A::t_w1, h1h, dh, id32_mm, a1);                                      // dW1^T += H1^T dO
             commit(bar);
         }
         grp_wait(bar, phase);
-        masked_half<NH>(tlane + A::t_a + NH * h, h1_hi, h1_lo, m, (HC / 2) * h, mask1);       // dH1 over H1
-        fence_async_smem(); fence_before_sync(); grp_sync2(g);
+        masked_half<NH>(tlane + T_A + NH * h, h1_hi, h1_lo, m, (HC / 2) * h, mask1, ts_hi, ts_lo);   // dH1 over H1
+        tmem_st_wait(); fence_async_smem(); fence_before_sync(); grp_sync2(g);
         if (issuer) {
             fence_after_sync();
             uint32_t acc = 0;
-            mma_km<HC / 2>(tb + A::t_a, h1h, h1l, w0h, w0l, HID, id32_bm, acc);               // d hash = dH1 W0[:, 0..31]
+            mma_ts_m<HC / 2>(tb + T_A, tb + T_S, tb + T_S + NH, w0h, w0l, HID, id32_bm, acc); // d hash = dH1 W0[:, 0..31]
             uint32_t a0 = wacc;
             mma_mm2(tb + A::t_w0, xh, xl, h1h, id2H_mm, idH_mm, a0);                          // dW0^T += X1^T dH1
             commit(bar);
@@ -975,7 +1017,7 @@ __global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights
         grp_wait(bar, phase);
         {
             float dx[16];
-            tmem_ld16(tlane + A::t_a + 16 * h, dx);
+            tmem_ld16(tlane + T_A + 16 * h, dx);
             if (live) {
                 float2* dj = reinterpret_cast<float2*>(dfeat) + (long long)(8 * h) * P;
 #pragma unroll
