@@ -427,6 +427,12 @@ def run_gpu(args, rank, world, local_rank):
             "ray_samples_per_s_fwd_bwd": samples / world / ((stage_ms["ray_fwd"] + stage_ms["ray_bwd"]) / 1e3),
             "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
             "touched_local_per_frame": tl0, "touched_global_per_frame": tg0,
+            # BA mode (gradients w.r.t. rays_o / rays_d as well; SURVEY §8d: 3328 algorithmic bytes per sample), same frame
+            "ba_mode": ({"ray_samples_per_s_fwd_bwd": P / ((kern["ba_fwd_ms"] + kern["ba_bwd_ms"]) / 1e3),
+                         "launch_ms": [kern["ba_fwd_ms"], kern["ba_bwd_ms"]], "kernels_ms": kern["ba_kernels_ms"],
+                         "hbm_form": {"achieved": 3328.0 * P / ((kern["ba_fwd_ms"] + kern["ba_bwd_ms"]) / 1e3) / 1e9, "peak": peak,
+                                      "frac": 3328.0 * P / ((kern["ba_fwd_ms"] + kern["ba_bwd_ms"]) / 1e3) / 1e9 / peak}}
+                        if "ba_fwd_ms" in kern else None),
         },
         "roofline": roof,
         "roofline_parts": {
@@ -600,6 +606,38 @@ def time_kernels(model, cfg, f, dev, params):
         acc += np.maximum(np.array(buf[:], dtype=np.float64), 0.0)
     L.rf_profile_enable(0)
     out["kernels_ms"] = {PROF_NAMES[i]: acc[i] / reps for i in PROF_NAMES if acc[i] > 0}
+    # BA mode (reported separately): clamp variant + gradients w.r.t. rays_o / rays_d on the same frame
+    cfgb = model._ray_cfg(clamp=True)
+    if cfgb.mlp_precision == cfgc.mlp_precision:
+        cfgb.n_rays_total = n
+        g_o = torch.empty(n, 3, device=dev); g_d = torch.empty(n, 3, device=dev)
+        grads_ba = abi.RayGrads(abi.dptr(g_hash), abi.dptr(gws[0]), abi.dptr(gws[1]), abi.dptr(gws[2]), abi.dptr(gws[3]), abi.dptr(g_o), abi.dptr(g_d))
+        del scratch
+        scratch_ba = torch.empty(int(L.rf_ray_scratch_floats(C.byref(cfgb), C.byref(meta["hash_desc"]), C.c_int64(n), C.c_int(1))), device=dev)
+
+        def fwd_ba():
+            part.zero_()
+            abi.check(L.rf_ray_query_forward(C.byref(cfgb), C.byref(meta["hash_desc"]), C.byref(meta["gbv_desc"]), C.byref(p), abi.dptr(f["rays_o"]),
+                                             abi.dptr(f["rays_d"]), abi.dptr(td), abi.dptr(f["tgt_c"]), abi.dptr(z), C.c_int64(n), abi.dptr(raw),
+                                             abi.dptr(rgbm), abi.dptr(dm), abi.dptr(part), abi.dptr(ws), abi.stream_ptr()), "fwd_ba")
+
+        def bwd_ba():
+            abi.check(L.rf_ray_query_backward(C.byref(cfgb), C.byref(meta["hash_desc"]), C.byref(meta["gbv_desc"]), C.byref(p), abi.dptr(f["rays_o"]),
+                                              abi.dptr(f["rays_d"]), abi.dptr(td), abi.dptr(f["tgt_c"]), C.c_int64(n), abi.dptr(z), abi.dptr(raw),
+                                              abi.dptr(rgbm), abi.dptr(dm), None, None, None, abi.dptr(lg), abi.dptr(part), C.byref(grads_ba),
+                                              abi.dptr(ws), abi.dptr(scratch_ba), abi.stream_ptr()), "bwd_ba")
+        out["ba_fwd_ms"] = timeit(fwd_ba, 3)
+        out["ba_bwd_ms"] = timeit(bwd_ba, 3)
+        L.rf_profile_enable(1)
+        accb = np.zeros(64)
+        for _ in range(reps):
+            bwd_ba()
+            buf = (C.c_float * 64)(); L.rf_profile_read(buf)
+            accb += np.maximum(np.array(buf[:], dtype=np.float64), 0.0)
+        L.rf_profile_enable(0)
+        out["ba_kernels_ms"] = {"mlp_bwd_tc_kernel(BA)": accb[8] / reps, "scatter_walk_kernel": accb[9] / reps, "raygrad_walk_kernel": accb[12] / reps,
+                                "sample_bwd_kernel": accb[11] / reps}
+        out["ba_kernels_ms"] = {k: v for k, v in out["ba_kernels_ms"].items() if v > 0}
     if os.environ.get("RF_DEBUG_PER_LEVEL"):
         print("per-level ms: scatter", [round(acc[16 + l] / reps, 3) for l in range(16)], "encode", [round(acc[40 + l] / reps, 3) for l in range(17)], file=sys.stderr)
     # gather / atomic peaks over a 40 MiB table (SURVEY §8d denominators)

@@ -14,8 +14,11 @@
 // per-sample arithmetic (pos = fma(scale, x, 0.5), corner order, fma accumulation order) is the one grid_encode.cuh
 // uses everywhere, so the features are bit-identical to the thread-per-sample fp32 kernels.
 //
+//   raygrad_walk_kernel BA mode (model/scene_rep.py:443 under mp_slam/mapper.py:456,484-485): dL/d rays_o, dL/d rays_d
+//                       through the trilinear weights of the hash levels and the GBV (Appendix B6) + the OneBlob part
+//
 // Workspace layout (floats), P = n_rays * S:   [0, 2L*P) hash features [L][S][N][2];  [2L*P, 2L*P + 4P) GBV [S][N][4];
-//                                              then xn [3][S][N].
+//                                              then xn [3][S][N]; then (rays only) z [S][N].
 #include <stdlib.h>
 #include <algorithm>
 #include "ray_common.cuh"
@@ -28,15 +31,16 @@ namespace rf {
 // the [N][S] read of z_vals and the [S][N] write of the planes are full 128-byte segments.  Block = 32 rays.
 __global__ void __launch_bounds__(256) ray_pos_kernel(RayK k, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                                                       const float* __restrict__ z_vals, long long P, float* __restrict__ xn) {
-    extern __shared__ float sx[];                       // [3][S][33]
+    extern __shared__ float sx[];                       // [4][S][33]: x, y, z of the normalised position, depth along the ray
     const int S = k.S;
     const long long r0 = blockIdx.x * 32ll;
     const int nr = (int)min(32ll, k.n_rays - r0);
     for (int i = threadIdx.x; i < nr * S; i += 256) {
         const int rl = i / S, s = i - rl * S;
         float x[3];
-        sample_x(k, rays_o, rays_d, r0 + rl, z_vals[r0 * S + i], x);
-        sx[s * 33 + rl] = x[0]; sx[(S + s) * 33 + rl] = x[1]; sx[(2 * S + s) * 33 + rl] = x[2];
+        const float zv = z_vals[r0 * S + i];
+        sample_x(k, rays_o, rays_d, r0 + rl, zv, x);
+        sx[s * 33 + rl] = x[0]; sx[(S + s) * 33 + rl] = x[1]; sx[(2 * S + s) * 33 + rl] = x[2]; sx[(3 * S + s) * 33 + rl] = zv;
     }
     __syncthreads();
     for (int j = threadIdx.x; j < 32 * S; j += 256) {
@@ -44,6 +48,7 @@ __global__ void __launch_bounds__(256) ray_pos_kernel(RayK k, const float* __res
         if (rl < nr) {
             const long long q = (long long)s * k.n_rays + r0 + rl;
             xn[q] = sx[s * 33 + rl]; xn[P + q] = sx[(S + s) * 33 + rl]; xn[2 * P + q] = sx[(2 * S + s) * 33 + rl];
+            xn[3 * P + q] = sx[(3 * S + s) * 33 + rl];
         }
     }
 }
@@ -192,6 +197,107 @@ __global__ void __launch_bounds__(128) scatter_walk_kernel(GridDev hg, ScatterRe
     }
 }
 
+
+// Ray gradients (BA mode).  Thread = (ray[, segment], level) as in the other walks: level < L differentiates the
+// trilinear weights of one hash level against the feature gradients dfeat (corner VALUES cached per cell run, Appendix
+// B6); level L does the same for the GBV texel gradient dgb and adds the OneBlob part dxb the decoder backward wrote.
+// Each thread sums d xn and z * d xn over its samples and finishes with six reductions onto the ray's rows:
+//   dL/d rays_o = sum_s dL/d pts,  dL/d rays_d = sum_s z_s dL/d pts,  pts = o + d z,  d pts = d xn / (b1 - b0)  (:443, :388)
+__global__ void __launch_bounds__(128) raygrad_walk_kernel(GridDev hg, GridDev gg, const float* __restrict__ hash_params,
+                                                           const float* __restrict__ gbv_params, const float* __restrict__ xn,
+                                                           const float* __restrict__ dfeat, const float* __restrict__ dgb,
+                                                           const float* __restrict__ dxb, long long P, long long N, int S, int seg,
+                                                           double bl0, double bl1, double bl2, float* __restrict__ g_o, float* __restrict__ g_d) {
+    const int l = blockIdx.y, L = hg.n_levels;
+    const long long unit = blockIdx.x * 128ll + threadIdx.x;
+    const long long r = unit % N;
+    const int s_begin = (int)(unit / N) * seg;
+    if (s_begin >= S) return;
+    const int s_end = min(S, s_begin + seg);
+    const long long first = (long long)s_begin * N + r;
+    const float* xs = xn + first; const float* ys = xn + P + first; const float* zs = xn + 2 * P + first; const float* ts = xn + 3 * P + first;
+    unsigned pcx = 0, pcy = 0, pcz = 0; bool have = false;
+    CornerIndexer ci;
+    unsigned idx[8];
+    float so[3] = {0.f, 0.f, 0.f}, sd[3] = {0.f, 0.f, 0.f};
+    // d/dx of the trilinear interpolant of the corner scalars u[c] (c = cx + 2 cy + 4 cz): differences along one axis,
+    // bilinear weights of the other two
+    auto tri_grad = [](const float (&u)[8], float fx, float fy, float fz, float& gx, float& gy, float& gz) {
+        const float ax = 1.f - fx, ay = 1.f - fy, az = 1.f - fz;
+        const float w00 = ay * az, w10 = fy * az, w01 = ay * fz, w11 = fy * fz;          // (y, z)
+        gx = (u[1] - u[0]) * w00 + (u[3] - u[2]) * w10 + (u[5] - u[4]) * w01 + (u[7] - u[6]) * w11;
+        const float x00 = ax * az, x10 = fx * az, x01 = ax * fz, x11 = fx * fz;          // (x, z)
+        gy = (u[2] - u[0]) * x00 + (u[3] - u[1]) * x10 + (u[6] - u[4]) * x01 + (u[7] - u[5]) * x11;
+        const float y00 = ax * ay, y10 = fx * ay, y01 = ax * fy, y11 = fx * fy;          // (x, y)
+        gz = (u[4] - u[0]) * y00 + (u[5] - u[1]) * y10 + (u[6] - u[2]) * y01 + (u[7] - u[3]) * y11;
+    };
+    float xa = __ldg(xs), ya = __ldg(ys), za = __ldg(zs), ta = __ldg(ts);
+    if (l < L) {
+        const float scale = hg.scale[l];
+        ci.init(hg.is_hash != 0, hg.size[l], hg.res[l]);
+        const float2* tab = reinterpret_cast<const float2*>(hash_params) + hg.offset[l];
+        const float2* dj = reinterpret_cast<const float2*>(dfeat) + (long long)l * P + first;
+        float2 v[8];
+        float2 da = __ldg(dj);
+        for (int s = s_begin; s < s_end; ++s) {
+            const float x = xa, y = ya, z = za, t = ta; const float2 d = da;
+            if (s + 1 < s_end) { xs += N; ys += N; zs += N; ts += N; dj += N; xa = __ldg(xs); ya = __ldg(ys); za = __ldg(zs); ta = __ldg(ts); da = __ldg(dj); }
+            if (d.x == 0.f && d.y == 0.f) continue;                      // masked sample: no gradient
+            unsigned cx, cy, cz; float fx, fy, fz;
+            pos_fract(x, scale, cx, fx); pos_fract(y, scale, cy, fy); pos_fract(z, scale, cz, fz);
+            if (!have || cx != pcx || cy != pcy || cz != pcz) {
+                ci.cell(cx, cy, cz, idx);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) v[c] = __ldg(tab + idx[c]);
+                pcx = cx; pcy = cy; pcz = cz; have = true;
+            }
+            float u[8], gx, gy, gz;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) u[c] = fmaf(d.x, v[c].x, d.y * v[c].y);
+            tri_grad(u, fx, fy, fz, gx, gy, gz);
+            const float dx0 = gx * scale, dx1 = gy * scale, dx2 = gz * scale;
+            so[0] += dx0; so[1] += dx1; so[2] += dx2;
+            sd[0] = fmaf(t, dx0, sd[0]); sd[1] = fmaf(t, dx1, sd[1]); sd[2] = fmaf(t, dx2, sd[2]);
+        }
+    } else {
+        const float scale = gg.scale[0];
+        ci.init(false, gg.size[0], gg.res[0]);
+        const float4* tab = reinterpret_cast<const float4*>(gbv_params);
+        const float4* dj = reinterpret_cast<const float4*>(dgb) + first;
+        const float* b0 = dxb + first; const float* b1 = dxb + P + first; const float* b2 = dxb + 2 * P + first;
+        float4 v[8];
+        float4 da = __ldg(dj); float ba0 = __ldg(b0), ba1 = __ldg(b1), ba2 = __ldg(b2);
+        for (int s = s_begin; s < s_end; ++s) {
+            const float x = xa, y = ya, z = za, t = ta; const float4 d = da; const float e0 = ba0, e1 = ba1, e2 = ba2;
+            if (s + 1 < s_end) {
+                xs += N; ys += N; zs += N; ts += N; dj += N; b0 += N; b1 += N; b2 += N;
+                xa = __ldg(xs); ya = __ldg(ys); za = __ldg(zs); ta = __ldg(ts); da = __ldg(dj); ba0 = __ldg(b0); ba1 = __ldg(b1); ba2 = __ldg(b2);
+            }
+            unsigned cx, cy, cz; float fx, fy, fz;
+            pos_fract(x, scale, cx, fx); pos_fract(y, scale, cy, fy); pos_fract(z, scale, cz, fz);
+            if (!have || cx != pcx || cy != pcy || cz != pcz) {
+                ci.cell(cx, cy, cz, idx);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) v[c] = __ldg(tab + idx[c]);
+                pcx = cx; pcy = cy; pcz = cz; have = true;
+            }
+            float u[8], gx, gy, gz;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) u[c] = d.x * v[c].x + d.y * v[c].y + d.z * v[c].z + d.w * v[c].w;
+            tri_grad(u, fx, fy, fz, gx, gy, gz);
+            const float dx0 = fmaf(gx, scale, e0), dx1 = fmaf(gy, scale, e1), dx2 = fmaf(gz, scale, e2);
+            so[0] += dx0; so[1] += dx1; so[2] += dx2;
+            sd[0] = fmaf(t, dx0, sd[0]); sd[1] = fmaf(t, dx1, sd[1]); sd[2] = fmaf(t, dx2, sd[2]);
+        }
+    }
+    const double bl[3] = {bl0, bl1, bl2};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        if (g_o && so[a] != 0.f) atomicAdd(g_o + 3 * r + a, (float)((double)so[a] / bl[a]));
+        if (g_d && sd[a] != 0.f) atomicAdd(g_d + 3 * r + a, (float)((double)sd[a] / bl[a]));
+    }
+}
+
 // g_hash[level entries] += sum over the level's replicas.  blockIdx.y = level.
 __global__ void __launch_bounds__(256) replica_reduce_kernel(GridDev hg, ScatterRep rep, const float* __restrict__ g_rep, float* __restrict__ g_hash) {
     const int l = blockIdx.y;
@@ -254,9 +360,9 @@ int launch_encode(const RayK& k, const GridDev& hg, const GridDev& gg, const rf_
     float* xn = feat + (2ll * L + 4) * P;
     {
         static bool attr_done = false;
-        if (!attr_done) { cudaFuncSetAttribute(ray_pos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * kMaxS * 33 * (int)sizeof(float)); attr_done = true; }
+        if (!attr_done) { cudaFuncSetAttribute(ray_pos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kMaxS * 33 * (int)sizeof(float)); attr_done = true; }
         ProfScope ps(RF_PROF_RAY_POS, s);
-        ray_pos_kernel<<<(unsigned)((k.n_rays + 31) / 32), 256, 3 * k.S * 33 * sizeof(float), s>>>(k, rays_o, rays_d, z_vals, P, xn);
+        ray_pos_kernel<<<(unsigned)((k.n_rays + 31) / 32), 256, 4 * k.S * 33 * sizeof(float), s>>>(k, rays_o, rays_d, z_vals, P, xn);
     }
     RF_CHECK_LAUNCH("ray_pos_kernel");
     const int seg = walk_segment(k.n_rays, k.S);
@@ -303,6 +409,25 @@ int launch_scatter(const RayK& k, const GridDev& hg, long long P, const float* f
         replica_reduce_kernel<<<dim3(64, L), 256, 0, s>>>(hg, rep, g_rep, g_hash);
         RF_CHECK_LAUNCH("replica_reduce_kernel");
     }
+    return 0;
+}
+
+
+// BA mode: dfeat [L][P][2], dgb [P][4], dxb [3][P] (all sample-major planes) -> g_rays_o / g_rays_d [N][3] (overwritten)
+int launch_raygrad(const RayK& k, const GridDev& hg, const GridDev& gg, const rf_ray_params* p, long long P, const float* feat,
+                   const float* dfeat, const float* dgb, const float* dxb, float* g_o, float* g_d, cudaStream_t s) {
+    const int L = hg.n_levels;
+    const float* xn = feat + (2ll * L + 4) * P;
+    cudaError_t e = cudaSuccess;
+    if (g_o) e = cudaMemsetAsync(g_o, 0, 3 * k.n_rays * sizeof(float), s);
+    if (e == cudaSuccess && g_d) e = cudaMemsetAsync(g_d, 0, 3 * k.n_rays * sizeof(float), s);
+    if (e != cudaSuccess) return set_error((int)e, "cudaMemsetAsync(ray gradients): %s", cudaGetErrorString(e));
+    const int seg = walk_segment(k.n_rays, k.S);
+    const long long units = k.n_rays * ((k.S + seg - 1) / seg);
+    ProfScope ps(RF_PROF_RAY_GRAD, s);
+    raygrad_walk_kernel<<<dim3((unsigned)((units + 127) / 128), L + 1), 128, 0, s>>>(hg, gg, p->hash_params, p->gbv_params, xn, dfeat, dgb, dxb, P,
+                                                                                   k.n_rays, k.S, seg, k.bl[0], k.bl[1], k.bl[2], g_o, g_d);
+    RF_CHECK_LAUNCH("raygrad_walk_kernel");
     return 0;
 }
 

@@ -757,17 +757,20 @@ __device__ __forceinline__ void masked_half(uint32_t taddr, unsigned char* hi, u
     }
 }
 
-struct TileHalf { float2 f[8]; float4 g; float x0, x1; };   // h = 0: levels 0-7, x, y; h = 1: levels 8-15, z, GBV texel
+struct TileHalf { float2 f[8]; float4 g; float x0, x1, xb; };   // h = 0: levels 0-7, x, y; h = 1: levels 8-15, z, GBV texel
 
+// xb (BA mode): the second coordinate whose OneBlob gradient this thread reduces: h = 0 handles x then z, h = 1 handles
+// y then the GBV texel gradient
+template <bool BA>
 __device__ __forceinline__ void load_half(TileHalf& t, const float* __restrict__ feat, long long P, long long p, bool live, int h) {
-    t.g = make_float4(0.f, 0.f, 0.f, 0.f); t.x0 = t.x1 = 0.5f;
+    t.g = make_float4(0.f, 0.f, 0.f, 0.f); t.x0 = t.x1 = t.xb = 0.5f;
     if (live) {
         const float2* fh = reinterpret_cast<const float2*>(feat) + (long long)(8 * h) * P;
 #pragma unroll
         for (int l = 0; l < 8; ++l) t.f[l] = __ldg(fh + (long long)l * P + p);
         const float* xn = feat + 36ll * P;
-        if (h == 0) { t.x0 = __ldg(xn + p); t.x1 = __ldg(xn + P + p); }
-        else { t.x0 = __ldg(xn + 2 * P + p); t.g = __ldg(reinterpret_cast<const float4*>(feat + 32ll * P) + p); }
+        if (h == 0) { t.x0 = __ldg(xn + p); t.x1 = __ldg(xn + P + p); if (BA) t.xb = __ldg(xn + 2 * P + p); }
+        else { t.x0 = __ldg(xn + 2 * P + p); t.g = __ldg(reinterpret_cast<const float4*>(feat + 32ll * P) + p); if (BA) t.xb = __ldg(xn + P + p); }
     } else {
 #pragma unroll
         for (int l = 0; l < 8; ++l) t.f[l] = make_float2(0.f, 0.f);
@@ -807,9 +810,39 @@ __device__ __forceinline__ void flush_wgrads2(uint32_t tlane, const Grads& gr, i
     }
 }
 
-template <int HID, int G>
+// sum_k d blob_k / dx * g_k for the 16 bins of one coordinate (Appendix B7 derivative: d out_k / dx = pdf_k - pdf_{k+1} at the
+// bin boundaries).  As in stage_oneblob, inside [-0.9, 1.9] only the two boundaries next to x have a non-zero kernel
+// value, so three bins carry gradient; elsewhere the general form.
+__device__ __forceinline__ float oneblob_dot_grad(float x, const float (&g)[16]) {
+    float acc = 0.f;
+    if (x > -0.9f && x < 1.9f) {
+        float xw = x - floorf(x);
+        if (xw >= 1.0f) xw = 0.0f;
+        const float t = xw * (float)kNB;
+        const int b = (int)t;
+        const float ub = (float)b - t;
+        const float pb = quartic_pdf(ub / (float)kNB, (float)kNB), pb1 = quartic_pdf((ub + 1.0f) / (float)kNB, (float)kNB);
+        const int km = (b - 1) & (kNB - 1), kp = (b + 1) & (kNB - 1);
+#pragma unroll
+        for (int k = 0; k < kNB; ++k) {
+            const float w = (k == km ? -pb : 0.f) + (k == b ? pb - pb1 : 0.f) + (k == kp ? pb1 : 0.f);
+            acc = fmaf(w, g[k], acc);
+        }
+    } else {
+        float gb[kNB];
+        oneblob_coord_grad<kNB>(x, gb);
+#pragma unroll
+        for (int k = 0; k < kNB; ++k) acc = fmaf(gb[k], g[k], acc);
+    }
+    return acc;
+}
+
+// BA: additionally writes, per sample, the gradient w.r.t. the GBV texel (dgb [P][4]) and the OneBlob part of the
+// gradient w.r.t. the normalised position (dxb [3][P]) for raygrad_walk_kernel: one more tensor-core phase per tile.
+template <int HID, int G, bool BA>
 __global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights wts, const float* __restrict__ feat, long long P,
-                                                                 const float* __restrict__ d_raw_tot, float* __restrict__ dfeat, Grads gr) {
+                                                                 const float* __restrict__ d_raw_tot, float* __restrict__ dfeat, Grads gr,
+                                                                 float* __restrict__ dgb, float* __restrict__ dxb) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint64_t bars[G];
     __shared__ uint32_t tmem_base_s;
@@ -859,7 +892,7 @@ __global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights
     float4 dr_next = make_float4(0.f, 0.f, 0.f, 0.f);
     {
         const long long q0 = ((long long)blockIdx.x * G + g) * kTile + m;
-        load_half(t, feat, P, q0, q0 < P, h);
+        load_half<BA>(t, feat, P, q0, q0 < P, h);
         if (h && q0 < P) dr_next = __ldg(reinterpret_cast<const float4*>(d_raw_tot) + tp.raw_index(m));
     }
     for (long long tile = (long long)blockIdx.x * G + g; tile * kTile < P; tile += tstep, tp.next()) {
@@ -868,6 +901,7 @@ __global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights
         if (h == 0) prefetch_tile(feat, P, (tile + 2 * tstep) * kTile, m);
         const float4 dr = dr_next;                                                            // h = 1 only
         const float gy = t.g.y;
+        const float xg1 = h ? t.xb : t.x0, xg2 = h ? t.g.x : t.xb;                            // BA: see load_half
         {                                                                                     // X row m, half h
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
@@ -892,7 +926,7 @@ __global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights
         }
         {                                                                                     // next tile's inputs
             const long long qn = (tile + tstep) * kTile + m;
-            load_half(t, feat, P, qn, qn < P, h);
+            load_half<BA>(t, feat, P, qn, qn < P, h);
             if (h) {
                 TilePos tn = tp; tn.next();
                 dr_next = (qn < P) ? __ldg(reinterpret_cast<const float4*>(d_raw_tot) + tn.raw_index(m)) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1008,7 +1042,15 @@ __global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights
         if (issuer) {
             fence_after_sync();
             uint32_t acc = 0;
-            mma_ts_m<HC / 2>(tb + T_A, tb + T_S, tb + T_S + NH, w0h, w0l, HID, id32_bm, acc); // d hash = dH1 W0[:, 0..31]
+            if constexpr (BA) {
+                // d [hash | blob(x, y)] = dH1 W0[:, 0..63] (+ dH2 W2[:, blob(x, y)]): 64 columns from T_A, over the operand slot
+                constexpr uint32_t id64_bm = idesc_bf16(64, false, true);
+                mma_km<HC / 2>(tb + T_A, h1h, h1l, w0h, w0l, HID, id64_bm, acc);
+                uint32_t one = 1;
+                mma_km<HC / 2>(tb + T_A + 32, h2h, h2l, w2h, w2l, HID, id32_bm, one);
+            } else {
+                mma_ts_m<HC / 2>(tb + T_A, tb + T_S, tb + T_S + NH, w0h, w0l, HID, id32_bm, acc); // d hash = dH1 W0[:, 0..31]
+            }
             uint32_t a0 = wacc;
             mma_mm2(tb + A::t_w0, xh, xl, h1h, id2H_mm, idH_mm, a0);                          // dW0^T += X1^T dH1
             commit(bar);
@@ -1022,6 +1064,39 @@ __global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights
                 float2* dj = reinterpret_cast<float2*>(dfeat) + (long long)(8 * h) * P;
 #pragma unroll
                 for (int l = 0; l < 8; ++l) dj[(long long)l * P + q] = make_float2(dx[2 * l], dx[2 * l + 1]);
+            }
+        }
+        if constexpr (BA) {
+            {                                                                                 // OneBlob gradient of x (h = 0) / y (h = 1)
+                float gb[16];
+                tmem_ld16(tlane + T_A + 32 + 16 * h, gb);
+                if (live) dxb[(long long)h * P + q] = oneblob_dot_grad(xg1, gb);
+            }
+            fence_before_sync(); grp_sync2(g);
+            if (issuer) {
+                // [blob(z) | tail 0..15] -> columns 0..31, tail 16..31 -> columns 32..47, from both nets
+                fence_after_sync();
+                uint32_t acc = 0;
+                mma_km<HC / 2>(tb + T_A, h1h, h1l, w0h + 8 * HID * 16, w0l + 8 * HID * 16, HID, id32_bm, acc);
+                mma_km<HC / 2>(tb + T_A, h2h, h2l, w2h + 4 * HID * 16, w2l + 4 * HID * 16, HID, id32_bm, acc);
+                acc = 0;
+                mma_km<HC / 2>(tb + T_A + 32, h1h, h1l, w0h + 12 * HID * 16, w0l + 12 * HID * 16, HID, id16_bm, acc);
+                mma_km<HC / 2>(tb + T_A + 32, h2h, h2l, w2h + 8 * HID * 16, w2l + 8 * HID * 16, HID, id16_bm, acc);
+                commit(bar);
+            }
+            grp_wait(bar, phase);
+            if (h == 0) {
+                float gb[16];
+                tmem_ld16(tlane + T_A, gb);
+                if (live) dxb[2 * P + q] = oneblob_dot_grad(xg2, gb);
+            } else {
+                float ta[16], tc[16];
+                tmem_ld16(tlane + T_A + 16, ta);                                              // tail 0..15: [geo15 | gbv r]
+                tmem_ld16(tlane + T_A + 32, tc);                                              // tail 16..31: [gbv g, b | decoder tsdf input | 0]
+                float t_add, cin, dg_add, dg_cin;
+                tsdf_terms(k, 0, xg2, t_add, cin, dg_add, dg_cin);
+                // GBV texel gradient: colour-net inputs + the residual adds (:344-345); tsdf through the decoder input and the add
+                if (live) reinterpret_cast<float4*>(dgb)[q] = make_float4(tc[2] * dg_cin + dr.w * dg_add, ta[15] + dr.x, tc[0] + dr.y, tc[1] + dr.z);
             }
         }
         if (++since_flush == kFlushTiles) { flush_wgrads2<HID>(tlane, gr, m, h); wacc = 0; since_flush = 0; }
@@ -1051,16 +1126,22 @@ static int launch_fwd_g(const RayK& k, const Weights& w, const float* feat, long
 }
 template <int HID, int G>
 static int launch_bwd_g(const RayK& k, const Weights& w, const float* feat, long long P, const float* d_raw_tot, float* dfeat, const Grads& gr,
-                        cudaStream_t s) {
+                        float* dgb, float* dxb, cudaStream_t s) {
+    // RF_MLP_BWD_TPR=1 selects the one-thread-per-row kernel (kept for A/B timing; it has no ray gradients)
     static const int tpr = [] { const char* e = getenv("RF_MLP_BWD_TPR"); return e ? atoi(e) : 2; }();
-    auto fn = (tpr == 2) ? mlp_bwd_tc2_kernel<HID, G> : mlp_bwd_tc_kernel<HID, G>;
+    const bool ba = dgb != nullptr;
+    const bool one = tpr == 1 && !ba;
+    auto fn2 = ba ? mlp_bwd_tc2_kernel<HID, G, true> : mlp_bwd_tc2_kernel<HID, G, false>;
+    auto fn1 = mlp_bwd_tc_kernel<HID, G>;
     size_t sm = bwd_bytes<HID, G>();
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    cudaError_t e = one ? cudaFuncSetAttribute(fn1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)
+                        : cudaFuncSetAttribute(fn2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return set_error((int)e, "cudaFuncSetAttribute(mlp_bwd_tc, %zu B): %s", sm, cudaGetErrorString(e));
     long long tiles = (P + kTile - 1) / kTile;
     int blocks = (int)std::min<long long>((tiles + G - 1) / G, (long long)num_sms());
     ProfScope ps(RF_PROF_MLP_BWD, s);
-    fn<<<blocks, G * (tpr == 2 ? 256 : 128), sm, s>>>(k, w, feat, P, d_raw_tot, dfeat, gr);
+    if (one) fn1<<<blocks, G * 128, sm, s>>>(k, w, feat, P, d_raw_tot, dfeat, gr);
+    else fn2<<<blocks, G * 256, sm, s>>>(k, w, feat, P, d_raw_tot, dfeat, gr, dgb, dxb);
     RF_CHECK_LAUNCH("mlp_bwd_tc_kernel");
     return 0;
 }
@@ -1074,7 +1155,7 @@ int launch_encode_points(const GridDev& hg, const GridDev& gg, const rf_ray_para
 
 bool tc_supported(const RayK& k, int hidden) { return k.n_hash_out == 32 && (hidden == 32 || hidden == 64); }
 
-// workspace `feat`: (2L + 4 + 3) * P floats written here and read back by launch_bwd_tc
+// workspace `feat`: (2L + 4 + 3 + 1) * P floats written here and read back by launch_bwd_tc
 int launch_fwd_tc(const RayK& k, int hidden, const GridDev& hg, const GridDev& gg, const rf_ray_params* p, const float* rays_o,
                   const float* rays_d, const float* z_vals, long long P, float* raw, float* feat, cudaStream_t s) {
     int rc = launch_encode(k, hg, gg, p, rays_o, rays_d, z_vals, P, feat, s);
@@ -1093,13 +1174,21 @@ int launch_points_tc(RayK k, int hidden, const GridDev& hg, const GridDev& gg, c
     return hidden == 64 ? launch_fwd_g<64, 2>(k, w, feat, n, variant, raw, s) : launch_fwd_g<32, 4>(k, w, feat, n, variant, raw, s);
 }
 
-// dfeat: 2L * P floats of scratch, followed by scatter_scratch_floats() floats for the table replicas
-int launch_bwd_tc(const RayK& k, int hidden, const GridDev& hg, const rf_ray_params* p, long long P, const float* feat,
-                  const float* d_raw_tot, float* dfeat, const Grads& gr, cudaStream_t s) {
+// dfeat: 2L * P floats of scratch, then (ray gradients only) 4P + 3P floats for the GBV-texel and OneBlob gradients,
+// then scatter_scratch_floats() floats for the table replicas
+int launch_bwd_tc(const RayK& k, int hidden, const GridDev& hg, const GridDev& gg, const rf_ray_params* p, long long P, const float* feat,
+                  const float* d_raw_tot, float* dfeat, const Grads& gr, float* g_rays_o, float* g_rays_d, cudaStream_t s) {
     Weights w{p->w_sdf0, p->w_sdf1, p->w_col0, p->w_col1};
-    int rc = hidden == 64 ? launch_bwd_g<64, 1>(k, w, feat, P, d_raw_tot, dfeat, gr, s) : launch_bwd_g<32, 2>(k, w, feat, P, d_raw_tot, dfeat, gr, s);
+    const bool ba = g_rays_o || g_rays_d;
+    float* dgb = ba ? dfeat + 2ll * hg.n_levels * P : nullptr;
+    float* dxb = ba ? dgb + 4 * P : nullptr;
+    float* rep = ba ? dxb + 3 * P : dfeat + 2ll * hg.n_levels * P;
+    int rc = hidden == 64 ? launch_bwd_g<64, 1>(k, w, feat, P, d_raw_tot, dfeat, gr, dgb, dxb, s)
+                          : launch_bwd_g<32, 2>(k, w, feat, P, d_raw_tot, dfeat, gr, dgb, dxb, s);
     if (rc) return rc;
-    if (gr.g_hash) rc = launch_scatter(k, hg, P, feat, dfeat, gr.g_hash, dfeat + 2ll * hg.n_levels * P, s);
+    if (gr.g_hash) rc = launch_scatter(k, hg, P, feat, dfeat, gr.g_hash, rep, s);
+    if (rc) return rc;
+    if (ba) rc = launch_raygrad(k, hg, gg, p, P, feat, dfeat, dgb, dxb, g_rays_o, g_rays_d, s);
     return rc;
 }
 

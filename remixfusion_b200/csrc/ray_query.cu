@@ -713,9 +713,9 @@ extern "C" int rf_ray_query_backward(const rf_ray_cfg* cfg, const rf_grid_desc* 
     RF_CHECK_LAUNCH("composite_bwd_kernel");
     Grads gr{g->g_hash, g->g_w_sdf0, g->g_w_sdf1, g->g_w_col0, g->g_w_col1};
     const bool ba = g->g_rays_o || g->g_rays_d;
-    if (!ba && cfg->mlp_precision == 1 && tc_supported(k, cfg->hidden)) {
+    if (cfg->mlp_precision == 1 && tc_supported(k, cfg->hidden)) {
         RF_REQUIRE(workspace, RF_E_NULL, "rf_ray_query_backward: mlp_precision 1 needs the forward's workspace");
-        return launch_bwd_tc(k, cfg->hidden, hg, p, P, workspace, d_raw_tot, scratch + 4 * P, gr, s);
+        return launch_bwd_tc(k, cfg->hidden, hg, gg, p, P, workspace, d_raw_tot, scratch + 4 * P, gr, g->g_rays_o, g->g_rays_d, s);
     }
     if (cfg->hidden == 64) rc = ba ? launch_bwd<64, true>(k, hg, gg, p, rays_o, rays_d, z_vals, P, d_raw_tot, gr, d_pts, s)
                                    : launch_bwd<64, false>(k, hg, gg, p, rays_o, rays_d, z_vals, P, d_raw_tot, gr, d_pts, s);
@@ -731,7 +731,7 @@ extern "C" int rf_ray_query_backward(const rf_ray_cfg* cfg, const rf_grid_desc* 
 
 extern "C" int64_t rf_ray_workspace_floats(const rf_ray_cfg* cfg, const rf_grid_desc* hash, int64_t n_rays) {
     if (!cfg || !hash || cfg->mlp_precision != 1 || n_rays <= 0) return 0;
-    return (int64_t)(2 * hash->n_levels + 4 + 3) * n_rays * (cfg->n_range_d + cfg->n_samples_d);
+    return (int64_t)(2 * hash->n_levels + 4 + 3 + 1) * n_rays * (cfg->n_range_d + cfg->n_samples_d);
 }
 
 extern "C" int64_t rf_point_workspace_floats(const rf_ray_cfg* cfg, const rf_grid_desc* hash, int64_t n) {
@@ -742,10 +742,10 @@ extern "C" int64_t rf_point_workspace_floats(const rf_ray_cfg* cfg, const rf_gri
 extern "C" int64_t rf_ray_scratch_floats(const rf_ray_cfg* cfg, const rf_grid_desc* hash, int64_t n_rays, int ray_grads) {
     if (!cfg || !hash || n_rays <= 0) return 0;
     const int64_t P = n_rays * (cfg->n_range_d + cfg->n_samples_d);
-    if (ray_grads) return 7 * P;
-    if (cfg->mlp_precision != 1) return 4 * P;
+    RayK k; k.n_hash_out = hash->n_levels * 2;
+    if (cfg->mlp_precision != 1 || !tc_supported(k, cfg->hidden)) return ray_grads ? 7 * P : 4 * P;
     GridDev hg = to_dev(hash);
-    return (4 + 2 * hash->n_levels) * P + (int64_t)scatter_scratch_floats(hg, (long long)n_rays);
+    return (4 + 2 * hash->n_levels + (ray_grads ? 7 : 0)) * P + (int64_t)scatter_scratch_floats(hg, (long long)n_rays);
 }
 
 extern "C" int rf_point_query_forward(const rf_ray_cfg* cfg, const rf_grid_desc* hash, const rf_grid_desc* gbv, const rf_ray_params* p,

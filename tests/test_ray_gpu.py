@@ -223,6 +223,50 @@ def test_mapping_matches_cpu_oracle_fresh(cuda, rf_lib, hidden, S_cfg, n, prec):
 
 
 @pytest.mark.parametrize("prec", PRECISIONS)
+@pytest.mark.parametrize("hidden,S_cfg,n", [(32, (48, 11), 300), (64, (21, 20), 1500)])
+def test_ba_mode_ray_gradients_match_cpu_oracle(cuda, rf_lib, hidden, S_cfg, n, prec):
+    """BA mode (clamp=True, gradients w.r.t. rays_o / rays_d: mp_slam/mapper.py:456,484-485 through model/scene_rep.py:443)
+    on fresh seeded inputs vs oracle/ray_oracle.py; 1500 rays = several tiles per CTA of the tensor-core backward."""
+    cfg = R.base_config(hash_size=11, R=32, hidden=hidden)
+    cfg["b200"] = {"mlp_precision": prec}
+    cfg["training"].update(n_range_d=S_cfg[0], n_samples_d=S_cfg[1])
+    bb = torch.from_numpy(np.array(cfg["mapping"]["bound"])).to(torch.float64)
+    torch.manual_seed(2000 + hidden + n)
+    m = JointEncoding(cfg, bb)
+    g = torch.Generator().manual_seed(7 + hidden)
+    h = R.hash_standin(cfg); gb = R.gbv_standin(cfg)
+    with torch.no_grad():
+        h.params.copy_((torch.rand(h.params.shape, generator=g) - 0.5) * 0.1)
+        gb.params.copy_(torch.from_numpy(G["in_gbv"]))
+        m.embed_res_fn.params.copy_(h.params); m.GBV.params.copy_(gb.params)
+    gb.params.requires_grad_(False)
+    ws = [w.detach().cpu().clone().requires_grad_(True) for w in m.decoder_res.fused_weights()]
+    from oracle.ray_oracle import RayOracle
+    orc = RayOracle(cfg, bb, h, gb, *ws)
+    b = torch.tensor(R.BOUND)
+    ro = b[:, 0] + (0.3 + 0.4 * torch.rand(n, 3, generator=g)) * (b[:, 1] - b[:, 0])
+    rd = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1)
+    tc = torch.rand(n, 3, generator=g)
+    td = (0.3 + 2.5 * torch.rand(n, 1, generator=g)) * (torch.rand(n, 1, generator=g) > 0.05)
+    u = torch.rand(n, sum(S_cfg), generator=g)
+    ro_r = ro.clone().requires_grad_(True); rd_r = rd.clone().requires_grad_(True)
+    r_ref = orc.mapping(ro_r, rd_r, tc, td, clamp=True, u=u)
+    orc.total_loss(r_ref).backward()
+    m.train()
+    ro_c = ro.to(cuda).requires_grad_(True); rd_c = rd.to(cuda).requires_grad_(True)
+    r = m.mapping(ro_c, rd_c, tc.to(cuda), td.to(cuda), clamp=True, u=u)
+    _total(cfg, r).backward()
+    for k in ("rgb_res_loss", "depth_res_loss", "sdf_res_loss", "fs_res_loss", "rgb_res", "depth_res"):
+        _close(r[k], r_ref[k].detach().numpy(), 2e-4, k)
+    big = n > 1000
+    _close_grad(ro_c.grad, ro_r.grad.numpy(), "g_rays_o", prec, kink_aware=big)
+    _close_grad(rd_c.grad, rd_r.grad.numpy(), "g_rays_d", prec, kink_aware=big)
+    _close_grad(m.embed_res_fn.params.grad, h.params.grad.numpy(), "g_hash", prec, kink_aware=big)
+    for w_cuda, w_ref, nm in zip(m.decoder_res.fused_weights(), ws, ("sdf0", "sdf1", "col0", "col1")):
+        _close_grad(w_cuda.grad, w_ref.grad.numpy(), "g_w_" + nm, prec, kink_aware=big)
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
 def test_point_queries_match_oracle(cuda, rf_lib, prec):
     cfg, m = _model_from_golden("A", cuda, prec=prec)
     _, orc = R.oracle_from_golden(G, "A", requires_grad=False)
