@@ -497,7 +497,7 @@ def ncu_traffic():
             key = next((k for k in PROF_NAMES.values() if k.replace("_kernel", "") in n or n.startswith(k[:12])), None)
             if key is None and "mlp_fwd" in n: key = "mlp_fwd_tc_kernel"
             if key is None and "mlp_bwd" in n: key = "mlp_bwd_tc_kernel"
-            if key:
+            if key and key not in out:          # first launch of a kernel = the mapping-mode step (BA-mode launches follow)
                 out[key] = float(rd[2 + i]) * scale.get(rd[1], 1.0) + float(wr[2 + i]) * scale.get(wr[1], 1.0)
     except Exception:
         return {}, None
