@@ -217,10 +217,12 @@ int rf_ray_query_forward(const rf_ray_cfg* cfg, const rf_grid_desc* hash, const 
                          double* loss_partials, float* workspace, void* stream);
 
 /* Floats of `workspace` the forward needs (and the backward reads back): 0 for mlp_precision 0;
- * (2*n_levels + 4 + 3) * N * S for mlp_precision 1 (hash feature planes, GBV features, normalised positions). */
+ * (2*n_levels + 4 + 3 + 1) * N * S for mlp_precision 1 (hash feature planes, GBV features, normalised positions,
+ * depth along the ray). */
 int64_t rf_ray_workspace_floats(const rf_ray_cfg* cfg, const rf_grid_desc* hash, int64_t n_rays);
-/* Floats of `scratch` the backward needs: 4*N*S (mlp_precision 1: + 2*n_levels*N*S feature-gradient planes + the
- * replicated gradient tables of the small levels; 7*N*S with ray gradients). */
+/* Floats of `scratch` the backward needs.  mlp_precision 0: 4*N*S (7*N*S with ray gradients).  mlp_precision 1:
+ * (4 + 2*n_levels)*N*S (d_raw + feature-gradient planes) + the replicated gradient tables of the small levels, and with
+ * ray gradients 7*N*S more (GBV-texel gradient and the OneBlob part of the position gradient). */
 int64_t rf_ray_scratch_floats(const rf_ray_cfg* cfg, const rf_grid_desc* hash, int64_t n_rays, int ray_grads);
 
 typedef struct rf_ray_grads {

@@ -124,7 +124,8 @@ int launch_points_tc(RayK k, int hidden, const GridDev& hg, const GridDev& gg, c
                      int variant, float* raw, float* feat, cudaStream_t s);
 int launch_bwd_tc(const RayK& k, int hidden, const GridDev& hg, const GridDev& gg, const rf_ray_params* p, long long P, const float* feat,
                   const float* d_raw_tot, float* dfeat, const Grads& gr, float* g_rays_o, float* g_rays_d, cudaStream_t s);
-int launch_raygrad(const RayK& k, const GridDev& hg, const GridDev& gg, const rf_ray_params* p, long long P, const float* feat,
-                   const float* dfeat, const float* dgb, const float* dxb, float* g_o, float* g_d, cudaStream_t s);
+int launch_scatter_raygrad(const RayK& k, const GridDev& hg, const GridDev& gg, const rf_ray_params* p, long long P, const float* feat,
+                           const float* dfeat, const float* dgb, const float* dxb, float* g_hash, float* g_rep, float* g_o, float* g_d,
+                           cudaStream_t s);
 
 }  // namespace rf

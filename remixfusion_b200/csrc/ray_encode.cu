@@ -140,14 +140,42 @@ __global__ void __launch_bounds__(128) encode_walk_kernel(GridDev hg, GridDev gg
 // reductions onto one L2 line serialise.  Those levels accumulate into K private replicas of their gradient table
 // (replica = block index mod K, so that neighbouring blocks — neighbouring pixels — never share one) which
 // replica_reduce_kernel folds into the caller's table afterwards.
+// d/dx of the trilinear interpolant of the corner scalars u[c] (c = cx + 2 cy + 4 cz): differences along one axis,
+// bilinear weights of the other two (Appendix B6)
+__device__ __forceinline__ void tri_grad(const float (&u)[8], float fx, float fy, float fz, float& gx, float& gy, float& gz) {
+    const float ax = 1.f - fx, ay = 1.f - fy, az = 1.f - fz;
+    const float w00 = ay * az, w10 = fy * az, w01 = ay * fz, w11 = fy * fz;          // (y, z)
+    gx = (u[1] - u[0]) * w00 + (u[3] - u[2]) * w10 + (u[5] - u[4]) * w01 + (u[7] - u[6]) * w11;
+    const float x00 = ax * az, x10 = fx * az, x01 = ax * fz, x11 = fx * fz;          // (x, z)
+    gy = (u[2] - u[0]) * x00 + (u[3] - u[1]) * x10 + (u[6] - u[4]) * x01 + (u[7] - u[5]) * x11;
+    const float y00 = ax * ay, y10 = fx * ay, y01 = ax * fy, y11 = fx * fy;          // (x, y)
+    gz = (u[4] - u[0]) * y00 + (u[5] - u[1]) * y10 + (u[6] - u[2]) * y01 + (u[7] - u[3]) * y11;
+}
+
+// what the BA-mode walks need besides the planes
+struct RayGradArgs {
+    const float* hash_params; double bl[3]; float* g_o; float* g_d;
+};
+__device__ __forceinline__ void raygrad_flush(const RayGradArgs& rg, long long r, const float (&so)[3], const float (&sd)[3]) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {                      // through the float64 normalisation (:388)
+        if (rg.g_o && so[a] != 0.f) atomicAdd(rg.g_o + 3 * r + a, (float)((double)so[a] / rg.bl[a]));
+        if (rg.g_d && sd[a] != 0.f) atomicAdd(rg.g_d + 3 * r + a, (float)((double)sd[a] / rg.bl[a]));
+    }
+}
+
 struct ScatterRep {
     unsigned k[RF_MAX_LEVELS];            // replicas per level (power of two; 1 = accumulate straight into g_hash)
     unsigned base[RF_MAX_LEVELS];         // first entry of the level's replica block in the scratch (float2 units)
 };
 
+// BA: the same walk also differentiates the trilinear weights of its level against the corner VALUES (gathered once per
+// cell run) and sums dL/d xn and z * dL/d xn over the ray's samples — the hash-level part of raygrad_walk_kernel, without
+// reading the planes a second time.
+template <bool BA>
 __global__ void __launch_bounds__(128) scatter_walk_kernel(GridDev hg, ScatterRep rep, const float* __restrict__ xn, const float* __restrict__ dfeat,
                                                            long long P, long long N, int S, int seg, int level0, float* __restrict__ g_hash,
-                                                           float* __restrict__ g_rep) {
+                                                           float* __restrict__ g_rep, RayGradArgs rg) {
     const int l = blockIdx.y + level0;
     const long long unit = blockIdx.x * 128ll + threadIdx.x;                // (ray, segment), as in encode_walk_kernel
     const long long r = unit % N;
@@ -167,13 +195,22 @@ __global__ void __launch_bounds__(128) scatter_walk_kernel(GridDev hg, ScatterRe
 #pragma unroll
     for (int c = 0; c < 8; ++c) acc[c] = make_float2(0.f, 0.f);
     float xa = __ldg(xs), ya = __ldg(ys), za = __ldg(zs); float2 da = __ldg(dj);
+    const float* ts = xn + 3 * P + first;
+    float ta = BA ? __ldg(ts) : 0.f;
+    const float2* tab = BA ? reinterpret_cast<const float2*>(rg.hash_params) + hg.offset[l] : nullptr;
+    float2 v[BA ? 8 : 1];
+    bool vhave = false;                                                      // v holds the corners of cell (pcx, pcy, pcz)
+    float so[3] = {0.f, 0.f, 0.f}, sd[3] = {0.f, 0.f, 0.f};
     for (int s = s_begin; s <= s_end; ++s) {
         unsigned cx = 0, cy = 0, cz = 0; float fx = 0.f, fy = 0.f, fz = 0.f;
-        const float2 d = da;
+        const float2 d = da; const float t = ta;
         const bool last = (s == s_end);
         if (!last) {
             pos_fract(xa, scale, cx, fx); pos_fract(ya, scale, cy, fy); pos_fract(za, scale, cz, fz);
-            if (s + 1 < s_end) { xs += N; ys += N; zs += N; dj += N; xa = __ldg(xs); ya = __ldg(ys); za = __ldg(zs); da = __ldg(dj); }
+            if (s + 1 < s_end) {
+                xs += N; ys += N; zs += N; dj += N; xa = __ldg(xs); ya = __ldg(ys); za = __ldg(zs); da = __ldg(dj);
+                if (BA) { ts += N; ta = __ldg(ts); }
+            }
         }
         if (have && (last || cx != pcx || cy != pcy || cz != pcz)) {
             if (nz) {
@@ -184,17 +221,35 @@ __global__ void __launch_bounds__(128) scatter_walk_kernel(GridDev hg, ScatterRe
             }
 #pragma unroll
             for (int c = 0; c < 8; ++c) acc[c] = make_float2(0.f, 0.f);
-            nz = false;
+            nz = false; vhave = false;
         }
         if (last) break;
         pcx = cx; pcy = cy; pcz = cz; have = true;
-        nz = nz || d.x != 0.f || d.y != 0.f;
+        const bool dnz = d.x != 0.f || d.y != 0.f;
+        nz = nz || dnz;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             float w = corner_weight(c, fx, fy, fz);
             acc[c].x = fmaf(w, d.x, acc[c].x); acc[c].y = fmaf(w, d.y, acc[c].y);
         }
+        if (BA && dnz) {
+            if (!vhave) {
+                unsigned idx[8];
+                ci.cell(cx, cy, cz, idx);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) v[c] = __ldg(tab + idx[c]);
+                vhave = true;
+            }
+            float u[8], gx, gy, gz;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) u[c] = fmaf(d.x, v[c].x, d.y * v[c].y);
+            tri_grad(u, fx, fy, fz, gx, gy, gz);
+            const float dx0 = gx * scale, dx1 = gy * scale, dx2 = gz * scale;
+            so[0] += dx0; so[1] += dx1; so[2] += dx2;
+            sd[0] = fmaf(t, dx0, sd[0]); sd[1] = fmaf(t, dx1, sd[1]); sd[2] = fmaf(t, dx2, sd[2]);
+        }
     }
+    if (BA) raygrad_flush(rg, r, so, sd);
 }
 
 
@@ -207,8 +262,8 @@ __global__ void __launch_bounds__(128) raygrad_walk_kernel(GridDev hg, GridDev g
                                                            const float* __restrict__ gbv_params, const float* __restrict__ xn,
                                                            const float* __restrict__ dfeat, const float* __restrict__ dgb,
                                                            const float* __restrict__ dxb, long long P, long long N, int S, int seg,
-                                                           double bl0, double bl1, double bl2, float* __restrict__ g_o, float* __restrict__ g_d) {
-    const int l = blockIdx.y, L = hg.n_levels;
+                                                           int level0, RayGradArgs rg) {
+    const int l = blockIdx.y + level0, L = hg.n_levels;
     const long long unit = blockIdx.x * 128ll + threadIdx.x;
     const long long r = unit % N;
     const int s_begin = (int)(unit / N) * seg;
@@ -220,17 +275,6 @@ __global__ void __launch_bounds__(128) raygrad_walk_kernel(GridDev hg, GridDev g
     CornerIndexer ci;
     unsigned idx[8];
     float so[3] = {0.f, 0.f, 0.f}, sd[3] = {0.f, 0.f, 0.f};
-    // d/dx of the trilinear interpolant of the corner scalars u[c] (c = cx + 2 cy + 4 cz): differences along one axis,
-    // bilinear weights of the other two
-    auto tri_grad = [](const float (&u)[8], float fx, float fy, float fz, float& gx, float& gy, float& gz) {
-        const float ax = 1.f - fx, ay = 1.f - fy, az = 1.f - fz;
-        const float w00 = ay * az, w10 = fy * az, w01 = ay * fz, w11 = fy * fz;          // (y, z)
-        gx = (u[1] - u[0]) * w00 + (u[3] - u[2]) * w10 + (u[5] - u[4]) * w01 + (u[7] - u[6]) * w11;
-        const float x00 = ax * az, x10 = fx * az, x01 = ax * fz, x11 = fx * fz;          // (x, z)
-        gy = (u[2] - u[0]) * x00 + (u[3] - u[1]) * x10 + (u[6] - u[4]) * x01 + (u[7] - u[5]) * x11;
-        const float y00 = ax * ay, y10 = fx * ay, y01 = ax * fy, y11 = fx * fy;          // (x, y)
-        gz = (u[4] - u[0]) * y00 + (u[5] - u[1]) * y10 + (u[6] - u[2]) * y01 + (u[7] - u[3]) * y11;
-    };
     float xa = __ldg(xs), ya = __ldg(ys), za = __ldg(zs), ta = __ldg(ts);
     if (l < L) {
         const float scale = hg.scale[l];
@@ -290,12 +334,7 @@ __global__ void __launch_bounds__(128) raygrad_walk_kernel(GridDev hg, GridDev g
             sd[0] = fmaf(t, dx0, sd[0]); sd[1] = fmaf(t, dx1, sd[1]); sd[2] = fmaf(t, dx2, sd[2]);
         }
     }
-    const double bl[3] = {bl0, bl1, bl2};
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        if (g_o && so[a] != 0.f) atomicAdd(g_o + 3 * r + a, (float)((double)so[a] / bl[a]));
-        if (g_d && sd[a] != 0.f) atomicAdd(g_d + 3 * r + a, (float)((double)sd[a] / bl[a]));
-    }
+    raygrad_flush(rg, r, so, sd);
 }
 
 // g_hash[level entries] += sum over the level's replicas.  blockIdx.y = level.
@@ -382,8 +421,10 @@ int launch_encode(const RayK& k, const GridDev& hg, const GridDev& gg, const rf_
     return 0;
 }
 
-// g_rep: scatter_scratch_floats() floats of scratch for the replicas (zeroed here)
-int launch_scatter(const RayK& k, const GridDev& hg, long long P, const float* feat, const float* dfeat, float* g_hash, float* g_rep, cudaStream_t s) {
+// g_rep: scatter_scratch_floats() floats of scratch for the replicas (zeroed here).  rg (BA mode, optional): the walk
+// also accumulates the hash-level part of the ray gradients (g_o / g_d must be zeroed by the caller).
+int launch_scatter(const RayK& k, const GridDev& hg, long long P, const float* feat, const float* dfeat, float* g_hash, float* g_rep,
+                   const RayGradArgs* rg, cudaStream_t s) {
     const int L = hg.n_levels;
     const float* xn = feat + (2ll * L + 4) * P;
     ScatterRep rep;
@@ -395,14 +436,16 @@ int launch_scatter(const RayK& k, const GridDev& hg, long long P, const float* f
     const int seg = walk_segment(k.n_rays, k.S);
     const long long units = k.n_rays * ((k.S + seg - 1) / seg);
     const unsigned gx = (unsigned)((units + 127) / 128);
-    if (prof_enabled() && getenv("RF_DEBUG_PER_LEVEL")) {                 // per-level timing (diagnostics only)
+    RayGradArgs none{};
+    if (prof_enabled() && getenv("RF_DEBUG_PER_LEVEL") && !rg) {          // per-level timing (diagnostics only)
         for (int l = 0; l < L; ++l) {
             ProfScope pl(RF_PROF_SCATTER_LEVEL0 + l, s);
-            scatter_walk_kernel<<<dim3(gx, 1), 128, 0, s>>>(hg, rep, xn, dfeat, P, k.n_rays, k.S, seg, l, g_hash, g_rep);
+            scatter_walk_kernel<false><<<dim3(gx, 1), 128, 0, s>>>(hg, rep, xn, dfeat, P, k.n_rays, k.S, seg, l, g_hash, g_rep, none);
         }
     } else {
         ProfScope ps(RF_PROF_SCATTER, s);
-        scatter_walk_kernel<<<dim3(gx, L), 128, 0, s>>>(hg, rep, xn, dfeat, P, k.n_rays, k.S, seg, 0, g_hash, g_rep);
+        if (rg) scatter_walk_kernel<true><<<dim3(gx, L), 128, 0, s>>>(hg, rep, xn, dfeat, P, k.n_rays, k.S, seg, 0, g_hash, g_rep, *rg);
+        else scatter_walk_kernel<false><<<dim3(gx, L), 128, 0, s>>>(hg, rep, xn, dfeat, P, k.n_rays, k.S, seg, 0, g_hash, g_rep, none);
     }
     RF_CHECK_LAUNCH("scatter_walk_kernel");
     if (rep_entries) {
@@ -412,21 +455,25 @@ int launch_scatter(const RayK& k, const GridDev& hg, long long P, const float* f
     return 0;
 }
 
-
-// BA mode: dfeat [L][P][2], dgb [P][4], dxb [3][P] (all sample-major planes) -> g_rays_o / g_rays_d [N][3] (overwritten)
-int launch_raygrad(const RayK& k, const GridDev& hg, const GridDev& gg, const rf_ray_params* p, long long P, const float* feat,
-                   const float* dfeat, const float* dgb, const float* dxb, float* g_o, float* g_d, cudaStream_t s) {
+// BA mode: dfeat [L][P][2], dgb [P][4], dxb [3][P] (all sample-major planes) -> g_rays_o / g_rays_d [N][3] (overwritten).
+// With a table gradient the hash levels ride on the scatter walk and only the GBV / OneBlob level runs here.
+int launch_scatter_raygrad(const RayK& k, const GridDev& hg, const GridDev& gg, const rf_ray_params* p, long long P, const float* feat,
+                           const float* dfeat, const float* dgb, const float* dxb, float* g_hash, float* g_rep, float* g_o, float* g_d,
+                           cudaStream_t s) {
     const int L = hg.n_levels;
     const float* xn = feat + (2ll * L + 4) * P;
     cudaError_t e = cudaSuccess;
     if (g_o) e = cudaMemsetAsync(g_o, 0, 3 * k.n_rays * sizeof(float), s);
     if (e == cudaSuccess && g_d) e = cudaMemsetAsync(g_d, 0, 3 * k.n_rays * sizeof(float), s);
     if (e != cudaSuccess) return set_error((int)e, "cudaMemsetAsync(ray gradients): %s", cudaGetErrorString(e));
+    RayGradArgs rg{p->hash_params, {k.bl[0], k.bl[1], k.bl[2]}, g_o, g_d};
+    if (g_hash) { int rc = launch_scatter(k, hg, P, feat, dfeat, g_hash, g_rep, &rg, s); if (rc) return rc; }
+    const int level0 = g_hash ? L : 0, nlev = g_hash ? 1 : L + 1;
     const int seg = walk_segment(k.n_rays, k.S);
     const long long units = k.n_rays * ((k.S + seg - 1) / seg);
     ProfScope ps(RF_PROF_RAY_GRAD, s);
-    raygrad_walk_kernel<<<dim3((unsigned)((units + 127) / 128), L + 1), 128, 0, s>>>(hg, gg, p->hash_params, p->gbv_params, xn, dfeat, dgb, dxb, P,
-                                                                                   k.n_rays, k.S, seg, k.bl[0], k.bl[1], k.bl[2], g_o, g_d);
+    raygrad_walk_kernel<<<dim3((unsigned)((units + 127) / 128), nlev), 128, 0, s>>>(hg, gg, p->hash_params, p->gbv_params, xn, dfeat, dgb, dxb, P,
+                                                                                  k.n_rays, k.S, seg, level0, rg);
     RF_CHECK_LAUNCH("raygrad_walk_kernel");
     return 0;
 }

@@ -1150,7 +1150,9 @@ static int launch_bwd_g(const RayK& k, const Weights& w, const float* feat, long
 
 int launch_encode(const RayK& k, const GridDev& hg, const GridDev& gg, const rf_ray_params* p, const float* rays_o, const float* rays_d,
                   const float* z_vals, long long P, float* feat, cudaStream_t s);
-int launch_scatter(const RayK& k, const GridDev& hg, long long P, const float* feat, const float* dfeat, float* g_hash, float* g_rep, cudaStream_t s);
+struct RayGradArgs;
+int launch_scatter(const RayK& k, const GridDev& hg, long long P, const float* feat, const float* dfeat, float* g_hash, float* g_rep,
+                   const RayGradArgs* rg, cudaStream_t s);
 int launch_encode_points(const GridDev& hg, const GridDev& gg, const rf_ray_params* p, const float* x, long long n, float* feat, cudaStream_t s);
 
 bool tc_supported(const RayK& k, int hidden) { return k.n_hash_out == 32 && (hidden == 32 || hidden == 64); }
@@ -1182,13 +1184,12 @@ int launch_bwd_tc(const RayK& k, int hidden, const GridDev& hg, const GridDev& g
     const bool ba = g_rays_o || g_rays_d;
     float* dgb = ba ? dfeat + 2ll * hg.n_levels * P : nullptr;
     float* dxb = ba ? dgb + 4 * P : nullptr;
-    float* rep = ba ? dxb + 3 * P : dfeat + 2ll * hg.n_levels * P;
+    float* rep = ba ? dxb + ((3 * P + 3) & ~3ll) : dfeat + 2ll * hg.n_levels * P;     // replicas are float2 / float4 accessed
     int rc = hidden == 64 ? launch_bwd_g<64, 1>(k, w, feat, P, d_raw_tot, dfeat, gr, dgb, dxb, s)
                           : launch_bwd_g<32, 2>(k, w, feat, P, d_raw_tot, dfeat, gr, dgb, dxb, s);
     if (rc) return rc;
-    if (gr.g_hash) rc = launch_scatter(k, hg, P, feat, dfeat, gr.g_hash, rep, s);
-    if (rc) return rc;
-    if (ba) rc = launch_raygrad(k, hg, gg, p, P, feat, dfeat, dgb, dxb, g_rays_o, g_rays_d, s);
+    if (ba) return launch_scatter_raygrad(k, hg, gg, p, P, feat, dfeat, dgb, dxb, gr.g_hash, rep, g_rays_o, g_rays_d, s);
+    if (gr.g_hash) rc = launch_scatter(k, hg, P, feat, dfeat, gr.g_hash, rep, nullptr, s);
     return rc;
 }
 

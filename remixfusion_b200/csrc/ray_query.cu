@@ -745,7 +745,7 @@ extern "C" int64_t rf_ray_scratch_floats(const rf_ray_cfg* cfg, const rf_grid_de
     RayK k; k.n_hash_out = hash->n_levels * 2;
     if (cfg->mlp_precision != 1 || !tc_supported(k, cfg->hidden)) return ray_grads ? 7 * P : 4 * P;
     GridDev hg = to_dev(hash);
-    return (4 + 2 * hash->n_levels + (ray_grads ? 7 : 0)) * P + (int64_t)scatter_scratch_floats(hg, (long long)n_rays);
+    return (4 + 2 * hash->n_levels + (ray_grads ? 7 : 0)) * P + (ray_grads ? 4 : 0) + (int64_t)scatter_scratch_floats(hg, (long long)n_rays);
 }
 
 extern "C" int rf_point_query_forward(const rf_ray_cfg* cfg, const rf_grid_desc* hash, const rf_grid_desc* gbv, const rf_ray_params* p,
