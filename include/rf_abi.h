@@ -71,6 +71,31 @@ int rf_tsdf_recenter(float* tsdf, float* weight, float* color,                  
                      int odx, int ody, int odz, const float old_origin[3],
                      float voxel_size, void* stream);
 
+/* N2, second half — the volume-reading kernels of the random-optimisation tracker.
+ *
+ * rf_track_vertex_normal replaces `compute_vertex` + `compute_normal` (model/ROtracker.py:273-344, :346-400; host
+ * init_depth_vertex :436-456, init_normal :458-470): depth_vertex [H*W][4] = back-projected vertex at depth + a random
+ * offset along z, and the TSDF value that offset implies; normal [H*W][3] from central differences (border pixels are not
+ * written: zero-fill the map once, as the reference's allocation does).  The reference seeds curand with subsequence =
+ * row index, i.e. one random offset per image ROW; `row_sample` (device, H floats) receives those offsets.  `seed` is the
+ * reference's `seed_num`.  All pointers are device pointers; K is a host array. */
+int rf_track_vertex_normal(const float* depth, int H, int W, const float K[9], float cut_dist, float trunc, int seed,
+                           float sample_range, float* row_sample, float* depth_vertex, float* normal, void* stream);
+
+/* rf_track_fitness replaces `compute_tsdf_value` (model/ROtracker.py:144-271; host evaluate_tsdf :536-604): for each of
+ * the n pose candidates (candidates [n][6] = translation + quaternion vector part, in units of search_size), transform
+ * every `level`-th valid vertex (offset level_index) by candidate o current pose (R, T), and accumulate
+ * |tsdf_vol[nearest voxel] - expected tsdf| into search_value[n] and the hit count into search_count[n] (both float,
+ * overwritten).  Deterministic (fixed summation order), unlike the reference's system-scope atomics.  vol_origin is
+ * truncated to int as the reference kernel does (:163-165).  scratch: rf_track_fitness_scratch_floats() floats, 8-byte
+ * aligned.  vol_dim, vol_origin, K, R, T, search_size are host arrays; the rest device pointers. */
+int rf_track_fitness(const float* tsdf_vol, const int vol_dim[3], const float vol_origin[3], float voxel_size,
+                     const float* depth_vertex, const float* normal, int H, int W, const float K[9],
+                     const float R[9], const float T[3], const float* candidates, int n_candidates,
+                     const float search_size[6], int level, int level_index,
+                     float* search_value, float* search_count, float* scratch, void* stream);
+int64_t rf_track_fitness_scratch_floats(int n_candidates, int H, int W, int level);
+
 /* The per-pixel factor 1/sqrt(vx^2 + vy^2 + 1), vx = (px - cx)/fx, vy = (py - cy)/fy, of the projective SDF
  * (model/Volume.py:280-283, mp_slam/mapper.py:108-111).  It depends on the intrinsics only, so a caller computes it
  * once per camera and passes it to every integrate; the kernels then load it next to the depth instead of spending two
@@ -283,7 +308,7 @@ int rf_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, i
 #define RF_PROF_SLOTS 64
 enum { RF_PROF_TSDF_LOCAL = 0, RF_PROF_TSDF_GLOBAL = 1, RF_PROF_RAY_Z = 2, RF_PROF_RAY_POS = 3, RF_PROF_ENCODE = 4,
        RF_PROF_MLP_FWD = 5, RF_PROF_COMPOSITE_FWD = 6, RF_PROF_COMPOSITE_BWD = 7, RF_PROF_MLP_BWD = 8,
-       RF_PROF_SCATTER = 9, RF_PROF_SAMPLE_FWD = 10, RF_PROF_SAMPLE_BWD = 11, RF_PROF_RAY_GRAD = 12, RF_PROF_TSDF_RECENTER = 13,
+       RF_PROF_SCATTER = 9, RF_PROF_SAMPLE_FWD = 10, RF_PROF_SAMPLE_BWD = 11, RF_PROF_RAY_GRAD = 12, RF_PROF_TSDF_RECENTER = 13, RF_PROF_TRACK_FITNESS = 14,
        RF_PROF_SCATTER_LEVEL0 = 16 /* +level, only with RF_DEBUG_PER_LEVEL=1 */, RF_PROF_ENCODE_LEVEL0 = 40 /* +level */ };
 int rf_profile_enable(int on);
 int rf_profile_read(float* ms);

@@ -28,7 +28,10 @@ SOURCES = {
     # cubin name -> reference file holding the SourceModule string
     "ref_local_volume.cubin": "model/Volume.py",
     "ref_global_volume.cubin": "mp_slam/mapper.py",
+    "ref_tracker.cubin": "model/ROtracker.py",          # compute_tsdf_value / compute_vertex / compute_normal (:141-400)
 }
+# model/ROtracker.py:398 passes no_extern_c=True (the string carries its own extern "C" block and includes curand)
+NO_EXTERN_C = {"ref_tracker.cubin"}
 
 
 def build(verbose: bool = False) -> bool:
@@ -45,13 +48,16 @@ def build(verbose: bool = False) -> bool:
         if os.path.exists(dst) and os.path.getmtime(dst) >= os.path.getmtime(src_path):
             continue
         text = open(src_path, "r", encoding="utf-8").read()
-        m = re.search(r'SourceModule\("""(.*?)"""\)', text, re.S)
+        m = re.search(r'SourceModule\("""(.*?)"""', text, re.S)
         if m is None:
             raise RuntimeError(f"no SourceModule string found in {src_path}")
         with tempfile.TemporaryDirectory(prefix="rf_ref_") as tmp:
             cu = os.path.join(tmp, "kernel.cu")
             with open(cu, "w") as f:
-                f.write('extern "C" {\n' + m.group(1) + "\n}\n")   # what PyCUDA's SourceModule does
+                if cubin in NO_EXTERN_C:
+                    f.write(m.group(1))
+                else:
+                    f.write('extern "C" {\n' + m.group(1) + "\n}\n")   # what PyCUDA's SourceModule does
             cmd = ["nvcc", "--cubin", "-arch=sm_100a", "-w", "-o", dst, cu]   # nvcc defaults, as PyCUDA
             if verbose:
                 print("[build_ref]", " ".join(cmd))

@@ -5,6 +5,7 @@ reproducing the host wrappers of the reference launch for launch:
   * moving_volume.integrate       model/Volume.py:713-757   (grid/block: model/Volume.py:110-123)
   * Mapper.integrate_kf           mp_slam/mapper.py:823-872 (grid/block: mp_slam/mapper.py:239-251)
   * Mapper.init_mapvolume         mp_slam/mapper.py:267-282
+  * RO_tracker.init_depth_vertex / init_normal / evaluate_tsdf   model/ROtracker.py:436-470, :536-604
 
 Every scalar travels as float32 inside small device arrays exactly as PyCUDA's ``cuda.In`` would ship it.
 """
@@ -23,7 +24,8 @@ REF_DIR = os.path.join(HERE, "_ref")
 def available() -> bool:
     return (torch.cuda.is_available()
             and os.path.exists(os.path.join(REF_DIR, "ref_local_volume.cubin"))
-            and os.path.exists(os.path.join(REF_DIR, "ref_global_volume.cubin")))
+            and os.path.exists(os.path.join(REF_DIR, "ref_global_volume.cubin"))
+            and os.path.exists(os.path.join(REF_DIR, "ref_tracker.cubin")))
 
 
 def _check(res):
@@ -139,3 +141,37 @@ def ref_clear_global(trgb, R):
         keep.append(other)
         m.launch("clean_tsdf", grid, (1024, 1, 1), [trgb.data_ptr(), keep[0].data_ptr(), other.data_ptr()])
     torch.cuda.synchronize()
+
+
+def ref_track_vertex_normal(depth, K, cut_dist, trunc, seed_num, sample_range):
+    """model/ROtracker.py:436-470: launch the reference `compute_vertex` and `compute_normal`.  depth: CUDA fp32 [H,W].
+    Returns (depth_vertex [H*W*4], normal [H*W*3]) CUDA fp32 (normal zero-initialised, as the reference's allocation)."""
+    m = _mod("ref_tracker.cubin")
+    H, W = depth.shape
+    vertex = torch.zeros(H * W * 4, device="cuda"); normal = torch.zeros(H * W * 3, device="cuda")
+    block = (int((H + 32 - 1) / 32), int((W + 32 - 1) / 32), 1)
+    k = _dev(K)
+    o1 = _dev([H, W, cut_dist, trunc, seed_num, sample_range])
+    m.launch("compute_vertex", (32, 32, 1), block, [depth.data_ptr(), vertex.data_ptr(), k.data_ptr(), o1.data_ptr()])
+    o2 = _dev([H, W])
+    m.launch("compute_normal", (32, 32, 1), block, [vertex.data_ptr(), normal.data_ptr(), o2.data_ptr()])
+    torch.cuda.synchronize()
+    return vertex, normal
+
+
+def ref_track_fitness(tsdf, vol_dim, vol_origin, voxel_size, vertex, normal, H, W, K, R, T, cand, search_size, level, level_index):
+    """model/ROtracker.py:536-604: launch the reference `compute_tsdf_value`; cand: numpy [n,6], n a multiple of 1024.
+    Returns (search_value, search_count) CUDA fp32 [n]."""
+    m = _mod("ref_tracker.cubin")
+    n = cand.shape[0]
+    value = torch.zeros(n, device="cuda"); count = torch.zeros(n, device="cuda")
+    dummy = torch.zeros(1, device="cuda")                     # weight_vol / depth_map are never read by the kernel
+    keep = [_dev(search_size), _dev(R), _dev(T), _dev(cand), _dev(K),
+            _dev([vol_dim[0], vol_dim[1], vol_dim[2], vol_origin[0], vol_origin[1], vol_origin[2], voxel_size, n, level,
+                  int(H / level), int(W / level), level_index, H, W, 0, 0, 0])]
+    m.launch("compute_tsdf_value", (int(n / (32 * 32)), int(H / level), int(W / level)), (32 * 32, 1, 1),
+             [tsdf.data_ptr(), dummy.data_ptr(), dummy.data_ptr(), vertex.data_ptr(), value.data_ptr(), count.data_ptr(),
+              keep[0].data_ptr(), keep[1].data_ptr(), keep[2].data_ptr(), keep[3].data_ptr(), keep[5].data_ptr(), keep[4].data_ptr(),
+              normal.data_ptr()])
+    torch.cuda.synchronize()
+    return value, count

@@ -77,6 +77,7 @@ def lib() -> C.CDLL:
         _lib.rf_ray_workspace_floats.restype = C.c_int64
         _lib.rf_ray_scratch_floats.restype = C.c_int64
         _lib.rf_point_workspace_floats.restype = C.c_int64
+        _lib.rf_track_fitness_scratch_floats.restype = C.c_int64
     return _lib
 
 
@@ -124,6 +125,13 @@ def farr(values, n=None):
     if n is not None and a.size != n:
         raise RfError(f"expected {n} floats, got {a.size}")
     return a, a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def fptr(a: np.ndarray):
+    """Host float32 array (contiguous; kept alive by the caller) -> const float*."""
+    if a.dtype != np.float32 or not a.flags["C_CONTIGUOUS"]:
+        raise RfError("expected a contiguous float32 numpy array")
+    return a.ctypes.data_as(C.POINTER(C.c_float))
 
 
 def require_f32_cuda(t: torch.Tensor, name: str) -> torch.Tensor:

@@ -1,0 +1,254 @@
+// track_search.cu — SURVEY §8f N2, second half: the kernels of the random-optimisation tracker that read the moving
+// volume (model/ROtracker.py:141-400; host :436-470, :536-604).
+//
+//   track_row_sample_kernel   the per-row random offset of compute_vertex (:306-330): the reference seeds one XORWOW
+//                             stream per pixel with subsequence = ROW index, so every pixel of a row draws the same
+//                             numbers — one thread per row does the (expensive) curand_init here instead of one per pixel
+//   track_vertex_kernel       compute_vertex (:273-344): back-projected vertex at depth + z offset, and the TSDF value that
+//                             offset implies
+//   track_normal_kernel       compute_normal (:346-400)
+//   track_fitness_kernel      compute_tsdf_value (:144-271): for every pose candidate, sum over the sub-sampled pixels of
+//                             |tsdf(nearest voxel of the transformed vertex) - expected tsdf|, and the number of hits
+//
+// The reference launches one thread per (candidate, pixel) that adds into two per-candidate floats with system-scope
+// atomics (nondeterministic order).  Here a thread owns one candidate (its quaternion set-up is done once), the block
+// stages a chunk of valid pixels (vertex rotated into the world frame once per pixel, not once per candidate) in shared
+// memory, every thread accumulates in registers, and per-chunk partial sums are folded in a fixed order: the result is
+// deterministic.  Per-term arithmetic is written with explicit round-to-nearest intrinsics in exactly the fused form
+// nvcc 12.9 / ptxas emit for the reference kernel on sm_100a (read from its SASS: which products are rounded on their
+// own and which are contracted into FFMA decides, in rare cases, which voxel a vertex rounds to); tests compare
+// single-pixel sums — and through them every term — bit for bit with the literal reference kernel.
+#include <curand_kernel.h>
+#include "rf_common.cuh"
+
+namespace rf {
+namespace {
+
+constexpr int kCand = 128;          // candidates (threads) per block
+constexpr int kPixChunk = 128;      // pixels staged per shared-memory round
+
+struct TrackCam { float k[9]; };
+struct TrackPose { float R[9]; float T[3]; float ss[6]; };
+
+__global__ void track_row_sample_kernel(int H, unsigned long long seed, float sample_range, float* __restrict__ row_sample) {
+    const int pi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pi >= H) return;
+    curandState state;
+    curand_init(seed, pi, 0, &state);                                       // :307-309
+    float sample = (curand_uniform(&state) * (sample_range + 1)) - sample_range;   // :318
+    if (sample_range < 1) sample = (curand_uniform(&state) * 2 * sample_range) - sample_range;   // :321-324
+    row_sample[pi] = sample;
+}
+
+__global__ void track_vertex_kernel(const float* __restrict__ depth, const float* __restrict__ row_sample, TrackCam cam, int H, int W,
+                                    float cutdist, float trunc, float4* __restrict__ vertex) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= H * W) return;
+    const int pi = i / W, pj = i - pi * W;
+    float depth_value = depth[i];
+    if (depth_value > cutdist) depth_value = 0.f;                            // :292-294
+    if (depth_value <= 0) { vertex[i] = make_float4(0.f, 0.f, 0.f, 0.f); return; }   // :296-303
+    const float sample = row_sample[pi];
+    const float z_val = sample * trunc;
+    float gt_tsdf = -sample;                                                 // :326-334
+    if (z_val < -1 * trunc) gt_tsdf = 1.0;
+    if (z_val > 1 * trunc) gt_tsdf = 1.0;
+    const float c_z = depth_value + z_val;                                   // :337-339
+    const float c_x = ((float)pj - cam.k[0 * 3 + 2]) * c_z / cam.k[0];
+    const float c_y = ((float)pi - cam.k[1 * 3 + 2]) * c_z / cam.k[1 * 3 + 1];
+    vertex[i] = make_float4(c_x, c_y, c_z, gt_tsdf);
+}
+
+// Border pixels are left untouched, as in the reference (:353-355): the caller zero-fills the map once.
+__global__ void track_normal_kernel(const float4* __restrict__ vertex, int H, int W, float* __restrict__ normal) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= H * W) return;
+    const int pi = i / W, pj = i - pi * W;
+    if (pi > H - 2 || pj > W - 2 || pi < 1 || pj < 1) return;
+    const float4 c = vertex[i], l = vertex[i - 1], r = vertex[i + 1], u = vertex[i - W], d = vertex[i + W];
+    if (c.z == 0 || l.z == 0 || r.z == 0 || u.z == 0 || d.z == 0) {          // :364-369
+        normal[3 * i] = 0.f; normal[3 * i + 1] = 0.f; normal[3 * i + 2] = 0.f;
+        return;
+    }
+    float hor_x = l.x - r.x, hor_y = l.y - r.y, hor_z = l.z - r.z;           // :371-377
+    float ver_x = u.x - d.x, ver_y = u.y - d.y, ver_z = u.z - d.z;
+    float normal_x = -hor_z * ver_y + hor_y * ver_z;                         // :379-385
+    float normal_y = hor_z * ver_x - hor_x * ver_z;
+    float normal_z = -hor_y * ver_x + hor_x * ver_y;
+    float lens = sqrt(normal_x * normal_x + normal_y * normal_y + normal_z * normal_z);
+    normal_x = normal_x / lens; normal_y = normal_y / lens; normal_z = normal_z / lens;
+    if (normal_z > 0) { normal_x *= -1; normal_y *= -1; normal_z *= -1; }    // :387-391
+    normal[3 * i] = normal_x; normal[3 * i + 1] = normal_y; normal[3 * i + 2] = normal_z;
+}
+
+struct FitArgs {
+    const float* tsdf; int dx, dy, dz; int ox, oy, oz; float voxel;
+    const float4* vertex; const float* normal; int H, W;
+    TrackCam cam; TrackPose pose;
+    const float* cand; int n; int level, level_index, ph, pw;               // ph x pw = sub-sampled pixel grid
+    int chunks, pix_per_chunk;
+};
+
+// grid = (ceil(n / kCand), chunks); partial[(chunk * n + node) * 2 + {0,1}] = (sum, count) over the chunk's pixels
+__global__ void __launch_bounds__(kCand) track_fitness_kernel(FitArgs a, float* __restrict__ partial) {
+    __shared__ float4 sv[kPixChunk];               // vertex rotated into the world frame (:211-213), gt tsdf
+    __shared__ unsigned char sok[kPixChunk];       // pixel passes the validity tests (:182-203)
+    const int node = blockIdx.x * kCand + threadIdx.x;
+    const bool live = node < a.n;
+    const float* R = a.pose.R; const float* T = a.pose.T;
+    // candidate set-up (:215-222)
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f, q0 = 1.f;
+    if (live) {
+        c0 = a.cand[node * 6 + 0]; c1 = a.cand[node * 6 + 1]; c2 = a.cand[node * 6 + 2];     // t = c * ss is contracted below
+        q1 = __fmul_rn(a.cand[node * 6 + 3], a.pose.ss[3]);
+        q2 = __fmul_rn(a.cand[node * 6 + 4], a.pose.ss[4]);
+        q3 = __fmul_rn(a.cand[node * 6 + 5], a.pose.ss[5]);
+        q0 = __fsqrt_rn(__fmaf_rn(-q3, q3, __fmaf_rn(-q2, q2, __fmaf_rn(-q1, q1, 1.0f))));   // :222
+    }
+    const float ss0 = a.pose.ss[0], ss1 = a.pose.ss[1], ss2 = a.pose.ss[2];
+    float sum = 0.f, cnt = 0.f;
+    const int im_h = a.ph * a.level, im_w = a.pw * a.level;                 // :171-172
+    const int p_begin = blockIdx.y * a.pix_per_chunk, p_end = min(a.ph * a.pw, p_begin + a.pix_per_chunk);
+    for (int base = p_begin; base < p_end; base += kPixChunk) {
+        __syncthreads();
+        const int m = min(kPixChunk, p_end - base);
+        for (int j = threadIdx.x; j < m; j += kCand) {
+            const int p = base + j;
+            const int pi = (p / a.pw) * a.level + a.level_index, pj = (p % a.pw) * a.level + a.level_index;   // :179-180
+            bool ok = !(pi > im_h - 1 || pj > im_w - 1 || pi < 0 || pj < 0);                                 // :182
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok) {
+                const int i = pi * a.W + pj;
+                ok = !(a.normal[3 * i] == 0 && a.normal[3 * i + 1] == 0 && a.normal[3 * i + 2] == 0);        // :186
+                if (ok) { v = a.vertex[i]; ok = !(v.x == 0 && v.y == 0 && v.z == 0); }                       // :201
+            }
+            sok[j] = ok ? 1 : 0;
+            if (ok) {
+                const float x = v.x, y = v.y, z = v.z;
+                float global_x = __fmaf_rn(z, R[2], __fmaf_rn(x, R[0], __fmul_rn(y, R[1])));   // :211-213
+                float global_y = __fmaf_rn(z, R[5], __fmaf_rn(x, R[3], __fmul_rn(y, R[4])));
+                float global_z = __fmaf_rn(z, R[8], __fmaf_rn(x, R[6], __fmul_rn(y, R[7])));
+                sv[j] = make_float4(global_x, global_y, global_z, v.w);
+            }
+        }
+        __syncthreads();
+        if (live) {
+            for (int j = 0; j < m; ++j) {
+                if (!sok[j]) continue;                                                 // block-uniform
+                const float4 g = sv[j];
+                const float global_x = g.x, global_y = g.y, global_z = g.z, gt_tsdf = g.w;
+                // :224-227; S = -q_w
+                const float q_z = __fmaf_rn(global_z, q0, __fmaf_rn(global_y, q1, -__fmul_rn(global_x, q2)));
+                const float S   = __fmaf_rn(global_z, q3, __fmaf_rn(global_x, q1, __fmul_rn(global_y, q2)));
+                const float q_y = __fmaf_rn(-global_z, q1, __fmaf_rn(global_x, q3, __fmul_rn(global_y, q0)));
+                const float q_x = __fmaf_rn(global_z, q2, __fmaf_rn(global_x, q0, -__fmul_rn(global_y, q3)));
+                // :229-231 (the translation c * search_size is contracted into the chain, then + T)
+                const float x = __fadd_rn(__fmaf_rn(c0, ss0, __fmaf_rn(-q3, q_y, __fmaf_rn(q2, q_z, __fmaf_rn(q1, S, __fmul_rn(q_x, q0))))), T[0]);
+                const float y = __fadd_rn(__fmaf_rn(c1, ss1, __fmaf_rn(q3, q_x, __fmaf_rn(q2, S, __fmaf_rn(q_y, q0, -__fmul_rn(q1, q_z))))), T[1]);
+                const float z = __fadd_rn(__fmaf_rn(c2, ss2, __fmaf_rn(q3, S, __fmaf_rn(-q2, q_x, __fmaf_rn(q_z, q0, __fmul_rn(q1, q_y))))), T[2]);
+                const float vcx = __fadd_rn(x, -T[0]), vcy = __fadd_rn(y, -T[1]), vcz = __fadd_rn(z, -T[2]);          // :233-235
+                const float cam_x = __fmaf_rn(R[6], vcz, __fmaf_rn(R[0], vcx, __fmul_rn(R[3], vcy)));                  // :237-239
+                const float cam_y = __fmaf_rn(R[7], vcz, __fmaf_rn(R[1], vcx, __fmul_rn(R[4], vcy)));
+                const float cam_z = __fmaf_rn(R[8], vcz, __fmaf_rn(R[2], vcx, __fmul_rn(R[5], vcy)));
+                const int pixel_x = __float2int_rz(__fadd_rn(__fadd_rn(a.cam.k[2], __fdiv_rn(__fmul_rn(cam_x, a.cam.k[0]), cam_z)), 0.5f));   // :241-242
+                const int pixel_y = __float2int_rz(__fadd_rn(__fadd_rn(a.cam.k[5], __fdiv_rn(__fmul_rn(cam_y, a.cam.k[4]), cam_z)), 0.5f));
+                if (pixel_x >= 0 && pixel_y >= 0 && pixel_x < a.W && pixel_y < a.H && cam_z >= 0) {          // :245
+                    const int voxel_x = (int)roundf(__fdiv_rn(__fadd_rn(x, -(float)a.ox), a.voxel));                   // :246-248
+                    const int voxel_y = (int)roundf(__fdiv_rn(__fadd_rn(y, -(float)a.oy), a.voxel));
+                    const int voxel_z = (int)roundf(__fdiv_rn(__fadd_rn(z, -(float)a.oz), a.voxel));
+                    if (voxel_x < 1 || voxel_x >= a.dx - 1 || voxel_y < 1 || voxel_y >= a.dy - 1 || voxel_z < 1 || voxel_z >= a.dz - 1) continue;   // :250
+                    int index = voxel_z + voxel_y * a.dz + voxel_x * a.dy * a.dz;                            // :254
+                    const float add_value = fabsf(__fadd_rn(__ldg(a.tsdf + index), -gt_tsdf));                      // :261
+                    sum += add_value; cnt += 1.f;
+                }
+            }
+        }
+    }
+    if (live) {
+        float2* out = reinterpret_cast<float2*>(partial) + (size_t)blockIdx.y * a.n + node;
+        *out = make_float2(sum, cnt);
+    }
+}
+
+__global__ void track_fold_kernel(const float* __restrict__ partial, int n, int chunks, float* __restrict__ value, float* __restrict__ count) {
+    const int node = blockIdx.x * blockDim.x + threadIdx.x;
+    if (node >= n) return;
+    float s = 0.f, c = 0.f;
+    for (int k = 0; k < chunks; ++k) {
+        float2 v = reinterpret_cast<const float2*>(partial)[(size_t)k * n + node];
+        s += v.x; c += v.y;
+    }
+    value[node] = s; count[node] = c;
+}
+
+// Pixel chunks per candidate block: enough blocks for ~16 per SM (the per-pair chain of five IEEE divisions and a
+// dependent gather needs many warps to hide), at least 32 pixels per chunk.
+static int fit_chunks(int n, int pixels) {
+    const int cand_blocks = (n + kCand - 1) / kCand;
+    int chunks = (16 * num_sms() + cand_blocks - 1) / cand_blocks;
+    chunks = std::max(1, std::min(chunks, (pixels + 31) / 32));
+    return std::min(chunks, 512);
+}
+
+}  // namespace
+}  // namespace rf
+
+using namespace rf;
+
+extern "C" int rf_track_vertex_normal(const float* depth, int H, int W, const float K[9], float cut_dist, float trunc, int seed,
+                                      float sample_range, float* row_sample, float* depth_vertex, float* normal, void* stream) {
+    RF_REQUIRE(depth && K && row_sample && depth_vertex && normal, RF_E_NULL, "rf_track_vertex_normal: NULL pointer");
+    RF_REQUIRE(H >= 3 && W >= 3 && (long long)H * W < (1ll << 31), RF_E_RANGE, "rf_track_vertex_normal: bad image size %dx%d", W, H);
+    RF_REQUIRE(((uintptr_t)depth_vertex & 15) == 0, RF_E_ALIGN, "rf_track_vertex_normal: depth_vertex must be 16-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    TrackCam cam; for (int i = 0; i < 9; ++i) cam.k[i] = K[i];
+    // the reference ships the seed inside a float32 array (:447-456) and converts it back with int(): same rounding here
+    const unsigned long long seed_u = (unsigned long long)(int)(float)seed;
+    track_row_sample_kernel<<<(H + 127) / 128, 128, 0, s>>>(H, seed_u, sample_range, row_sample);
+    RF_CHECK_LAUNCH("track_row_sample_kernel");
+    const int n = H * W;
+    track_vertex_kernel<<<(n + 255) / 256, 256, 0, s>>>(depth, row_sample, cam, H, W, cut_dist, trunc, reinterpret_cast<float4*>(depth_vertex));
+    RF_CHECK_LAUNCH("track_vertex_kernel");
+    track_normal_kernel<<<(n + 255) / 256, 256, 0, s>>>(reinterpret_cast<const float4*>(depth_vertex), H, W, normal);
+    RF_CHECK_LAUNCH("track_normal_kernel");
+    return 0;
+}
+
+extern "C" int64_t rf_track_fitness_scratch_floats(int n_candidates, int H, int W, int level) {
+    if (n_candidates <= 0 || level <= 0) return 0;
+    return 2ll * n_candidates * fit_chunks(n_candidates, (H / level) * (W / level));
+}
+
+extern "C" int rf_track_fitness(const float* tsdf_vol, const int vol_dim[3], const float vol_origin[3], float voxel_size,
+                                const float* depth_vertex, const float* normal, int H, int W, const float K[9],
+                                const float R[9], const float T[3], const float* candidates, int n_candidates,
+                                const float search_size[6], int level, int level_index,
+                                float* search_value, float* search_count, float* scratch, void* stream) {
+    RF_REQUIRE(tsdf_vol && vol_dim && vol_origin && depth_vertex && normal && K && R && T && candidates && search_size && search_value && search_count && scratch,
+               RF_E_NULL, "rf_track_fitness: NULL pointer");
+    RF_REQUIRE(n_candidates > 0 && level > 0 && level_index >= 0 && H > 0 && W > 0, RF_E_RANGE, "rf_track_fitness: bad sizes");
+    RF_REQUIRE((((uintptr_t)depth_vertex & 15) | ((uintptr_t)scratch & 7)) == 0, RF_E_ALIGN, "rf_track_fitness: depth_vertex 16-byte / scratch 8-byte alignment");
+    RF_REQUIRE((long long)vol_dim[0] * vol_dim[1] * vol_dim[2] < (1ll << 31), RF_E_RANGE, "rf_track_fitness: volume too large for the reference's int index");
+    FitArgs a;
+    a.tsdf = tsdf_vol; a.dx = vol_dim[0]; a.dy = vol_dim[1]; a.dz = vol_dim[2];
+    a.ox = (int)vol_origin[0]; a.oy = (int)vol_origin[1]; a.oz = (int)vol_origin[2];      // :163-165: origin truncated to int
+    a.voxel = voxel_size;
+    a.vertex = reinterpret_cast<const float4*>(depth_vertex); a.normal = normal; a.H = H; a.W = W;
+    for (int i = 0; i < 9; ++i) { a.cam.k[i] = K[i]; a.pose.R[i] = R[i]; }
+    for (int i = 0; i < 3; ++i) a.pose.T[i] = T[i];
+    for (int i = 0; i < 6; ++i) a.pose.ss[i] = search_size[i];
+    a.cand = candidates; a.n = n_candidates; a.level = level; a.level_index = level_index;
+    a.ph = H / level; a.pw = W / level;                                                    // host :587-588: int(im_h/level)
+    const int pixels = a.ph * a.pw;
+    a.chunks = fit_chunks(n_candidates, pixels);
+    a.pix_per_chunk = std::max(1, (pixels + a.chunks - 1) / a.chunks);
+    cudaStream_t s = (cudaStream_t)stream;
+    {
+        ProfScope ps(RF_PROF_TRACK_FITNESS, s);
+        track_fitness_kernel<<<dim3((n_candidates + kCand - 1) / kCand, a.chunks), kCand, 0, s>>>(a, scratch);
+    }
+    RF_CHECK_LAUNCH("track_fitness_kernel");
+    track_fold_kernel<<<(n_candidates + 255) / 256, 256, 0, s>>>(scratch, n_candidates, a.chunks, search_value, search_count);
+    RF_CHECK_LAUNCH("track_fold_kernel");
+    return 0;
+}
