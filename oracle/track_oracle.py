@@ -1,0 +1,116 @@
+"""TEST INFRASTRUCTURE ONLY — never imported by remixfusion_b200/.
+
+NumPy restatement of the tracker kernels of the reference (model/ROtracker.py:141-400), one array expression per
+source line, vectorised over pixels / (candidate, pixel) pairs:
+
+  * vertex_map   compute_vertex  :273-344 — given the per-ROW random sample (the reference draws it with curand XORWOW,
+                 subsequence = row index; the generator itself is NVIDIA's and is not restated: golden vectors carry the
+                 samples the literal kernel drew)
+  * normal_map   compute_normal  :346-400
+  * fitness      compute_tsdf_value :144-271 (+ host evaluate_tsdf :536-604)
+
+PARITY: pinned by tests/golden/track_golden.npz = outputs of the literal reference kernels (oracle/_ref/ref_tracker.cubin)
+on a B200 (tests/golden/make_track_golden.py).  fp32 throughout; fused multiply-adds are emulated where the compiled
+reference kernel has them (fma32: exact product and sum in float64, one rounding to float32 — double rounding can
+differ from a hardware FMA by one ulp in rare cases, hence the tolerances in tests/test_track_oracle.py)."""
+from __future__ import annotations
+
+import numpy as np
+
+f32 = np.float32
+
+
+def fma32(a, b, c):
+    return (np.asarray(a, np.float64) * np.asarray(b, np.float64) + np.asarray(c, np.float64)).astype(np.float32)
+
+
+def vertex_map(depth, K, cut_dist, trunc, row_sample, sample_range):
+    """depth [H,W] fp32, row_sample [H] fp32 -> depth_vertex [H,W,4]."""
+    H, W = depth.shape
+    K = np.asarray(K, f32).reshape(-1)
+    d = depth.astype(f32).copy()
+    d[d > f32(cut_dist)] = 0                                               # :292-294
+    sample = row_sample.astype(f32)[:, None] * np.ones((1, W), f32)
+    z_val = sample * f32(trunc)
+    gt = -sample                                                           # :326-334
+    gt = np.where(z_val < f32(-1) * f32(trunc), f32(1), gt)
+    gt = np.where(z_val > f32(1) * f32(trunc), f32(1), gt)
+    c_z = d + z_val                                                        # :337-339
+    pj = np.arange(W, dtype=f32)[None, :]; pi = np.arange(H, dtype=f32)[:, None]
+    c_x = ((pj - K[2]) * c_z) / K[0]
+    c_y = ((pi - K[5]) * c_z) / K[4]
+    out = np.stack([c_x, c_y, c_z, gt.astype(f32)], -1).astype(f32)
+    out[d <= 0] = 0                                                        # :296-303
+    return out
+
+
+def normal_map(vertex):
+    """vertex [H,W,4] -> normal [H,W,3]; border pixels stay zero (:353-355)."""
+    H, W, _ = vertex.shape
+    n = np.zeros((H, W, 3), f32)
+    c = vertex[1:-1, 1:-1]; l = vertex[1:-1, :-2]; r = vertex[1:-1, 2:]; u = vertex[:-2, 1:-1]; d = vertex[2:, 1:-1]
+    ok = (c[..., 2] != 0) & (l[..., 2] != 0) & (r[..., 2] != 0) & (u[..., 2] != 0) & (d[..., 2] != 0)
+    hor = l[..., :3] - r[..., :3]; ver = u[..., :3] - d[..., :3]
+    # :379-385 as compiled: a*b + c*d -> fma(a, b, c*d)
+    nx = fma32(hor[..., 1], ver[..., 2], (-hor[..., 2]) * ver[..., 1])
+    ny = fma32(hor[..., 2], ver[..., 0], -(hor[..., 0] * ver[..., 2]))
+    nz = fma32(hor[..., 0], ver[..., 1], (-hor[..., 1]) * ver[..., 0])
+    with np.errstate(invalid="ignore", divide="ignore"):
+        lens = np.sqrt(fma32(nz, nz, fma32(ny, ny, nx * nx)))
+        nx, ny, nz = nx / lens, ny / lens, nz / lens
+    flip = nz > 0
+    nx = np.where(flip, -nx, nx); ny = np.where(flip, -ny, ny); nz = np.where(flip, -nz, nz)
+    inner = np.stack([nx, ny, nz], -1).astype(f32)
+    inner[~ok] = 0
+    n[1:-1, 1:-1] = inner
+    return n
+
+
+def fitness(tsdf, vol_dim, vol_origin, voxel, vertex, normal, K, R, T, cand, search_size, level, level_index):
+    """tsdf flat fp32 (index z + y*dz + x*dy*dz); vertex [H,W,4]; normal [H,W,3]; cand [n,6] -> (value [n], count [n])."""
+    H, W, _ = vertex.shape
+    K = np.asarray(K, f32).reshape(-1); R = np.asarray(R, f32).reshape(-1); T = np.asarray(T, f32).reshape(-1)
+    ss = np.asarray(search_size, f32).reshape(-1); cand = np.asarray(cand, f32)
+    dx, dy, dz = (int(v) for v in vol_dim)
+    ox, oy, oz = (f32(int(v)) for v in vol_origin)                         # :163-165 origin truncated to int
+    ph, pw = int(H / level), int(W / level)
+    pi = (np.arange(ph) * level + level_index)[:, None] * np.ones((1, pw), int)
+    pj = (np.arange(pw) * level + level_index)[None, :] * np.ones((ph, 1), int)
+    ok = (pi <= ph * level - 1) & (pj <= pw * level - 1)
+    pi, pj = pi[ok], pj[ok]
+    nrm = normal[pi, pj]; v = vertex[pi, pj]
+    keep = ~((nrm == 0).all(-1)) & ~((v[:, :3] == 0).all(-1))              # :186, :201
+    v = v[keep]
+    x, y, z, gt = v[:, 0], v[:, 1], v[:, 2], v[:, 3]
+    gx = fma32(z, R[2], fma32(x, R[0], y * R[1]))                           # :211-213 (as compiled)
+    gy = fma32(z, R[5], fma32(x, R[3], y * R[4]))
+    gz = fma32(z, R[8], fma32(x, R[6], y * R[7]))
+    q1 = (cand[:, 3] * ss[3])[:, None]; q2 = (cand[:, 4] * ss[4])[:, None]; q3 = (cand[:, 5] * ss[5])[:, None]   # :219-221
+    q0 = np.sqrt(fma32(-q3, q3, fma32(-q2, q2, fma32(-q1, q1, f32(1)))))    # :222
+    gx, gy, gz, gt = gx[None], gy[None], gz[None], gt[None]
+    q_z = fma32(gz, q0, fma32(gy, q1, -(gx * q2)))                          # :224-227
+    S = fma32(gz, q3, fma32(gx, q1, gy * q2))
+    q_y = fma32(-gz, q1, fma32(gx, q3, gy * q0))
+    q_x = fma32(gz, q2, fma32(gx, q0, -(gy * q3)))
+    c0, c1, c2 = cand[:, 0:1], cand[:, 1:2], cand[:, 2:3]
+    X = fma32(c0, ss[0], fma32(-q3, q_y, fma32(q2, q_z, fma32(q1, S, q_x * q0)))) + T[0]      # :229-231
+    Y = fma32(c1, ss[1], fma32(q3, q_x, fma32(q2, S, fma32(q_y, q0, -(q1 * q_z))))) + T[1]
+    Z = fma32(c2, ss[2], fma32(q3, S, fma32(-q2, q_x, fma32(q_z, q0, q1 * q_y)))) + T[2]
+    vx, vy, vz = X - T[0], Y - T[1], Z - T[2]                               # :233-235
+    cam_x = fma32(R[6], vz, fma32(R[0], vx, R[3] * vy))                     # :237-239
+    cam_y = fma32(R[7], vz, fma32(R[1], vx, R[4] * vy))
+    cam_z = fma32(R[8], vz, fma32(R[2], vx, R[5] * vy))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        px = np.trunc((K[2] + (cam_x * K[0]) / cam_z) + f32(0.5))           # :241-242
+        py = np.trunc((K[5] + (cam_y * K[4]) / cam_z) + f32(0.5))
+        hit = (px >= 0) & (py >= 0) & (px < W) & (py < H) & (cam_z >= 0)    # :245
+        rnd = lambda a: np.sign(a) * np.floor(np.abs(a) + f32(0.5))         # roundf: half away from zero
+        vxi = rnd((X - ox) / f32(voxel)); vyi = rnd((Y - oy) / f32(voxel)); vzi = rnd((Z - oz) / f32(voxel))   # :246-248
+    inside = (vxi >= 1) & (vxi < dx - 1) & (vyi >= 1) & (vyi < dy - 1) & (vzi >= 1) & (vzi < dz - 1)            # :250
+    hit &= inside
+    idx = (np.where(hit, vzi, 0) + np.where(hit, vyi, 0) * dz + np.where(hit, vxi, 0) * dy * dz).astype(np.int64)   # :254
+    add = np.abs(tsdf[idx] - gt).astype(f32)                                # :261
+    add = np.where(hit, add, f32(0))
+    value = add.astype(np.float64).sum(1).astype(f32)                       # the reference sums with fp32 atomics in arbitrary order
+    count = hit.sum(1).astype(f32)
+    return value, count
