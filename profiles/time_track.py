@@ -1,5 +1,9 @@
+"""Kernel-only timing of the tracker kernels, product vs the literal reference kernel (DESIGN.md §7, N2 second half).
+
+    python profiles/time_track.py        (GPU box; oracle/_ref cubins required)
+"""
 import sys, os, time
-sys.path.insert(0, os.getcwd())
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from oracle import ref_kernels as RK
 from remixfusion_b200 import configs, synth
