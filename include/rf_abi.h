@@ -96,6 +96,14 @@ int rf_track_fitness(const float* tsdf_vol, const int vol_dim[3], const float vo
                      float* search_value, float* search_count, float* scratch, void* stream);
 int64_t rf_track_fitness_scratch_floats(int n_candidates, int H, int W, int level);
 
+/* rf_track_cal_transform replaces the Python loop of `cal_transform` (model/ROtracker.py:606-714) on the arrays the call
+ * above left on the device: fit_j = search_value[j] / (search_count[j] + 1e-6) (evaluate_tsdf :604); among candidates
+ * 1..n-1 with fit_j < fit_0, the first `count_search` in index order are averaged with weights fit_0 - fit_j.
+ * out9 (device, 9 floats): success flag (0 / 1), min_tsdf, mean_transform = (tx, ty, tz, qw, qx, qy, qz).
+ * No qualifying candidate: (0, fit_0, zeros).  search_size is a host array. */
+int rf_track_cal_transform(const float* search_value, const float* search_count, const float* candidates, int n_candidates,
+                           const float search_size[6], int count_search, float* out9, void* stream);
+
 /* The per-pixel factor 1/sqrt(vx^2 + vy^2 + 1), vx = (px - cx)/fx, vy = (py - cy)/fy, of the projective SDF
  * (model/Volume.py:280-283, mp_slam/mapper.py:108-111).  It depends on the intrinsics only, so a caller computes it
  * once per camera and passes it to every integrate; the kernels then load it next to the depth instead of spending two

@@ -8,6 +8,7 @@ source line, vectorised over pixels / (candidate, pixel) pairs:
                  samples the literal kernel drew)
   * normal_map   compute_normal  :346-400
   * fitness      compute_tsdf_value :144-271 (+ host evaluate_tsdf :536-604)
+  * cal_transform  the host loop of :606-714, statement by statement
 
 PARITY: pinned by tests/golden/track_golden.npz = outputs of the literal reference kernels (oracle/_ref/ref_tracker.cubin)
 on a B200 (tests/golden/make_track_golden.py).  fp32 throughout; fused multiply-adds are emulated where the compiled
@@ -114,3 +115,36 @@ def fitness(tsdf, vol_dim, vol_origin, voxel, vertex, normal, K, R, T, cand, sea
     value = add.astype(np.float64).sum(1).astype(f32)                       # the reference sums with fp32 atomics in arbitrary order
     count = hit.sum(1).astype(f32)
     return value, count
+
+
+def cal_transform(search_value, transform_candidate, search_size, count_search_max):
+    """model/ROtracker.py:606-714, literally (Python floats accumulate float32 products, as under NumPy 1.x)."""
+    search_value = np.asarray(search_value, f32); cand = np.asarray(transform_candidate, f32); ss = np.asarray(search_size, f32)
+    mean_transform = np.zeros(7, f32)
+    origin_tsdf = search_value[0]
+    sum_tx = sum_ty = sum_tz = sum_qw = sum_qx = sum_qy = sum_qz = sum_weight = sum_tsdf = 0.0
+    count_search = 0
+    for j in range(1, len(search_value)):
+        if search_value[j] < origin_tsdf:
+            tx, ty, tz, qx, qy, qz = (cand[j][k] for k in range(6))
+            cur_fit = search_value[j]
+            weight = origin_tsdf - cur_fit
+            sum_tx += float(tx * weight); sum_ty += float(ty * weight); sum_tz += float(tz * weight)
+            sum_qx += float(qx * weight); sum_qy += float(qy * weight); sum_qz += float(qz * weight)
+            qx = qx * ss[3]; qy = qy * ss[4]; qz = qz * ss[5]
+            qw = np.sqrt(f32(1) - qx * qx - qy * qy - qz * qz)
+            sum_qw += float(qw * weight); sum_weight += float(weight); sum_tsdf += float(cur_fit * weight)
+            count_search += 1
+            if count_search == count_search_max:
+                break
+    if count_search <= 0:
+        return False, float(origin_tsdf), mean_transform
+    mean_tsdf = sum_tsdf / sum_weight
+    mean_transform[0] = (sum_tx / sum_weight) * float(ss[0])
+    mean_transform[1] = (sum_ty / sum_weight) * float(ss[1])
+    mean_transform[2] = (sum_tz / sum_weight) * float(ss[2])
+    qww = sum_qw / sum_weight
+    qxx = (sum_qx / sum_weight) * float(ss[3]); qyy = (sum_qy / sum_weight) * float(ss[4]); qzz = (sum_qz / sum_weight) * float(ss[5])
+    lens = 1 / np.sqrt(qww * qww + qxx * qxx + qyy * qyy + qzz * qzz)
+    mean_transform[3] = qww * lens; mean_transform[4] = qxx * lens; mean_transform[5] = qyy * lens; mean_transform[6] = qzz * lens
+    return True, float(mean_tsdf), mean_transform

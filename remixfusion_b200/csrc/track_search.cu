@@ -181,6 +181,75 @@ __global__ void track_fold_kernel(const float* __restrict__ partial, int n, int 
     value[node] = s; count[node] = c;
 }
 
+// cal_transform (model/ROtracker.py:606-714): weighted mean of the FIRST `count_search` candidates (in index order) that
+// fit better than candidate 0, weights = origin_tsdf - fit.  One block: every thread owns a contiguous range of
+// candidates, a block scan of the per-range qualifier counts gives each qualifier its ordinal, partial sums are kept in
+// double (the reference accumulates float32 products into Python floats) and folded in a fixed order.
+// out[0] = success (0 / 1), out[1] = min_tsdf, out[2..8] = mean_transform (tx, ty, tz, qw, qx, qy, qz).
+constexpr int kCalThreads = 1024;
+__global__ void __launch_bounds__(kCalThreads) track_cal_transform_kernel(const float* __restrict__ value, const float* __restrict__ count,
+                                                                          const float* __restrict__ cand, int n, TrackPose pose, int count_search,
+                                                                          float* __restrict__ out) {
+    __shared__ int s_cnt[kCalThreads];
+    __shared__ double s_sum[9][32];
+    const int t = threadIdx.x;
+    auto fit = [&](int j) { return __fdiv_rn(value[j], __fadd_rn(count[j], 1e-6f)); };       // evaluate_tsdf :604
+    const float origin = fit(0);                                                             // :622
+    const int per = (n - 1 + kCalThreads - 1) / kCalThreads;
+    const int j0 = 1 + t * per, j1 = min(n, j0 + per);
+    int mine = 0;
+    for (int j = j0; j < j1; ++j) mine += fit(j) < origin ? 1 : 0;                           // :638
+    s_cnt[t] = mine;
+    __syncthreads();
+    for (int off = 1; off < kCalThreads; off <<= 1) {                                        // inclusive scan
+        int v = (t >= off) ? s_cnt[t - off] : 0;
+        __syncthreads();
+        s_cnt[t] += v;
+        __syncthreads();
+    }
+    int ordinal = s_cnt[t] - mine;                                                           // qualifiers before this range
+    const int total = min(s_cnt[kCalThreads - 1], count_search);                             // :677-678
+    double a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // tx ty tz qx qy qz qw weight tsdf
+    for (int j = j0; j < j1 && ordinal < count_search; ++j) {
+        const float cur_fit = fit(j);
+        if (!(cur_fit < origin)) continue;
+        ++ordinal;
+        const float weight = __fadd_rn(origin, -cur_fit);                                    // :647
+        const float* c = cand + (size_t)j * 6;
+        a[0] += (double)__fmul_rn(c[0], weight); a[1] += (double)__fmul_rn(c[1], weight); a[2] += (double)__fmul_rn(c[2], weight);   // :649-654
+        a[3] += (double)__fmul_rn(c[3], weight); a[4] += (double)__fmul_rn(c[4], weight); a[5] += (double)__fmul_rn(c[5], weight);
+        const float qx = __fmul_rn(c[3], pose.ss[3]), qy = __fmul_rn(c[4], pose.ss[4]), qz = __fmul_rn(c[5], pose.ss[5]);           // :657-659
+        const float qw = __fsqrt_rn(__fadd_rn(__fadd_rn(__fadd_rn(1.0f, -__fmul_rn(qx, qx)), -__fmul_rn(qy, qy)), -__fmul_rn(qz, qz)));   // :670
+        a[6] += (double)__fmul_rn(qw, weight); a[7] += (double)weight; a[8] += (double)__fmul_rn(cur_fit, weight);                 // :671-673
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        double v = a[k];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if ((t & 31) == 0) s_sum[k][t >> 5] = v;
+    }
+    __syncthreads();
+    if (t == 0) {
+        double r[9];
+        for (int k = 0; k < 9; ++k) { double v = 0; for (int w = 0; w < kCalThreads / 32; ++w) v += s_sum[k][w]; r[k] = v; }
+        if (total <= 0) {                                                                    // :681-684
+            out[0] = 0.f; out[1] = origin;
+            for (int k = 2; k < 9; ++k) out[k] = 0.f;
+        } else {
+            const double sw = r[7];
+            out[0] = 1.f;
+            out[1] = (float)(r[8] / sw);                                                     // :687, :712
+            out[2] = (float)((r[0] / sw) * (double)pose.ss[0]);                              // :688-690
+            out[3] = (float)((r[1] / sw) * (double)pose.ss[1]);
+            out[4] = (float)((r[2] / sw) * (double)pose.ss[2]);
+            const double qww = r[6] / sw, qxx = (r[3] / sw) * (double)pose.ss[3], qyy = (r[4] / sw) * (double)pose.ss[4],
+                         qzz = (r[5] / sw) * (double)pose.ss[5];                              // :691-694
+            const double lens = 1.0 / sqrt(qww * qww + qxx * qxx + qyy * qyy + qzz * qzz);   // :701
+            out[5] = (float)(qww * lens); out[6] = (float)(qxx * lens); out[7] = (float)(qyy * lens); out[8] = (float)(qzz * lens);
+        }
+    }
+}
+
 // Pixel chunks per candidate block: enough blocks for ~16 per SM (the per-pair chain of five IEEE divisions and a
 // dependent gather needs many warps to hide), at least 32 pixels per chunk.
 static int fit_chunks(int n, int pixels) {
@@ -250,5 +319,16 @@ extern "C" int rf_track_fitness(const float* tsdf_vol, const int vol_dim[3], con
     RF_CHECK_LAUNCH("track_fitness_kernel");
     track_fold_kernel<<<(n_candidates + 255) / 256, 256, 0, s>>>(scratch, n_candidates, a.chunks, search_value, search_count);
     RF_CHECK_LAUNCH("track_fold_kernel");
+    return 0;
+}
+
+extern "C" int rf_track_cal_transform(const float* search_value, const float* search_count, const float* candidates, int n_candidates,
+                                      const float search_size[6], int count_search, float* out9, void* stream) {
+    RF_REQUIRE(search_value && search_count && candidates && search_size && out9, RF_E_NULL, "rf_track_cal_transform: NULL pointer");
+    RF_REQUIRE(n_candidates >= 1 && count_search >= 0, RF_E_RANGE, "rf_track_cal_transform: bad sizes");
+    TrackPose pose; memset(&pose, 0, sizeof(pose));
+    for (int i = 0; i < 6; ++i) pose.ss[i] = search_size[i];
+    track_cal_transform_kernel<<<1, kCalThreads, 0, (cudaStream_t)stream>>>(search_value, search_count, candidates, n_candidates, pose, count_search, out9);
+    RF_CHECK_LAUNCH("track_cal_transform_kernel");
     return 0;
 }

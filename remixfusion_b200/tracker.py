@@ -33,6 +33,8 @@ class ROSearch:
         self.transform_candidate = np.zeros((0, 6), dtype=np.float32)
         self.search_size = np.zeros(6, dtype=np.float32)
         self._cand_key, self._cand_dev = None, None
+        self._last = None                                  # (value, count, n) of the last evaluate_tsdf, on the device
+        self.count_search = 0                              # cfg["RO"]["count_search"] (model/ROtracker.py:58)
 
     # ---- model/ROtracker.py:436-456 --------------------------------------------------------------------------
     def init_depth_vertex(self, depth_im, cam_intr, seed_num=None):
@@ -78,7 +80,24 @@ class ROSearch:
                                     abi.fptr(R), abi.fptr(T), abi.dptr(self._cand_dev), n, abi.fptr(ss), int(level), int(level_index),
                                     abi.dptr(value), abi.dptr(count), abi.dptr(scratch), abi.stream_ptr())
             abi.check(rc, "rf_track_fitness")
+        self._last = (value, count, n)
         if not as_numpy:
             return value / (count + 1e-6), value, count
         v = value.cpu().numpy(); c = count.cpu().numpy()
         return v / (c + 1e-6), v, c                       # :601-604
+
+    # ---- model/ROtracker.py:606-714 --------------------------------------------------------------------------
+    def cal_transform(self, search_value=None):
+        """(success, min_tsdf, mean_transform[7]) from the fitness arrays the last ``evaluate_tsdf`` left on the device:
+        the reference's Python loop over all candidates as one kernel and a 9-float read-back.  ``search_value`` is
+        accepted for signature parity and ignored (it is the first array ``evaluate_tsdf`` returned)."""
+        if self._last is None:
+            raise abi.RfError("cal_transform: call evaluate_tsdf first")
+        value, count, n = self._last
+        ss = np.ascontiguousarray(np.asarray(self.search_size, dtype=np.float32).reshape(-1))
+        out = torch.empty(9, dtype=torch.float32, device=self.device)
+        rc = abi.lib().rf_track_cal_transform(abi.dptr(value), abi.dptr(count), abi.dptr(self._cand_dev), int(max(n, 1)), abi.fptr(ss),
+                                              int(self.count_search), abi.dptr(out), abi.stream_ptr())
+        abi.check(rc, "rf_track_cal_transform")
+        o = out.cpu().numpy()
+        return bool(o[0] > 0.5), float(o[1]), o[2:9].copy()

@@ -121,3 +121,34 @@ def test_fitness_matches_reference(scene, n, level, level_index):
     assert torch.equal(val, val2) and torch.equal(cnt, cnt2)
     # the current pose (candidate 0) fits the volume it was integrated from better than the average perturbed pose
     assert float(norm[0]) <= float(norm[1:].mean())
+
+
+@pytest.mark.parametrize("n,count_search,mode", [(10240, 30, "half"), (3072, 2000, "half"), (1024, 100000, "few"), (1024, 30, "none"), (2048, 1, "half")])
+def test_cal_transform_matches_host_loop(cuda, rf_lib, n, count_search, mode):
+    """rf_track_cal_transform vs the statement-by-statement restatement of the reference's Python loop
+    (oracle/track_oracle.py: cal_transform; model/ROtracker.py:606-714)."""
+    from oracle import track_oracle as TO
+    from remixfusion_b200.tracker import ROSearch
+    g = np.random.default_rng(n + count_search)
+    cand = (g.random((n, 6)).astype(np.float32) * 2 - 1); cand[0] = 0
+    ss = np.array([0.02, 0.03, 0.01, 0.01, 0.02, 0.015], np.float32)
+    count = np.floor(g.random(n) * 700 + 1).astype(np.float32)
+    fit = (0.2 + 0.1 * g.random(n)).astype(np.float32)
+    if mode == "few":
+        fit[1:] += 0.2; fit[g.integers(1, n, 7)] = 0.1
+    if mode == "none":
+        fit[0] = 0.05
+    value = (fit * count).astype(np.float32)
+
+    class MV:                                               # only the attributes ROSearch.__init__ reads
+        tsdf_vol_gpu = torch.zeros(8, device=cuda)
+    s = ROSearch(MV, 8, 8, 6.0, 0.06, 3.0)
+    s.transform_candidate, s.search_size, s.count_search = cand, ss, count_search
+    s._cand_dev = torch.from_numpy(cand).to(cuda)
+    s._last = (torch.from_numpy(value).to(cuda), torch.from_numpy(count).to(cuda), n)
+    ok, min_tsdf, mt = s.cal_transform()
+    sv = (value / (count + np.float32(1e-6))).astype(np.float32)          # evaluate_tsdf :604
+    ok_ref, min_ref, mt_ref = TO.cal_transform(sv, cand, ss, count_search)
+    assert ok == ok_ref and (mode != "none" or not ok)
+    assert abs(min_tsdf - min_ref) <= 1e-6 * abs(min_ref) + 1e-9
+    np.testing.assert_allclose(mt, mt_ref, rtol=2e-6, atol=1e-9)
