@@ -344,7 +344,10 @@ def run_gpu(args, rank, world, local_rank):
     if rank == 0 and not os.environ.get("RF_BENCH_NO_SAMPLER"):
         sampler.start()
     for i in range(args.warmup):
-        step(i, False)
+        # keep the previous step's loss referenced while the next step runs, exactly as the timed loop does: its autograd
+        # node owns the 7.7 GB feature workspace, so two workspaces are live at a time and the caching allocator must
+        # already hold both blocks (a first cudaMalloc of the second one inside the timed region stalls the host 5-60 ms)
+        _, loss = step(i, False)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

@@ -810,6 +810,62 @@ __device__ __forceinline__ void flush_wgrads2(uint32_t tlane, const Grads& gr, i
     }
 }
 
+// Input-layer weight gradients with the hidden-gradient block as the A operand (MN-major, M = 128 rows = 16 consecutive
+// chunks: [dH hi | dH lo] of one net at hidden 64, of both nets at hidden 32) and X as the B operand (MN-major, N = 8 per
+// chunk), first its hi part then its lo part into the SAME columns: D[row][f] += sum_m dH_part[m][row] (X_hi + X_lo)[m][f].
+// The hi and lo rows of a unit are added when the accumulators are flushed.  Compared with X as the A operand this reads
+// 15 KB instead of 22 KB of operands per k-step for both nets and needs half the MMAs.
+__device__ __forceinline__ void mma_wx(uint32_t d, uint32_t a, uint32_t bh, uint32_t bl, uint32_t idesc, uint32_t& acc) {
+    uint64_t da = smem_desc(a, 128, kChunkB), dbh = smem_desc(bh, 128, kChunkB), dbl = smem_desc(bl, 128, kChunkB);
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+        mma_bf16(d, da, dbh, idesc, acc); acc = 1;
+        mma_bf16(d, da, dbl, idesc, 1);
+        da = desc_advance(da, 2 * 128); dbh = desc_advance(dbh, 2 * 128); dbl = desc_advance(dbl, 2 * 128);
+    }
+}
+
+// Flush for the mma_wx layout.  Hidden 32: lanes = [dH1 hi | dH1 lo | dH2 hi | dH2 lo] x 32 units, columns = the 112 X-order
+// features (the colour net uses columns 32..97); the two threads of a lane split the columns.  Hidden 64: t_w0 holds the
+// sdf net (lanes = [hi | lo] x 64 units, 112 columns; thread h = 0), t_w2 the colour net (80 columns; thread h = 1).
+template <int HID>
+__device__ __forceinline__ void flush_wgrads3(uint32_t tlane, const Grads& gr, int m, int h) {
+    using A = BwdL<HID>;
+    fence_after_sync();
+    const int j = m & (HID - 1);
+    const bool colour = (HID == 32) ? (m >= 64) : (h == 1);
+    float* gx = colour ? gr.g_w_col0 : gr.g_w_sdf0;
+    const int ld = colour ? kIn2 : 81;
+    const uint32_t tx = tlane + ((HID == 64 && h == 1) ? A::t_w2 : A::t_w0);
+    const int q0 = (HID == 32) ? (h ? 4 : 0) : 0;
+    const int q1 = (HID == 32) ? (h ? 7 : 4) : (h ? 5 : 7);
+    const int fshift = (HID == 32 && colour) ? -32 : 0;       // X-order column -> colour-net input (blob | tail)
+#pragma unroll 1
+    for (int q = q0; q < q1; ++q) {
+        float v[16];
+        tmem_ld16(tx + 16 * q, v);
+        if (!gx) continue;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int f = 16 * q + i + fshift;
+            int c = -1;
+            if (colour) { if (f >= 0 && f < kIn2) c = f; }
+            else { if (f < 80) c = f; else if (f == 80 + kTailTsdf) c = 80; }
+            if (c >= 0) atomicAdd(gx + j * ld + c, v[i]);
+        }
+    }
+    // H-based: rows [0,HID) = hi features (columns: x hi | x lo), rows [HID,2HID) = lo features (column block x hi)
+    float v32[32];
+    tmem_ld32(tlane + (h ? A::t_w3 : A::t_w1), v32);
+    float* gh = h ? gr.g_w_col1 : gr.g_w_sdf1;
+    const int rows = h ? 3 : 16;
+    if (gh && m < 2 * HID) {
+        const int jj = (m < HID) ? m : m - HID;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) if (i < rows) atomicAdd(gh + i * HID + jj, (m < HID) ? v32[i] + v32[16 + i] : v32[i]);
+    }
+}
+
 // sum_k d blob_k / dx * g_k for the 16 bins of one coordinate (Appendix B7 derivative: d out_k / dx = pdf_k - pdf_{k+1} at the
 // bin boundaries).  As in stage_oneblob, inside [-0.9, 1.9] only the two boundaries next to x have a non-zero kernel
 // value, so three bins carry gradient; elsewhere the general form.
@@ -1009,8 +1065,10 @@ __global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights
             fence_after_sync();
             uint32_t acc = 0;
             mma_ts_m<HC / 2>(tb + T_B, tb + T_S, tb + T_S + NH, w2h + 6 * HID * 16, w2l + 6 * HID * 16, HID, id16_bm, acc);   // d tail[0..15] = dH2 W2[:, 48..63]
-            uint32_t a2 = wacc;
-            mma_mm2(tb + A::t_w2, xh + kXBlob * kChunkB, xl + kXBlob * kChunkB, h2h, id2H_mm, idH_mm, a2);   // dW2^T += X2^T dH2
+            if constexpr (HID == 64) {                                                        // dW2 += dH2^T X2 (hidden 32: with dW0 below)
+                uint32_t a2 = wacc;
+                mma_wx(tb + A::t_w2, h2h, xh + kXBlob * kChunkB, xl + kXBlob * kChunkB, idesc_bf16(80, true, true), a2);
+            }
             commit(bar);
         }
         grp_wait(bar, phase);
@@ -1052,7 +1110,7 @@ __global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights
                 mma_ts_m<HC / 2>(tb + T_A, tb + T_S, tb + T_S + NH, w0h, w0l, HID, id32_bm, acc); // d hash = dH1 W0[:, 0..31]
             }
             uint32_t a0 = wacc;
-            mma_mm2(tb + A::t_w0, xh, xl, h1h, id2H_mm, idH_mm, a0);                          // dW0^T += X1^T dH1
+            mma_wx(tb + A::t_w0, h1h, xh, xl, idesc_bf16(112, true, true), a0);               // dW0 += dH1^T X1 (hidden 32: and dW2 += dH2^T X)
             commit(bar);
         }
         wacc = 1;
@@ -1099,10 +1157,10 @@ __global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights
                 if (live) reinterpret_cast<float4*>(dgb)[q] = make_float4(tc[2] * dg_cin + dr.w * dg_add, ta[15] + dr.x, tc[0] + dr.y, tc[1] + dr.z);
             }
         }
-        if (++since_flush == kFlushTiles) { flush_wgrads2<HID>(tlane, gr, m, h); wacc = 0; since_flush = 0; }
+        if (++since_flush == kFlushTiles) { flush_wgrads3<HID>(tlane, gr, m, h); wacc = 0; since_flush = 0; }
         fence_before_sync();
     }
-    if (wacc) flush_wgrads2<HID>(tlane, gr, m, h);
+    if (wacc) flush_wgrads3<HID>(tlane, gr, m, h);
     fence_before_sync();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base_s, TCOLS);
