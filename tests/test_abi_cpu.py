@@ -30,6 +30,27 @@ def test_version_and_error_string(rf_lib):
     assert rc == -2
 
 
+def test_argument_validation_without_a_gpu(rf_lib):
+    """Bad arguments are rejected before anything is launched (no device needed): NULL pointers, ranges, alignment."""
+    import numpy as np
+    f = lambda *v: np.asarray(v, np.float32).ctypes.data_as(C.POINTER(C.c_float))
+    null, p16, p4 = C.c_void_p(0), C.c_void_p(64), C.c_void_p(68)
+    K = np.eye(3, dtype=np.float32).reshape(-1); Kp = K.ctypes.data_as(C.POINTER(C.c_float))
+    # tracker maps: NULL, image too small, misaligned vertex buffer
+    assert rf_lib.rf_track_vertex_normal(null, 8, 8, Kp, C.c_float(6), C.c_float(.06), 1, C.c_float(3), p16, p16, p16, null) == -1
+    assert rf_lib.rf_track_vertex_normal(p16, 2, 8, Kp, C.c_float(6), C.c_float(.06), 1, C.c_float(3), p16, p16, p16, null) == -2
+    assert rf_lib.rf_track_vertex_normal(p16, 8, 8, Kp, C.c_float(6), C.c_float(.06), 1, C.c_float(3), p16, p4, p16, null) == -3
+    assert b"16-byte" in rf_lib.rf_last_error()
+    # candidate reduction: NULL / empty
+    ss = np.ones(6, np.float32); ssp = ss.ctypes.data_as(C.POINTER(C.c_float))
+    assert rf_lib.rf_track_cal_transform(null, p16, p16, 4, ssp, 3, p16, null) == -1
+    assert rf_lib.rf_track_cal_transform(p16, p16, p16, 0, ssp, 3, p16, null) == -2
+    # scratch sizes are pure host functions
+    rf_lib.rf_track_fitness_scratch_floats.restype = C.c_int64
+    assert rf_lib.rf_track_fitness_scratch_floats(0, 680, 1200, 8) == 0
+    assert rf_lib.rf_track_fitness_scratch_floats(1024, 680, 1200, 8) % (2 * 1024) == 0
+
+
 def test_grid_desc_init_matches_tcnn_table(rf_lib):
     import numpy as np
     from oracle.tcnn_standin import grid_levels
