@@ -8,15 +8,17 @@
 //             raw = (rgb + gbv_rgb, sdf + tsdf)                                   (:344-345)
 //   backward  recomputes the forward, then dH2 = (dRGB W3) . relu', dgeo = dH2 W2[:,geo], dO = [dsdf, dgeo],
 //             dH1 = (dO W1) . relu', dhash = dH1 W0[:,hash]; the four weight gradients X^T dH are accumulated in
-//             TMEM across all tiles a CTA processes and flushed once at the end.
+//             TMEM across the tiles a CTA processes and handed over with atomics every kFlushTiles tiles.
+//             BA mode additionally produces the gradients w.r.t. the OneBlob inputs and the GBV texel (ray gradients).
 //
 // Numerics: every GEMM is a bf16x3 product (a_hi b_hi + a_hi b_lo + a_lo b_hi, fp32 accumulation in TMEM), i.e.
 // ~2^-16 relative per product — the "rendered colour / depth and gradients within 1e-3" bar with two orders of margin;
 // the fp32 SIMT kernels of ray_query.cu (mlp_precision 0) stay as the accuracy anchor.
 //
 // Structure: a CTA holds the decoder weights once (bf16 hi/lo, chunked no-swizzle layout of umma.cuh) and G
-// independent groups of 128 threads.  A group owns one tile at a time: thread m stages row m of the operands, one
-// elected thread issues the MMAs, everybody waits on the group's mbarrier and reads its own TMEM lane.  Groups run
+// independent groups of 128 threads (forward) or 256 threads (backward: two threads per tile row, mlp_bwd_tc2_kernel; the
+// one-thread-per-row mlp_bwd_tc_kernel is kept for A/B timing).  A group owns one tile at a time: thread m stages row m
+// of the operands, one elected thread issues the MMAs, everybody waits on the group's mbarrier and reads its own TMEM lane.  Groups run
 // out of phase, so one group's tensor-core latency is covered by another group's staging.  Inputs are the feature
 // planes written by ray_encode.cu (sample-major: a tile is 128 consecutive rays at one sample index; coalesced,
 // streaming); no random access happens here.  Only raw / d_raw ([N][S][4], the reference's layout) are strided.
@@ -774,39 +776,6 @@ __device__ __forceinline__ void load_half(TileHalf& t, const float* __restrict__
     } else {
 #pragma unroll
         for (int l = 0; l < 8; ++l) t.f[l] = make_float2(0.f, 0.f);
-    }
-}
-
-// Weight gradients of a group, split between the two threads of a lane: h = 0 flushes dW0^T and dW1^T, h = 1 dW2^T and dW3^T.
-template <int HID>
-__device__ __forceinline__ void flush_wgrads2(uint32_t tlane, const Grads& gr, int f, int h) {
-    using A = BwdL<HID>;
-    fence_after_sync();
-    float* gx = h ? gr.g_w_col0 : gr.g_w_sdf0;
-    const int ld = h ? kIn2 : 81;
-    int c0 = -1;                                              // column of the first-layer weight for X row f
-    if (h == 0) { if (f < 80) c0 = f; else if (f == 80 + kTailTsdf) c0 = 80; }
-    else if (f < kIn2) c0 = f;
-    const uint32_t tx = tlane + (h ? A::t_w2 : A::t_w0);
-#pragma unroll 1
-    for (int q = 0; q < HID / 16; ++q) {                      // X-based: value = (hh + lh)[j] + hl[j]
-        float v[16], u[16];
-        tmem_ld16(tx + 16 * q, v);
-        tmem_ld16(tx + HID + 16 * q, u);
-        if (gx && c0 >= 0) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) atomicAdd(gx + (16 * q + j) * ld + c0, v[j] + u[j]);
-        }
-    }
-    // H-based: rows [0,HID) = hi features (columns: x hi | x lo), rows [HID,2HID) = lo features (column block x hi)
-    float v32[32];
-    tmem_ld32(tlane + (h ? A::t_w3 : A::t_w1), v32);
-    float* gh = h ? gr.g_w_col1 : gr.g_w_sdf1;
-    const int rows = h ? 3 : 16;
-    if (gh && f < 2 * HID) {
-        const int j = (f < HID) ? f : f - HID;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) if (i < rows) atomicAdd(gh + i * HID + j, (f < HID) ? v32[i] + v32[16 + i] : v32[i]);
     }
 }
 
