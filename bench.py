@@ -675,8 +675,22 @@ def run_e2e(args, cfg, K, frames, model, mvol, local, params, dev, rank, world, 
     h2d = 2 * (H * W * 4 + H * W * 12) + H * W * (12 + 12 + 12 + 4)
     d2h = 4 * 4
 
-    def step(i):
+    # Ray inputs are staged the way a caller of the public API would: pinned host tensors copied with non_blocking=True on a
+    # copy stream, one step ahead, so that the 33 MB of rays / targets of step i+1 cross PCIe while step i computes.  Every
+    # step's copy is issued (and completes) inside the timed region; the TSDF frames go through the reference's numpy
+    # signature (moving_volume.integrate / integrate_kf) and are copied synchronously in there.
+    copy_stream = torch.cuda.Stream(device=dev)
+
+    def prefetch(i):
         f = host[i % len(host)]
+        with torch.cuda.stream(copy_stream):
+            t = tuple(f[k].to(dev, non_blocking=True) for k in ("rays_o", "rays_d", "tgt_c", "tgt_d"))
+        ev = torch.cuda.Event(); ev.record(copy_stream)
+        return t, ev
+
+    def step(i, pre, more):
+        f = host[i % len(host)]
+        nxt = prefetch(i + 1) if more else None
         local.integrate(f["rgb255"], f["depth"], K, f["c2w"], None, 1.0, 0.0)
         mvol.integrate_kf({"rgb": f["rgb_t"], "depth": f["depth_t"]}, torch.from_numpy(f["c2w"]).float(), 1.0)
         if world > 1:
@@ -685,24 +699,30 @@ def run_e2e(args, cfg, K, frames, model, mvol, local, params, dev, rank, world, 
             model.GBV.params.data.copy_(rdist.gather_slabs(mvol.model.GBV.params, sizes, group))
         for p in params:
             p.grad = None
-        ro = f["rays_o"].to(dev, non_blocking=True); rd = f["rays_d"].to(dev, non_blocking=True)
-        tc = f["tgt_c"].to(dev, non_blocking=True); td = f["tgt_d"].to(dev, non_blocking=True)
+        (ro, rd, tc, td), ev = pre
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev)
+        for t in (ro, rd, tc, td):
+            t.record_stream(cur)
         ret = model.mapping(ro, rd, tc, td)
         loss = configs.total_loss(cfg, ret)
         loss.backward()
         if world > 1:
             rdist.allreduce_grads(params, group)
-        return torch.stack([ret["rgb_res_loss"], ret["depth_res_loss"], ret["sdf_res_loss"], ret["fs_res_loss"]]).cpu()
+        out = torch.stack([ret["rgb_res_loss"], ret["depth_res_loss"], ret["sdf_res_loss"], ret["fs_res_loss"]]).cpu()
+        return out, nxt
 
     n_steps = max(2, min(args.steps, 4))
-    step(0); step(1)
+    pre = prefetch(0)
+    _, pre = step(0, pre, True); _, pre = step(1, pre, False)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
+    pre = prefetch(0)                                      # the first step's inputs are copied inside the timed region too
     for i in range(n_steps):
-        step(i)
+        _, pre = step(i, pre, i + 1 < n_steps)
     b.record(); torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
