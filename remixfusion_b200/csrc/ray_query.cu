@@ -171,45 +171,73 @@ __device__ __forceinline__ float sigmoidf_(float a) { return 1.0f / (1.0f + expf
 
 struct RayState { int first; float zthr; float denom; };
 
-// first sign change (argmax of the 0/1 mask => 0 if none), truncation threshold, normaliser
-__device__ __forceinline__ RayState ray_state(const RayK& k, const float4* __restrict__ raw_r, const float* __restrict__ z_r, int lane) {
+// A ray's samples in registers: lane l holds samples l, l + 32, ... (S <= kMaxS = 128: at most four), with the
+// unnormalised weight e = sigmoid(s / trunc) sigmoid(-s / trunc) (model/scene_rep.py:116) computed once.
+constexpr int kPerLane = kMaxS / 32;
+struct RaySamples { float4 v[kPerLane]; float z[kPerLane]; float sg[kPerLane]; float e[kPerLane]; };
+
+__device__ __forceinline__ void load_ray(const RayK& k, const float4* __restrict__ raw_r, const float* __restrict__ z_r, int lane, RaySamples& rs) {
+#pragma unroll
+    for (int i = 0; i < kPerLane; ++i) {
+        const int s = lane + 32 * i;
+        if (s < k.S) {
+            rs.v[i] = raw_r[s]; rs.z[i] = z_r[s];
+            const float a = __fdiv_rn(rs.v[i].w, k.trunc);
+            rs.sg[i] = sigmoidf_(a);
+            rs.e[i] = rs.sg[i] * sigmoidf_(-a);
+        } else {
+            rs.v[i] = make_float4(0.f, 0.f, 0.f, 0.f); rs.z[i] = 0.f; rs.sg[i] = 0.f; rs.e[i] = 0.f;
+        }
+    }
+}
+
+// first sign change (argmax of the 0/1 mask => 0 if none), truncation threshold, normaliser (:119-127)
+__device__ __forceinline__ RayState ray_state(const RayK& k, const float4* __restrict__ raw_r, const float* __restrict__ z_r, int lane,
+                                              const RaySamples& rs) {
     const int S = k.S;
     int first = 0x7fffffff;
-    for (int s = lane; s < S - 1; s += 32)
-        if (raw_r[s + 1].w * raw_r[s].w < 0.f) { first = s; break; }
+#pragma unroll
+    for (int i = 0; i < kPerLane; ++i) {
+        const int s = lane + 32 * i;
+        if (s < S - 1 && first == 0x7fffffff && raw_r[s + 1].w * rs.v[i].w < 0.f) first = s;
+    }
     for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
     if (first == 0x7fffffff) first = 0;
     RayState st; st.first = first;
     st.zthr = __fadd_rn(z_r[first], k.sc_trunc);
     float sum = 0.f;
-    for (int s = lane; s < S; s += 32) {
-        float a = __fdiv_rn(raw_r[s].w, k.trunc);
-        float e = sigmoidf_(a) * sigmoidf_(-a);
-        sum += (z_r[s] < st.zthr) ? e : 0.f;
+#pragma unroll
+    for (int i = 0; i < kPerLane; ++i) {
+        const int s = lane + 32 * i;
+        if (s < S) sum += (rs.z[i] < st.zthr) ? rs.e[i] : 0.f;
     }
     st.denom = warp_sum(sum) + 1e-8f;
     return st;
 }
 
-__global__ void composite_fwd_kernel(RayK k, const float* __restrict__ raw, const float* __restrict__ z_vals,
-                                     const float* __restrict__ target_d, const float* __restrict__ target_rgb,
-                                     float* __restrict__ rgb_map, float* __restrict__ depth_map, double* __restrict__ partials) {
+// Warp per ray, four rays per block; the seven loss partial sums (double) are added per block.  (A persistent variant with
+// one set of atomics per block of many rays was slower: 91 registers, 1.02 vs 0.91 ms — the atomics are not the bound.)
+__global__ void __launch_bounds__(128) composite_fwd_kernel(RayK k, const float* __restrict__ raw, const float* __restrict__ z_vals,
+                                                            const float* __restrict__ target_d, const float* __restrict__ target_rgb,
+                                                            float* __restrict__ rgb_map, float* __restrict__ depth_map, double* __restrict__ partials) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    long long r = blockIdx.x * 4ll + warp;
     double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    const int S = k.S;
+    const long long r = blockIdx.x * 4ll + warp;
     if (r < k.n_rays) {
-        const int S = k.S;
         const float4* raw_r = reinterpret_cast<const float4*>(raw) + r * S;
         const float* z_r = z_vals + r * S;
-        RayState st = ray_state(k, raw_r, z_r, lane);
+        RaySamples rs; load_ray(k, raw_r, z_r, lane, rs);
+        RayState st = ray_state(k, raw_r, z_r, lane, rs);
         float c0 = 0.f, c1 = 0.f, c2 = 0.f, dm = 0.f;
         float d = partials ? target_d[r] : 0.f;
         bool valid = (d > 0.f) && (d < k.depth_trunc);
         float fs = 0.f, sd = 0.f; int nf = 0, ns = 0;
-        for (int s = lane; s < S; s += 32) {
-            float4 v = raw_r[s]; float z = z_r[s];
-            float a = __fdiv_rn(v.w, k.trunc);
-            float w = (z < st.zthr) ? sigmoidf_(a) * sigmoidf_(-a) : 0.f;
+#pragma unroll
+        for (int i = 0; i < kPerLane; ++i) {
+            if (lane + 32 * i >= S) continue;
+            const float4 v = rs.v[i]; const float z = rs.z[i];
+            float w = (z < st.zthr) ? rs.e[i] : 0.f;
             w = w / st.denom;
             c0 = fmaf(w, v.x, c0); c1 = fmaf(w, v.y, c1); c2 = fmaf(w, v.z, c2); dm = fmaf(w, z, dm);
             if (partials) {
@@ -247,19 +275,20 @@ __global__ void composite_fwd_kernel(RayK k, const float* __restrict__ raw, cons
 // Backward of composite + losses: writes the total gradient w.r.t. raw [N,S,4] into d_raw_out.
 // Upstream: d_rgb_map [N,3], d_depth_map [N], d_raw [N,S,4] (each may be NULL) and loss_grads (device float[4]:
 // d/d rgb_loss, depth_loss, sdf_loss, fs_loss; may be NULL) with the forward's `partials`.
-__global__ void composite_bwd_kernel(RayK k, const float* __restrict__ raw, const float* __restrict__ z_vals,
-                                     const float* __restrict__ rgb_map, const float* __restrict__ depth_map,
-                                     const float* __restrict__ target_d, const float* __restrict__ target_rgb,
-                                     const float* __restrict__ d_rgb_map, const float* __restrict__ d_depth_map,
-                                     const float* __restrict__ d_raw, const float* __restrict__ loss_grads,
-                                     const double* __restrict__ partials, float* __restrict__ d_raw_out) {
+__global__ void __launch_bounds__(128) composite_bwd_kernel(RayK k, const float* __restrict__ raw, const float* __restrict__ z_vals,
+                                                            const float* __restrict__ rgb_map, const float* __restrict__ depth_map,
+                                                            const float* __restrict__ target_d, const float* __restrict__ target_rgb,
+                                                            const float* __restrict__ d_rgb_map, const float* __restrict__ d_depth_map,
+                                                            const float* __restrict__ d_raw, const float* __restrict__ loss_grads,
+                                                            const double* __restrict__ partials, float* __restrict__ d_raw_out) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     long long r = blockIdx.x * 4ll + warp;
     if (r >= k.n_rays) return;
     const int S = k.S;
     const float4* raw_r = reinterpret_cast<const float4*>(raw) + r * S;
     const float* z_r = z_vals + r * S;
-    RayState st = ray_state(k, raw_r, z_r, lane);
+    RaySamples rs; load_ray(k, raw_r, z_r, lane, rs);
+    RayState st = ray_state(k, raw_r, z_r, lane, rs);
     float G0 = 0.f, G1 = 0.f, G2 = 0.f, GD = 0.f;
     if (d_rgb_map) { G0 = d_rgb_map[3 * r]; G1 = d_rgb_map[3 * r + 1]; G2 = d_rgb_map[3 * r + 2]; }
     if (d_depth_map) GD = d_depth_map[r];
@@ -282,21 +311,24 @@ __global__ void composite_bwd_kernel(RayK k, const float* __restrict__ raw, cons
     }
     // pass 1: dot = sum_j dw_j * w_j
     float dot = 0.f;
-    for (int s = lane; s < S; s += 32) {
-        float4 v = raw_r[s]; float z = z_r[s];
-        float a = __fdiv_rn(v.w, k.trunc);
-        float w = ((z < st.zthr) ? sigmoidf_(a) * sigmoidf_(-a) : 0.f) / st.denom;
+#pragma unroll
+    for (int i = 0; i < kPerLane; ++i) {
+        if (lane + 32 * i >= S) continue;
+        const float4 v = rs.v[i]; const float z = rs.z[i];
+        float w = ((z < st.zthr) ? rs.e[i] : 0.f) / st.denom;
         float dw = G0 * v.x + G1 * v.y + G2 * v.z + GD * z;
         dot = fmaf(dw, w, dot);
     }
     dot = warp_sum(dot);
     float4* out_r = reinterpret_cast<float4*>(d_raw_out) + r * S;
     const float4* up_r = d_raw ? reinterpret_cast<const float4*>(d_raw) + r * S : nullptr;
-    for (int s = lane; s < S; s += 32) {
-        float4 v = raw_r[s]; float z = z_r[s];
-        float a = __fdiv_rn(v.w, k.trunc);
-        float sg = sigmoidf_(a);
-        float e = (z < st.zthr) ? sg * sigmoidf_(-a) : 0.f;
+#pragma unroll
+    for (int i = 0; i < kPerLane; ++i) {
+        const int s = lane + 32 * i;
+        if (s >= S) continue;
+        const float4 v = rs.v[i]; const float z = rs.z[i];
+        float sg = rs.sg[i];
+        float e = (z < st.zthr) ? rs.e[i] : 0.f;
         float w = e / st.denom;
         float dw = G0 * v.x + G1 * v.y + G2 * v.z + GD * z;
         float de = (dw - dot) / st.denom;
