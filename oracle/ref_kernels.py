@@ -28,6 +28,15 @@ def available() -> bool:
             and os.path.exists(os.path.join(REF_DIR, "ref_tracker.cubin")))
 
 
+def require() -> None:
+    """On a CUDA box the literal reference kernels are a mandatory part of the parity suite: fail, never skip."""
+    missing = [c for c in ("ref_local_volume.cubin", "ref_global_volume.cubin", "ref_tracker.cubin")
+               if not os.path.exists(os.path.join(REF_DIR, c))]
+    assert not missing, (f"oracle/_ref is missing {missing}: run `python -c 'import __graft_entry__ as g; g.build()'` where "
+                         "/root/reference exists (oracle/build_ref.py); the built cubins travel to the GPU box")
+    assert torch.cuda.is_available(), "the reference kernels need a CUDA device"
+
+
 def _check(res):
     err = res[0]
     if int(err) != 0:

@@ -114,18 +114,35 @@ struct Weights { const float* w_sdf0; const float* w_sdf1; const float* w_col0; 
 
 struct Grads { float* g_hash; float* g_w_sdf0; float* g_w_sdf1; float* g_w_col0; float* g_w_col1; };
 
-// Tensor-core path (mlp_precision 1): ray_encode.cu (feature planes, table-gradient scatter) + ray_mlp_tc.cu (tcgen05
-// decoder).  Return 0 or an error code with rf_last_error set.
+// ---- Tensor-core path (mlp_precision 1): ray_encode.cu (operand tiles, table-gradient scatter) + ray_mlp_tc.cu ------------
+// Workspace written by the forward and re-read by the backward (floats; P = n_rays * S samples, plane index q = s * n_rays + r,
+// tile = 128 consecutive plane indices):
+//   [0, 4096 NT)            hash features as READY tcgen05 operands, one 16 KB block per tile: bf16 hi parts of the four
+//                           8-column chunks (2 KB each: row m at byte m * 16 = levels c, c+4, c+8, c+12 x 2 features), then the lo parts
+//   [gbv, gbv + 4P)         GBV trilinear features [P] float4
+//   [xn, xn + 3P)           normalised positions [3][P];   then (rays only) depth along the ray [P]
+// Feature gradients (backward scratch): [4 chunks][P][8 floats], same column order.
+// X-order of the hash features: operand chunk c (8 columns) holds levels c, c + 4, c + 8, c + 12 — one coarse, two middle and
+// one fine level per chunk, so that the walking roles of ray_encode.cu (one chunk each) carry equal work.  Column
+// 8 c + 2 j + f of X (and of W0, dX) <-> level c + 4 j, feature f, i.e. column 2 (c + 4 j) + f of the reference's layout.
+__host__ __device__ inline int hash_col_to_feature(int kx) { return 2 * ((kx >> 3) + 4 * ((kx >> 1) & 3)) + (kx & 1); }
+__host__ __device__ inline long long ws_tiles(long long P) { return (P + 127) >> 7; }
+__host__ __device__ inline long long ws_off_gbv(long long P) { return ws_tiles(P) * 4096; }
+__host__ __device__ inline long long ws_off_xn(long long P) { return ws_off_gbv(P) + 4 * P; }
+inline long long ws_floats(long long P, bool with_z) { return ws_off_xn(P) + (with_z ? 4 : 3) * P; }
+constexpr int kHopTileBytes = 16384;
+
 bool tc_supported(const RayK& k, int hidden);
 size_t scatter_scratch_floats(const GridDev& hg, long long n_rays);
 int launch_fwd_tc(const RayK& k, int hidden, const GridDev& hg, const GridDev& gg, const rf_ray_params* p, const float* rays_o,
                   const float* rays_d, const float* z_vals, long long P, float* raw, float* feat, cudaStream_t s);
 int launch_points_tc(RayK k, int hidden, const GridDev& hg, const GridDev& gg, const rf_ray_params* p, const float* x, long long n,
                      int variant, float* raw, float* feat, cudaStream_t s);
+// n_live [n_rays]: samples s >= n_live[r] of ray r have an all-zero upstream gradient (composite_bwd_kernel)
 int launch_bwd_tc(const RayK& k, int hidden, const GridDev& hg, const GridDev& gg, const rf_ray_params* p, long long P, const float* feat,
-                  const float* d_raw_tot, float* dfeat, const Grads& gr, float* g_rays_o, float* g_rays_d, cudaStream_t s);
+                  const float* d_raw_tot, const int* n_live, float* dfeat, const Grads& gr, float* g_rays_o, float* g_rays_d, cudaStream_t s);
 int launch_scatter_raygrad(const RayK& k, const GridDev& hg, const GridDev& gg, const rf_ray_params* p, long long P, const float* feat,
-                           const float* dfeat, const float* dgb, const float* dxb, float* g_hash, float* g_rep, float* g_o, float* g_d,
-                           cudaStream_t s);
+                           const float* dfeat, const float* dgb, const float* dxb, const int* n_live, float* g_hash, float* g_rep, float* g_o,
+                           float* g_d, cudaStream_t s);
 
 }  // namespace rf

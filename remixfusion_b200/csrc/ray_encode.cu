@@ -1,122 +1,148 @@
 // ray_encode.cu — the gather / scatter half of the Stage-2 tensor-core path (mlp_precision 1).
 //
-//   ray_pos_kernel      pts = o + d*z, float64 normalisation by the bounding box (model/scene_rep.py:443,388) -> xn planes
-//   encode_walk_kernel  hash levels + GBV trilinear features (tiny-cuda-nn grid forward, SURVEY Appendix B2-B4;
-//                       model/scene_rep.py:325,329) -> feature planes
-//   scatter_walk_kernel hash-table gradient (Appendix B5; autograd of model/scene_rep.py:325)
+//   encode_walk4_kernel   pts = o + d*z, float64 normalisation by the bounding box (model/scene_rep.py:443,388), hash levels +
+//                         GBV trilinear features (tiny-cuda-nn grid forward; model/scene_rep.py:325,329)
+//                         -> hash features as ready tcgen05 operand tiles (bf16 hi / lo), GBV features, position planes
+//   scatter_walk4_kernel  hash-table gradient (Appendix B5; autograd of model/scene_rep.py:325); BA mode: + the hash-level part of
+//                         dL/d rays_o, dL/d rays_d
+//   raygrad_walk_kernel   BA mode (model/scene_rep.py:443 under mp_slam/mapper.py:456,484-485): dL/d rays_o, dL/d rays_d through
+//                         the trilinear weights of the GBV (Appendix B6) + the OneBlob part
 //
-// Both grid kernels run one thread per (ray, level) that WALKS the samples of its ray in order.  Samples along a ray are
-// sorted in depth (model/scene_rep.py:428), so consecutive samples stay in the same grid cell for a while on all but
-// the finest levels: the forward keeps the 8 corner values in registers until the cell changes (one gather per cell
-// run instead of one per sample); the backward accumulates the 8 corner gradients in registers and issues its 8
-// vector reductions (RED.ADD.F32x2) only when the cell changes.  All planes are SAMPLE-MAJOR (index s * n_rays + r),
-// so the lanes of a warp (consecutive rays) read and write consecutive addresses at every step of the walk.  The
-// per-sample arithmetic (pos = fma(scale, x, 0.5), corner order, fma accumulation order) is the one grid_encode.cuh
-// uses everywhere, so the features are bit-identical to the thread-per-sample fp32 kernels.
+// The grid kernels WALK the samples of a ray in order.  Samples along a ray are sorted in depth (model/scene_rep.py:428), so
+// consecutive samples stay in the same grid cell for a while on all but the finest levels: the forward keeps the 8 corner
+// values in registers until the cell changes (one gather per cell run instead of one per sample); the backward accumulates
+// the 8 corner gradients in registers and issues its 8 vector reductions (RED.ADD.F32x2) only when the cell changes.
 //
-//   raygrad_walk_kernel BA mode (model/scene_rep.py:443 under mp_slam/mapper.py:456,484-485): dL/d rays_o, dL/d rays_d
-//                       through the trilinear weights of the hash levels and the GBV (Appendix B6) + the OneBlob part
+// Work split: a block owns 32 rays (lanes = consecutive rays, so every plane access of a warp is one contiguous segment)
+// and its warps are ROLES: warp c walks hash levels c, c+4, c+8, c+12 (one 8-column operand chunk in the X-order of
+// ray_common.cuh: a coarse, two middle and a fine level each, so the roles of a block finish together), the last warp walks the GBV.
+// The block first computes the positions of its rays' samples ONCE into shared memory (the forward from rays_o / rays_d /
+// z_vals, so no separate position pass and no position planes are re-read per level; the backward from the planes the
+// forward wrote, one coalesced read), then every role reads them from there.  The per-sample arithmetic (pos = fma(scale, x,
+// 0.5), corner order, fma accumulation order) is the one grid_encode.cuh uses everywhere, so features are bit-identical to
+// the thread-per-sample fp32 kernels of ray_query.cu.
 //
-// Workspace layout (floats), P = n_rays * S:   [0, 2L*P) hash features [L][S][N][2];  [2L*P, 2L*P + 4P) GBV [S][N][4];
-//                                              then xn [3][S][N]; then (rays only) z [S][N].
+// The backward walks stop at n_live[r]: composite_bwd_kernel records, per ray, the last sample with a non-zero upstream
+// gradient — samples beyond the truncation band behind the surface carry neither a rendering weight nor a loss term
+// (model/scene_rep.py:124, model/utils.py:170-198), their gradient is exactly zero and nothing is computed for them.
 #include <stdlib.h>
 #include <algorithm>
 #include "ray_common.cuh"
+#include "umma.cuh"
 
 namespace rf {
 
-// Plane index of sample s of ray r: sample-major, so that threads that each walk one ray touch consecutive addresses.
-//   q = s * n_rays + r
-// Positions: pts = o + d*z (:443), float64 normalisation (:388), written through a shared-memory transpose so that both
-// the [N][S] read of z_vals and the [S][N] write of the planes are full 128-byte segments.  Block = 32 rays.
-__global__ void __launch_bounds__(256) ray_pos_kernel(RayK k, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
-                                                      const float* __restrict__ z_vals, long long P, float* __restrict__ xn) {
-    extern __shared__ float sx[];                       // [4][S][33]: x, y, z of the normalised position, depth along the ray
+// the 8 corner indices of cell (cx, cy, cz) of a level (Appendix B3); same arithmetic as grid_index, shared between corners
+__device__ __forceinline__ void cell_indices(bool is_hash, unsigned size, unsigned res, unsigned cx, unsigned cy, unsigned cz, unsigned (&idx)[8]) {
+    CornerIndexer ci; ci.init(is_hash, size, res);
+    ci.cell(cx, cy, cz, idx);
+}
+
+// samples per walking thread: the whole ray for big batches; for small ones segments of >= 8 samples such that a launch has
+// ~32 k (ray, segment) units
+static int walk_segment(long long n_rays, int S) {
+    long long nseg = std::min<long long>((32768 + n_rays - 1) / std::max<long long>(n_rays, 1), std::max(1, S / 8));
+    if (nseg < 1) nseg = 1;
+    return (int)((S + nseg - 1) / nseg);
+}
+
+constexpr int kEncThreads = 160;        // 4 hash-quad roles + 1 GBV role, 32 (ray, segment) units per block
+
+// Forward.  ws: the workspace of ray_common.cuh.  POINTS: z_vals holds n already-normalised positions [n][3] (point queries,
+// model/scene_rep.py:212-310): n "rays" of one sample.
+template <bool POINTS>
+__global__ void __launch_bounds__(kEncThreads) encode_walk4_kernel(const __grid_constant__ RayK k, const __grid_constant__ GridDev hg,
+                                                                   const __grid_constant__ GridDev gg, const float* __restrict__ hash_params,
+                                                                   const float* __restrict__ gbv_params, const float* __restrict__ rays_o,
+                                                                   const float* __restrict__ rays_d, const float* __restrict__ z_vals,
+                                                                   long long P, int seg, float* __restrict__ ws) {
+    extern __shared__ float sx[];                       // [4][seg][33]: normalised x, y, z and the depth along the ray
+    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+    const long long N = k.n_rays;
     const int S = k.S;
-    const long long r0 = blockIdx.x * 32ll;
-    const int nr = (int)min(32ll, k.n_rays - r0);
-    for (int i = threadIdx.x; i < nr * S; i += 256) {
-        const int rl = i / S, s = i - rl * S;
-        float x[3];
-        const float zv = z_vals[r0 * S + i];
-        sample_x(k, rays_o, rays_d, r0 + rl, zv, x);
-        sx[s * 33 + rl] = x[0]; sx[(S + s) * 33 + rl] = x[1]; sx[(2 * S + s) * 33 + rl] = x[2]; sx[(3 * S + s) * 33 + rl] = zv;
+    const long long unit0 = blockIdx.x * 32ll;
+    const long long n_units = N * ((S + seg - 1) / seg);
+    for (int i = threadIdx.x; i < 32 * seg; i += kEncThreads) {
+        const int ul = i / seg, sl = i - ul * seg;
+        const long long unit = unit0 + ul;
+        if (unit >= n_units) continue;
+        const long long r = unit % N;
+        const int s = (int)(unit / N) * seg + sl;
+        if (s >= S) continue;
+        float x[3], zv = 0.f;
+        if (POINTS) { x[0] = z_vals[3 * r]; x[1] = z_vals[3 * r + 1]; x[2] = z_vals[3 * r + 2]; }
+        else { zv = z_vals[r * S + s]; sample_x(k, rays_o, rays_d, r, zv, x); }
+        sx[sl * 33 + ul] = x[0]; sx[(seg + sl) * 33 + ul] = x[1]; sx[(2 * seg + sl) * 33 + ul] = x[2]; sx[(3 * seg + sl) * 33 + ul] = zv;
     }
     __syncthreads();
-    for (int j = threadIdx.x; j < 32 * S; j += 256) {
-        const int s = j >> 5, rl = j & 31;
-        if (rl < nr) {
-            const long long q = (long long)s * k.n_rays + r0 + rl;
-            xn[q] = sx[s * 33 + rl]; xn[P + q] = sx[(S + s) * 33 + rl]; xn[2 * P + q] = sx[(2 * S + s) * 33 + rl];
-            xn[3 * P + q] = sx[(3 * S + s) * 33 + rl];
-        }
-    }
-}
-
-// Point queries (model/scene_rep.py:212-310): positions are given, already normalised: [n][3] -> planes [3][n].
-__global__ void __launch_bounds__(256) point_pos_kernel(const float* __restrict__ x, long long n, float* __restrict__ xn) {
-    const long long i = blockIdx.x * 256ll + threadIdx.x;
-    if (i >= n) return;
-    xn[i] = x[3 * i]; xn[n + i] = x[3 * i + 1]; xn[2 * n + i] = x[3 * i + 2];
-}
-
-// Features.  Thread = (ray, level), blockIdx.y + level0 = level (0..L-1 hash levels, L = GBV); lanes = consecutive rays.
-__global__ void __launch_bounds__(128) encode_walk_kernel(GridDev hg, GridDev gg, const float* __restrict__ hash_params,
-                                                          const float* __restrict__ gbv_params, const float* __restrict__ xn,
-                                                          long long P, long long N, int S, int seg, int level0, float* __restrict__ feat) {
-    const int l = blockIdx.y + level0, L = hg.n_levels;
-    // unit = (ray, segment of `seg` samples): lanes are consecutive rays of one segment.  Large batches use one segment
-    // (the whole ray); small ones are cut so that the dependent walk is short and the grid fills the machine.
-    const long long unit = blockIdx.x * 128ll + threadIdx.x;
+    const long long unit = unit0 + lane;
+    if (unit >= n_units) return;
     const long long r = unit % N;
     const int s_begin = (int)(unit / N) * seg;
-    if (s_begin >= S) return;
-    const int s_end = min(S, s_begin + seg);
-    const long long first = (long long)s_begin * N + r;
-    const float* xs = xn + first; const float* ys = xn + P + first; const float* zs = xn + 2 * P + first;
-    unsigned pcx = 0, pcy = 0, pcz = 0; bool have = false;
-    float xa = __ldg(xs), ya = __ldg(ys), za = __ldg(zs);
-    CornerIndexer ci;
-    unsigned idx[8];
-    if (l < L) {
-        const float scale = hg.scale[l];
-        ci.init(hg.is_hash != 0, hg.size[l], hg.res[l]);
-        const float2* tab = reinterpret_cast<const float2*>(hash_params) + hg.offset[l];
-        float2* out = reinterpret_cast<float2*>(feat) + (long long)l * P + first;
-        float2 v[8];
-        for (int s = s_begin; s < s_end; ++s) {
-            const float x = xa, y = ya, z = za;
-            if (s + 1 < s_end) { xs += N; ys += N; zs += N; xa = __ldg(xs); ya = __ldg(ys); za = __ldg(zs); }
-            unsigned cx, cy, cz; float fx, fy, fz;
-            pos_fract(x, scale, cx, fx); pos_fract(y, scale, cy, fy); pos_fract(z, scale, cz, fz);
-            if (!have || cx != pcx || cy != pcy || cz != pcz) {
-                ci.cell(cx, cy, cz, idx);
+    const int n_steps = min(S, s_begin + seg) - s_begin;
+    long long q = (long long)s_begin * N + r;
+    const float* px = sx + lane; const float* py = sx + seg * 33 + lane; const float* pz = sx + 2 * seg * 33 + lane;
+    if (role < 4) {
+        // hash levels role, role + 4, role + 8, role + 12 -> chunk `role` of the tile's operand block
+        unsigned char* hop = reinterpret_cast<unsigned char*>(ws) + role * 2048;
+        float2 v[4][8];
+        unsigned pc[4][3];
+        unsigned have = 0;
+        for (int sl = 0; sl < n_steps; ++sl, q += N) {
+            const float x = px[sl * 33], y = py[sl * 33], z = pz[sl * 33];
+            // phase 1: cells of the four levels, gathers where a cell changed (four independent chains in flight)
+            float fr[4][3];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) v[c] = __ldg(tab + idx[c]);
-                pcx = cx; pcy = cy; pcz = cz; have = true;
-            }
-            float f0 = 0.f, f1 = 0.f;
+            for (int j = 0; j < 4; ++j) {
+                const int l = role + 4 * j;
+                const float scale = hg.scale[l];
+                unsigned cx, cy, cz;
+                pos_fract(x, scale, cx, fr[j][0]); pos_fract(y, scale, cy, fr[j][1]); pos_fract(z, scale, cz, fr[j][2]);
+                if (!((have >> j) & 1u) || cx != pc[j][0] || cy != pc[j][1] || cz != pc[j][2]) {
+                    unsigned idx[8];
+                    cell_indices(hg.is_hash != 0, hg.size[l], hg.res[l], cx, cy, cz, idx);
+                    const float2* tab = reinterpret_cast<const float2*>(hash_params) + hg.offset[l];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                float w = corner_weight(c, fx, fy, fz);
-                f0 = fmaf(w, v[c].x, f0); f1 = fmaf(w, v[c].y, f1);
+                    for (int c = 0; c < 8; ++c) v[j][c] = __ldg(tab + idx[c]);
+                    pc[j][0] = cx; pc[j][1] = cy; pc[j][2] = cz; have |= 1u << j;
+                }
             }
-            *out = make_float2(f0, f1);
-            out += N;
+            // phase 2: trilinear interpolation (Appendix B4 weight and accumulation order)
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float f0 = 0.f, f1 = 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float w = corner_weight(c, fr[j][0], fr[j][1], fr[j][2]);
+                    f0 = fmaf(w, v[j][c].x, f0); f1 = fmaf(w, v[j][c].y, f1);
+                }
+                f[2 * j] = f0; f[2 * j + 1] = f1;
+            }
+            uint4 hi, lo;
+            umma::split8(f, hi, lo);
+            unsigned char* row = hop + (q >> 7) * kHopTileBytes + (q & 127) * 16;
+            *reinterpret_cast<uint4*>(row) = hi;
+            *reinterpret_cast<uint4*>(row + kHopTileBytes / 2) = lo;
         }
     } else {
+        // GBV level; this role also writes the position planes the decoder (OneBlob) and the backward walks read
         const float scale = gg.scale[0];
-        ci.init(false, gg.size[0], gg.res[0]);
         const float4* tab = reinterpret_cast<const float4*>(gbv_params);
-        float4* out = reinterpret_cast<float4*>(feat + 2ll * L * P) + first;
+        float4* out = reinterpret_cast<float4*>(ws + ws_off_gbv(P));
+        float* xn = ws + ws_off_xn(P);
+        const float* pt = sx + 3 * seg * 33 + lane;
         float4 v[8];
-        for (int s = s_begin; s < s_end; ++s) {
-            const float x = xa, y = ya, z = za;
-            if (s + 1 < s_end) { xs += N; ys += N; zs += N; xa = __ldg(xs); ya = __ldg(ys); za = __ldg(zs); }
+        unsigned pcx = 0, pcy = 0, pcz = 0; bool have = false;
+        for (int sl = 0; sl < n_steps; ++sl, q += N) {
+            const float x = px[sl * 33], y = py[sl * 33], z = pz[sl * 33];
+            xn[q] = x; xn[P + q] = y; xn[2 * P + q] = z;
+            if (!POINTS) xn[3 * P + q] = pt[sl * 33];
             unsigned cx, cy, cz; float fx, fy, fz;
             pos_fract(x, scale, cx, fx); pos_fract(y, scale, cy, fy); pos_fract(z, scale, cz, fz);
             if (!have || cx != pcx || cy != pcy || cz != pcz) {
-                ci.cell(cx, cy, cz, idx);
+                unsigned idx[8];
+                cell_indices(false, gg.size[0], gg.res[0], cx, cy, cz, idx);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) v[c] = __ldg(tab + idx[c]);
                 pcx = cx; pcy = cy; pcz = cz; have = true;
@@ -124,22 +150,14 @@ __global__ void __launch_bounds__(128) encode_walk_kernel(GridDev hg, GridDev gg
             float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                float w = corner_weight(c, fx, fy, fz);
+                const float w = corner_weight(c, fx, fy, fz);
                 o4.x = fmaf(w, v[c].x, o4.x); o4.y = fmaf(w, v[c].y, o4.y); o4.z = fmaf(w, v[c].z, o4.z); o4.w = fmaf(w, v[c].w, o4.w);
             }
-            *out = o4;
-            out += N;
+            out[q] = o4;
         }
     }
 }
 
-// Table-gradient scatter, run-length reduced.  dfeat [L][P][2] (sample-major planes); thread = (ray, level): each lane
-// accumulates the 8 corner gradients of its current cell in registers and issues the 8 vector reductions
-// (RED.ADD.F32x2) when its cell changes; runs whose gradients are all zero (samples past the truncation mask) issue none.
-// Small (coarse) levels are the contended ones: every ray of the batch lands on the same few thousand entries, and
-// reductions onto one L2 line serialise.  Those levels accumulate into K private replicas of their gradient table
-// (replica = block index mod K, so that neighbouring blocks — neighbouring pixels — never share one) which
-// replica_reduce_kernel folds into the caller's table afterwards.
 // d/dx of the trilinear interpolant of the corner scalars u[c] (c = cx + 2 cy + 4 cz): differences along one axis,
 // bilinear weights of the other two (Appendix B6)
 __device__ __forceinline__ void tri_grad(const float (&u)[8], float fx, float fy, float fz, float& gx, float& gy, float& gz) {
@@ -169,128 +187,169 @@ struct ScatterRep {
     unsigned base[RF_MAX_LEVELS];         // first entry of the level's replica block in the scratch (float2 units)
 };
 
-// BA: the same walk also differentiates the trilinear weights of its level against the corner VALUES (gathered once per
-// cell run) and sums dL/d xn and z * dL/d xn over the ray's samples — the hash-level part of raygrad_walk_kernel, without
-// reading the planes a second time.
-template <bool BA>
-__global__ void __launch_bounds__(128) scatter_walk_kernel(GridDev hg, ScatterRep rep, const float* __restrict__ xn, const float* __restrict__ dfeat,
-                                                           long long P, long long N, int S, int seg, int level0, float* __restrict__ g_hash,
-                                                           float* __restrict__ g_rep, RayGradArgs rg) {
-    const int l = blockIdx.y + level0;
-    const long long unit = blockIdx.x * 128ll + threadIdx.x;                // (ray, segment), as in encode_walk_kernel
-    const long long r = unit % N;
-    const int s_begin = (int)(unit / N) * seg;
-    if (s_begin >= S) return;
-    const int s_end = min(S, s_begin + seg);
-    const long long first = (long long)s_begin * N + r;
-    const unsigned size = hg.size[l];
-    float2* gtab = (rep.k[l] > 1) ? reinterpret_cast<float2*>(g_rep) + rep.base[l] + (size_t)(blockIdx.x & (rep.k[l] - 1)) * size
-                                  : reinterpret_cast<float2*>(g_hash) + hg.offset[l];
-    const float* xs = xn + first; const float* ys = xn + P + first; const float* zs = xn + 2 * P + first;
-    const float2* dj = reinterpret_cast<const float2*>(dfeat) + (long long)l * P + first;
-    const float scale = hg.scale[l];
-    CornerIndexer ci; ci.init(hg.is_hash != 0, size, hg.res[l]);
-    unsigned pcx = 0, pcy = 0, pcz = 0; bool have = false, nz = false;
-    float2 acc[8];
+// Table-gradient scatter, run-length reduced.  dfeat [4 chunks][P][8] ; a block owns 32 (ray, segment) units, warp = role =
+// LPT levels of one chunk (4 in mapping mode; 2 in BA mode, where a thread also keeps the corner VALUES of its cells to
+// differentiate the trilinear weights).  Each lane accumulates the 8 corner gradients of its current cell in registers and
+// issues the 8 vector reductions when the cell changes; runs whose gradients are all zero issue none.
+// Small (coarse) levels are the contended ones: every ray of the batch lands on the same few thousand entries, and
+// reductions onto one L2 line serialise.  Those levels accumulate into K private replicas of their gradient table
+// (replica = block index mod K, so that neighbouring blocks — neighbouring pixels — never share one) which
+// replica_reduce_kernel folds into the caller's table afterwards.
+template <int LPT, bool BA>
+__global__ void __launch_bounds__(512 / LPT, LPT == 4 ? 4 : 2) scatter_walk4_kernel(const __grid_constant__ GridDev hg, const __grid_constant__ ScatterRep rep,
+                                                                  const float* __restrict__ xn,
+                                                                  const float* __restrict__ dfeat, const int* __restrict__ n_live,
+                                                                  long long P, long long N, int S, int seg, float* __restrict__ g_hash,
+                                                                  float* __restrict__ g_rep, RayGradArgs rg) {
+    extern __shared__ float sx[];                       // [3 (+1 BA)][seg][32]
+    constexpr int NT = 512 / LPT;
+    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+    const long long unit0 = blockIdx.x * 32ll;
+    const long long n_units = N * ((S + seg - 1) / seg);
+    // this lane's unit (every warp of the block sees the same 32 units)
+    const long long unit = unit0 + lane;
+    long long r = 0; int s_begin = 0, n_steps = 0;
+    if (unit < n_units) {
+        r = unit % N;
+        s_begin = (int)(unit / N) * seg;
+        const int lim = n_live ? min(S, __ldg(n_live + r)) : S;
+        n_steps = max(0, min(lim, s_begin + seg) - s_begin);
+    }
+    // positions of the live samples: warp w loads steps w, w + NT/32, ... (lanes = consecutive rays: coalesced)
+    for (int sl = role; sl < seg; sl += NT / 32) {
+        if (sl < n_steps) {
+            const long long q = (long long)(s_begin + sl) * N + r;
+            sx[sl * 32 + lane] = __ldg(xn + q); sx[(seg + sl) * 32 + lane] = __ldg(xn + P + q); sx[(2 * seg + sl) * 32 + lane] = __ldg(xn + 2 * P + q);
+            if (BA) sx[(3 * seg + sl) * 32 + lane] = __ldg(xn + 3 * P + q);
+        }
+    }
+    __syncthreads();
+    if (n_steps == 0) return;
+    long long q = (long long)s_begin * N + r;
+    const float* px = sx + lane; const float* py = sx + seg * 32 + lane; const float* pz = sx + 2 * seg * 32 + lane; const float* pt = sx + 3 * seg * 32 + lane;
+    // this role's levels: chunk ch of the X-order, its entries j0 .. j0 + LPT - 1, i.e. levels ch + 4 (j0 + j)
+    constexpr int RPC = 4 / LPT;                              // roles per chunk
+    const int ch = role / RPC, j0 = (role % RPC) * LPT;
+    const float* dq = dfeat + ((long long)ch * P) * 8 + 2 * j0;
+    float2 acc[LPT][8];
+    float2 v[BA ? LPT : 1][8];
+    unsigned pc[LPT][3];
+    unsigned have = 0, nz = 0, vhave = 0;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[c] = make_float2(0.f, 0.f);
-    float xa = __ldg(xs), ya = __ldg(ys), za = __ldg(zs); float2 da = __ldg(dj);
-    const float* ts = xn + 3 * P + first;
-    float ta = BA ? __ldg(ts) : 0.f;
-    const float2* tab = BA ? reinterpret_cast<const float2*>(rg.hash_params) + hg.offset[l] : nullptr;
-    float2 v[BA ? 8 : 1];
-    bool vhave = false;                                                      // v holds the corners of cell (pcx, pcy, pcz)
+    for (int j = 0; j < LPT; ++j)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[j][c] = make_float2(0.f, 0.f);
     float so[3] = {0.f, 0.f, 0.f}, sd[3] = {0.f, 0.f, 0.f};
-    for (int s = s_begin; s <= s_end; ++s) {
-        unsigned cx = 0, cy = 0, cz = 0; float fx = 0.f, fy = 0.f, fz = 0.f;
-        const float2 d = da; const float t = ta;
-        const bool last = (s == s_end);
+    // feature gradients are streamed from HBM: the loads of step sl + 1 are issued before step sl is processed
+    float4 na, nb = make_float4(0.f, 0.f, 0.f, 0.f);
+    na = __ldg(reinterpret_cast<const float4*>(dq + q * 8));
+    if (LPT == 4) nb = __ldg(reinterpret_cast<const float4*>(dq + q * 8) + 1);
+    for (int sl = 0; sl <= n_steps; ++sl, q += N) {
+        const bool last = (sl == n_steps);
+        float x = 0.f, y = 0.f, z = 0.f, t = 0.f;
+        float d[2 * LPT];
+        d[0] = na.x; d[1] = na.y; d[2] = na.z; d[3] = na.w;
+        if (LPT == 4) { d[4] = nb.x; d[5] = nb.y; d[6] = nb.z; d[7] = nb.w; }
         if (!last) {
-            pos_fract(xa, scale, cx, fx); pos_fract(ya, scale, cy, fy); pos_fract(za, scale, cz, fz);
-            if (s + 1 < s_end) {
-                xs += N; ys += N; zs += N; dj += N; xa = __ldg(xs); ya = __ldg(ys); za = __ldg(zs); da = __ldg(dj);
-                if (BA) { ts += N; ta = __ldg(ts); }
+            x = px[sl * 32]; y = py[sl * 32]; z = pz[sl * 32];
+            if (BA) t = pt[sl * 32];
+            if (sl + 1 < n_steps) {
+                na = __ldg(reinterpret_cast<const float4*>(dq + (q + N) * 8));
+                if (LPT == 4) nb = __ldg(reinterpret_cast<const float4*>(dq + (q + N) * 8) + 1);
             }
         }
-        if (have && (last || cx != pcx || cy != pcy || cz != pcz)) {
-            if (nz) {
-                unsigned idx[8];
-                ci.cell(pcx, pcy, pcz, idx);
 #pragma unroll
-                for (int c = 0; c < 8; ++c) atomicAdd(gtab + idx[c], acc[c]);
+        for (int j = 0; j < LPT; ++j) {
+            const int l = ch + 4 * (j0 + j);
+            const float scale = hg.scale[l];
+            unsigned cx = 0, cy = 0, cz = 0; float fx = 0.f, fy = 0.f, fz = 0.f;
+            if (!last) { pos_fract(x, scale, cx, fx); pos_fract(y, scale, cy, fy); pos_fract(z, scale, cz, fz); }
+            const bool hv = (have >> j) & 1u;
+            if (hv && (last || cx != pc[j][0] || cy != pc[j][1] || cz != pc[j][2])) {
+                if ((nz >> j) & 1u) {
+                    const unsigned size = hg.size[l];
+                    float2* gtab = (rep.k[l] > 1) ? reinterpret_cast<float2*>(g_rep) + rep.base[l] + (size_t)(blockIdx.x & (rep.k[l] - 1)) * size
+                                                  : reinterpret_cast<float2*>(g_hash) + hg.offset[l];
+                    unsigned idx[8];
+                    cell_indices(hg.is_hash != 0, size, hg.res[l], pc[j][0], pc[j][1], pc[j][2], idx);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) atomicAdd(gtab + idx[c], acc[j][c]);
+                }
+#pragma unroll
+                for (int c = 0; c < 8; ++c) acc[j][c] = make_float2(0.f, 0.f);
+                nz &= ~(1u << j); vhave &= ~(1u << j);
             }
+            if (last) continue;
+            pc[j][0] = cx; pc[j][1] = cy; pc[j][2] = cz; have |= 1u << j;
+            const float d0 = d[2 * j], d1 = d[2 * j + 1];
+            const bool dnz = d0 != 0.f || d1 != 0.f;
+            if (dnz) nz |= 1u << j;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) acc[c] = make_float2(0.f, 0.f);
-            nz = false; vhave = false;
-        }
-        if (last) break;
-        pcx = cx; pcy = cy; pcz = cz; have = true;
-        const bool dnz = d.x != 0.f || d.y != 0.f;
-        nz = nz || dnz;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            float w = corner_weight(c, fx, fy, fz);
-            acc[c].x = fmaf(w, d.x, acc[c].x); acc[c].y = fmaf(w, d.y, acc[c].y);
-        }
-        if (BA && dnz) {
-            if (!vhave) {
-                unsigned idx[8];
-                ci.cell(cx, cy, cz, idx);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) v[c] = __ldg(tab + idx[c]);
-                vhave = true;
+            for (int c = 0; c < 8; ++c) {
+                const float w = corner_weight(c, fx, fy, fz);
+                acc[j][c].x = fmaf(w, d0, acc[j][c].x); acc[j][c].y = fmaf(w, d1, acc[j][c].y);
             }
-            float u[8], gx, gy, gz;
+            if (BA && dnz) {
+                if (!((vhave >> j) & 1u)) {
+                    unsigned idx[8];
+                    cell_indices(hg.is_hash != 0, hg.size[l], hg.res[l], cx, cy, cz, idx);
+                    const float2* tab = reinterpret_cast<const float2*>(rg.hash_params) + hg.offset[l];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) u[c] = fmaf(d.x, v[c].x, d.y * v[c].y);
-            tri_grad(u, fx, fy, fz, gx, gy, gz);
-            const float dx0 = gx * scale, dx1 = gy * scale, dx2 = gz * scale;
-            so[0] += dx0; so[1] += dx1; so[2] += dx2;
-            sd[0] = fmaf(t, dx0, sd[0]); sd[1] = fmaf(t, dx1, sd[1]); sd[2] = fmaf(t, dx2, sd[2]);
+                    for (int c = 0; c < 8; ++c) v[BA ? j : 0][c] = __ldg(tab + idx[c]);
+                    vhave |= 1u << j;
+                }
+                float u[8], gx, gy, gz;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) u[c] = fmaf(d0, v[BA ? j : 0][c].x, d1 * v[BA ? j : 0][c].y);
+                tri_grad(u, fx, fy, fz, gx, gy, gz);
+                const float dx0 = gx * scale, dx1 = gy * scale, dx2 = gz * scale;
+                so[0] += dx0; so[1] += dx1; so[2] += dx2;
+                sd[0] = fmaf(t, dx0, sd[0]); sd[1] = fmaf(t, dx1, sd[1]); sd[2] = fmaf(t, dx2, sd[2]);
+            }
         }
     }
     if (BA) raygrad_flush(rg, r, so, sd);
 }
 
-
-// Ray gradients (BA mode).  Thread = (ray[, segment], level) as in the other walks: level < L differentiates the
-// trilinear weights of one hash level against the feature gradients dfeat (corner VALUES cached per cell run, Appendix
-// B6); level L does the same for the GBV texel gradient dgb and adds the OneBlob part dxb the decoder backward wrote.
-// Each thread sums d xn and z * d xn over its samples and finishes with six reductions onto the ray's rows:
+// Ray gradients (BA mode).  Thread = (ray[, segment], level): level < L differentiates the trilinear weights of one hash
+// level against the feature gradients dfeat (corner VALUES cached per cell run, Appendix B6) — only launched when no table
+// gradient is requested, otherwise the hash levels ride on scatter_walk4_kernel<., true>; level L does the same for the GBV
+// texel gradient dgb and adds the OneBlob part dxb the decoder backward wrote.  Each thread sums d xn and z * d xn over its
+// live samples and finishes with six reductions onto the ray's rows:
 //   dL/d rays_o = sum_s dL/d pts,  dL/d rays_d = sum_s z_s dL/d pts,  pts = o + d z,  d pts = d xn / (b1 - b0)  (:443, :388)
 __global__ void __launch_bounds__(128) raygrad_walk_kernel(GridDev hg, GridDev gg, const float* __restrict__ hash_params,
                                                            const float* __restrict__ gbv_params, const float* __restrict__ xn,
                                                            const float* __restrict__ dfeat, const float* __restrict__ dgb,
-                                                           const float* __restrict__ dxb, long long P, long long N, int S, int seg,
-                                                           int level0, RayGradArgs rg) {
+                                                           const float* __restrict__ dxb, const int* __restrict__ n_live, long long P,
+                                                           long long N, int S, int seg, int level0, RayGradArgs rg) {
     const int l = blockIdx.y + level0, L = hg.n_levels;
     const long long unit = blockIdx.x * 128ll + threadIdx.x;
     const long long r = unit % N;
     const int s_begin = (int)(unit / N) * seg;
     if (s_begin >= S) return;
-    const int s_end = min(S, s_begin + seg);
+    const int lim = n_live ? min(S, __ldg(n_live + r)) : S;
+    const int s_end = min(lim, s_begin + seg);
+    if (s_end <= s_begin) return;
     const long long first = (long long)s_begin * N + r;
     const float* xs = xn + first; const float* ys = xn + P + first; const float* zs = xn + 2 * P + first; const float* ts = xn + 3 * P + first;
     unsigned pcx = 0, pcy = 0, pcz = 0; bool have = false;
-    CornerIndexer ci;
     unsigned idx[8];
     float so[3] = {0.f, 0.f, 0.f}, sd[3] = {0.f, 0.f, 0.f};
     float xa = __ldg(xs), ya = __ldg(ys), za = __ldg(zs), ta = __ldg(ts);
     if (l < L) {
         const float scale = hg.scale[l];
-        ci.init(hg.is_hash != 0, hg.size[l], hg.res[l]);
         const float2* tab = reinterpret_cast<const float2*>(hash_params) + hg.offset[l];
-        const float2* dj = reinterpret_cast<const float2*>(dfeat) + (long long)l * P + first;
+        const float* dj = dfeat + ((long long)(l & 3) * P + first) * 8 + 2 * (l >> 2);      // X-order: chunk l % 4, entry l / 4
         float2 v[8];
-        float2 da = __ldg(dj);
+        float2 da = __ldg(reinterpret_cast<const float2*>(dj));
         for (int s = s_begin; s < s_end; ++s) {
             const float x = xa, y = ya, z = za, t = ta; const float2 d = da;
-            if (s + 1 < s_end) { xs += N; ys += N; zs += N; ts += N; dj += N; xa = __ldg(xs); ya = __ldg(ys); za = __ldg(zs); ta = __ldg(ts); da = __ldg(dj); }
+            if (s + 1 < s_end) { xs += N; ys += N; zs += N; ts += N; dj += 8 * N; xa = __ldg(xs); ya = __ldg(ys); za = __ldg(zs); ta = __ldg(ts); da = __ldg(reinterpret_cast<const float2*>(dj)); }
             if (d.x == 0.f && d.y == 0.f) continue;                      // masked sample: no gradient
             unsigned cx, cy, cz; float fx, fy, fz;
             pos_fract(x, scale, cx, fx); pos_fract(y, scale, cy, fy); pos_fract(z, scale, cz, fz);
             if (!have || cx != pcx || cy != pcy || cz != pcz) {
-                ci.cell(cx, cy, cz, idx);
+                cell_indices(hg.is_hash != 0, hg.size[l], hg.res[l], cx, cy, cz, idx);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) v[c] = __ldg(tab + idx[c]);
                 pcx = cx; pcy = cy; pcz = cz; have = true;
@@ -305,7 +364,6 @@ __global__ void __launch_bounds__(128) raygrad_walk_kernel(GridDev hg, GridDev g
         }
     } else {
         const float scale = gg.scale[0];
-        ci.init(false, gg.size[0], gg.res[0]);
         const float4* tab = reinterpret_cast<const float4*>(gbv_params);
         const float4* dj = reinterpret_cast<const float4*>(dgb) + first;
         const float* b0 = dxb + first; const float* b1 = dxb + P + first; const float* b2 = dxb + 2 * P + first;
@@ -320,7 +378,7 @@ __global__ void __launch_bounds__(128) raygrad_walk_kernel(GridDev hg, GridDev g
             unsigned cx, cy, cz; float fx, fy, fz;
             pos_fract(x, scale, cx, fx); pos_fract(y, scale, cy, fy); pos_fract(z, scale, cz, fz);
             if (!have || cx != pcx || cy != pcy || cz != pcz) {
-                ci.cell(cx, cy, cz, idx);
+                cell_indices(false, gg.size[0], gg.res[0], cx, cy, cz, idx);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) v[c] = __ldg(tab + idx[c]);
                 pcx = cx; pcy = cy; pcz = cz; have = true;
@@ -353,8 +411,7 @@ __global__ void __launch_bounds__(256) replica_reduce_kernel(GridDev hg, Scatter
 
 // Replication plan: K = 2^20 / size rounded up to a power of two, clamped to [1, 32].  Returns the scratch entries used.
 static size_t scatter_plan(const GridDev& hg, long long n_rays, ScatterRep& rep) {
-    static int budget0 = -1;
-    if (budget0 < 0) { const char* e = getenv("RF_SCATTER_REPLICA_ENTRIES"); budget0 = e ? atoi(e) : (1 << 20); }
+    static const int budget0 = [] { const char* e = getenv("RF_SCATTER_REPLICA_ENTRIES"); return e ? atoi(e) : (1 << 20); }();
     // contention grows with the batch: small batches (a few thousand rays, the reference's training batches) get few or
     // no replicas, so that zeroing and folding them does not become their fixed cost
     const long long budget = std::min<long long>(budget0, 16 * n_rays);
@@ -372,61 +429,47 @@ static size_t scatter_plan(const GridDev& hg, long long n_rays, ScatterRep& rep)
 }
 size_t scatter_scratch_floats(const GridDev& hg, long long n_rays) { ScatterRep rep; return 2 * scatter_plan(hg, n_rays, rep); }
 
-// samples per walking thread: the whole ray for big batches; for small ones segments of >= 8 samples such that a level
-// launch has ~32 k threads
-static int walk_segment(long long n_rays, int S) {
-    long long nseg = std::min<long long>((32768 + n_rays - 1) / std::max<long long>(n_rays, 1), std::max(1, S / 8));
-    if (nseg < 1) nseg = 1;
-    return (int)((S + nseg - 1) / nseg);
+// the last tile of the operand blocks is only partly written when P is not a multiple of 128: its dead rows are read by
+// the decoder's bulk copies (and enter the weight-gradient GEMMs with zero upstream gradients), so they must be finite
+static int zero_last_tile(long long P, float* ws, cudaStream_t s) {
+    if ((P & 127) == 0) return 0;
+    cudaError_t e = cudaMemsetAsync(reinterpret_cast<unsigned char*>(ws) + (ws_tiles(P) - 1) * (size_t)kHopTileBytes, 0, kHopTileBytes, s);
+    if (e != cudaSuccess) return set_error((int)e, "cudaMemsetAsync(last operand tile): %s", cudaGetErrorString(e));
+    return 0;
 }
 
 // point queries: n "rays" of one sample each (planes degenerate to [n]; the walk is one step long)
 int launch_encode_points(const GridDev& hg, const GridDev& gg, const rf_ray_params* p, const float* x, long long n, float* feat, cudaStream_t s) {
-    const int L = hg.n_levels;
-    float* xn = feat + (2ll * L + 4) * n;
-    point_pos_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, n, xn);
-    RF_CHECK_LAUNCH("point_pos_kernel");
-    dim3 grid((unsigned)((n + 127) / 128), (unsigned)(L + 1));
+    RayK k; memset(&k, 0, sizeof(k));
+    k.n_rays = n; k.S = 1;
+    int rc = zero_last_tile(n, feat, s); if (rc) return rc;
     ProfScope ps(RF_PROF_ENCODE, s);
-    encode_walk_kernel<<<grid, 128, 0, s>>>(hg, gg, p->hash_params, p->gbv_params, xn, n, n, 1, 1, 0, feat);
-    RF_CHECK_LAUNCH("encode_walk_kernel");
+    encode_walk4_kernel<true><<<(unsigned)((n + 31) / 32), kEncThreads, 4 * 33 * sizeof(float), s>>>(k, hg, gg, p->hash_params, p->gbv_params, nullptr,
+                                                                                                  nullptr, x, n, 1, feat);
+    RF_CHECK_LAUNCH("encode_walk4_kernel<points>");
     return 0;
 }
 
 int launch_encode(const RayK& k, const GridDev& hg, const GridDev& gg, const rf_ray_params* p, const float* rays_o, const float* rays_d,
                   const float* z_vals, long long P, float* feat, cudaStream_t s) {
-    const int L = hg.n_levels;
-    float* xn = feat + (2ll * L + 4) * P;
-    {
-        static bool attr_done = false;
-        if (!attr_done) { cudaFuncSetAttribute(ray_pos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kMaxS * 33 * (int)sizeof(float)); attr_done = true; }
-        ProfScope ps(RF_PROF_RAY_POS, s);
-        ray_pos_kernel<<<(unsigned)((k.n_rays + 31) / 32), 256, 4 * k.S * 33 * sizeof(float), s>>>(k, rays_o, rays_d, z_vals, P, xn);
-    }
-    RF_CHECK_LAUNCH("ray_pos_kernel");
+    int rc = zero_last_tile(P, feat, s); if (rc) return rc;
     const int seg = walk_segment(k.n_rays, k.S);
     const long long units = k.n_rays * ((k.S + seg - 1) / seg);
-    dim3 grid((unsigned)((units + 127) / 128), (unsigned)(L + 1));
-    if (prof_enabled() && getenv("RF_DEBUG_PER_LEVEL")) {                 // per-level timing (diagnostics only)
-        for (int l = 0; l <= L; ++l) {
-            ProfScope pl(RF_PROF_ENCODE_LEVEL0 + l, s);
-            encode_walk_kernel<<<dim3(grid.x, 1), 128, 0, s>>>(hg, gg, p->hash_params, p->gbv_params, xn, P, k.n_rays, k.S, seg, l, feat);
-        }
-        RF_CHECK_LAUNCH("encode_walk_kernel");
-        return 0;
-    }
+    const size_t sm = 4 * (size_t)seg * 33 * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(encode_walk4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * kMaxS * 33 * sizeof(float)));
+    if (e != cudaSuccess) return set_error((int)e, "cudaFuncSetAttribute(encode_walk4_kernel): %s", cudaGetErrorString(e));
     ProfScope ps(RF_PROF_ENCODE, s);
-    encode_walk_kernel<<<grid, 128, 0, s>>>(hg, gg, p->hash_params, p->gbv_params, xn, P, k.n_rays, k.S, seg, 0, feat);
-    RF_CHECK_LAUNCH("encode_walk_kernel");
+    encode_walk4_kernel<false><<<(unsigned)((units + 31) / 32), kEncThreads, sm, s>>>(k, hg, gg, p->hash_params, p->gbv_params, rays_o, rays_d,
+                                                                                    z_vals, P, seg, feat);
+    RF_CHECK_LAUNCH("encode_walk4_kernel");
     return 0;
 }
 
 // g_rep: scatter_scratch_floats() floats of scratch for the replicas (zeroed here).  rg (BA mode, optional): the walk
 // also accumulates the hash-level part of the ray gradients (g_o / g_d must be zeroed by the caller).
-int launch_scatter(const RayK& k, const GridDev& hg, long long P, const float* feat, const float* dfeat, float* g_hash, float* g_rep,
-                   const RayGradArgs* rg, cudaStream_t s) {
-    const int L = hg.n_levels;
-    const float* xn = feat + (2ll * L + 4) * P;
+int launch_scatter(const RayK& k, const GridDev& hg, long long P, const float* feat, const float* dfeat, const int* n_live, float* g_hash,
+                   float* g_rep, const RayGradArgs* rg, cudaStream_t s) {
+    const float* xn = feat + ws_off_xn(P);
     ScatterRep rep;
     const size_t rep_entries = scatter_plan(hg, k.n_rays, rep);
     if (rep_entries) {
@@ -435,45 +478,49 @@ int launch_scatter(const RayK& k, const GridDev& hg, long long P, const float* f
     }
     const int seg = walk_segment(k.n_rays, k.S);
     const long long units = k.n_rays * ((k.S + seg - 1) / seg);
-    const unsigned gx = (unsigned)((units + 127) / 128);
+    const unsigned gx = (unsigned)((units + 31) / 32);
     RayGradArgs none{};
-    if (prof_enabled() && getenv("RF_DEBUG_PER_LEVEL") && !rg) {          // per-level timing (diagnostics only)
-        for (int l = 0; l < L; ++l) {
-            ProfScope pl(RF_PROF_SCATTER_LEVEL0 + l, s);
-            scatter_walk_kernel<false><<<dim3(gx, 1), 128, 0, s>>>(hg, rep, xn, dfeat, P, k.n_rays, k.S, seg, l, g_hash, g_rep, none);
-        }
-    } else {
+    {
         ProfScope ps(RF_PROF_SCATTER, s);
-        if (rg) scatter_walk_kernel<true><<<dim3(gx, L), 128, 0, s>>>(hg, rep, xn, dfeat, P, k.n_rays, k.S, seg, 0, g_hash, g_rep, *rg);
-        else scatter_walk_kernel<false><<<dim3(gx, L), 128, 0, s>>>(hg, rep, xn, dfeat, P, k.n_rays, k.S, seg, 0, g_hash, g_rep, none);
+        cudaError_t e;
+        if (rg) {
+            const size_t sm = 4 * (size_t)seg * 32 * sizeof(float);
+            e = cudaFuncSetAttribute(scatter_walk4_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * kMaxS * 32 * sizeof(float)));
+            if (e == cudaSuccess) scatter_walk4_kernel<2, true><<<gx, 256, sm, s>>>(hg, rep, xn, dfeat, n_live, P, k.n_rays, k.S, seg, g_hash, g_rep, *rg);
+        } else {
+            const size_t sm = 3 * (size_t)seg * 32 * sizeof(float);
+            e = cudaFuncSetAttribute(scatter_walk4_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * kMaxS * 32 * sizeof(float)));
+            if (e == cudaSuccess) scatter_walk4_kernel<4, false><<<gx, 128, sm, s>>>(hg, rep, xn, dfeat, n_live, P, k.n_rays, k.S, seg, g_hash, g_rep, none);
+        }
+        if (e != cudaSuccess) return set_error((int)e, "cudaFuncSetAttribute(scatter_walk4_kernel): %s", cudaGetErrorString(e));
     }
-    RF_CHECK_LAUNCH("scatter_walk_kernel");
+    RF_CHECK_LAUNCH("scatter_walk4_kernel");
     if (rep_entries) {
-        replica_reduce_kernel<<<dim3(64, L), 256, 0, s>>>(hg, rep, g_rep, g_hash);
+        replica_reduce_kernel<<<dim3(64, hg.n_levels), 256, 0, s>>>(hg, rep, g_rep, g_hash);
         RF_CHECK_LAUNCH("replica_reduce_kernel");
     }
     return 0;
 }
 
-// BA mode: dfeat [L][P][2], dgb [P][4], dxb [3][P] (all sample-major planes) -> g_rays_o / g_rays_d [N][3] (overwritten).
+// BA mode: dfeat [4][P][8], dgb [P][4], dxb [3][P] (sample-major planes) -> g_rays_o / g_rays_d [N][3] (overwritten).
 // With a table gradient the hash levels ride on the scatter walk and only the GBV / OneBlob level runs here.
 int launch_scatter_raygrad(const RayK& k, const GridDev& hg, const GridDev& gg, const rf_ray_params* p, long long P, const float* feat,
-                           const float* dfeat, const float* dgb, const float* dxb, float* g_hash, float* g_rep, float* g_o, float* g_d,
-                           cudaStream_t s) {
+                           const float* dfeat, const float* dgb, const float* dxb, const int* n_live, float* g_hash, float* g_rep, float* g_o,
+                           float* g_d, cudaStream_t s) {
     const int L = hg.n_levels;
-    const float* xn = feat + (2ll * L + 4) * P;
+    const float* xn = feat + ws_off_xn(P);
     cudaError_t e = cudaSuccess;
     if (g_o) e = cudaMemsetAsync(g_o, 0, 3 * k.n_rays * sizeof(float), s);
     if (e == cudaSuccess && g_d) e = cudaMemsetAsync(g_d, 0, 3 * k.n_rays * sizeof(float), s);
     if (e != cudaSuccess) return set_error((int)e, "cudaMemsetAsync(ray gradients): %s", cudaGetErrorString(e));
     RayGradArgs rg{p->hash_params, {k.bl[0], k.bl[1], k.bl[2]}, g_o, g_d};
-    if (g_hash) { int rc = launch_scatter(k, hg, P, feat, dfeat, g_hash, g_rep, &rg, s); if (rc) return rc; }
+    if (g_hash) { int rc = launch_scatter(k, hg, P, feat, dfeat, n_live, g_hash, g_rep, &rg, s); if (rc) return rc; }
     const int level0 = g_hash ? L : 0, nlev = g_hash ? 1 : L + 1;
     const int seg = walk_segment(k.n_rays, k.S);
     const long long units = k.n_rays * ((k.S + seg - 1) / seg);
     ProfScope ps(RF_PROF_RAY_GRAD, s);
-    raygrad_walk_kernel<<<dim3((unsigned)((units + 127) / 128), nlev), 128, 0, s>>>(hg, gg, p->hash_params, p->gbv_params, xn, dfeat, dgb, dxb, P,
-                                                                                  k.n_rays, k.S, seg, level0, rg);
+    raygrad_walk_kernel<<<dim3((unsigned)((units + 127) / 128), nlev), 128, 0, s>>>(hg, gg, p->hash_params, p->gbv_params, xn, dfeat, dgb, dxb, n_live,
+                                                                                  P, k.n_rays, k.S, seg, level0, rg);
     RF_CHECK_LAUNCH("raygrad_walk_kernel");
     return 0;
 }

@@ -16,12 +16,15 @@
 // the fp32 SIMT kernels of ray_query.cu (mlp_precision 0) stay as the accuracy anchor.
 //
 // Structure: a CTA holds the decoder weights once (bf16 hi/lo, chunked no-swizzle layout of umma.cuh) and G
-// independent groups of 128 threads (forward) or 256 threads (backward: two threads per tile row, mlp_bwd_tc2_kernel; the
-// one-thread-per-row mlp_bwd_tc_kernel is kept for A/B timing).  A group owns one tile at a time: thread m stages row m
-// of the operands, one elected thread issues the MMAs, everybody waits on the group's mbarrier and reads its own TMEM lane.  Groups run
-// out of phase, so one group's tensor-core latency is covered by another group's staging.  Inputs are the feature
-// planes written by ray_encode.cu (sample-major: a tile is 128 consecutive rays at one sample index; coalesced,
-// streaming); no random access happens here.  Only raw / d_raw ([N][S][4], the reference's layout) are strided.
+// independent groups of 128 threads (forward) or 256 threads (backward: two threads per tile row, mlp_bwd_tc2_kernel).
+// A group owns one tile at a time: thread m stages row m of the operands, one elected thread issues the MMAs, everybody
+// waits on the group's mbarrier and reads its own TMEM lane.  Groups run out of phase, so one group's tensor-core latency is
+// covered by another group's staging.  Inputs are what ray_encode.cu wrote (sample-major: a tile is 128 consecutive rays at
+// one sample index): the hash features arrive as READY bf16 hi / lo operand chunks, 16 KB per tile — the forward moves its row
+// of them straight into tensor memory, the backward's elected thread fetches the whole block into the X operand with two TMA
+// bulk copies (cp.async.bulk -> mbarrier) — plus the GBV features and positions (coalesced, streaming); no random access
+// happens here.  Only raw / d_raw ([N][S][4], the reference's layout) are strided.  The backward skips tiles none of whose
+// rows has a live upstream gradient (n_live, see ray_encode.cu).
 #include "ray_common.cuh"
 #include "umma.cuh"
 #include <stdlib.h>
@@ -64,7 +67,8 @@ __device__ void load_weights(unsigned char* w, const Weights& wt, int nthreads) 
     for (int i = threadIdx.x; i < HID * kKX; i += nthreads) {
         int j = i / kKX, kx = i - j * kKX;
         float v = 0.f;
-        if (kx < 80) v = wt.w_sdf0[j * in1 + kx];
+        if (kx < 32) v = wt.w_sdf0[j * in1 + hash_col_to_feature(kx)];      // X-order of the hash columns (ray_common.cuh)
+        else if (kx < 80) v = wt.w_sdf0[j * in1 + kx];
         else if (kx == 80 + kTailTsdf) v = wt.w_sdf0[j * in1 + 80];
         store_split(w + L::o_w0h, w + L::o_w0l, HID, j, kx, v);
     }
@@ -172,48 +176,7 @@ __device__ __forceinline__ void mma_mm1(uint32_t d, uint32_t a, uint32_t b, uint
         da = desc_advance(da, 2 * 128); db = desc_advance(db, 2 * 128);
     }
 }
-// X-based weight gradients: A = X (hi, lo separate), B = [dH_hi | dH_lo] contiguous: A_hi x [B_hi|B_lo] (N = 2n) and
-// A_lo x B_hi (N = n) accumulate hh + lh in columns [0,n) and hl in columns [n,2n).
-__device__ __forceinline__ void mma_mm2(uint32_t d, uint32_t ah, uint32_t al, uint32_t b, uint32_t idesc_2n, uint32_t idesc_n, uint32_t& acc) {
-    uint64_t dah = smem_desc(ah, 128, kChunkB), dal = smem_desc(al, 128, kChunkB), db = smem_desc(b, 128, kChunkB);
-#pragma unroll
-    for (int s = 0; s < 8; ++s) {
-        mma_bf16(d, dah, db, idesc_2n, acc); acc = 1;
-        mma_bf16(d, dal, db, idesc_n, 1);
-        dah = desc_advance(dah, 2 * 128); dal = desc_advance(dal, 2 * 128); db = desc_advance(db, 2 * 128);
-    }
-}
-
-// hidden pre-activations of this thread's TMEM lane -> relu -> operand chunks; returns the relu mask
-template <int HID>
-__device__ __forceinline__ void relu_to_smem(uint32_t taddr, unsigned char* hi, unsigned char* lo, int m, uint32_t (&mask)[HID / 32]) {
-#pragma unroll
-    for (int q = 0; q < HID / 32; ++q) {
-        float v[32];
-        tmem_ld32(taddr + 32 * q, v);
-        uint32_t mk = 0;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) { if (v[i] > 0.f) mk |= (1u << i); v[i] = fmaxf(v[i], 0.f); }
-        mask[q] = mk;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) stage8(hi, lo, m, 4 * q + c, v + 8 * c);
-    }
-}
-// gradient w.r.t. the hidden pre-activation: TMEM lane . mask -> operand chunks
-template <int HID>
-__device__ __forceinline__ void masked_to_smem(uint32_t taddr, unsigned char* hi, unsigned char* lo, int m, const uint32_t (&mask)[HID / 32]) {
-#pragma unroll
-    for (int q = 0; q < HID / 32; ++q) {
-        float v[32];
-        tmem_ld32(taddr + 32 * q, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = ((mask[q] >> i) & 1u) ? v[i] : 0.f;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) stage8(hi, lo, m, 4 * q + c, v + 8 * c);
-    }
-}
-
-struct TileIn { float2 f[16]; float4 g; float x[3]; };
+struct TileIn { uint4 hh[4], hl[4]; float4 g; float x[3]; };   // row m: 4 hash operand chunks (hi, lo), GBV texel, position
 
 // Plane index q = s * N + r of the first row of a group's current tile, kept as (s, r) and advanced by a fixed number of
 // rows per iteration: no 64-bit division per thread per tile.
@@ -225,71 +188,48 @@ struct TilePos {
         N = n_rays; S = S_; s = q0 / N; r = q0 - s * N; ds = step / N; dr = step - ds * N;
     }
     __device__ void next() { s += ds; r += dr; if (r >= N) { r -= N; ++s; } }
-    // raw index r * S + s of row m (m < 128; N may be smaller than 128)
-    __device__ long long raw_index(int m) const {
-        long long rr = r + m, ss = s;
+    // (sample, ray) of row m (m < 128; N may be smaller than 128)
+    __device__ void row(int m, long long& ss, long long& rr) const {
+        rr = r + m; ss = s;
         while (rr >= N) { rr -= N; ++ss; }
+    }
+    // raw index r * S + s of row m
+    __device__ long long raw_index(int m) const {
+        long long rr, ss; row(m, ss, rr);
         return rr * S + ss;
     }
 };
 
-__device__ __forceinline__ void load_tile(TileIn& t, const float* __restrict__ feat, long long P, long long p, bool live) {
-    if (live) {
-        const float2* fh = reinterpret_cast<const float2*>(feat);
+// row m of tile `tile` (plane index q = tile * 128 + m).  The operand block of the last tile is zero-filled beyond P.
+__device__ __forceinline__ void load_tile(TileIn& t, const float* __restrict__ feat, long long P, long long tile, int m) {
+    const long long q = tile * kTile + m;
+    if (tile * kTile < P) {
+        const uint4* hop = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(feat) + tile * kHopTileBytes);
 #pragma unroll
-        for (int l = 0; l < 16; ++l) t.f[l] = __ldg(fh + (long long)l * P + p);
-        t.g = __ldg(reinterpret_cast<const float4*>(feat + 32ll * P) + p);
-        const float* xn = feat + 36ll * P;
-        t.x[0] = __ldg(xn + p); t.x[1] = __ldg(xn + P + p); t.x[2] = __ldg(xn + 2 * P + p);
+        for (int c = 0; c < 4; ++c) { t.hh[c] = __ldg(hop + c * 128 + m); t.hl[c] = __ldg(hop + 512 + c * 128 + m); }
     } else {
 #pragma unroll
-        for (int l = 0; l < 16; ++l) t.f[l] = make_float2(0.f, 0.f);
+        for (int c = 0; c < 4; ++c) { t.hh[c] = make_uint4(0, 0, 0, 0); t.hl[c] = make_uint4(0, 0, 0, 0); }
+    }
+    if (q < P) {
+        t.g = __ldg(reinterpret_cast<const float4*>(feat + ws_off_gbv(P)) + q);
+        const float* xn = feat + ws_off_xn(P);
+        t.x[0] = __ldg(xn + q); t.x[1] = __ldg(xn + P + q); t.x[2] = __ldg(xn + 2 * P + q);
+    } else {
         t.g = make_float4(0.f, 0.f, 0.f, 0.f);
         t.x[0] = t.x[1] = t.x[2] = 0.5f;
     }
 }
 
-// Pull the next tile of this group towards L2 while the current one is processed: the 16 hash planes are 8 lines of
-// 128 B each per tile (one line per thread), GBV 16 lines, xn 3 x 4 lines.
-__device__ __forceinline__ void prefetch_tile(const float* __restrict__ feat, long long P, long long q0, int m) {
+// Pull a later tile of this group towards L2 while the current one is processed: the operand block is 128 lines of 128 B
+// (one per thread), GBV 16 lines, xn 3 x 4 lines.
+__device__ __forceinline__ void prefetch_tile(const float* __restrict__ feat, long long P, long long tile, int m, bool with_hash) {
+    const long long q0 = tile * kTile;
     if (q0 >= P) return;
     const long long last = P - 1;
-    prefetch_l2(feat + 2 * ((long long)(m >> 3) * P + min(q0 + 16 * (m & 7), last)));
-    if (m < 16) prefetch_l2(feat + 32ll * P + 4 * min(q0 + 8 * m, last));
-    else if (m < 28) prefetch_l2(feat + 36ll * P + (long long)((m - 16) >> 2) * P + min(q0 + 32 * ((m - 16) & 3), last));
-}
-
-// X row of thread m: hash chunks, OneBlob chunks, tail = [0 x15 | gbv rgb | decoder tsdf input | 0]
-__device__ __forceinline__ void stage_x(const TileIn& t, float cin, bool live, int m, unsigned char* hash_hi, unsigned char* hash_lo,
-                                        unsigned char* blob_hi, unsigned char* blob_lo, unsigned char* tail_hi, unsigned char* tail_lo) {
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        float v[8] = {t.f[4 * c].x, t.f[4 * c].y, t.f[4 * c + 1].x, t.f[4 * c + 1].y, t.f[4 * c + 2].x, t.f[4 * c + 2].y, t.f[4 * c + 3].x, t.f[4 * c + 3].y};
-        stage8(hash_hi, hash_lo, m, c, v);
-    }
-    if (live) {
-#pragma unroll 1
-        for (int a = 0; a < 3; ++a) stage_oneblob(t.x[a], blob_hi, blob_lo, m, 2 * a);
-    } else {
-        for (int c = 0; c < 6; ++c) stage_zero(blob_hi, blob_lo, m, c);
-    }
-    stage_zero(tail_hi, tail_lo, m, 0);
-    float v1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, t.g.y};
-    float v2[8] = {t.g.z, t.g.w, cin, 0.f, 0.f, 0.f, 0.f, 0.f};
-    stage8(tail_hi, tail_lo, m, 1, v1);
-    stage8(tail_hi, tail_lo, m, 2, v2);
-    stage_zero(tail_hi, tail_lo, m, 3);
-}
-// geo features (decoder.py:108-110 output 1..15) into the tail once the SDF net has produced them
-__device__ __forceinline__ void stage_geo(const float (&o16)[16], float gy, int m, unsigned char* tail_hi, unsigned char* tail_lo) {
-    float v0[8], v1[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v0[i] = o16[1 + i];
-#pragma unroll
-    for (int i = 0; i < 7; ++i) v1[i] = o16[9 + i];
-    v1[7] = gy;
-    stage8(tail_hi, tail_lo, m, 0, v0);
-    stage8(tail_hi, tail_lo, m, 1, v1);
+    if (with_hash) prefetch_l2(reinterpret_cast<const unsigned char*>(feat) + tile * kHopTileBytes + m * 128);
+    if (m < 16) prefetch_l2(feat + ws_off_gbv(P) + 4 * min(q0 + 8 * m, last));
+    else if (m < 28) prefetch_l2(feat + ws_off_xn(P) + (long long)((m - 16) >> 2) * P + min(q0 + 32 * ((m - 16) & 3), last));
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -378,21 +318,18 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_fwd_tc_kernel(RayK k, Weights 
     const long long tstep = (long long)gridDim.x * G;
     TilePos tp; tp.init(k.n_rays, k.S, ((long long)blockIdx.x * G + g) * kTile, tstep * kTile);
     TileIn t;
-    { const long long q0 = ((long long)blockIdx.x * G + g) * kTile + m; load_tile(t, feat, P, q0, q0 < P); }
+    load_tile(t, feat, P, (long long)blockIdx.x * G + g, m);
     for (long long tile = (long long)blockIdx.x * G + g; tile * kTile < P; tile += tstep, tp.next()) {
         const long long q = tile * kTile + m;                                                 // plane index s * N + r
         const bool live = q < P;
         const long long p = live ? tp.raw_index(m) : 0;                                       // raw index r * S + s
-        prefetch_tile(feat, P, (tile + 2 * tstep) * kTile, m);
+        prefetch_tile(feat, P, tile + 2 * tstep, m, true);
         const float4 gb = t.g;                                                                // GBV features of this tile
         float t_add, cin, d0, d1;
         tsdf_terms(k, variant, gb.x, t_add, cin, d0, d1);                                     // scene_rep.py:330-337 (:230-233, :292-294)
-        // X row: hash -> TMEM, OneBlob -> shared memory, tail = [0 x15 | gbv rgb | decoder tsdf input | 0] -> TMEM
+        // X row: hash (ready bf16 hi / lo chunks) -> TMEM, OneBlob -> shared memory, tail = [0 x15 | gbv rgb | decoder tsdf input | 0] -> TMEM
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            float v[8] = {t.f[4 * c].x, t.f[4 * c].y, t.f[4 * c + 1].x, t.f[4 * c + 1].y, t.f[4 * c + 2].x, t.f[4 * c + 2].y, t.f[4 * c + 3].x, t.f[4 * c + 3].y};
-            tstage8(tlane + A::t_hash_hi, tlane + A::t_hash_lo, c, v);
-        }
+        for (int c = 0; c < 4; ++c) { tmem_st4(tlane + A::t_hash_hi + 4 * c, t.hh[c]); tmem_st4(tlane + A::t_hash_lo + 4 * c, t.hl[c]); }
         if (live) {
 #pragma unroll 1
             for (int a = 0; a < 3; ++a) stage_oneblob(t.x[a], blob_hi, blob_lo, m, 2 * a);
@@ -407,7 +344,7 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_fwd_tc_kernel(RayK k, Weights 
             tstage8(tlane + A::t_tail_hi, tlane + A::t_tail_lo, 2, v2);
             tstage_zero(tlane + A::t_tail_hi, tlane + A::t_tail_lo, 3);
         }
-        { const long long qn = (tile + tstep) * kTile + m; load_tile(t, feat, P, qn, qn < P); }   // next tile's inputs (see above)
+        load_tile(t, feat, P, tile + tstep, m);                                               // next tile's inputs (see above)
         tmem_st_wait();
         fence_async_smem(); fence_before_sync(); grp_sync(g);
         if (m == 0) {                                                                         // H1 = X1 W0^T
@@ -488,221 +425,6 @@ struct BwdL {
     static constexpr int tcols = (HID == 32) ? 256 : 512;
 };
 
-// Weight gradients of a group: TMEM accumulators (lane = row, see BwdL) -> global, with atomics.
-template <int HID>
-__device__ __forceinline__ void flush_wgrads(uint32_t tlane, const Grads& gr, int m) {
-    using A = BwdL<HID>;
-    {
-        fence_after_sync();
-        const int f = m;
-        int c0 = -1;                                          // column of w_sdf0 for X1 row f
-        if (f < 80) c0 = f; else if (f == 80 + kTailTsdf) c0 = 80;
-#pragma unroll
-        for (int q = 0; q < HID / 32; ++q) {                  // X-based: value = (hh + lh)[j] + hl[j]
-            float v[32], u[32];
-            tmem_ld32(tlane + A::t_w0 + 32 * q, v);
-            tmem_ld32(tlane + A::t_w0 + HID + 32 * q, u);
-            if (gr.g_w_sdf0 && c0 >= 0) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) atomicAdd(gr.g_w_sdf0 + (32 * q + j) * 81 + c0, v[j] + u[j]);
-            }
-            tmem_ld32(tlane + A::t_w2 + 32 * q, v);
-            tmem_ld32(tlane + A::t_w2 + HID + 32 * q, u);
-            if (gr.g_w_col0 && f < kIn2) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) atomicAdd(gr.g_w_col0 + (32 * q + j) * kIn2 + f, v[j] + u[j]);
-            }
-        }
-        // H-based: rows [0,HID) = hi features (columns: x hi | x lo), rows [HID,2HID) = lo features (column block x hi)
-        float v32[32];
-        tmem_ld32(tlane + A::t_w1, v32);
-        if (gr.g_w_sdf1 && f < 2 * HID) {
-            const int j = (f < HID) ? f : f - HID;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) atomicAdd(gr.g_w_sdf1 + i * HID + j, (f < HID) ? v32[i] + v32[16 + i] : v32[i]);
-        }
-        tmem_ld32(tlane + A::t_w3, v32);
-        if (gr.g_w_col1 && f < 2 * HID) {
-            const int j = (f < HID) ? f : f - HID;
-#pragma unroll
-            for (int i = 0; i < 3; ++i) atomicAdd(gr.g_w_col1 + i * HID + j, (f < HID) ? v32[i] + v32[16 + i] : v32[i]);
-        }
-    }
-}
-
-template <int HID, int G>
-__global__ void __launch_bounds__(G * 128, 1) mlp_bwd_tc_kernel(RayK k, Weights wts, const float* __restrict__ feat, long long P,
-                                                                const float* __restrict__ d_raw_tot, float* __restrict__ dfeat, Grads gr) {
-    extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ uint64_t bars[G];
-    __shared__ uint32_t tmem_base_s;
-    using W = WL<HID>; using A = BwdL<HID>;
-    constexpr int HC = HID / 8;
-    constexpr uint32_t TCOLS = G * A::tcols;
-    const int tid = threadIdx.x, g = tid >> 7, m = tid & 127, warp = tid >> 5;
-    // weights sit after the group regions: the M = 128 MN-major reads of the narrow H / D operands run past their
-    // own chunks (rows of D that are never read back) and must stay inside the allocation
-    unsigned char* wsm = smem + G * A::bytes;
-    unsigned char* act = smem + g * A::bytes;
-    if (warp == 0) tmem_alloc(&tmem_base_s, TCOLS);
-    if (tid == 0) { for (int i = 0; i < G; ++i) mbar_init(&bars[i], 1); fence_mbar_init(); }
-    load_weights<HID>(wsm, wts, G * 128);
-    fence_async_smem();
-    fence_before_sync();
-    __syncthreads();
-    fence_after_sync();
-    const uint32_t tb = tmem_base_s + (uint32_t)g * A::tcols;
-    const uint32_t tlane = tb + ((uint32_t)((warp & 3) * 32) << 16);
-    uint64_t* bar = &bars[g];
-    uint32_t phase = 0;
-    unsigned char *x_hi = act + A::c_x_hi * kChunkB, *x_lo = act + A::c_x_lo * kChunkB;
-    unsigned char *h1_hi = act + A::c_h1_hi * kChunkB, *h1_lo = act + A::c_h1_lo * kChunkB;
-    unsigned char *h2_hi = act + A::c_h2_hi * kChunkB, *h2_lo = act + A::c_h2_lo * kChunkB;
-    unsigned char *d_hi = act + A::c_d_hi * kChunkB, *d_lo = act + A::c_d_lo * kChunkB;
-    unsigned char *blob_hi = x_hi + kXBlob * kChunkB, *blob_lo = x_lo + kXBlob * kChunkB;
-    unsigned char *tail_hi = x_hi + kXTail * kChunkB, *tail_lo = x_lo + kXTail * kChunkB;
-    const uint32_t w0h = smem_u32(wsm + W::o_w0h), w0l = smem_u32(wsm + W::o_w0l), w1h = smem_u32(wsm + W::o_w1h), w1l = smem_u32(wsm + W::o_w1l);
-    const uint32_t w2h = smem_u32(wsm + W::o_w2h), w2l = smem_u32(wsm + W::o_w2l), w3h = smem_u32(wsm + W::o_w3h), w3l = smem_u32(wsm + W::o_w3l);
-    const uint32_t xh = smem_u32(x_hi), xl = smem_u32(x_lo), h1h = smem_u32(h1_hi), h1l = smem_u32(h1_lo), h2h = smem_u32(h2_hi), h2l = smem_u32(h2_lo);
-    const uint32_t dh = smem_u32(d_hi), dl = smem_u32(d_lo);
-    constexpr uint32_t idH = idesc_bf16(HID, false, false), id16 = idesc_bf16(16, false, false);
-    constexpr uint32_t idH_bm = idesc_bf16(HID, false, true), id16_bm = idesc_bf16(16, false, true), id32_bm = idesc_bf16(32, false, true);
-    constexpr uint32_t idH_mm = idesc_bf16(HID, true, true), id2H_mm = idesc_bf16(2 * HID, true, true), id32_mm = idesc_bf16(32, true, true);
-    uint32_t wacc = 0;            // 0 until this group's weight-gradient accumulators hold a first tile
-    int since_flush = 0;
-
-    // inputs software-pipelined through their own registers, as in the forward
-    const long long tstep = (long long)gridDim.x * G;
-    TilePos tp; tp.init(k.n_rays, k.S, ((long long)blockIdx.x * G + g) * kTile, tstep * kTile);
-    TileIn t;
-    float4 dr_next = make_float4(0.f, 0.f, 0.f, 0.f);
-    {
-        const long long q0 = ((long long)blockIdx.x * G + g) * kTile + m;
-        load_tile(t, feat, P, q0, q0 < P);
-        if (q0 < P) dr_next = __ldg(reinterpret_cast<const float4*>(d_raw_tot) + tp.raw_index(m));
-    }
-    for (long long tile = (long long)blockIdx.x * G + g; tile * kTile < P; tile += tstep, tp.next()) {
-        const long long q = tile * kTile + m;                                                 // plane index s * N + r
-        const bool live = q < P;
-        prefetch_tile(feat, P, (tile + 2 * tstep) * kTile, m);
-        const float4 dr = dr_next;
-        const float4 gb = t.g;
-        float t_add, cin, d0, d1;
-        tsdf_terms(k, 0, gb.x, t_add, cin, d0, d1);
-        stage_x(t, cin, live, m, x_hi, x_lo, blob_hi, blob_lo, tail_hi, tail_lo);
-        {                                                                                     // next tile's inputs
-            const long long qn = (tile + tstep) * kTile + m;
-            load_tile(t, feat, P, qn, qn < P);
-            TilePos tn = tp; tn.next();
-            dr_next = (qn < P) ? __ldg(reinterpret_cast<const float4*>(d_raw_tot) + tn.raw_index(m)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        fence_async_smem(); fence_before_sync(); grp_sync(g);
-        if (m == 0) {                                                                         // H1 = X1 W0^T
-            fence_after_sync();
-            uint32_t acc = 0;
-            mma_kk<kXCh / 2>(tb + A::t_a, xh, xl, w0h, w0l, HID, idH, acc);
-            commit(bar);
-        }
-        grp_wait(bar, phase);
-        uint32_t mask1[HID / 32], mask2[HID / 32];
-        relu_to_smem<HID>(tlane + A::t_a, h1_hi, h1_lo, m, mask1);
-        fence_async_smem(); fence_before_sync(); grp_sync(g);
-        if (m == 0) {                                                                         // O = H1 W1^T
-            fence_after_sync();
-            uint32_t acc = 0;
-            mma_kk<HC / 2>(tb + A::t_b, h1h, h1l, w1h, w1l, 16, id16, acc);
-            commit(bar);
-        }
-        grp_wait(bar, phase);
-        float o16[16];
-        tmem_ld16(tlane + A::t_b, o16);
-        stage_geo(o16, gb.y, m, tail_hi, tail_lo);
-        fence_async_smem(); fence_before_sync(); grp_sync(g);
-        if (m == 0) {                                                                         // H2 = X2 W2^T
-            fence_after_sync();
-            uint32_t acc = 0;
-            mma_kk<5>(tb + A::t_a, xh + kXBlob * kChunkB, xl + kXBlob * kChunkB, w2h, w2l, HID, idH, acc);
-            commit(bar);
-        }
-        grp_wait(bar, phase);
-        relu_to_smem<HID>(tlane + A::t_a, h2_hi, h2_lo, m, mask2);
-        {                                                                                     // dRGB (upstream of :344)
-            float v0[8] = {dr.x, dr.y, dr.z, 0.f, 0.f, 0.f, 0.f, 0.f};
-            stage8(d_hi, d_lo, m, 0, v0);
-            stage_zero(d_hi, d_lo, m, 1);
-        }
-        fence_async_smem(); fence_before_sync(); grp_sync(g);
-        if (m == 0) {
-            fence_after_sync();
-            uint32_t acc = 0;
-            mma_km<1>(tb + A::t_a, dh, dl, w3h, w3l, 16, idH_bm, acc);                        // dH2pre = dRGB W3
-            uint32_t a3 = wacc;
-            mma_mm1(tb + A::t_w3, h2h, dh, id32_mm, a3);                                      // dW3^T += H2^T dRGB
-            commit(bar);
-        }
-        grp_wait(bar, phase);
-        masked_to_smem<HID>(tlane + A::t_a, h2_hi, h2_lo, m, mask2);                          // dH2 over H2
-        fence_async_smem(); fence_before_sync(); grp_sync(g);
-        if (m == 0) {
-            fence_after_sync();
-            uint32_t acc = 0;
-            mma_km<HC / 2>(tb + A::t_b, h2h, h2l, w2h + 6 * HID * 16, w2l + 6 * HID * 16, HID, id16_bm, acc);   // d tail[0..15] = dH2 W2[:, 48..63]
-            uint32_t a2 = wacc;
-            mma_mm2(tb + A::t_w2, xh + kXBlob * kChunkB, xl + kXBlob * kChunkB, h2h, id2H_mm, idH_mm, a2);   // dW2^T += X2^T dH2
-            commit(bar);
-        }
-        grp_wait(bar, phase);
-        {
-            float dg[16];
-            tmem_ld16(tlane + A::t_b, dg);
-            float v0[8] = {dr.w, dg[0], dg[1], dg[2], dg[3], dg[4], dg[5], dg[6]};
-            float v1[8] = {dg[7], dg[8], dg[9], dg[10], dg[11], dg[12], dg[13], dg[14]};
-            stage8(d_hi, d_lo, m, 0, v0);                                                     // dO = [d sdf, d geo15]
-            stage8(d_hi, d_lo, m, 1, v1);
-        }
-        fence_async_smem(); fence_before_sync(); grp_sync(g);
-        if (m == 0) {
-            fence_after_sync();
-            uint32_t acc = 0;
-            mma_km<1>(tb + A::t_a, dh, dl, w1h, w1l, 16, idH_bm, acc);                        // dH1pre = dO W1
-            uint32_t a1 = wacc;
-            mma_mm1(tb + A::t_w1, h1h, dh, id32_mm, a1);                                      // dW1^T += H1^T dO
-            commit(bar);
-        }
-        grp_wait(bar, phase);
-        masked_to_smem<HID>(tlane + A::t_a, h1_hi, h1_lo, m, mask1);                          // dH1 over H1
-        fence_async_smem(); fence_before_sync(); grp_sync(g);
-        if (m == 0) {
-            fence_after_sync();
-            uint32_t acc = 0;
-            mma_km<HC / 2>(tb + A::t_a, h1h, h1l, w0h, w0l, HID, id32_bm, acc);               // d hash = dH1 W0[:, 0..31]
-            uint32_t a0 = wacc;
-            mma_mm2(tb + A::t_w0, xh, xl, h1h, id2H_mm, idH_mm, a0);                          // dW0^T += X1^T dH1
-            commit(bar);
-        }
-        wacc = 1;
-        grp_wait(bar, phase);
-        {
-            float dx[32];
-            tmem_ld32(tlane + A::t_a, dx);
-            if (live) {
-                float2* dj = reinterpret_cast<float2*>(dfeat);
-#pragma unroll
-                for (int l = 0; l < 16; ++l) dj[(long long)l * P + q] = make_float2(dx[2 * l], dx[2 * l + 1]);
-            }
-        }
-        // fp32 accumulation in TMEM over thousands of tiles drifts (2e-4 relative on 2^20 rays at one group per SM):
-        // hand the partial sums over every kFlushTiles tiles and restart the accumulators
-        if (++since_flush == kFlushTiles) { flush_wgrads<HID>(tlane, gr, m); wacc = 0; since_flush = 0; }
-        fence_before_sync();
-    }
-    if (wacc) flush_wgrads<HID>(tlane, gr, m);
-    fence_before_sync();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base_s, TCOLS);
-}
-
-
 // ------------------------------------------------------------------------------------------------------------
 // Backward, two threads per tile row.  Same MMAs, layouts and TMEM map as mlp_bwd_tc_kernel; a group is 256 threads and
 // thread (m, h) handles half h of everything row m stages or reads back (hash levels 8h..8h+7, hidden units
@@ -759,24 +481,32 @@ __device__ __forceinline__ void masked_half(uint32_t taddr, unsigned char* hi, u
     }
 }
 
-struct TileHalf { float2 f[8]; float4 g; float x0, x1, xb; };   // h = 0: levels 0-7, x, y; h = 1: levels 8-15, z, GBV texel
+struct TileHalf { float4 g; float x0, x1, xb; uint4 hh[2], hl[2]; };   // h = 0: x, y; h = 1: z, GBV texel; hash chunks 2h, 2h + 1 (register path)
 
 // xb (BA mode): the second coordinate whose OneBlob gradient this thread reduces: h = 0 handles x then z, h = 1 handles
-// y then the GBV texel gradient
-template <bool BA>
-__device__ __forceinline__ void load_half(TileHalf& t, const float* __restrict__ feat, long long P, long long p, bool live, int h) {
+// y then the GBV texel gradient.  TMAH: the hash chunks arrive by TMA bulk copy instead of through this thread's registers.
+template <bool BA, bool TMAH>
+__device__ __forceinline__ void load_half(TileHalf& t, const float* __restrict__ feat, long long P, long long tile, int m, int h) {
+    const long long q = tile * kTile + m;
     t.g = make_float4(0.f, 0.f, 0.f, 0.f); t.x0 = t.x1 = t.xb = 0.5f;
-    if (live) {
-        const float2* fh = reinterpret_cast<const float2*>(feat) + (long long)(8 * h) * P;
+    if (!TMAH) {                                              // the operand block of the last tile is zero-filled beyond P
+        const uint4* hop = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(feat) + tile * kHopTileBytes) + m;
 #pragma unroll
-        for (int l = 0; l < 8; ++l) t.f[l] = __ldg(fh + (long long)l * P + p);
-        const float* xn = feat + 36ll * P;
-        if (h == 0) { t.x0 = __ldg(xn + p); t.x1 = __ldg(xn + P + p); if (BA) t.xb = __ldg(xn + 2 * P + p); }
-        else { t.x0 = __ldg(xn + 2 * P + p); t.g = __ldg(reinterpret_cast<const float4*>(feat + 32ll * P) + p); if (BA) t.xb = __ldg(xn + P + p); }
-    } else {
-#pragma unroll
-        for (int l = 0; l < 8; ++l) t.f[l] = make_float2(0.f, 0.f);
+        for (int c = 0; c < 2; ++c) { t.hh[c] = __ldg(hop + (2 * h + c) * 128); t.hl[c] = __ldg(hop + 512 + (2 * h + c) * 128); }
     }
+    if (q < P) {
+        const float* xn = feat + ws_off_xn(P);
+        if (h == 0) { t.x0 = __ldg(xn + q); t.x1 = __ldg(xn + P + q); if (BA) t.xb = __ldg(xn + 2 * P + q); }
+        else { t.x0 = __ldg(xn + 2 * P + q); t.g = __ldg(reinterpret_cast<const float4*>(feat + ws_off_gbv(P)) + q); if (BA) t.xb = __ldg(xn + P + q); }
+    }
+}
+
+// group-wide OR of a predicate over the 256 threads of a backward group (named-barrier reduction)
+__device__ __forceinline__ bool grp_any2(int g, bool pred) {
+    uint32_t r;
+    asm volatile("{\n .reg .pred p, q;\n setp.ne.u32 q, %2, 0;\n bar.red.or.pred p, %1, 256, q;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(r) : "r"(g + 1), "r"((uint32_t)pred) : "memory");
+    return r != 0;
 }
 
 // Input-layer weight gradients with the hidden-gradient block as the A operand (MN-major, M = 128 rows = 16 consecutive
@@ -819,7 +549,7 @@ __device__ __forceinline__ void flush_wgrads3(uint32_t tlane, const Grads& gr, i
             const int f = 16 * q + i + fshift;
             int c = -1;
             if (colour) { if (f >= 0 && f < kIn2) c = f; }
-            else { if (f < 80) c = f; else if (f == 80 + kTailTsdf) c = 80; }
+            else { if (f < 32) c = hash_col_to_feature(f); else if (f < 80) c = f; else if (f == 80 + kTailTsdf) c = 80; }
             if (c >= 0) atomicAdd(gx + j * ld + c, v[i]);
         }
     }
@@ -864,12 +594,12 @@ __device__ __forceinline__ float oneblob_dot_grad(float x, const float (&g)[16])
 
 // BA: additionally writes, per sample, the gradient w.r.t. the GBV texel (dgb [P][4]) and the OneBlob part of the
 // gradient w.r.t. the normalised position (dxb [3][P]) for raygrad_walk_kernel: one more tensor-core phase per tile.
-template <int HID, int G, bool BA>
+template <int HID, int G, bool BA, bool TMAH>
 __global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights wts, const float* __restrict__ feat, long long P,
-                                                                 const float* __restrict__ d_raw_tot, float* __restrict__ dfeat, Grads gr,
-                                                                 float* __restrict__ dgb, float* __restrict__ dxb) {
+                                                                 const float* __restrict__ d_raw_tot, const int* __restrict__ n_live,
+                                                                 float* __restrict__ dfeat, Grads gr, float* __restrict__ dgb, float* __restrict__ dxb) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ uint64_t bars[G];
+    __shared__ uint64_t bars[G], tma_bars[G];
     __shared__ uint32_t tmem_base_s;
     using W = WL<HID>; using A = BwdL<HID>;
     constexpr int HC = HID / 8, NH = HID / 2;
@@ -880,10 +610,12 @@ __global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights
     constexpr uint32_t T_A = A::t_a, T_B = (HID == 32) ? A::t_a : A::t_b, T_S = (HID == 32) ? A::t_a + 32 : A::t_b + 16;
     static_assert(T_S + HID <= A::tcols, "operand slot exceeds the group's TMEM columns");
     const int tid = threadIdx.x, g = tid >> 8, m = tid & 127, h = (tid >> 7) & 1, warp = tid >> 5;
-    unsigned char* wsm = smem + G * A::bytes;                  // after the group regions (see mlp_bwd_tc_kernel)
+    // weights sit after the group regions: the M = 128 MN-major reads of the narrow H / D operands run past their own
+    // chunks (rows of D that are never read back) and must stay inside the allocation
+    unsigned char* wsm = smem + G * A::bytes;
     unsigned char* act = smem + g * A::bytes;
     if (warp == 0) tmem_alloc(&tmem_base_s, TCOLS);
-    if (tid == 0) { for (int i = 0; i < G; ++i) mbar_init(&bars[i], 1); fence_mbar_init(); }
+    if (tid == 0) { for (int i = 0; i < G; ++i) { mbar_init(&bars[i], 1); mbar_init(&tma_bars[i], 1); } fence_mbar_init(); }
     load_weights<HID>(wsm, wts, G * 256);
     fence_async_smem();
     fence_before_sync();
@@ -911,27 +643,63 @@ __global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights
     uint32_t wacc = 0;
     int since_flush = 0;
 
-    const long long tstep = (long long)gridDim.x * G;
+    uint64_t* tma_bar = &tma_bars[g];
+    uint32_t tma_phase = 0;                                                                   // tracked by the issuer only
+    const long long tstep = (long long)gridDim.x * G, n_tiles = ws_tiles(P);
     TilePos tp; tp.init(k.n_rays, k.S, ((long long)blockIdx.x * G + g) * kTile, tstep * kTile);
+    // a row is live if its sample index lies below its ray's n_live (composite_bwd_kernel): rows beyond carry an all-zero
+    // upstream gradient; a tile none of whose rows is live contributes nothing and is skipped as a whole
+    auto row_live = [&](const TilePos& pos, long long tile_) -> bool {
+        if (tile_ * kTile + m >= P) return false;
+        if (!n_live) return true;
+        long long ss, rr; pos.row(m, ss, rr);
+        return ss < (long long)__ldg(n_live + rr);
+    };
+    // hash chunks of tile `tile_` -> chunks 0..3 of X hi / X lo: two bulk copies of 8 KB, completion on tma_bar
+    auto fetch_hash = [&](long long tile_) {
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(feat) + tile_ * kHopTileBytes;
+        mbar_expect_tx(tma_bar, kHopTileBytes);
+        bulk_g2s(x_hi, src, kHopTileBytes / 2, tma_bar);
+        bulk_g2s(x_lo, src + kHopTileBytes / 2, kHopTileBytes / 2, tma_bar);
+    };
     TileHalf t;
     float4 dr_next = make_float4(0.f, 0.f, 0.f, 0.f);
-    {
-        const long long q0 = ((long long)blockIdx.x * G + g) * kTile + m;
-        load_half<BA>(t, feat, P, q0, q0 < P, h);
-        if (h && q0 < P) dr_next = __ldg(reinterpret_cast<const float4*>(d_raw_tot) + tp.raw_index(m));
-    }
-    for (long long tile = (long long)blockIdx.x * G + g; tile * kTile < P; tile += tstep, tp.next()) {
+    long long tile = (long long)blockIdx.x * G + g;
+    auto load_inputs = [&](const TilePos& pos, long long tile_) {                             // inputs of an alive tile
+        load_half<BA, TMAH>(t, feat, P, tile_, m, h);
+        if (h) dr_next = (tile_ * kTile + m < P) ? __ldg(reinterpret_cast<const float4*>(d_raw_tot) + pos.raw_index(m)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    // liveness is voted two tiles ahead (one group barrier per iteration): the tile after next is pulled towards L2 only if
+    // it will be processed, the next one has its inputs loaded / its hash chunks fetched while the current one is computed
+    TilePos tn = tp; tn.next();
+    bool alive = (tile < n_tiles) && grp_any2(g, row_live(tp, tile));
+    bool alive_n = (tile + tstep < n_tiles) && grp_any2(g, row_live(tn, tile + tstep));
+    if (alive) { if (TMAH && issuer) fetch_hash(tile); load_inputs(tp, tile); }
+    if (alive_n && h == 0) prefetch_tile(feat, P, tile + tstep, m, true);
+    for (; tile < n_tiles; tile += tstep, tp = tn, tn.next()) {
         const long long q = tile * kTile + m;                                                 // plane index s * N + r
         const bool live = q < P;
-        if (h == 0) prefetch_tile(feat, P, (tile + 2 * tstep) * kTile, m);
+        const long long tile_n = tile + tstep, tile_nn = tile_n + tstep;
+        TilePos tnn = tn; tnn.next();
+        const bool alive_nn = (tile_nn < n_tiles) && grp_any2(g, row_live(tnn, tile_nn));
+        if (alive_nn && h == 0) prefetch_tile(feat, P, tile_nn, m, true);
+        const bool alive_cur = alive, alive_nx = alive_n;
+        alive = alive_n; alive_n = alive_nn;                                                  // shifted for the next iteration
+        if (!alive_cur) {                                                                     // nothing of this tile is needed
+            if (alive_nx) { if (TMAH && issuer) fetch_hash(tile_n); load_inputs(tn, tile_n); }
+            continue;
+        }
         const float4 dr = dr_next;                                                            // h = 1 only
         const float gy = t.g.y;
         const float xg1 = h ? t.xb : t.x0, xg2 = h ? t.g.x : t.xb;                            // BA: see load_half
         {                                                                                     // X row m, half h
+            if (!TMAH) {                                                                      // ready operand chunks 2h, 2h + 1
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                float v[8] = {t.f[4 * c].x, t.f[4 * c].y, t.f[4 * c + 1].x, t.f[4 * c + 1].y, t.f[4 * c + 2].x, t.f[4 * c + 2].y, t.f[4 * c + 3].x, t.f[4 * c + 3].y};
-                stage8(x_hi, x_lo, m, 2 * h + c, v);
+                for (int c = 0; c < 2; ++c) {
+                    const uint32_t off = chunk_off(128, m, 2 * h + c);
+                    *reinterpret_cast<uint4*>(x_hi + off) = t.hh[c];
+                    *reinterpret_cast<uint4*>(x_lo + off) = t.hl[c];
+                }
             }
             if (h == 0) {
                 if (live) { stage_oneblob(t.x0, blob_hi, blob_lo, m, 0); stage_oneblob(t.x1, blob_hi, blob_lo, m, 2); }
@@ -949,16 +717,13 @@ __global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights
                 stage_zero(tail_hi, tail_lo, m, 3);
             }
         }
-        {                                                                                     // next tile's inputs
-            const long long qn = (tile + tstep) * kTile + m;
-            load_half<BA>(t, feat, P, qn, qn < P, h);
-            if (h) {
-                TilePos tn = tp; tn.next();
-                dr_next = (qn < P) ? __ldg(reinterpret_cast<const float4*>(d_raw_tot) + tn.raw_index(m)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        }
+        if (alive_nx) load_inputs(tn, tile_n);                                                // next tile's inputs
         fence_async_smem(); fence_before_sync(); grp_sync2(g);
         if (issuer) {                                                                         // H1 = X1 W0^T
+            if (TMAH) {                                                                       // this tile's hash chunks have landed
+                if (!mbar_wait(tma_bar, tma_phase)) __trap();
+                tma_phase ^= 1u;
+            }
             fence_after_sync();
             uint32_t acc = 0;
             mma_kk<kXCh / 2>(tb + T_A, xh, xl, w0h, w0l, HID, idH, acc);
@@ -1084,13 +849,15 @@ __global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights
         }
         wacc = 1;
         grp_wait(bar, phase);
+        // every MMA that reads this tile's X operand has completed: the next alive tile's hash chunks may land on it
+        if (TMAH && issuer && alive_nx) fetch_hash(tile_n);
         {
             float dx[16];
             tmem_ld16(tlane + T_A + 16 * h, dx);
-            if (live) {
-                float2* dj = reinterpret_cast<float2*>(dfeat) + (long long)(8 * h) * P;
-#pragma unroll
-                for (int l = 0; l < 8; ++l) dj[(long long)l * P + q] = make_float2(dx[2 * l], dx[2 * l + 1]);
+            if (live) {                                                                       // dfeat [4 quads][P][8]: quads 2h, 2h + 1
+                float4* dj = reinterpret_cast<float4*>(dfeat) + ((long long)(2 * h) * P + q) * 2;
+                dj[0] = make_float4(dx[0], dx[1], dx[2], dx[3]); dj[1] = make_float4(dx[4], dx[5], dx[6], dx[7]);
+                dj[2 * P] = make_float4(dx[8], dx[9], dx[10], dx[11]); dj[2 * P + 1] = make_float4(dx[12], dx[13], dx[14], dx[15]);
             }
         }
         if constexpr (BA) {
@@ -1152,24 +919,21 @@ static int launch_fwd_g(const RayK& k, const Weights& w, const float* feat, long
     return 0;
 }
 template <int HID, int G>
-static int launch_bwd_g(const RayK& k, const Weights& w, const float* feat, long long P, const float* d_raw_tot, float* dfeat, const Grads& gr,
-                        float* dgb, float* dxb, cudaStream_t s) {
-    // RF_MLP_BWD_TPR=1 selects the one-thread-per-row kernel (kept for A/B timing; it has no ray gradients)
-    static const int tpr = [] { const char* e = getenv("RF_MLP_BWD_TPR"); return e ? atoi(e) : 2; }();
+static int launch_bwd_g(const RayK& k, const Weights& w, const float* feat, long long P, const float* d_raw_tot, const int* n_live, float* dfeat,
+                        const Grads& gr, float* dgb, float* dxb, cudaStream_t s) {
     const bool ba = dgb != nullptr;
-    const bool one = tpr == 1 && !ba;
-    auto fn2 = ba ? mlp_bwd_tc2_kernel<HID, G, true> : mlp_bwd_tc2_kernel<HID, G, false>;
-    auto fn1 = mlp_bwd_tc_kernel<HID, G>;
+    // RF_BWD_HASH_TMA=0 moves the hash operand chunks through registers (LDG.128 -> STS.128) instead of TMA bulk copies
+    static const bool tma = [] { const char* e = getenv("RF_BWD_HASH_TMA"); return e ? atoi(e) != 0 : true; }();
+    auto fn = ba ? (tma ? mlp_bwd_tc2_kernel<HID, G, true, true> : mlp_bwd_tc2_kernel<HID, G, true, false>)
+                 : (tma ? mlp_bwd_tc2_kernel<HID, G, false, true> : mlp_bwd_tc2_kernel<HID, G, false, false>);
     size_t sm = bwd_bytes<HID, G>();
-    cudaError_t e = one ? cudaFuncSetAttribute(fn1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)
-                        : cudaFuncSetAttribute(fn2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    if (e != cudaSuccess) return set_error((int)e, "cudaFuncSetAttribute(mlp_bwd_tc, %zu B): %s", sm, cudaGetErrorString(e));
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return set_error((int)e, "cudaFuncSetAttribute(mlp_bwd_tc2, %zu B): %s", sm, cudaGetErrorString(e));
     long long tiles = (P + kTile - 1) / kTile;
     int blocks = (int)std::min<long long>((tiles + G - 1) / G, (long long)num_sms());
     ProfScope ps(RF_PROF_MLP_BWD, s);
-    if (one) fn1<<<blocks, G * 128, sm, s>>>(k, w, feat, P, d_raw_tot, dfeat, gr);
-    else fn2<<<blocks, G * 256, sm, s>>>(k, w, feat, P, d_raw_tot, dfeat, gr, dgb, dxb);
-    RF_CHECK_LAUNCH("mlp_bwd_tc_kernel");
+    fn<<<blocks, G * 256, sm, s>>>(k, w, feat, P, d_raw_tot, n_live, dfeat, gr, dgb, dxb);
+    RF_CHECK_LAUNCH("mlp_bwd_tc2_kernel");
     return 0;
 }
 
@@ -1178,13 +942,13 @@ static int launch_bwd_g(const RayK& k, const Weights& w, const float* feat, long
 int launch_encode(const RayK& k, const GridDev& hg, const GridDev& gg, const rf_ray_params* p, const float* rays_o, const float* rays_d,
                   const float* z_vals, long long P, float* feat, cudaStream_t s);
 struct RayGradArgs;
-int launch_scatter(const RayK& k, const GridDev& hg, long long P, const float* feat, const float* dfeat, float* g_hash, float* g_rep,
-                   const RayGradArgs* rg, cudaStream_t s);
+int launch_scatter(const RayK& k, const GridDev& hg, long long P, const float* feat, const float* dfeat, const int* n_live, float* g_hash,
+                   float* g_rep, const RayGradArgs* rg, cudaStream_t s);
 int launch_encode_points(const GridDev& hg, const GridDev& gg, const rf_ray_params* p, const float* x, long long n, float* feat, cudaStream_t s);
 
 bool tc_supported(const RayK& k, int hidden) { return k.n_hash_out == 32 && (hidden == 32 || hidden == 64); }
 
-// workspace `feat`: (2L + 4 + 3 + 1) * P floats written here and read back by launch_bwd_tc
+// workspace `feat`: ws_floats(P) floats (ray_common.cuh) written here and read back by launch_bwd_tc
 int launch_fwd_tc(const RayK& k, int hidden, const GridDev& hg, const GridDev& gg, const rf_ray_params* p, const float* rays_o,
                   const float* rays_d, const float* z_vals, long long P, float* raw, float* feat, cudaStream_t s) {
     int rc = launch_encode(k, hg, gg, p, rays_o, rays_d, z_vals, P, feat, s);
@@ -1203,20 +967,20 @@ int launch_points_tc(RayK k, int hidden, const GridDev& hg, const GridDev& gg, c
     return hidden == 64 ? launch_fwd_g<64, 2>(k, w, feat, n, variant, raw, s) : launch_fwd_g<32, 4>(k, w, feat, n, variant, raw, s);
 }
 
-// dfeat: 2L * P floats of scratch, then (ray gradients only) 4P + 3P floats for the GBV-texel and OneBlob gradients,
-// then scatter_scratch_floats() floats for the table replicas
+// dfeat: 2L * P floats of scratch ([4 quads][P][8]), then (ray gradients only) 4P + 3P floats for the GBV-texel and OneBlob
+// gradients, then scatter_scratch_floats() floats for the table replicas
 int launch_bwd_tc(const RayK& k, int hidden, const GridDev& hg, const GridDev& gg, const rf_ray_params* p, long long P, const float* feat,
-                  const float* d_raw_tot, float* dfeat, const Grads& gr, float* g_rays_o, float* g_rays_d, cudaStream_t s) {
+                  const float* d_raw_tot, const int* n_live, float* dfeat, const Grads& gr, float* g_rays_o, float* g_rays_d, cudaStream_t s) {
     Weights w{p->w_sdf0, p->w_sdf1, p->w_col0, p->w_col1};
     const bool ba = g_rays_o || g_rays_d;
     float* dgb = ba ? dfeat + 2ll * hg.n_levels * P : nullptr;
     float* dxb = ba ? dgb + 4 * P : nullptr;
     float* rep = ba ? dxb + ((3 * P + 3) & ~3ll) : dfeat + 2ll * hg.n_levels * P;     // replicas are float2 / float4 accessed
-    int rc = hidden == 64 ? launch_bwd_g<64, 1>(k, w, feat, P, d_raw_tot, dfeat, gr, dgb, dxb, s)
-                          : launch_bwd_g<32, 2>(k, w, feat, P, d_raw_tot, dfeat, gr, dgb, dxb, s);
+    int rc = hidden == 64 ? launch_bwd_g<64, 1>(k, w, feat, P, d_raw_tot, n_live, dfeat, gr, dgb, dxb, s)
+                          : launch_bwd_g<32, 2>(k, w, feat, P, d_raw_tot, n_live, dfeat, gr, dgb, dxb, s);
     if (rc) return rc;
-    if (ba) return launch_scatter_raygrad(k, hg, gg, p, P, feat, dfeat, dgb, dxb, gr.g_hash, rep, g_rays_o, g_rays_d, s);
-    if (gr.g_hash) rc = launch_scatter(k, hg, P, feat, dfeat, gr.g_hash, rep, nullptr, s);
+    if (ba) return launch_scatter_raygrad(k, hg, gg, p, P, feat, dfeat, dgb, dxb, n_live, gr.g_hash, rep, g_rays_o, g_rays_d, s);
+    if (gr.g_hash) rc = launch_scatter(k, hg, P, feat, dfeat, n_live, gr.g_hash, rep, nullptr, s);
     return rc;
 }
 

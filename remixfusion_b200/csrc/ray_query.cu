@@ -280,7 +280,8 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(RayK k, const float*
                                                             const float* __restrict__ target_d, const float* __restrict__ target_rgb,
                                                             const float* __restrict__ d_rgb_map, const float* __restrict__ d_depth_map,
                                                             const float* __restrict__ d_raw, const float* __restrict__ loss_grads,
-                                                            const double* __restrict__ partials, float* __restrict__ d_raw_out) {
+                                                            const double* __restrict__ partials, float* __restrict__ d_raw_out,
+                                                            int* __restrict__ n_live) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     long long r = blockIdx.x * 4ll + warp;
     if (r >= k.n_rays) return;
@@ -321,6 +322,7 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(RayK k, const float*
     }
     dot = warp_sum(dot);
     float4* out_r = reinterpret_cast<float4*>(d_raw_out) + r * S;
+    int last_nz = 0;
     const float4* up_r = d_raw ? reinterpret_cast<const float4*>(d_raw) + r * S : nullptr;
 #pragma unroll
     for (int i = 0; i < kPerLane; ++i) {
@@ -343,6 +345,14 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(RayK k, const float*
         }
         if (up_r) { float4 uu = up_r[s]; o.x += uu.x; o.y += uu.y; o.z += uu.z; o.w += uu.w; }
         out_r[s] = o;
+        if (o.x != 0.f || o.y != 0.f || o.z != 0.f || o.w != 0.f) last_nz = s + 1;
+    }
+    // n_live: one past the last sample with a non-zero gradient.  Samples behind the truncation band have zero rendering
+    // weight (scene_rep.py:124) and no loss term (utils.py:170-198), so the tail of most rays is exactly zero and the
+    // decoder backward / table scatter skip it.
+    if (n_live) {
+        for (int o = 16; o > 0; o >>= 1) last_nz = max(last_nz, __shfl_xor_sync(0xffffffffu, last_nz, o));
+        if (lane == 0) n_live[r] = last_nz;
     }
 }
 
@@ -735,19 +745,22 @@ extern "C" int rf_ray_query_backward(const rf_ray_cfg* cfg, const rf_grid_desc* 
     GridDev hg = to_dev(hash), gg = to_dev(gbv);
     cudaStream_t s = (cudaStream_t)stream;
     long long P = n_rays * k.S;
+    const bool tc = cfg->mlp_precision == 1 && tc_supported(k, cfg->hidden);
     float* d_raw_tot = scratch;                 // [P,4]
-    float* d_pts = scratch + 4 * P;             // [P,3] (BA mode only)
+    int* n_live = tc ? reinterpret_cast<int*>(scratch + 4 * P) : nullptr;   // [N] (tensor-core path), padded to 4
+    float* d_pts = scratch + 4 * P;             // [P,3] (BA mode, fp32 SIMT path only)
     {
         ProfScope ps(RF_PROF_COMPOSITE_BWD, s);
         composite_bwd_kernel<<<(unsigned)((n_rays + 3) / 4), 128, 0, s>>>(k, raw, z_vals, rgb_map, depth_map, target_d, target_rgb,
-                                                                           d_rgb_map, d_depth_map, d_raw, loss_grads, loss_partials, d_raw_tot);
+                                                                           d_rgb_map, d_depth_map, d_raw, loss_grads, loss_partials, d_raw_tot, n_live);
     }
     RF_CHECK_LAUNCH("composite_bwd_kernel");
     Grads gr{g->g_hash, g->g_w_sdf0, g->g_w_sdf1, g->g_w_col0, g->g_w_col1};
     const bool ba = g->g_rays_o || g->g_rays_d;
-    if (cfg->mlp_precision == 1 && tc_supported(k, cfg->hidden)) {
+    if (tc) {
         RF_REQUIRE(workspace, RF_E_NULL, "rf_ray_query_backward: mlp_precision 1 needs the forward's workspace");
-        return launch_bwd_tc(k, cfg->hidden, hg, gg, p, P, workspace, d_raw_tot, scratch + 4 * P, gr, g->g_rays_o, g->g_rays_d, s);
+        return launch_bwd_tc(k, cfg->hidden, hg, gg, p, P, workspace, d_raw_tot, n_live, scratch + 4 * P + ((n_rays + 3) & ~3ll), gr,
+                             g->g_rays_o, g->g_rays_d, s);
     }
     if (cfg->hidden == 64) rc = ba ? launch_bwd<64, true>(k, hg, gg, p, rays_o, rays_d, z_vals, P, d_raw_tot, gr, d_pts, s)
                                    : launch_bwd<64, false>(k, hg, gg, p, rays_o, rays_d, z_vals, P, d_raw_tot, gr, d_pts, s);
@@ -763,12 +776,12 @@ extern "C" int rf_ray_query_backward(const rf_ray_cfg* cfg, const rf_grid_desc* 
 
 extern "C" int64_t rf_ray_workspace_floats(const rf_ray_cfg* cfg, const rf_grid_desc* hash, int64_t n_rays) {
     if (!cfg || !hash || cfg->mlp_precision != 1 || n_rays <= 0) return 0;
-    return (int64_t)(2 * hash->n_levels + 4 + 3 + 1) * n_rays * (cfg->n_range_d + cfg->n_samples_d);
+    return (int64_t)ws_floats((long long)n_rays * (cfg->n_range_d + cfg->n_samples_d), true);
 }
 
 extern "C" int64_t rf_point_workspace_floats(const rf_ray_cfg* cfg, const rf_grid_desc* hash, int64_t n) {
     if (!cfg || !hash || cfg->mlp_precision != 1 || n <= 0) return 0;
-    return (int64_t)(2 * hash->n_levels + 4 + 3) * n;
+    return (int64_t)ws_floats((long long)n, false);
 }
 
 extern "C" int64_t rf_ray_scratch_floats(const rf_ray_cfg* cfg, const rf_grid_desc* hash, int64_t n_rays, int ray_grads) {
@@ -777,7 +790,8 @@ extern "C" int64_t rf_ray_scratch_floats(const rf_ray_cfg* cfg, const rf_grid_de
     RayK k; k.n_hash_out = hash->n_levels * 2;
     if (cfg->mlp_precision != 1 || !tc_supported(k, cfg->hidden)) return ray_grads ? 7 * P : 4 * P;
     GridDev hg = to_dev(hash);
-    return (4 + 2 * hash->n_levels + (ray_grads ? 7 : 0)) * P + (ray_grads ? 4 : 0) + (int64_t)scatter_scratch_floats(hg, (long long)n_rays);
+    return (4 + 2 * hash->n_levels + (ray_grads ? 7 : 0)) * P + (ray_grads ? 4 : 0) + ((n_rays + 3) & ~(int64_t)3) +
+           (int64_t)scatter_scratch_floats(hg, (long long)n_rays);
 }
 
 extern "C" int rf_point_query_forward(const rf_ray_cfg* cfg, const rf_grid_desc* hash, const rf_grid_desc* gbv, const rf_ray_params* p,

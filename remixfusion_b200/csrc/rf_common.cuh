@@ -34,15 +34,11 @@ struct ProfScope {
     ~ProfScope() { prof_mark(slot, 1, s); }
 };
 
-static inline int num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
-    return n;
+static inline int num_sms() {                      // per device (a process may drive several GPUs); no cached static
+    int dev = 0, n = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n > 0 ? n : 148;
 }
 
 template <typename T>

@@ -49,6 +49,16 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
     return false;
 }
 
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP): global -> shared, completion counted in bytes on an mbarrier ---------
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 16-byte aligned source / destination, size a multiple of 16
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 // ---- descriptors -----------------------------------------------------------------------------------------
 // 64-bit shared-memory matrix descriptor, SWIZZLE_NONE, version 1 (Blackwell)
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {

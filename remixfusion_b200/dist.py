@@ -51,12 +51,41 @@ def broadcast_frame(depth: torch.Tensor, color: torch.Tensor, src: int = 0, grou
     return depth, color
 
 
+class FlatGrads:
+    """One persistent flat gradient buffer whose views ARE the parameters' ``.grad``: the per-step gradient sum is a single
+    in-place all-reduce of that buffer — no concatenation and no copy back (hash table + the four decoder matrices)."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        p0 = self.params[0]
+        self.flat = torch.zeros(n, dtype=p0.dtype, device=p0.device)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero(self):
+        """Instead of ``p.grad = None``: autograd accumulates into the views."""
+        self.flat.zero_()
+
+    def allreduce(self, group=None, async_op=False):
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+        return None
+
+
 def allreduce_grads(params, group=None):
-    """Sum the gradients of `params` over ranks with ONE all-reduce of a flat buffer (hash table + 4 weight matrices)."""
+    """Sum the gradients of `params` over ranks with ONE all-reduce of a flat buffer (hash table + 4 weight matrices).
+    Prefer ``FlatGrads`` in a training loop: it keeps the flat buffer alive and needs no copies."""
     if not (dist.is_initialized() and dist.get_world_size(group) > 1):
         return
     grads = [p.grad for p in params if p.grad is not None]
     if not grads:
+        return
+    base = grads[0]._base if grads[0]._base is not None else None
+    if base is not None and all(g._base is base for g in grads) and sum(g.numel() for g in grads) == base.numel():
+        dist.all_reduce(base, op=dist.ReduceOp.SUM, group=group)          # already views of one flat buffer
         return
     flat = torch.cat([g.reshape(-1) for g in grads])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
@@ -67,12 +96,63 @@ def allreduce_grads(params, group=None):
         off += n
 
 
-def gather_slabs(local: torch.Tensor, sizes, group=None):
-    """All-gather variable-size slabs into the full volume on every rank (GBV after a keyframe: 160 MB at R=200)."""
+def gather_slabs(local: torch.Tensor, sizes, group=None, out: torch.Tensor | None = None):
+    """All-gather the ranks' slabs into the full volume on every rank (GBV after a keyframe: 160 MB at R = 200).
+    Equal slabs (R divisible by the world size) go straight into ``out`` with one ``all_gather_into_tensor`` — no staging,
+    no concatenation; unequal slabs are padded to the largest one first."""
     if not (dist.is_initialized() and dist.get_world_size(group) > 1):
+        if out is not None and out.data_ptr() != local.data_ptr():
+            out[:local.numel()].copy_(local)
+            return out
         return local
-    m = max(sizes)                                   # equal-size all-gather of padded slabs, then trim
+    total = int(sum(sizes))
+    if out is None:
+        out = torch.empty(total, dtype=local.dtype, device=local.device)
+    if len(set(int(s) for s in sizes)) == 1:
+        dist.all_gather_into_tensor(out[:total], local[:int(sizes[0])].contiguous(), group=group)
+        return out
+    m = int(max(sizes))
     pad = local if local.numel() == m else torch.cat([local, local.new_zeros(m - local.numel())])
-    outs = [torch.empty(m, dtype=local.dtype, device=local.device) for _ in sizes]
-    dist.all_gather(outs, pad, group=group)
-    return torch.cat([o[:s] for o, s in zip(outs, sizes)])
+    stage = torch.empty(m * len(sizes), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(stage, pad, group=group)
+    off = 0
+    for k, sz in enumerate(sizes):
+        out[off:off + int(sz)].copy_(stage[k * m:k * m + int(sz)])
+        off += int(sz)
+    return out
+
+
+def frustum_box(K, c2w, H, W, max_depth, box, R):
+    """Voxel index range [lo, hi) per axis of the GBV (resolution R over `box` = [[x0,x1],[y0,y1],[z0,z1]]) that the camera
+    frustum up to `max_depth` can touch: the axis-aligned hull of the frustum's corners, clamped to the volume."""
+    import numpy as np
+    K = np.asarray(K, dtype=np.float64).reshape(3, 3); c2w = np.asarray(c2w, dtype=np.float64).reshape(4, 4)
+    pts = [np.zeros(3)]
+    for px, py in ((-1.0, -1.0), (W + 1.0, -1.0), (-1.0, H + 1.0), (W + 1.0, H + 1.0)):
+        pts.append(np.array([(px - K[0, 2]) / K[0, 0] * max_depth, (py - K[1, 2]) / K[1, 1] * max_depth, max_depth]))
+    w = np.stack([c2w[:3, :3] @ p + c2w[:3, 3] for p in pts])
+    lo, hi = [], []
+    for a in range(3):
+        b0, b1 = float(box[a][0]), float(box[a][1])
+        v0 = (w[:, a].min() - b0) / (b1 - b0) * R
+        v1 = (w[:, a].max() - b0) / (b1 - b0) * R
+        lo.append(int(min(max(np.floor(v0) - 1, 0), R))); hi.append(int(min(max(np.ceil(v1) + 2, 0), R)))
+    return lo, hi
+
+
+def gather_touched_box(full: torch.Tensor, local: torch.Tensor, R: int, z_slabs, lo, hi, group=None, channels: int = 4):
+    """After a keyframe only the voxels inside the frustum's hull changed: all-gather just the [y, x] sub-box of every rank's
+    z-slab (equal slabs: one pack, one ``all_gather_into_tensor``, one unpack) instead of the whole volume — at BS3D scale
+    (R = 512 / 1024 over 50 x 50 x 10 m) the frustum covers a few per cent of the x-y extent.  `full`: [R^3 * channels] replicated
+    copy, `local`: this rank's z-slab [dz * R * R * channels]; lo / hi from ``frustum_box``.  Falls back to ``gather_slabs`` when the slabs differ."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    dzs = [int(b - a) for a, b in z_slabs]
+    if world == 1 or len(set(dzs)) != 1 or hi[0] <= lo[0] or hi[1] <= lo[1]:
+        return gather_slabs(local, [dz * R * R * channels for dz in dzs], group, out=full)
+    dz = dzs[0]
+    loc = local[:dz * R * R * channels].view(dz, R, R, channels)
+    piece = loc[:, lo[1]:hi[1], lo[0]:hi[0], :].contiguous()
+    stage = torch.empty((world,) + tuple(piece.shape), dtype=piece.dtype, device=piece.device)
+    dist.all_gather_into_tensor(stage.view(-1), piece.view(-1), group=group)
+    full[:world * dz * R * R * channels].view(world, dz, R, R, channels)[:, :, lo[1]:hi[1], lo[0]:hi[0], :] = stage
+    return full

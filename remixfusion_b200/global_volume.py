@@ -30,6 +30,7 @@ class MapVolume:
         self.create_global_volume(config["globalV"]["base_resolution"])
         self.z_slab = (0, int(self.vol_dim[2])) if z_slab is None else (int(z_slab[0]), int(z_slab[1]))
         self.slab_local = 0 if z_slab is None else 1
+        self._check_params()
 
     def create_global_volume(self, base_resolution):
         """mp_slam/mapper.py:213-254 (launch geometry is the kernels' business here)."""
@@ -44,8 +45,28 @@ class MapVolume:
         R = int(self.vol_dim[0])
         return (self.z_slab[1] - self.z_slab[0]) * R * R
 
+    def _check_params(self):
+        """The parameter tensors must match the addressing mode: a z-slab object owns slab-sized tensors (the kernels then
+        write at offset 0), the unsharded object the full R^3 grids (tcnn pads to a multiple of 8 entries).  A full-size model
+        passed together with a z_slab would silently be written at the wrong offset."""
+        R = int(self.vol_dim[0])
+        if not (0 <= self.z_slab[0] < self.z_slab[1] <= R):
+            raise abi.RfError(f"MapVolume: z_slab {self.z_slab} outside [0, {R}]")
+        n = self._n_own()
+        nv, nw = self.model.GBV.params.numel(), self.model.GBW.params.numel()
+        pad = 1024                                   # allocation slack a caller may add (tcnn pads to 8 entries)
+        if self.slab_local:
+            ok = 4 * n <= nv <= 4 * (n + pad) and n <= nw <= n + pad
+        else:
+            ok = 4 * R ** 3 <= nv <= 4 * (R ** 3 + pad) and R ** 3 <= nw <= R ** 3 + pad
+        if not ok:
+            raise abi.RfError(f"MapVolume: GBV/GBW parameter sizes ({nv}, {nw}) do not match "
+                              f"{'the z-slab ' + str(self.z_slab) if self.slab_local else 'the full volume'} at R = {R} "
+                              f"(expected {4 * n} and {n} floats, up to {pad} entries of padding)")
+
     def init_mapvolume(self):
         """GBV[v] = (1, 0, 0, 0) for every voxel (mp_slam/mapper.py:267-282, kernel :161-183)."""
+        self._check_params()
         p = self.model.GBV.params
         rc = abi.lib().rf_tsdf_clear_global(abi.dptr(p.data), C.c_int64(self._n_own()), abi.stream_ptr())
         abi.check(rc, "rf_tsdf_clear_global")
@@ -55,6 +76,7 @@ class MapVolume:
 
         batch['rgb']: (H,W,3) or (1,H,W,3) float in [0,1]; batch['depth']: (H,W) or (1,H,W) metres (host or device);
         pose: (4,4) camera-to-world tensor (device tensors are read in place, no host sync)."""
+        self._check_params()
         dev = self.model.GBV.params.device
         color_im = batch["rgb"].squeeze().to(dev, non_blocking=True).float().contiguous()
         depth_im = batch["depth"].squeeze().to(dev, non_blocking=True).float().contiguous()

@@ -20,6 +20,9 @@ class GraphedMappingStep:
         loss_fn(ret) -> scalar (e.g. ``lambda r: configs.total_loss(cfg, r)``, mp_slam/slam.py:162-169).  The first
         ``eager_steps`` calls run eagerly (they are real optimisation steps: lazy initialisation happens there), the next
         call captures the graph and every call from then on replays it."""
+        if int(eager_steps) < 1:
+            raise abi.RfError("GraphedMappingStep: eager_steps must be >= 1 (lazy initialisation — sampling tables, optimiser "
+                              "state, per-camera caches — runs in the eager steps and cannot be captured)")
         if not all(g.get("capturable", False) for g in optimizer.param_groups):
             raise abi.RfError("GraphedMappingStep needs remixfusion_b200.optim.Adam(..., capturable=True)")
         dev = next(model.parameters()).device

@@ -247,15 +247,35 @@ class JointEncoding(nn.Module):
             raise abi.RfError("fused decoder needs the 2-layer SDF / colour nets")
         return w
 
+    # batches at least this large are rendered valid-depth rays first (see _render)
+    GROUP_RAYS_MIN = 1 << 16
+
     def _render(self, rays_o, rays_d, target_d, target_rgb, with_losses, u=None):
         if target_d is None:
             raise abi.RfError("render_rays without target_d (uniform near..far sampling, scene_rep.py:431-433) is never "
                               "reached by the reference's callers and is not built")
-        z_vals = self.sample_z(target_d, rays_o.shape[0], u)
+        n = rays_o.shape[0]
+        # Training batches are processed with the rays that have a depth measurement first, the others (sensor holes, no
+        # return) last.  Every per-ray result is independent of the order; what changes is how the backward's 128-ray tiles
+        # are composed: rays with a measurement stop contributing a few centimetres behind the surface (n_live, see
+        # csrc/ray_encode.cu) at nearly the same sample index, rays without one carry gradient along their whole length, and
+        # one such ray in a tile keeps the whole tile alive.  The permutation is undone on the per-ray outputs.
+        inv = None
+        if (with_losses and n >= self.GROUP_RAYS_MIN and rays_o.is_cuda and not torch.cuda.is_current_stream_capturing()):
+            perm = torch.sort((target_d.detach().reshape(-1) <= 0).to(torch.uint8), stable=True).indices
+            inv = torch.empty_like(perm)
+            inv[perm] = torch.arange(n, device=perm.device)
+            rays_o, rays_d = rays_o.index_select(0, perm), rays_d.index_select(0, perm)
+            target_d, target_rgb = target_d.index_select(0, perm), target_rgb.index_select(0, perm)
+            if u is not None:
+                u = u.to(perm.device).index_select(0, perm)          # row r of the jitter belongs to ray r
+        z_vals = self.sample_z(target_d, n, u)
         w = self._weights()
         rgb_map, depth_map, raw, losses = _RayQueryFn.apply(
             rays_o, rays_d, self.embed_res_fn.params, w[0], w[1], w[2], w[3], self.GBV.params, z_vals, target_d, target_rgb,
             self._meta(with_losses))
+        if inv is not None:                                           # raw / z_vals are not handed out by mapping()
+            rgb_map, depth_map = rgb_map.index_select(0, inv), depth_map.index_select(0, inv)
         return rgb_map, depth_map, raw, z_vals, losses
 
     # ---- model/scene_rep.py:407-456 -------------------------------------------------------------------------

@@ -20,6 +20,7 @@ from . import abi
 
 class moving_volume:
     """Moving volume of RGB-D images (reference: model/Volume.py:19)."""
+    _STAGE_SLOTS = 3
 
     def __init__(self, cfg, traj, init_pose, gpu_mode=True, start=0, device=None, x_slab=None):
         self.config = cfg
@@ -58,6 +59,7 @@ class moving_volume:
         self.weight_vol_gpu = torch.zeros(n_own, dtype=torch.float32, device=self.device)    # :86
         self.color_vol_gpu = torch.zeros(n_own, dtype=torch.float32, device=self.device)     # :87
         self._frame = None
+        self._in_flight = []
 
     # ---- bounds (model/Volume.py:910-925, :1133-1149) ----------------------------------------------------
     def initialize_vol_bnd(self, cam_pose_iter, traj, version):
@@ -75,6 +77,46 @@ class moving_volume:
             vol_bnds[ax, 0] = center_cam[ax] - ln
             vol_bnds[ax, 1] = center_cam[ax] + ln
         return vol_bnds
+
+    # ---- move policy (model/Volume.py:930-1108): called by the tracker every frame (model/ROtracker.py:920-934) -----
+    def check_move_volume_new(self, cur_id, cam_pose_iter, traj, version="center", larger_flag=False, get_pc=False, gap=100):
+        """Decide whether the camera has left the volume's comfort zone and, if so, re-centre the volume on it.
+
+        ``traj`` carries the camera position at the last move (``kfx``, ``kfy``, ``kfz``; set by ``center_volbnd``).  An axis
+        that is not fixed and whose translation since then exceeds ``volume.t_treshold`` shifts the bounds by that translation;
+        the shifted bounds are rounded to whole metres and, if they differ from the current ones, the volume is moved
+        (``copy_volume`` + ``update_tsdf_swap_rot_trans``).  Returns ``(moved, old_bnds)`` like the reference; the caller
+        records ``frame_to_Vrange[(start, end)] = old_bnds`` (model/ROtracker.py:925-934).  ``larger_flag`` / ``get_pc`` /
+        ``gap`` only matter to the angle-based "more" policy."""
+        if version != "center":
+            raise NotImplementedError("volume.version != 'center' (angle-based swap, model/Volume.py:1008-1081) is volume "
+                                      "bookkeeping no shipped config selects")
+        pose = np.asarray(cam_pose_iter.detach().cpu().numpy() if isinstance(cam_pose_iter, torch.Tensor) else cam_pose_iter)
+        old_bnds = self.vol_bnds.copy()
+        new_bnds = self.vol_bnds.copy()
+        moved_axis = False
+        for ax, (name, fixed) in enumerate((("kfx", self.fix_x), ("kfy", self.fix_y), ("kfz", self.fix_z))):
+            shift = pose[ax, 3] - getattr(traj, name)
+            if np.abs(shift) > self.t_treshold and not fixed:
+                new_bnds[ax, :] += shift
+                setattr(traj, name, pose[ax, 3])
+                moved_axis = True
+        if not moved_axis:
+            return False, old_bnds
+        new_bnds = np.round(new_bnds, 0)                     # whole metres (round half to even, as Python's round on float64)
+        if (new_bnds == old_bnds).all():
+            return False, old_bnds
+        self.copy_volume()
+        self.update_tsdf_swap_rot_trans(new_bnds, old_bnds)
+        return True, old_bnds
+
+    def frameid_to_Vrange(self, value):
+        """Bounds of the volume that was live at frame ``value`` (model/Volume.py:1084-1105): the recorded range that contains
+        it, else the current bounds."""
+        for (start, end), bnds in self.frame_to_Vrange.items():
+            if start <= value <= end:
+                return bnds
+        return self.vol_bnds
 
     # ---- re-centring (N2): model/Volume.py:883-908 copy_volume, :796-858 update_tsdf_swap_rot_trans ----------------
     def copy_volume(self):
@@ -120,21 +162,40 @@ class moving_volume:
 
     # ---- hot path ---------------------------------------------------------------------------------------
     def _stage(self, arr, key):
-        """Host numpy / CPU tensor -> device fp32 (pinned staging buffer, async copy); CUDA tensors pass through."""
+        """Host numpy / CPU tensor -> device fp32 through a ring of pinned staging buffers (async copy); CUDA tensors
+        pass through.  A slot is a (pinned host, device, event) triple: the event is recorded after the slot's copy AND
+        the kernels that read its device buffer have been enqueued (``_release``), and the host buffer is rewritten only
+        after that event has completed — back-to-back integrate() calls queued behind a long-running kernel therefore never
+        overwrite a frame that is still in flight (the reference's ``cuda.In`` copies were synchronous, model/Volume.py:733-749)."""
         if isinstance(arr, torch.Tensor) and arr.is_cuda:
             return arr.to(torch.float32).contiguous()
         a = arr.numpy() if isinstance(arr, torch.Tensor) else np.asarray(arr)
         a = np.ascontiguousarray(a, dtype=np.float32)
         if self._frame is None:
             self._frame = {}
-        slot = self._frame.get(key)
-        if slot is None or slot[0].shape != a.shape:
-            slot = (torch.empty(a.shape, dtype=torch.float32).pin_memory(),
-                    torch.empty(a.shape, dtype=torch.float32, device=self.device))
-            self._frame[key] = slot
+        ring = self._frame.get(key)
+        if ring is None or ring["shape"] != a.shape:
+            ring = {"shape": a.shape, "next": 0, "slots": [
+                [torch.empty(a.shape, dtype=torch.float32).pin_memory(), torch.empty(a.shape, dtype=torch.float32, device=self.device), None]
+                for _ in range(self._STAGE_SLOTS)]}
+            self._frame[key] = ring
+        slot = ring["slots"][ring["next"]]
+        ring["next"] = (ring["next"] + 1) % len(ring["slots"])
+        if slot[2] is not None:
+            slot[2].synchronize()                    # the previous user of this slot (copy + kernels) has finished
         slot[0].numpy()[...] = a
         slot[1].copy_(slot[0], non_blocking=True)
+        self._in_flight.append(slot)
         return slot[1]
+
+    def _release(self):
+        """Mark the staged slots of this call as busy until everything enqueued so far on the stream has run."""
+        if self._in_flight:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            for slot in self._in_flight:
+                slot[2] = ev
+            self._in_flight = []
 
     def integrate(self, color_im, depth_im, cam_intr, cam_pose, old_bnd, obs_weight=1., reintegrate_flag=0.0):
         """Integrate an RGB-D frame into the TSDF volume (model/Volume.py:713-757).
@@ -157,6 +218,7 @@ class moving_volume:
         st = abi.stream_ptr()
         abi.check(L.rf_pack_bgr(abi.dptr(rgb), abi.dptr(packed), C.c_int(im_h * im_w), st), "rf_pack_bgr")
         self.integrate_packed(depth, packed, cam_intr, cam_pose, old_bnd, obs_weight, reintegrate_flag)
+        self._release()
 
     def integrate_packed(self, depth, packed, cam_intr, cam_pose, old_bnd=None, obs_weight=1., reintegrate_flag=0.0):
         """Same as integrate() with the frame already resident: depth [H,W], packed BGR [H*W] CUDA fp32."""

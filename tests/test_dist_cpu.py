@@ -33,6 +33,29 @@ def _worker(rank, world, port, q):
     lo, hi = rdist.slab(5, rank, world)
     full = rdist.gather_slabs(torch.arange(lo * 4, hi * 4, dtype=torch.float32), [(rdist.slab(5, k, world)[1] - rdist.slab(5, k, world)[0]) * 4 for k in range(world)])
     ok &= bool(torch.equal(full, torch.arange(20.)))
+    # equal slabs go straight into the replicated buffer (all_gather_into_tensor, no staging)
+    out = torch.full((24 + 8,), -1.0)
+    rdist.gather_slabs(torch.arange(rank * 12, rank * 12 + 12, dtype=torch.float32), [12, 12], out=out)
+    ok &= bool(torch.equal(out[:24], torch.arange(24.)) and (out[24:] == -1).all())
+    # gradients that live in ONE flat buffer (FlatGrads): in-place all-reduce, .grad stays a view
+    q1 = torch.nn.Parameter(torch.zeros(5)); q2 = torch.nn.Parameter(torch.zeros(2, 3))
+    fg = rdist.FlatGrads([q1, q2])
+    (q1 * torch.arange(5.)).sum().backward(); (q2 * (rank + 1.0)).sum().backward()
+    fg.allreduce()
+    ok &= bool(torch.equal(q1.grad, 2 * torch.arange(5.)) and torch.equal(q2.grad, torch.full((2, 3), 3.0)) and q1.grad._base is fg.flat)
+    rdist.allreduce_grads([q1, q2])                              # recognises the shared flat buffer
+    ok &= bool(torch.equal(q1.grad, 4 * torch.arange(5.)))
+    fg.zero()
+    ok &= bool(float(q2.grad.abs().sum()) == 0.0)
+    # touched sub-box gather of a z-slab-sharded volume: only the [y, x] box changes on the replicated copy
+    R, C = 4, 2
+    zs = [rdist.slab(R, k, world) for k in range(world)]
+    truth = torch.arange(R * R * R * C, dtype=torch.float32)
+    mine = truth.view(R, R, R, C)[zs[rank][0]:zs[rank][1]].reshape(-1).clone()
+    full = torch.zeros(R * R * R * C)
+    rdist.gather_touched_box(full, mine, R, zs, lo=[1, 0, 0], hi=[3, 2, R], channels=C)
+    exp = torch.zeros(R, R, R, C); exp[:, 0:2, 1:3, :] = truth.view(R, R, R, C)[:, 0:2, 1:3, :]
+    ok &= bool(torch.equal(full.view(R, R, R, C), exp))
     # sharded loss sums: all-reduced partial sums reproduce the single-process normalised losses
     g = torch.Generator().manual_seed(0)
     vals = torch.rand(10, 7, generator=g, dtype=torch.float64)
@@ -65,3 +88,25 @@ def test_slab_partition_covers_axis():
             assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
             sizes = [hi - lo for lo, hi in cuts]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_frustum_box_contains_every_projected_voxel():
+    """The hull used to restrict the GBV all-gather must contain every voxel the integrate kernel can touch."""
+    from remixfusion_b200 import synth
+    rng = np.random.default_rng(0)
+    R, box = 64, [[-1.0, 7.0], [-1.3, 3.7], [-1.7, 1.4]]
+    K = synth.intrinsics(60.0, 60.0, 59.5, 33.5); H, W = 68, 120
+    scene = synth.make_scene(box, 0)
+    for c2w in synth.loop_trajectory(scene, 6):
+        lo, hi = rdist.frustum_box(K, c2w, H, W, 6.0, box, R)
+        g = (np.stack(np.meshgrid(*[np.arange(R)] * 3, indexing="ij"), -1).reshape(-1, 3) / R)
+        pts = np.array([b[0] for b in box]) + g * np.array([b[1] - b[0] for b in box])
+        cam = (pts - c2w[:3, 3]) @ c2w[:3, :3]
+        z = cam[:, 2]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            px = np.rint(K[0, 0] * cam[:, 0] / z + K[0, 2]); py = np.rint(K[1, 1] * cam[:, 1] / z + K[1, 2])
+        vis = (z > 0) & (z <= 6.0) & (px >= 0) & (px < W) & (py >= 0) & (py < H)
+        idx = np.rint(g[vis] * R).astype(int)
+        assert vis.sum() > 0
+        for a in range(3):
+            assert idx[:, a].min() >= lo[a] and idx[:, a].max() < hi[a], (a, lo, hi, idx[:, a].min(), idx[:, a].max())

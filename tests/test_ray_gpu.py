@@ -41,6 +41,19 @@ def _close(got, ref, rtol, name, atol_frac=1e-4):
     np.testing.assert_allclose(got, ref, rtol=rtol, atol=atol_frac * scale + 1e-12, err_msg=name)
 
 
+def _log_parity(name, prec, n_bad, n, l2, max_err_frac):
+    """Observed kink-outlier counts, one JSON line per gradient check (drift becomes visible run over run): printed, and
+    appended to gpurun_out/parity_stats.jsonl when that directory exists (it travels back from the GPU box)."""
+    import json
+    import os
+    rec = {"check": name, "mlp_precision": prec, "outside_tol": n_bad, "elements": n, "rel_l2": l2, "max_err_over_max_g": max_err_frac}
+    print("parity:", json.dumps(rec))
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "parity_stats.jsonl"), "a") as f:
+            f.write(json.dumps(rec) + "\n")
+
+
 def _close_grad(got, ref, name, prec, rtol=1e-3, atol_frac=2e-4, kink_aware=False):
     """Gradient parity.  prec 0 (fp32 decoder): every element within rtol + atol_frac * max|g|.
     prec 1 (bf16x3 tensor-core decoder, ~1e-6 absolute error on the hidden pre-activations): a pre-activation that the
@@ -56,6 +69,7 @@ def _close_grad(got, ref, name, prec, rtol=1e-3, atol_frac=2e-4, kink_aware=Fals
     err = np.abs(got - ref)
     bad = err > rtol * np.abs(ref) + atol_frac * scale + 1e-12
     l2 = float(np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-30))
+    _log_parity(name, prec, int(bad.sum()), int(bad.size), l2, float(err.max()) / max(scale, 1e-30))
     assert l2 <= 1e-3, f"{name}: relative L2 error {l2:.3e}"
     assert bad.mean() <= 5e-3, f"{name}: {int(bad.sum())} of {bad.size} elements outside tolerance"
     assert float(err.max()) <= 5e-2 * scale, f"{name}: max abs error {err.max():.3e} vs max |g| {scale:.3e}"

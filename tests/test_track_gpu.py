@@ -10,8 +10,7 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture(scope="module")
 def scene(cuda, rf_lib):
     from oracle import ref_kernels as RK
-    if not RK.available():
-        pytest.skip("reference cubins not built (oracle/build_ref.py)")
+    RK.require()                                   # mandatory on the GPU box: fail, never skip
     from remixfusion_b200 import configs, synth
     from remixfusion_b200.volume import moving_volume
     cfg = configs.replica()

@@ -44,7 +44,8 @@ def _run_local(cuda, rf_lib, cam, lens, voxel, poses_frames, clamp=1.0, trunc=0.
     n = int(np.prod(dims))
     tsdf = np.ones(n, np.float32); w = np.zeros(n, np.float32); col = np.zeros(n, np.float32)
     ref = None
-    if with_ref and ref_kernels.available():
+    if with_ref:
+        ref_kernels.require()                      # the literal reference kernel is part of the check, never skipped
         ref = [torch.ones(n + 64, device=cuda), torch.zeros(n + 64, device=cuda), torch.zeros(n + 64, device=cuda)]
     n_touched_total = 0
     for K, c2w, depth, rgb in poses_frames:
@@ -120,10 +121,9 @@ def _run_global(cuda, rf_lib, cam, R, bound, frames, trunc=0.1, obs=1.0):
     mvol.init_mapvolume()
     trgb = np.zeros(4 * R ** 3, np.float32); O.clear_global(trgb); gw = np.zeros(R ** 3, np.float32)
     box = [v for ax in bound for v in ax]
-    ref = None
-    if ref_kernels.available():
-        ref = _Model(R, cuda)
-        ref_kernels.ref_clear_global(ref.GBV.params, R)
+    ref_kernels.require()
+    ref = _Model(R, cuda)
+    ref_kernels.ref_clear_global(ref.GBV.params, R)
     for K, c2w, depth, rgb in frames:
         batch = {"rgb": torch.from_numpy(rgb)[None], "depth": torch.from_numpy(depth)[None]}
         pose = torch.from_numpy(c2w).float().to(cuda)
@@ -283,7 +283,8 @@ def test_recenter_matches_oracle_and_reference_kernel(cuda, rf_lib, lens, voxel,
         assert np.array_equal(_bits(a), _bits(b)), f"{name}: product != C oracle ({(a != b).sum()} voxels)"
     kept = float((got[1] != 0).mean())
     assert (kept > 0) == all(abs(m) < 2 * l for m, l in zip(move, lens))
-    if ref_kernels.available():
+    ref_kernels.require()
+    if True:
         new = [torch.full((n + 64,), 7.0, device=cuda) for _ in range(3)]
         oldp = [torch.cat([t, t.new_zeros(64)]) for t in old]
         ref_kernels.ref_recenter(new, oldp, mv.vol_dim, mv.vol_origin, old_dim, old_origin, mv.voxel_size)
@@ -294,3 +295,31 @@ def test_recenter_matches_oracle_and_reference_kernel(cuda, rf_lib, lens, voxel,
     mv.update_tsdf_swap_rot_trans(old_bnds.copy(), new_bnds.copy())
     back = mv.weight_vol_gpu.cpu().numpy()
     assert np.array_equal(back[back != 0], old[1].cpu().numpy()[back != 0])
+
+
+def test_back_to_back_integrate_behind_a_busy_stream(cuda, rf_lib):
+    """moving_volume.integrate() stages host frames through pinned buffers with asynchronous copies.  Six different frames
+    are queued back to back while the stream is still busy with earlier work (twice the number of staging slots, so slots
+    are reused while their copies may still be in flight): the result must equal integrating them one at a time with a
+    synchronisation in between (the reference's copies were synchronous, model/Volume.py:733-749)."""
+    cam = dict(H=120, W=160, fx=131.0, fy=131.0, cx=79.5, cy=59.5)
+    K = synth.intrinsics(cam["fx"], cam["fy"], cam["cx"], cam["cy"])
+    scene = synth.make_scene([[-3, 3], [-3, 3], [-2, 2]], 1)
+    poses = synth.loop_trajectory(scene, 12)
+    frames = []
+    for i in range(6):
+        d, c = synth.render_frame(scene, K, cam["H"], cam["W"], poses[i], seed=i)
+        frames.append((poses[i], d * (1.0 + 0.05 * i), np.floor(c * 255.0).astype(np.float32)))
+    cfg = _cfg(0.05, (3, 3, 2))
+    a = moving_volume(cfg, None, np.eye(4), device=cuda)
+    b = moving_volume(cfg, None, np.eye(4), device=cuda)
+    for c2w, d, c in frames:                                   # one at a time
+        b.integrate(c, d, K, c2w, None)
+        torch.cuda.synchronize()
+    torch.cuda._sleep(int(4e8))                                # ~0.2 s of queued work ahead of the first copy
+    for c2w, d, c in frames:                                   # back to back, nothing waits on the host side by itself
+        a.integrate(c, d, K, c2w, None)
+    torch.cuda.synchronize()
+    for x, y, name in ((a.tsdf_vol_gpu, b.tsdf_vol_gpu, "tsdf"), (a.weight_vol_gpu, b.weight_vol_gpu, "weight"), (a.color_vol_gpu, b.color_vol_gpu, "color")):
+        assert torch.equal(x, y), f"{name}: back-to-back integrate() differs from the synchronised sequence"
+    assert float(a.weight_vol_gpu.sum()) > 0
