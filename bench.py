@@ -193,6 +193,10 @@ def cpu_reference_step(cfg, K, frame, n_rays, threads, state=None):
 
 
 def run_reference(args, rank, world):
+    """The reference's CPU path on the host cores: each step = one full TSDF fuse + mapping fwd+bwd on a BOUNDED ray sample
+    (`--cpu-rays`, default 65536 of the frame's 816000).  `ms_per_step` is the time actually measured per step; `value` is the
+    full-workload throughput composed from the two measured rates (TSDF at full size, rays scaled linearly by `scale_factor`
+    <= 12.5) and flagged `extrapolated`; `measured_units_per_s` is the plain units / time of the sample itself."""
     if rank != 0:
         return
     cfg = configs.replica()
@@ -202,29 +206,33 @@ def run_reference(args, rank, world):
     cam = cfg["cam"]
     S = cfg["training"]["n_range_d"] + cfg["training"]["n_samples_d"]
     full_samples = cam["H"] * cam["W"] * S
-    n_rays = args.cpu_rays
+    n_rays = min(args.cpu_rays, cam["H"] * cam["W"])
     state = None
-    for _ in range(max(args.warmup, 0) and 1):
-        state, _r = cpu_reference_step(cfg, K, frames[0], n_rays, threads, state)
+    if args.warmup > 0:
+        state, _r = cpu_reference_step(cfg, K, frames[0], min(n_rays, 4096), threads, state)
     ts = []
-    for _ in range(args.steps):
+    for _ in range(max(1, min(args.steps, args.cpu_steps))):
         state, r = cpu_reference_step(cfg, K, frames[0], n_rays, threads, state)
         ts.append(r)
     t_tsdf = statistics.mean(x["t_tsdf"] for x in ts)
     t_ray = statistics.mean(x["t_ray"] for x in ts)
-    touched = ts[-1]["touched"]
-    t_full = t_tsdf + t_ray * (full_samples / ts[-1]["samples"])            # ray part scaled linearly to the full frame
+    touched = ts[-1]["touched"]; samples = ts[-1]["samples"]
+    scale = full_samples / samples
+    t_full = t_tsdf + t_ray * scale                                          # ray part scaled linearly to the full frame
     value = (touched + full_samples) / t_full
-    sample = (f"full TSDF fuse of one 1200x680 frame (400x400x300 local + 200^3 GBV, C oracle) + mapping fwd+bwd on {n_rays} "
-              f"rays x {S} (torch CPU restatement of the reference + stand-in encoders), ray time scaled x{full_samples / ts[-1]['samples']:.1f} to 816000 rays")
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": t_full * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    sample = (f"per step: full TSDF fuse of one 1200x680 frame (400x400x300 local + 200^3 GBV, C oracle, {threads} threads: {t_tsdf:.2f} s) + mapping "
+              f"fwd+bwd on {n_rays} rays x {S} (torch CPU restatement of the reference's scene_rep + stand-in encoders: {t_ray:.2f} s); value = "
+              f"full-workload throughput with the ray time scaled x{scale:.2f} to 816000 rays")
+    extra = {"extrapolated": True, "measured_rays": n_rays, "scale_factor": scale, "measured_units_per_s": (touched + samples) / (t_tsdf + t_ray),
+             "measured_steps": len(ts), "ms_per_step_full_workload_scaled": t_full * 1e3}
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(ts),
+            "warmup": min(args.warmup, 1), "ms_per_step": (t_tsdf + t_ray) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic analytic scene (seeded)",
             "config": workload_config(cfg, 1),
-            "parts": {"tsdf_voxel_updates_per_s": touched / t_tsdf, "ray_samples_per_s": ts[-1]["samples"] / t_ray},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "parts": {"tsdf_voxel_updates_per_s": touched / t_tsdf, "ray_samples_per_s": samples / t_ray},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, **extra},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0, **extra}
     print(json.dumps(line), flush=True)
 
 
@@ -395,6 +403,27 @@ def run_gpu(args, rank, world, local_rank):
     # ---- e2e: public API with HOST buffers, H2D/D2H inside the timed region ----------------------------------------
     e2e = run_e2e(args, cfg, K, frames, model, mvol, local, params, dev, rank, world, group, per_frame_units, S)
 
+    # ---- the other BASELINE configurations (bench_workloads.py), every rank takes part --------------------------------
+    extra_parts = {}
+    if not args.no_extra:
+        import bench_workloads as BW
+        del loss
+        local = mvol = None
+        torch.cuda.empty_cache()
+        peak_gbs = measured_peak()[0]
+        for name, fn in (("cfg1", (lambda: BW.cfg1_part(dev, peak_gbs)) if world == 1 else None),
+                         ("cfg3", lambda: BW.cfg3_part(dev, rank, world, group, frames, K, peak_gbs)),
+                         ("cfg4", lambda: BW.cfg4_part(dev, rank, world, group, peak_gbs)),
+                         ("cfg5", lambda: BW.cfg5_part(dev, rank, world, group))):
+            if fn is None:
+                continue
+            try:
+                extra_parts[name] = fn()
+            except Exception as ex:                           # a failing side workload must not take the headline line with it
+                if world > 1:
+                    raise                                     # (with several ranks a one-sided failure would hang the collectives)
+                extra_parts[name] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+
     # ---- reduce over ranks ------------------------------------------------------------------------------------------
     vec = torch.tensor([total_ms, e2e["ms"]], dtype=torch.float64, device=dev)
     cnt = torch.tensor([units["touched_local"], units["touched_global"], units["samples"]], dtype=torch.float64, device=dev)
@@ -459,11 +488,13 @@ def run_gpu(args, rank, world, local_rank):
         },
         "e2e": {"value": float(e2e_units[0]) / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"], "steps": e2e["steps"],
                 "ms_per_step": e2e_ms / e2e["steps"]},
-        "gpu_launches": (3 + len(kern["kernels_ms"])) * args.steps,     # 2 TSDF integrates + ray_z + the ray kernels above
+        # per step: 2 TSDF integrates, ray_z, encode walk, decoder fwd, composite fwd / bwd, decoder bwd, scatter walk, replica fold
+        "gpu_launches": 10 * args.steps,
         "clocks": clocks,
     }
+    line["parts"].update(extra_parts)
     if not args.no_cpu_baseline and world == 1:
-        line["cpu_baseline"] = cpu_baseline(cfg, K, frames[0], H * W * S)
+        line["cpu_baseline"] = cpu_baseline(cfg, K, frames[0], H * W * S, args.cpu_rays)
     print(json.dumps(line), flush=True)
 
 
@@ -476,8 +507,8 @@ def gather_form(P, kern):
     return {"t_roof_ms": t_roof, "t_measured_ms": t_meas, "frac": t_roof / t_meas}
 
 
-PROF_NAMES = {3: "ray_pos_kernel", 4: "encode_walk_kernel", 5: "mlp_fwd_tc_kernel", 6: "composite_fwd_kernel",
-              7: "composite_bwd_kernel", 8: "mlp_bwd_tc_kernel", 9: "scatter_walk_kernel", 10: "sample_fwd_kernel",
+PROF_NAMES = {4: "encode_walk4_kernel", 5: "mlp_fwd_tc_kernel", 6: "composite_fwd_kernel",
+              7: "composite_bwd_kernel", 8: "mlp_bwd_tc2_kernel", 9: "scatter_walk4_kernel", 10: "sample_fwd_kernel",
               11: "sample_bwd_kernel"}
 
 
@@ -499,7 +530,9 @@ def ncu_traffic():
         for i, n in enumerate(names):
             key = next((k for k in PROF_NAMES.values() if k.replace("_kernel", "") in n or n.startswith(k[:12])), None)
             if key is None and "mlp_fwd" in n: key = "mlp_fwd_tc_kernel"
-            if key is None and "mlp_bwd" in n: key = "mlp_bwd_tc_kernel"
+            if key is None and "mlp_bwd" in n: key = "mlp_bwd_tc2_kernel"
+            if key is None and "encode_walk" in n: key = "encode_walk4_kernel"
+            if key is None and "scatter_walk" in n: key = "scatter_walk4_kernel"
             if key and key not in out:          # first launch of a kernel = the mapping-mode step (BA-mode launches follow)
                 out[key] = float(rd[2 + i]) * scale.get(rd[1], 1.0) + float(wr[2 + i]) * scale.get(wr[1], 1.0)
     except Exception:
@@ -512,12 +545,12 @@ def kernel_roofline(name, ms, P, hidden, peaks):
     corners x 8 B + 8 GBV corners x 16 B), table-gradient reductions 1024 B (16 x 8 x 2 x 4 B), decoder 2*166*h FLOP
     forward and twice that backward."""
     hbm, hbm_src, tf, tf_src = peaks
-    if name in ("mlp_fwd_tc_kernel", "mlp_bwd_tc_kernel"):
+    if name in ("mlp_fwd_tc_kernel", "mlp_bwd_tc2_kernel"):
         flop = 2.0 * 166 * hidden * (1 if name == "mlp_fwd_tc_kernel" else 2)
         a = flop * P / (ms / 1e3) / 1e12
         return {"bound": "tensor", "kernel": name, "achieved": a, "peak": tf, "unit": "TFLOP/s", "frac": a / tf, "traffic": None,
                 "peak_source": tf_src, "algorithmic_flop_per_sample": flop, "launch_ms": ms}
-    alg = {"encode_walk_kernel": 1152.0, "sample_fwd_kernel": 1152.0, "scatter_walk_kernel": 1024.0, "sample_bwd_kernel": 1024.0}.get(name, 40.0)
+    alg = {"encode_walk4_kernel": 1152.0, "sample_fwd_kernel": 1152.0, "scatter_walk4_kernel": 1024.0, "sample_bwd_kernel": 1024.0}.get(name, 40.0)
     a = alg * P / (ms / 1e3) / 1e9
     return {"bound": "hbm", "kernel": name, "achieved": a, "peak": hbm, "unit": "GB/s", "frac": a / hbm, "traffic": None,
             "peak_source": hbm_src, "algorithmic_bytes_per_sample": alg, "launch_ms": ms}
@@ -638,7 +671,7 @@ def time_kernels(model, cfg, f, dev, params):
             buf = (C.c_float * 64)(); L.rf_profile_read(buf)
             accb += np.maximum(np.array(buf[:], dtype=np.float64), 0.0)
         L.rf_profile_enable(0)
-        out["ba_kernels_ms"] = {"mlp_bwd_tc_kernel(BA)": accb[8] / reps, "scatter_walk_kernel": accb[9] / reps, "raygrad_walk_kernel": accb[12] / reps,
+        out["ba_kernels_ms"] = {"mlp_bwd_tc2_kernel(BA)": accb[8] / reps, "scatter_walk4_kernel(BA)": accb[9] / reps, "raygrad_walk_kernel": accb[12] / reps,
                                 "sample_bwd_kernel": accb[11] / reps}
         out["ba_kernels_ms"] = {k: v for k, v in out["ba_kernels_ms"].items() if v > 0}
     if os.environ.get("RF_DEBUG_PER_LEVEL"):
@@ -733,17 +766,19 @@ def run_e2e(args, cfg, K, frames, model, mvol, local, params, dev, rank, world, 
     return {"ms": a.elapsed_time(b), "steps": n_steps, "units": units, "h2d": h2d, "d2h": d2h}
 
 
-def cpu_baseline(cfg, K, frame, full_samples):
+def cpu_baseline(cfg, K, frame, full_samples, n_rays=65536):
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    n_rays = 8192
     state, _ = cpu_reference_step(cfg, K, frame, 2048, threads, None)       # warm-up (allocations, first-touch)
     state, r = cpu_reference_step(cfg, K, frame, n_rays, threads, state)
-    t_full = r["t_tsdf"] + r["t_ray"] * (full_samples / r["samples"])
+    scale = full_samples / r["samples"]
+    t_full = r["t_tsdf"] + r["t_ray"] * scale
     return {"value": (r["touched"] + full_samples) / t_full, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"full TSDF fuse of one 1200x680 frame (C oracle, {threads} threads: {r['t_tsdf']:.2f} s) + mapping fwd+bwd on "
                       f"{n_rays} rays x {r['samples'] // n_rays} (torch CPU restatement of the reference + stand-in encoders: {r['t_ray']:.2f} s), "
-                      f"ray time scaled x{full_samples / r['samples']:.1f} to the full frame",
+                      f"ray time scaled x{scale:.2f} to the full frame",
+            "extrapolated": True, "measured_rays": n_rays, "scale_factor": scale,
+            "measured_units_per_s": (r["touched"] + r["samples"]) / (r["t_tsdf"] + r["t_ray"]),
             "tsdf_voxel_updates_per_s": r["touched"] / r["t_tsdf"], "ray_samples_per_s": r["samples"] / r["t_ray"]}
 
 
@@ -755,7 +790,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--hidden", type=int, default=None, help="decoder width (default: Replica yaml, 32)")
     ap.add_argument("--hash-size", type=int, default=None, help="log2 hash-table size (default: Replica yaml, 16)")
-    ap.add_argument("--cpu-rays", type=int, default=8192, help="rays per CPU reference step")
+    ap.add_argument("--cpu-rays", type=int, default=65536, help="rays per CPU reference step (816000 in the full frame)")
+    ap.add_argument("--cpu-steps", type=int, default=6, help="cap on the timed CPU reference steps (each ~10 s)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the cfg 1 / 3 / 4 / 5 parts")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))

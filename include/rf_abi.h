@@ -235,6 +235,16 @@ typedef struct rf_ray_params {
 int rf_ray_sample_z(const rf_ray_cfg* cfg, const float* target_d, const float* u, const float* z_tables,
                     int64_t n_rays, float* z_vals, void* stream);
 
+/* SDF-to-weight compositing alone (JointEncoding.raw2outputs / sdf2weights, model/scene_rep.py:156-179, :107-127):
+ * raw [N,S,4], z_vals [N,S] -> rgb_map [N,3], depth_map [N].  Forward only. */
+int rf_ray_composite(const rf_ray_cfg* cfg, const float* raw, const float* z_vals, int64_t n_rays, float* rgb_map,
+                     float* depth_map, void* stream);
+
+/* The four mapping losses from the (all-reduced) partial sums of rf_ray_query_forward (model/scene_rep.py:501-517,
+ * model/utils.py:190-196, :242-245): losses (device float[4]) = rgb, depth, sdf, fs.  n_rays_total: rays in the whole
+ * (multi-GPU) batch; n_samples: samples per ray. */
+int rf_ray_loss_finalize(const double* loss_partials, int64_t n_rays_total, int n_samples, float* losses, void* stream);
+
 /* Forward.  rays_o, rays_d [N,3]; z_vals [N,S] (from rf_ray_sample_z);
  * outputs: raw [N,S,4], rgb_map [N,3], depth_map [N];
  * loss_partials (device double[8], may be NULL; caller zeroes it): accumulates the sums the four losses of

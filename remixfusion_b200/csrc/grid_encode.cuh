@@ -11,6 +11,8 @@ namespace rf {
 
 struct GridDev {               // kernel-side copy of rf_grid_desc
     int   n_levels, n_features, is_hash;
+    unsigned hash_pow2_mask;   // bit l: level l uses the prime hash and its table size is a power of two
+    unsigned dense_mask;       // bit l: level l is indexed densely (size >= res^3)
     float scale[RF_MAX_LEVELS];
     unsigned res[RF_MAX_LEVELS];
     unsigned size[RF_MAX_LEVELS];
@@ -22,6 +24,15 @@ static inline GridDev to_dev(const rf_grid_desc* d) {
     g.n_levels = d->n_levels; g.n_features = d->n_features; g.is_hash = d->is_hash;
     for (int i = 0; i < RF_MAX_LEVELS; ++i) { g.scale[i] = d->scale[i]; g.res[i] = d->resolution[i]; g.size[i] = d->size[i]; }
     for (int i = 0; i <= RF_MAX_LEVELS; ++i) g.offset[i] = d->offset[i];
+    g.hash_pow2_mask = 0; g.dense_mask = 0;
+    for (int l = 0; l < d->n_levels && l < RF_MAX_LEVELS; ++l) {          // the rule of grid_index / CornerIndexer::init
+        const unsigned long long size = d->size[l], res = d->resolution[l];
+        unsigned long long stride = 1;
+        for (int k = 0; k < 3; ++k) if (stride <= size) stride *= res;
+        const bool hashed = d->is_hash && size < stride;
+        if (hashed && size && (size & (size - 1)) == 0) g.hash_pow2_mask |= 1u << l;
+        if (!hashed && res * res * res <= size) g.dense_mask |= 1u << l;
+    }
     return g;
 }
 
@@ -93,6 +104,30 @@ struct CornerIndexer {
         }
     }
 };
+
+// The 8 corner indices with the two common cases specialised (same values as CornerIndexer / grid_index, Appendix B3):
+//   * hashed level with a power-of-two table: (a ^ b ^ c) & mask == (a & mask) ^ (b & mask) ^ (c & mask), one 3-input
+//     logic op per corner;
+//   * dense level, cell strictly inside the grid: base + constant offsets, no wrap-around modulo;
+// everything else (samples outside the unit cube on dense levels, odd table sizes) takes the general path.
+__device__ __forceinline__ void cell_indices(const GridDev& g, int l, unsigned cx, unsigned cy, unsigned cz, unsigned (&idx)[8]) {
+    const unsigned size = g.size[l], res = g.res[l];
+    if ((g.hash_pow2_mask >> l) & 1u) {
+        const unsigned mask = size - 1u;
+        const unsigned a[2] = {cx & mask, (cx + 1u) & mask};
+        const unsigned b0 = cy * 2654435761u, c0 = cz * 805459861u;
+        const unsigned b[2] = {b0 & mask, (b0 + 2654435761u) & mask}, c[2] = {c0 & mask, (c0 + 805459861u) & mask};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) idx[k] = a[k & 1] ^ b[(k >> 1) & 1] ^ c[(k >> 2) & 1];
+    } else if (((g.dense_mask >> l) & 1u) && cx + 1u < res && cy + 1u < res && cz + 1u < res && cx + 1u != 0u && cy + 1u != 0u && cz + 1u != 0u) {
+        const unsigned s2 = res, s3 = res * res, base = cx + cy * s2 + cz * s3;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) idx[k] = base + (unsigned)(k & 1) + ((k & 2) ? s2 : 0u) + ((k & 4) ? s3 : 0u);
+    } else {
+        CornerIndexer ci; ci.init(g.is_hash != 0, size, res);
+        ci.cell(cx, cy, cz, idx);
+    }
+}
 
 // Corner weight, Appendix B4 (weight = 1; for dim: weight *= frac or 1-frac).
 __device__ __forceinline__ float corner_weight(int corner, float fx, float fy, float fz) {

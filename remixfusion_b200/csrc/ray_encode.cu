@@ -32,12 +32,6 @@
 
 namespace rf {
 
-// the 8 corner indices of cell (cx, cy, cz) of a level (Appendix B3); same arithmetic as grid_index, shared between corners
-__device__ __forceinline__ void cell_indices(bool is_hash, unsigned size, unsigned res, unsigned cx, unsigned cy, unsigned cz, unsigned (&idx)[8]) {
-    CornerIndexer ci; ci.init(is_hash, size, res);
-    ci.cell(cx, cy, cz, idx);
-}
-
 // samples per walking thread: the whole ray for big batches; for small ones segments of >= 8 samples such that a launch has
 // ~32 k (ray, segment) units
 static int walk_segment(long long n_rays, int S) {
@@ -51,7 +45,7 @@ constexpr int kEncThreads = 160;        // 4 hash-quad roles + 1 GBV role, 32 (r
 // Forward.  ws: the workspace of ray_common.cuh.  POINTS: z_vals holds n already-normalised positions [n][3] (point queries,
 // model/scene_rep.py:212-310): n "rays" of one sample.
 template <bool POINTS>
-__global__ void __launch_bounds__(kEncThreads) encode_walk4_kernel(const __grid_constant__ RayK k, const __grid_constant__ GridDev hg,
+__global__ void __launch_bounds__(kEncThreads, 4) encode_walk4_kernel(const __grid_constant__ RayK k, const __grid_constant__ GridDev hg,
                                                                    const __grid_constant__ GridDev gg, const float* __restrict__ hash_params,
                                                                    const float* __restrict__ gbv_params, const float* __restrict__ rays_o,
                                                                    const float* __restrict__ rays_d, const float* __restrict__ z_vals,
@@ -100,7 +94,7 @@ __global__ void __launch_bounds__(kEncThreads) encode_walk4_kernel(const __grid_
                 pos_fract(x, scale, cx, fr[j][0]); pos_fract(y, scale, cy, fr[j][1]); pos_fract(z, scale, cz, fr[j][2]);
                 if (!((have >> j) & 1u) || cx != pc[j][0] || cy != pc[j][1] || cz != pc[j][2]) {
                     unsigned idx[8];
-                    cell_indices(hg.is_hash != 0, hg.size[l], hg.res[l], cx, cy, cz, idx);
+                    cell_indices(hg, l, cx, cy, cz, idx);
                     const float2* tab = reinterpret_cast<const float2*>(hash_params) + hg.offset[l];
 #pragma unroll
                     for (int c = 0; c < 8; ++c) v[j][c] = __ldg(tab + idx[c]);
@@ -142,7 +136,7 @@ __global__ void __launch_bounds__(kEncThreads) encode_walk4_kernel(const __grid_
             pos_fract(x, scale, cx, fx); pos_fract(y, scale, cy, fy); pos_fract(z, scale, cz, fz);
             if (!have || cx != pcx || cy != pcy || cz != pcz) {
                 unsigned idx[8];
-                cell_indices(false, gg.size[0], gg.res[0], cx, cy, cz, idx);
+                cell_indices(gg, 0, cx, cy, cz, idx);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) v[c] = __ldg(tab + idx[c]);
                 pcx = cx; pcy = cy; pcz = cz; have = true;
@@ -271,7 +265,7 @@ __global__ void __launch_bounds__(512 / LPT, LPT == 4 ? 4 : 2) scatter_walk4_ker
                     float2* gtab = (rep.k[l] > 1) ? reinterpret_cast<float2*>(g_rep) + rep.base[l] + (size_t)(blockIdx.x & (rep.k[l] - 1)) * size
                                                   : reinterpret_cast<float2*>(g_hash) + hg.offset[l];
                     unsigned idx[8];
-                    cell_indices(hg.is_hash != 0, size, hg.res[l], pc[j][0], pc[j][1], pc[j][2], idx);
+                    cell_indices(hg, l, pc[j][0], pc[j][1], pc[j][2], idx);
 #pragma unroll
                     for (int c = 0; c < 8; ++c) atomicAdd(gtab + idx[c], acc[j][c]);
                 }
@@ -292,7 +286,7 @@ __global__ void __launch_bounds__(512 / LPT, LPT == 4 ? 4 : 2) scatter_walk4_ker
             if (BA && dnz) {
                 if (!((vhave >> j) & 1u)) {
                     unsigned idx[8];
-                    cell_indices(hg.is_hash != 0, hg.size[l], hg.res[l], cx, cy, cz, idx);
+                    cell_indices(hg, l, cx, cy, cz, idx);
                     const float2* tab = reinterpret_cast<const float2*>(rg.hash_params) + hg.offset[l];
 #pragma unroll
                     for (int c = 0; c < 8; ++c) v[BA ? j : 0][c] = __ldg(tab + idx[c]);
@@ -349,7 +343,7 @@ __global__ void __launch_bounds__(128) raygrad_walk_kernel(GridDev hg, GridDev g
             unsigned cx, cy, cz; float fx, fy, fz;
             pos_fract(x, scale, cx, fx); pos_fract(y, scale, cy, fy); pos_fract(z, scale, cz, fz);
             if (!have || cx != pcx || cy != pcy || cz != pcz) {
-                cell_indices(hg.is_hash != 0, hg.size[l], hg.res[l], cx, cy, cz, idx);
+                cell_indices(hg, l, cx, cy, cz, idx);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) v[c] = __ldg(tab + idx[c]);
                 pcx = cx; pcy = cy; pcz = cz; have = true;
@@ -378,7 +372,7 @@ __global__ void __launch_bounds__(128) raygrad_walk_kernel(GridDev hg, GridDev g
             unsigned cx, cy, cz; float fx, fy, fz;
             pos_fract(x, scale, cx, fx); pos_fract(y, scale, cy, fy); pos_fract(z, scale, cz, fz);
             if (!have || cx != pcx || cy != pcy || cz != pcz) {
-                cell_indices(false, gg.size[0], gg.res[0], cx, cy, cz, idx);
+                cell_indices(gg, 0, cx, cy, cz, idx);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) v[c] = __ldg(tab + idx[c]);
                 pcx = cx; pcy = cy; pcz = cz; have = true;

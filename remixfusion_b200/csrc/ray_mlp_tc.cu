@@ -670,18 +670,29 @@ __global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights
         if (h) dr_next = (tile_ * kTile + m < P) ? __ldg(reinterpret_cast<const float4*>(d_raw_tot) + pos.raw_index(m)) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
     // liveness is voted two tiles ahead (one group barrier per iteration): the tile after next is pulled towards L2 only if
-    // it will be processed, the next one has its inputs loaded / its hash chunks fetched while the current one is computed
+    // it will be processed, the next one has its inputs loaded / its hash chunks fetched while the current one is computed.
+    // The n_live value a vote needs is loaded one iteration before the vote, so the barrier never waits on memory.
     TilePos tn = tp; tn.next();
     bool alive = (tile < n_tiles) && grp_any2(g, row_live(tp, tile));
     bool alive_n = (tile + tstep < n_tiles) && grp_any2(g, row_live(tn, tile + tstep));
     if (alive) { if (TMAH && issuer) fetch_hash(tile); load_inputs(tp, tile); }
     if (alive_n && h == 0) prefetch_tile(feat, P, tile + tstep, m, true);
-    for (; tile < n_tiles; tile += tstep, tp = tn, tn.next()) {
+    // (n_live of this row's ray, this row's sample index) of a tile: the row is live iff sample < n_live; the load is not consumed here
+    auto row_fetch = [&](const TilePos& pos, long long tile_, int& ss_out) -> int {
+        if (tile_ * kTile + m >= P) { ss_out = 1; return 0; }
+        if (!n_live) { ss_out = 0; return 1; }
+        long long ss, rr; pos.row(m, ss, rr);
+        ss_out = (int)ss;
+        return __ldg(n_live + rr);
+    };
+    TilePos tnn = tn; tnn.next();
+    int ss_nn, nl_nn = row_fetch(tnn, tile + 2 * tstep, ss_nn);                               // for the next vote
+    for (; tile < n_tiles; tile += tstep, tp = tn, tn = tnn, tnn.next()) {
         const long long q = tile * kTile + m;                                                 // plane index s * N + r
         const bool live = q < P;
         const long long tile_n = tile + tstep, tile_nn = tile_n + tstep;
-        TilePos tnn = tn; tnn.next();
-        const bool alive_nn = (tile_nn < n_tiles) && grp_any2(g, row_live(tnn, tile_nn));
+        const bool alive_nn = (tile_nn < n_tiles) && grp_any2(g, ss_nn < nl_nn);
+        { TilePos t3 = tnn; t3.next(); nl_nn = row_fetch(t3, tile_nn + tstep, ss_nn); }       // consumed by the next iteration's vote
         if (alive_nn && h == 0) prefetch_tile(feat, P, tile_nn, m, true);
         const bool alive_cur = alive, alive_nx = alive_n;
         alive = alive_n; alive_n = alive_nn;                                                  // shifted for the next iteration

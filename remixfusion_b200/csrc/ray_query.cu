@@ -607,6 +607,17 @@ __global__ void ray_grad_kernel(RayK k, const float* __restrict__ d_pts, const f
     }
 }
 
+// losses[4] = (rgb, depth, sdf, fs) from the seven partial sums (float64 arithmetic, one thread): mse over N*3 (:501),
+// mean over the valid rays (:504-507), the two SDF losses with the front / band balance weights of get_masks
+// (model/utils.py:190-196, :242-245)
+__global__ void loss_finalize_kernel(const double* __restrict__ p, double n_total, double n_samples, float* __restrict__ losses) {
+    const double nn = p[5] + p[6];
+    losses[0] = (float)(p[0] / (3.0 * n_total));
+    losses[1] = (float)(p[1] / p[2]);
+    losses[2] = (float)(p[4] / (n_total * n_samples) * (1.0 - p[6] / nn));
+    losses[3] = (float)(p[3] / (n_total * n_samples) * (1.0 - p[5] / nn));
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
@@ -696,6 +707,32 @@ extern "C" int rf_ray_sample_z(const rf_ray_cfg* cfg, const float* target_d, con
         ray_z_kernel<<<(unsigned)((n_rays + 3) / 4), 128, 0, (cudaStream_t)stream>>>(k, target_d, u, z_tables, z_vals);
     }
     RF_CHECK_LAUNCH("ray_z_kernel");
+    return 0;
+}
+
+extern "C" int rf_ray_composite(const rf_ray_cfg* cfg, const float* raw, const float* z_vals, int64_t n_rays, float* rgb_map,
+                                float* depth_map, void* stream) {
+    RF_REQUIRE(cfg, RF_E_NULL, "rf_ray_composite: NULL cfg");
+    RF_REQUIRE(cfg->n_range_d >= 1 && cfg->n_samples_d >= 0 && cfg->n_range_d + cfg->n_samples_d <= kMaxS, RF_E_RANGE, "rf_ray_composite: bad sample counts");
+    RF_REQUIRE(cfg->trunc > 0.f, RF_E_RANGE, "rf_ray_composite: trunc must be positive");
+    if (n_rays == 0) return 0;
+    RF_REQUIRE(raw && z_vals && rgb_map && depth_map, RF_E_NULL, "rf_ray_composite: NULL pointer");
+    RF_REQUIRE(((uintptr_t)raw & 15) == 0, RF_E_ALIGN, "rf_ray_composite: raw must be 16-byte aligned");
+    RayK k; memset(&k, 0, sizeof(k));
+    k.S = cfg->n_range_d + cfg->n_samples_d; k.trunc = cfg->trunc; k.n_rays = n_rays;
+    k.sc_trunc = (float)((double)cfg->sc_factor * (double)cfg->trunc);
+    cudaStream_t s = (cudaStream_t)stream;
+    ProfScope ps(RF_PROF_COMPOSITE_FWD, s);
+    composite_fwd_kernel<<<(unsigned)((n_rays + 3) / 4), 128, 0, s>>>(k, raw, z_vals, nullptr, nullptr, rgb_map, depth_map, nullptr);
+    RF_CHECK_LAUNCH("composite_fwd_kernel");
+    return 0;
+}
+
+extern "C" int rf_ray_loss_finalize(const double* loss_partials, int64_t n_rays_total, int n_samples, float* losses, void* stream) {
+    RF_REQUIRE(loss_partials && losses, RF_E_NULL, "rf_ray_loss_finalize: NULL pointer");
+    RF_REQUIRE(n_rays_total > 0 && n_samples > 0, RF_E_RANGE, "rf_ray_loss_finalize: bad counts");
+    loss_finalize_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(loss_partials, (double)n_rays_total, (double)n_samples, losses);
+    RF_CHECK_LAUNCH("loss_finalize_kernel");
     return 0;
 }
 

@@ -74,14 +74,10 @@ class _RayQueryFn(torch.autograd.Function):
             if group is not None:
                 import torch.distributed as dist
                 dist.all_reduce(partials, group=group)          # loss means and mask counts are batch-global
-            NT = float(n_total)
-            nn_ = partials[5] + partials[6]
-            losses = torch.stack([
-                partials[0] / (3.0 * NT),                                       # rgb: mse over N*3   (scene_rep.py:501)
-                partials[1] / partials[2],                                      # depth: mean over valid rays (:504-507)
-                partials[4] / (NT * S) * (1.0 - partials[6] / nn_),             # sdf  (model/utils.py:245,196)
-                partials[3] / (NT * S) * (1.0 - partials[5] / nn_),             # fs   (model/utils.py:242,195)
-            ]).to(torch.float32)
+            # rgb: mse over N*3 (scene_rep.py:501); depth: mean over valid rays (:504-507); sdf / fs with the balance
+            # weights of get_masks (model/utils.py:190-196, :242-245) — one tiny kernel instead of a chain of scalar torch ops
+            abi.check(abi.lib().rf_ray_loss_finalize(abi.dptr(partials), C.c_int64(n_total), C.c_int(S), abi.dptr(losses),
+                                                     abi.stream_ptr()), "rf_ray_loss_finalize")
         ctx.meta = meta
         ctx.n_total = n_total
         ctx.ws = ws if any(ctx.needs_input_grad) else None
@@ -251,10 +247,25 @@ class JointEncoding(nn.Module):
     GROUP_RAYS_MIN = 1 << 16
 
     def _render(self, rays_o, rays_d, target_d, target_rgb, with_losses, u=None):
-        if target_d is None:
-            raise abi.RfError("render_rays without target_d (uniform near..far sampling, scene_rep.py:431-433) is never "
-                              "reached by the reference's callers and is not built")
         n = rays_o.shape[0]
+        if target_d is None:
+            # no depth prior: training.n_samples depths evenly spaced over [near, far] (model/scene_rep.py:431-433), jittered
+            # like the others (:437-441); the rest of the pipeline sees them as one group of S samples
+            t, cam = self.config["training"], self.config["cam"]
+            ns = int(t["n_samples"])
+            z_vals = torch.linspace(cam["near"], cam["far"], ns).to(rays_o.device, torch.float32)[None, :].repeat(n, 1)
+            if t["perturb"] > 0.:
+                mids = .5 * (z_vals[..., 1:] + z_vals[..., :-1])
+                upper = torch.cat([mids, z_vals[..., -1:]], -1)
+                lower = torch.cat([z_vals[..., :1], mids], -1)
+                uu = torch.rand(z_vals.shape).to(z_vals) if u is None else u.to(z_vals)
+                z_vals = lower + (upper - lower) * uu
+            meta = self._meta(False)
+            meta["cfg"].n_range_d, meta["cfg"].n_samples_d = ns, 0
+            w = self._weights()
+            rgb_map, depth_map, raw, losses = _RayQueryFn.apply(
+                rays_o, rays_d, self.embed_res_fn.params, w[0], w[1], w[2], w[3], self.GBV.params, z_vals.contiguous(), None, None, meta)
+            return rgb_map, depth_map, raw, z_vals, losses
         # Training batches are processed with the rays that have a depth measurement first, the others (sensor holes, no
         # return) last.  Every per-ray result is independent of the order; what changes is how the backward's 128-ray tiles
         # are composed: rays with a measurement stop contributing a few centimetres behind the surface (n_live, see
@@ -355,19 +366,15 @@ class JointEncoding(nn.Module):
         inputs_flat = torch.reshape(query_points, [-1, query_points.shape[-1]])
         return self.GBV(inputs_flat)[..., 1:]
 
-    # ---- kept for API parity (plain torch; the fused kernels do this inside render_rays) ---------------------
-    def sdf2weights(self, sdf, z_vals, args=None):
-        args = self.config if args is None else args
-        tr = args["training"]["trunc"]
-        weights = torch.sigmoid(sdf / tr) * torch.sigmoid(-sdf / tr)
-        signs = sdf[:, 1:] * sdf[:, :-1]
-        mask = torch.where(signs < 0.0, torch.ones_like(signs), torch.zeros_like(signs))
-        inds = torch.argmax(mask, axis=1)[..., None]
-        z_min = torch.gather(z_vals, 1, inds)
-        mask = torch.where(z_vals < z_min + args["data"]["sc_factor"] * tr, torch.ones_like(z_vals), torch.zeros_like(z_vals))
-        weights = weights * mask
-        return weights / (torch.sum(weights, axis=-1, keepdims=True) + 1e-8)
-
+    # ---- model/scene_rep.py:156-179 (and :107-127 inside the kernel) ------------------------------------------
     def raw2outputs(self, raw, z_vals):
-        weights = self.sdf2weights(raw[..., 3], z_vals, args=self.config)
-        return torch.sum(weights[..., None] * raw[..., :3], -2), torch.sum(weights * z_vals, -1)
+        """raw [N,S,4], z_vals [N,S] -> (rgb_map [N,3], depth_map [N]): the compositing kernel alone (forward only; gradients
+        flow through render_rays / mapping)."""
+        raw = raw.detach().to(torch.float32).contiguous(); z = z_vals.detach().to(torch.float32).contiguous()
+        n = raw.shape[0]
+        rgb_map = torch.empty(n, 3, dtype=torch.float32, device=raw.device)
+        depth_map = torch.empty(n, dtype=torch.float32, device=raw.device)
+        cfg = self._ray_cfg()
+        abi.check(abi.lib().rf_ray_composite(C.byref(cfg), abi.dptr(raw), abi.dptr(z), C.c_int64(n), abi.dptr(rgb_map), abi.dptr(depth_map),
+                                             abi.stream_ptr()), "rf_ray_composite")
+        return rgb_map, depth_map

@@ -510,3 +510,24 @@ def test_render_rays_upstream_gradients_match_oracle(cuda, rf_lib, prec):
     _close_grad(m.embed_res_fn.params.grad, orc.embed_res_fn.params.grad.numpy(), "g_hash", prec)
     for w_cuda, w_ref, nm in zip(m.decoder_res.fused_weights(), (orc.w_sdf0, orc.w_sdf1, orc.w_col0, orc.w_col1), ("sdf0", "sdf1", "col0", "col1")):
         _close_grad(w_cuda.grad, w_ref.grad.numpy(), "g_w_" + nm, prec)
+
+
+def test_render_rays_without_depth_prior_and_raw2outputs(cuda, rf_lib):
+    """render_rays(target_d=None): training.n_samples depths evenly spaced over [near, far] (model/scene_rep.py:431-433), and the
+    stand-alone compositing entry raw2outputs (:156-179), against the oracle's run_network + raw2outputs on the same depths."""
+    cfg, m = _model_from_golden("C", cuda)
+    cfg["training"]["n_samples"] = 40
+    _, orc = R.oracle_from_golden(G, "C", requires_grad=False)
+    ro = torch.from_numpy(G["in_rays_o"][:300]); rd = torch.from_numpy(G["in_rays_d"][:300])
+    m.eval()
+    with torch.no_grad():
+        ret = m.render_rays(ro.to(cuda), rd.to(cuda), target_d=None)
+        z = torch.linspace(cfg["cam"]["near"], cfg["cam"]["far"], 40)[None, :].repeat(300, 1)
+        assert torch.equal(ret["z_vals"].cpu(), z)
+        raw = orc.run_network(ro[..., None, :] + rd[..., None, :] * z[..., :, None])
+        rgb, dep = orc.raw2outputs(raw, z)
+        _close(ret["raw"], raw.numpy(), 2e-4, "raw")
+        _close(ret["rgb_res_map"], rgb.numpy(), 2e-4, "rgb_res_map")
+        _close(ret["depth_res_map"], dep.numpy(), 2e-4, "depth_res_map")
+        rgb2, dep2 = m.raw2outputs(ret["raw"], ret["z_vals"])
+        assert torch.equal(rgb2, ret["rgb_res_map"]) and torch.equal(dep2, ret["depth_res_map"])
