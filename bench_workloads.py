@@ -97,7 +97,17 @@ def cfg1_part(dev, peak_gbs):
     ms_g = _timed(lambda i: gv.integrate_kf({"rgb": c, "depth": d}, pose, 1.0), 20, 1, dev, warm=3)
     ntg = gv.count_touched(d, pose)
     b1g = 40.0 * ntg + 16.0 * H * W
-    out = {"workload": "640x480 frame -> 256^3 voxels of 2 cm (camera at the origin, +z)",
+    # the streaming upper bound of the same volume (SURVEY §8d "full-touch"): camera 6 m in front of the cube with the whole
+    # cube inside its frustum and a wall behind it, so EVERY voxel is free space in front of the surface and is updated
+    c2w_f = np.eye(4); c2w_f[:3, 3] = [-0.44, -0.44, -8.0]
+    d_f = torch.full((H, W), 11.6, device=dev)
+    ms_full = _timed(lambda i: mv.integrate_packed(d_f, packed, K, c2w_f, None, 1.0, 0.0), 20, 1, dev, warm=3)
+    ntf, nbf = mv.count_touched(d_f, K, c2w_f)
+    b1f = 16.0 * ntf + 8.0 * nbf + 8.0 * H * W
+    full = {"ms": ms_full, "touched": ntf, "band": nbf, "voxel_updates_per_s": ntf / (ms_full / 1e3), "algorithmic_bytes": b1f,
+            "achieved_gbs": b1f / (ms_full / 1e3) / 1e9, "frac": b1f / (ms_full / 1e3) / 1e9 / peak_gbs,
+            "note": "camera at (-0.44, -0.44, -8) looking along +z, constant depth 11.6 m: all 256^3 voxels lie in the frustum in front of the surface"}
+    out = {"workload": "640x480 frame -> 256^3 voxels of 2 cm (camera at the origin, +z)", "local_full_touch": full,
            "local": {"ms": ms_local, "touched": nt, "band": nb, "voxel_updates_per_s": nt / (ms_local / 1e3), "swept_voxels_per_s": 256 ** 3 / (ms_local / 1e3),
                      "algorithmic_bytes": b1, "achieved_gbs": b1 / (ms_local / 1e3) / 1e9, "frac": b1 / (ms_local / 1e3) / 1e9 / peak_gbs},
            "gbv_R256": {"ms": ms_g, "touched": ntg, "voxel_updates_per_s": ntg / (ms_g / 1e3), "swept_voxels_per_s": 256 ** 3 / (ms_g / 1e3),

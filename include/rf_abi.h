@@ -336,6 +336,18 @@ int rf_profile_read(float* ms);
  * Synchronous.  Returns 0, or 1001 if the MMA never completed. */
 int rf_umma_selftest(const float* A, const float* B, float* D, int K, int N, int mode, void* stream);
 
+/* ---- N4 (second half): marching cubes on the device (csrc/marching_cubes.cu) ---------------------------------------------
+ * Dual-grid marching cubes of thirdparty/NumpyMarchingCubes (`mcubes.marching_cubes(volume, isovalue, truncation)`,
+ * utils.py:169).  volume [X][Y][Z] fp32 (z fastest, the layout query_lattice produces); voxels with |d| >= truncation (or
+ * NaN / -inf) are invalid and no surface is built next to them.
+ *   rf_mc_count : corner_ws (rf_mc_corner_floats floats) <- dual-grid corner values; counts [X*Y*Z] <- triangles per cell.
+ *   rf_mc_emit  : offsets [X*Y*Z] = exclusive prefix sum of counts (int64); triangles [T][3][3] positions in voxel units in
+ *                 the reference's cell order; keys [T][3] int64 = identity of each vertex (dual edge or snapped corner) for welding. */
+int64_t rf_mc_corner_floats(int X, int Y, int Z);
+int rf_mc_count(const float* volume, int X, int Y, int Z, float isovalue, float truncation, float* corner_ws, int* counts, void* stream);
+int rf_mc_emit(const float* corner_ws, int X, int Y, int Z, float isovalue, const long long* offsets, float* triangles,
+               long long* keys, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

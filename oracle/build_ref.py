@@ -34,14 +34,35 @@ SOURCES = {
 NO_EXTERN_C = {"ref_tracker.cubin"}
 
 
+MC_SRC = "thirdparty/NumpyMarchingCubes/marching_cubes/src"
+MC_LIB = "libmc_ref.so"
+
+
+def build_marching_cubes(verbose: bool = False) -> None:
+    """The reference's C++ marching cubes (utils.py:169 `mcubes.marching_cubes`) as a CPU oracle: its marching_cubes.cpp is
+    compiled where it lies, with oracle/mc_ref_shim.h standing in for the NumPy accessor and oracle/mc_ref_entry.cpp as the C
+    entry point (the reference's own Cython / NumPy wrapper does not build against NumPy 2)."""
+    src = os.path.join(REF_ROOT, MC_SRC)
+    dst = os.path.join(OUT_DIR, MC_LIB)
+    deps = [os.path.join(src, "marching_cubes.cpp"), os.path.join(HERE, "mc_ref_shim.h"), os.path.join(HERE, "mc_ref_entry.cpp")]
+    if os.path.exists(dst) and all(os.path.getmtime(dst) >= os.path.getmtime(d) for d in deps):
+        return
+    cmd = ["g++", "-shared", "-fPIC", "-O2", "-std=c++14", "-w", "-D_EXTMODULE_H", "-include", os.path.join(HERE, "mc_ref_shim.h"),
+           "-I" + src, os.path.join(HERE, "mc_ref_entry.cpp"), os.path.join(src, "marching_cubes.cpp"), "-o", dst]
+    if verbose:
+        print("[build_ref]", " ".join(cmd))
+    subprocess.run(cmd, check=True)
+
+
 def build(verbose: bool = False) -> bool:
-    """Returns True when the cubins are present after the call (built now or earlier)."""
+    """Returns True when the cubins (and the marching-cubes oracle) are present after the call (built now or earlier)."""
     if not os.path.isdir(REF_ROOT):
-        ok = all(os.path.exists(os.path.join(OUT_DIR, k)) for k in SOURCES)
+        ok = all(os.path.exists(os.path.join(OUT_DIR, k)) for k in list(SOURCES) + [MC_LIB])
         if verbose:
-            print(f"[build_ref] {REF_ROOT} absent; prebuilt cubins present: {ok}")
+            print(f"[build_ref] {REF_ROOT} absent; prebuilt oracle binaries present: {ok}")
         return ok
     os.makedirs(OUT_DIR, exist_ok=True)
+    build_marching_cubes(verbose)
     for cubin, rel in SOURCES.items():
         dst = os.path.join(OUT_DIR, cubin)
         src_path = os.path.join(REF_ROOT, rel)
