@@ -273,6 +273,8 @@ def run_gpu(args, rank, world, local_rank):
         model.embed_res_fn.params.copy_((torch.rand_like(model.embed_res_fn.params) * 2 - 1) * 1e-2)
     model.train()
     params = [model.embed_res_fn.params] + list(model.decoder_res.fused_weights())
+    # several ranks: the gradients live in one flat buffer (views are the parameters' .grad) that is all-reduced in place
+    fg = rdist.FlatGrads(params) if world > 1 else None
 
     R = cfg["globalV"]["base_resolution"]
     z_slab = rdist.slab(R, rank, world)
@@ -322,20 +324,23 @@ def run_gpu(args, rank, world, local_rank):
         local.integrate_packed(b["depth"], b["packed"], K, b["c2w"], None, 1.0, 0.0)
         if timed: e[1].record()
         mvol.integrate_kf({"rgb": b["rgb"], "depth": b["depth"]}, torch.from_numpy(b["c2w"]).float(), 1.0)
-        if world > 1:                                            # replicate the GBV for the ray query (160 MB all-gather)
+        if world > 1:                                            # replicate the GBV for the ray query: slabs land in place (160 MB)
             sizes = [4 * (rdist.slab(R, k, world)[1] - rdist.slab(R, k, world)[0]) * R * R for k in range(world)]
-            full_gbv.params.data.copy_(rdist.gather_slabs(mvol.model.GBV.params, sizes, group))
+            rdist.gather_slabs(mvol.model.GBV.params, sizes, group, out=full_gbv.params.data)
         if timed: e[2].record()
-        for p in params:
-            p.grad = None
+        if fg is not None:
+            fg.zero()
+        else:
+            for p in params:
+                p.grad = None
         if timed and os.environ.get("RF_BENCH_DEBUG"):
             dbg = torch.cuda.Event(enable_timing=True); dbg.record(); e.append(dbg)
         ret = model.mapping(f["rays_o"], f["rays_d"], f["tgt_c"], f["tgt_d"])
         loss = configs.total_loss(cfg, ret)
         if timed: e[3].record()
         loss.backward()
-        if world > 1:
-            rdist.allreduce_grads(params, group)
+        if fg is not None:
+            fg.allreduce(group)
         if timed: e[4].record()
         return e, loss
 
@@ -401,7 +406,7 @@ def run_gpu(args, rank, world, local_rank):
     kern = time_kernels(model, cfg, dev_frames[0], dev, params)
 
     # ---- e2e: public API with HOST buffers, H2D/D2H inside the timed region ----------------------------------------
-    e2e = run_e2e(args, cfg, K, frames, model, mvol, local, params, dev, rank, world, group, per_frame_units, S)
+    e2e = run_e2e(args, cfg, K, frames, model, mvol, local, params, fg, dev, rank, world, group, per_frame_units, S)
 
     # ---- the other BASELINE configurations (bench_workloads.py), every rank takes part --------------------------------
     extra_parts = {}
@@ -689,7 +694,7 @@ def time_kernels(model, cfg, f, dev, params):
     return out
 
 
-def run_e2e(args, cfg, K, frames, model, mvol, local, params, dev, rank, world, group, per_frame_units, S):
+def run_e2e(args, cfg, K, frames, model, mvol, local, params, fg, dev, rank, world, group, per_frame_units, S):
     """Same step through the public API with HOST buffers: numpy frames into moving_volume.integrate / integrate_kf
     (H2D inside), rays + targets from pinned host memory, loss read back to the host."""
     import torch.distributed as dist
@@ -702,7 +707,7 @@ def run_e2e(args, cfg, K, frames, model, mvol, local, params, dev, rank, world, 
         rays_d = (dirs[:, None, :] * c2w32[None, :3, :3]).sum(-1).astype(np.float32)
         rays_o = np.broadcast_to(c2w32[:3, 3], rays_d.shape).copy()
         pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-        host.append(dict(c2w=c2w, depth=depth, rgb=rgb, rgb255=np.floor(rgb * 255.0).astype(np.float32),
+        host.append(dict(c2w=c2w, depth=depth, rgb=rgb, rgb255=pin(np.floor(rgb * 255.0).astype(np.float32)),
                          rays_o=pin(rays_o), rays_d=pin(rays_d), tgt_c=pin(rgb.reshape(-1, 3)), tgt_d=pin(depth.reshape(-1, 1)),
                          rgb_t=pin(rgb), depth_t=pin(depth)))
     h2d = 2 * (H * W * 4 + H * W * 12) + H * W * (12 + 12 + 12 + 4)
@@ -710,8 +715,9 @@ def run_e2e(args, cfg, K, frames, model, mvol, local, params, dev, rank, world, 
 
     # Ray inputs are staged the way a caller of the public API would: pinned host tensors copied with non_blocking=True on a
     # copy stream, one step ahead, so that the 33 MB of rays / targets of step i+1 cross PCIe while step i computes.  Every
-    # step's copy is issued (and completes) inside the timed region; the TSDF frames go through the reference's numpy
-    # signature (moving_volume.integrate / integrate_kf) and are copied synchronously in there.
+    # step's copy is issued (and completes) inside the timed region; the TSDF frames go through moving_volume.integrate /
+    # integrate_kf as page-locked host tensors (one asynchronous H2D copy each inside the call; numpy arrays would be staged
+    # through the object's pinned ring first).
     copy_stream = torch.cuda.Stream(device=dev)
 
     def prefetch(i):
@@ -724,14 +730,17 @@ def run_e2e(args, cfg, K, frames, model, mvol, local, params, dev, rank, world, 
     def step(i, pre, more):
         f = host[i % len(host)]
         nxt = prefetch(i + 1) if more else None
-        local.integrate(f["rgb255"], f["depth"], K, f["c2w"], None, 1.0, 0.0)
+        local.integrate(f["rgb255"], f["depth_t"], K, f["c2w"], None, 1.0, 0.0)
         mvol.integrate_kf({"rgb": f["rgb_t"], "depth": f["depth_t"]}, torch.from_numpy(f["c2w"]).float(), 1.0)
         if world > 1:
             R = cfg["globalV"]["base_resolution"]
             sizes = [4 * (rdist.slab(R, k, world)[1] - rdist.slab(R, k, world)[0]) * R * R for k in range(world)]
-            model.GBV.params.data.copy_(rdist.gather_slabs(mvol.model.GBV.params, sizes, group))
-        for p in params:
-            p.grad = None
+            rdist.gather_slabs(mvol.model.GBV.params, sizes, group, out=model.GBV.params.data)
+        if fg is not None:
+            fg.zero()
+        else:
+            for p in params:
+                p.grad = None
         (ro, rd, tc, td), ev = pre
         cur = torch.cuda.current_stream()
         cur.wait_event(ev)
@@ -740,8 +749,8 @@ def run_e2e(args, cfg, K, frames, model, mvol, local, params, dev, rank, world, 
         ret = model.mapping(ro, rd, tc, td)
         loss = configs.total_loss(cfg, ret)
         loss.backward()
-        if world > 1:
-            rdist.allreduce_grads(params, group)
+        if fg is not None:
+            fg.allreduce(group)
         out = torch.stack([ret["rgb_res_loss"], ret["depth_res_loss"], ret["sdf_res_loss"], ret["fs_res_loss"]]).cpu()
         return out, nxt
 

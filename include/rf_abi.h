@@ -58,6 +58,7 @@ int rf_tsdf_integrate_local(float* tsdf, float* weight, float* color,       /* d
                             const float old_bnd[6],                          /* host; may be NULL if !reintegrate */
                             int x0, int x1, int slab_local,
                             const float* rcp_lambda,                         /* device [H*W] from rf_tsdf_pixel_lambda, or NULL */
+                            const float* depth_max,                          /* device scalar from rf_tsdf_depth_max, or NULL */
                             void* stream);
 
 /* N2 — re-centring of the moving volume when the camera leaves it.  Replaces `copy_volume` +
@@ -137,7 +138,13 @@ int rf_tsdf_integrate_global(float* trgb, float* wgt,                        /* 
                              float trunc_margin, float obs_weight,
                              int z0, int z1, int slab_local,
                              const float* rcp_lambda,                        /* device [H*W] or NULL (see above) */
+                             const float* depth_max,                         /* device scalar or NULL (rf_tsdf_depth_max) */
                              void* stream);
+
+/* Largest depth of the frame -> depth_max (device scalar).  Passing it to the integrate calls adds a far plane to the row
+ * clip: no voxel farther than (depth_max + trunc)(1 + 0.5/fx + 0.5/fy) from the camera plane can pass the reference's
+ * `sdf >= -trunc` test, so the sweep stops behind the farthest surface.  Results are identical with and without it. */
+int rf_tsdf_depth_max(const float* depth, int64_t n, float* depth_max, void* stream);
 
 /* mp_slam/mapper.py:161-183 + :267-282 (`clean_tsdf` / init_mapvolume): trgb[v] = (1,0,0,0). */
 int rf_tsdf_clear_global(float* trgb, int64_t n_voxels, void* stream);

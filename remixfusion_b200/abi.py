@@ -120,6 +120,19 @@ def pixel_lambda(K, H, W, device):
     return t
 
 
+# The far plane of the TSDF row clip needs the frame's largest depth: a pre-pass of two tiny launches (~6 us).  It pays off
+# when sweeping the part of the volume behind the farthest surface costs more than that — large volumes (BS3D-scale GBV, the
+# shipped 1 cm Replica volume); below this many owned voxels the integrate calls run without it.
+FAR_PLANE_MIN_VOXELS = 1 << 26
+
+
+def depth_max(depth):
+    """Largest depth of a frame as a device scalar (rf_tsdf_depth_max): the far plane of the TSDF row clip."""
+    out = torch.empty(1, dtype=torch.float32, device=depth.device)
+    check(lib().rf_tsdf_depth_max(dptr(depth), C.c_int64(depth.numel()), dptr(out), stream_ptr()), "rf_tsdf_depth_max")
+    return out
+
+
 def farr(values, n=None):
     a = np.ascontiguousarray(np.asarray(values, dtype=np.float32).reshape(-1))
     if n is not None and a.size != n:

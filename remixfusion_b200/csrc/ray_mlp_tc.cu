@@ -111,38 +111,26 @@ __device__ __forceinline__ float cdf_u(float u) {
 // OneBlob of one coordinate (model/encodings.py:65-76; Appendix B7) into chunks c, c+1 of row m.  The quartic kernel
 // has support +-1/16, so only the bin holding x and its two neighbours are non-zero: inside [-0.9, 1.9] (where the
 // three periodic copies of Appendix B7 cover the support) the 16 bins are three values; elsewhere the general form.
-// The row is BUILT IN REGISTERS and written with four 16-byte stores: the three bins b-1, b, b+1 (mod 16) always fall
-// into two adjacent 32-bit words of the row's eight (a word = two bf16 bins), so each word is a two-way select.  (Writing
-// the three values as 2-byte stores at data-dependent columns cost a 4-way bank conflict each: rows m, m+8, m+16, m+24
-// of a warp share their banks in the chunked layout.)
 __device__ __forceinline__ void stage_oneblob(float x, unsigned char* hi, unsigned char* lo, int m, int c) {
     if (x > -0.9f && x < 1.9f) {
+        stage_zero(hi, lo, m, c); stage_zero(hi, lo, m, c + 1);
         float xw = x - floorf(x);
         if (xw >= 1.0f) xw = 0.0f;
         float t = xw * (float)kNB;
         int b = (int)t;
         float ub = (float)b - t;
         float cb = cdf_u(ub), cb1 = cdf_u(ub + 1.0f);
-        const float vm = cb, vb = cb1 - cb, vp = 1.0f - cb1;            // bins b-1, b, b+1
-        __nv_bfloat16 hm, lm, hb, lb, hp, lp;
-        split_bf16(vm, hm, lm); split_bf16(vb, hb, lb); split_bf16(vp, hp, lp);
-        const uint32_t hm_ = __bfloat16_as_ushort(hm), hb_ = __bfloat16_as_ushort(hb), hp_ = __bfloat16_as_ushort(hp);
-        const uint32_t lm_ = __bfloat16_as_ushort(lm), lb_ = __bfloat16_as_ushort(lb), lp_ = __bfloat16_as_ushort(lp);
-        // b odd : word (b-1)/2 = (bin b-1 | bin b << 16), next word = (bin b+1)
-        // b even: word b/2 - 1 = (bin b-1 << 16),          next word = (bin b | bin b+1 << 16)
-        const bool odd = b & 1;
-        const uint32_t wa_h = odd ? (hm_ | (hb_ << 16)) : (hm_ << 16), wb_h = odd ? hp_ : (hb_ | (hp_ << 16));
-        const uint32_t wa_l = odd ? (lm_ | (lb_ << 16)) : (lm_ << 16), wb_l = odd ? lp_ : (lb_ | (lp_ << 16));
-        const int wa = ((b - 1) >> 1) & 7, wb = (wa + 1) & 7;
-        uint32_t h[8], l[8];
-#pragma unroll
-        for (int w = 0; w < 8; ++w) {
-            h[w] = (w == wa) ? wa_h : (w == wb) ? wb_h : 0u;
-            l[w] = (w == wa) ? wa_l : (w == wb) ? wb_l : 0u;
-        }
-        const uint32_t o0 = chunk_off(128, m, c), o1 = chunk_off(128, m, c + 1);
-        *reinterpret_cast<uint4*>(hi + o0) = make_uint4(h[0], h[1], h[2], h[3]); *reinterpret_cast<uint4*>(hi + o1) = make_uint4(h[4], h[5], h[6], h[7]);
-        *reinterpret_cast<uint4*>(lo + o0) = make_uint4(l[0], l[1], l[2], l[3]); *reinterpret_cast<uint4*>(lo + o1) = make_uint4(l[4], l[5], l[6], l[7]);
+        const int km = (b - 1) & (kNB - 1), kp = (b + 1) & (kNB - 1);
+        __nv_bfloat16 h, l;
+        split_bf16(cb, h, l);
+        uint32_t o = chunk_off(128, m, c + (km >> 3)) + (uint32_t)(km & 7) * 2u;
+        *reinterpret_cast<__nv_bfloat16*>(hi + o) = h; *reinterpret_cast<__nv_bfloat16*>(lo + o) = l;
+        split_bf16(cb1 - cb, h, l);
+        o = chunk_off(128, m, c + (b >> 3)) + (uint32_t)(b & 7) * 2u;
+        *reinterpret_cast<__nv_bfloat16*>(hi + o) = h; *reinterpret_cast<__nv_bfloat16*>(lo + o) = l;
+        split_bf16(1.0f - cb1, h, l);
+        o = chunk_off(128, m, c + (kp >> 3)) + (uint32_t)(kp & 7) * 2u;
+        *reinterpret_cast<__nv_bfloat16*>(hi + o) = h; *reinterpret_cast<__nv_bfloat16*>(lo + o) = l;
     } else {
         float ob[kNB];
         oneblob_coord<kNB>(x, ob);

@@ -96,7 +96,8 @@ class MapVolume:
             c_p, C.c_int(on_dev), abi.dptr(depth_im), abi.dptr(color_im), C.c_int(im_h), C.c_int(im_w),
             C.c_float(self.trunc_margin), C.c_float(obs_weight),
             C.c_int(self.z_slab[0]), C.c_int(self.z_slab[1]), C.c_int(self.slab_local),
-            abi.dptr(abi.pixel_lambda(_k, im_h, im_w, dev)), abi.stream_ptr())
+            abi.dptr(abi.pixel_lambda(_k, im_h, im_w, dev)),
+            abi.dptr(abi.depth_max(depth_im) if self._n_own() >= abi.FAR_PLANE_MIN_VOXELS else None), abi.stream_ptr())
         abi.check(rc, "rf_tsdf_integrate_global")
 
     def count_touched(self, depth_im, pose, obs_weight=1.0):

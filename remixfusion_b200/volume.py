@@ -169,6 +169,10 @@ class moving_volume:
         overwrite a frame that is still in flight (the reference's ``cuda.In`` copies were synchronous, model/Volume.py:733-749)."""
         if isinstance(arr, torch.Tensor) and arr.is_cuda:
             return arr.to(torch.float32).contiguous()
+        if isinstance(arr, torch.Tensor) and arr.is_pinned() and arr.dtype == torch.float32 and arr.is_contiguous():
+            # already page-locked: one asynchronous copy, no staging pass over the frame on the host (the caller keeps the
+            # tensor unchanged until the stream has consumed it, as with any non_blocking copy)
+            return arr.to(self.device, non_blocking=True)
         a = arr.numpy() if isinstance(arr, torch.Tensor) else np.asarray(arr)
         a = np.ascontiguousarray(a, dtype=np.float32)
         if self._frame is None:
@@ -241,7 +245,8 @@ class moving_volume:
             C.c_float(self.trunc_margin), C.c_float(obs_weight),
             C.c_int(1 if float(self.weight_clamp) == 1.0 else 0), C.c_int(reint), b_p,
             C.c_int(self.x_slab[0]), C.c_int(self.x_slab[1]), C.c_int(1),
-            abi.dptr(abi.pixel_lambda(_k, im_h, im_w, depth.device)), abi.stream_ptr())
+            abi.dptr(abi.pixel_lambda(_k, im_h, im_w, depth.device)),
+            abi.dptr(abi.depth_max(depth) if self.tsdf_vol_gpu.numel() >= abi.FAR_PLANE_MIN_VOXELS else None), abi.stream_ptr())
         abi.check(rc, "rf_tsdf_integrate_local")
 
     def count_touched(self, depth, cam_intr, cam_pose, old_bnd=None, reintegrate_flag=0.0):

@@ -48,3 +48,52 @@ def test_graphed_iteration_matches_eager(cuda, rf_lib):
     for pe, pg in zip(m_e.parameters(), m_g.parameters()):
         if pe.requires_grad:
             torch.testing.assert_close(pg, pe, rtol=1e-3, atol=2e-5)
+
+
+def test_smoothness_matches_oracle_and_is_capturable(cuda, rf_lib):
+    """The feature-grid smoothness term (mp_slam/slam.py:193-217): value and hash-table gradient vs the stand-in encoder on the
+    CPU with the same two random draws; then an iteration whose loss includes it runs inside the captured graph (device-side
+    draws) and keeps reducing the same kind of loss as the eager loop."""
+    from oracle.ray_oracle import hash_standin
+    from remixfusion_b200.losses import Smoothness, make_loss_fn
+    cfg, m, opt = _make(cuda, True)
+    cfg["training"].update(smooth_weight=0.001, smooth_pts=24, smooth_vox=0.1, smooth_margin=0.05)
+    sm = Smoothness(m, 24, 0.1, 0.05)
+    g = torch.Generator().manual_seed(5)
+    r3 = torch.rand(3, generator=g); r1 = torch.rand((1, 1, 1, 3), generator=g)
+    with torch.no_grad():
+        m.embed_res_fn.params.copy_((torch.rand_like(m.embed_res_fn.params) * 2 - 1) * 0.05)
+    m.embed_res_fn.params.grad = None
+    val = sm(r3.to(cuda), r1.to(cuda))
+    val.backward()
+    val = float(val)            # drop the autograd graph: it holds the table's gradient accumulator, created on the default stream,
+                                # and a capture on a side stream must not be made to synchronise with that stream
+    # CPU restatement with the stand-in hash grid
+    h = hash_standin(cfg)
+    with torch.no_grad():
+        h.params.copy_(m.embed_res_fn.params.cpu())
+    bb = torch.tensor(cfg["mapping"]["bound"], dtype=torch.float64)
+    vol = bb[:, 1] - bb[:, 0]
+    off = r3.to(vol) * (vol - 23 * 0.1 - 2 * 0.05) + 0.05
+    ax = torch.arange(0, 23)
+    coords = torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), -1).float()
+    pts = (coords.to(vol) + r1.to(vol)) * 0.1 + bb[:, 0] + off
+    f = h(((pts - bb[:, 0]) / vol).reshape(-1, 3).float()).reshape(23, 23, 23, -1)
+    ref = (torch.pow(f[1:] - f[:-1], 2).sum() + torch.pow(f[:, 1:] - f[:, :-1], 2).sum() + torch.pow(f[:, :, 1:] - f[:, :, :-1], 2).sum()) / 24 ** 3
+    ref.backward()
+    assert abs(float(val) - float(ref)) <= 1e-4 * abs(float(ref)), (float(val), float(ref))
+    gc, gr = m.embed_res_fn.params.grad.cpu(), h.params.grad
+    assert float((gc - gr).norm()) <= 1e-3 * float(gr.norm())
+    # captured iteration with the smoothness term inside
+    n = 2048
+    m.embed_res_fn.params.grad = None
+    step = GraphedMappingStep(m, opt, n, make_loss_fn(cfg, m), eager_steps=2)
+    b = torch.tensor(cfg["mapping"]["bound"])
+    losses = []
+    for it in range(6):
+        ro = (b[:, 0] + (0.3 + 0.4 * torch.rand(n, 3, generator=g)) * (b[:, 1] - b[:, 0])).to(cuda)
+        rd = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1).to(cuda)
+        tc = torch.rand(n, 3, generator=g).to(cuda); td = (0.3 + 2.5 * torch.rand(n, 1, generator=g)).to(cuda)
+        loss, _ = step(ro, rd, tc, td)
+        losses.append(float(loss))
+    assert step.graph is not None and all(np.isfinite(losses))

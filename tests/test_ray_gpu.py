@@ -518,11 +518,12 @@ def test_render_rays_without_depth_prior_and_raw2outputs(cuda, rf_lib):
     cfg, m = _model_from_golden("C", cuda)
     cfg["training"]["n_samples"] = 40
     _, orc = R.oracle_from_golden(G, "C", requires_grad=False)
-    ro = torch.from_numpy(G["in_rays_o"][:300]); rd = torch.from_numpy(G["in_rays_d"][:300])
+    ro = torch.from_numpy(G["in_rays_o"]); rd = torch.from_numpy(G["in_rays_d"])
+    n = ro.shape[0]
     m.eval()
     with torch.no_grad():
         ret = m.render_rays(ro.to(cuda), rd.to(cuda), target_d=None)
-        z = torch.linspace(cfg["cam"]["near"], cfg["cam"]["far"], 40)[None, :].repeat(300, 1)
+        z = torch.linspace(cfg["cam"]["near"], cfg["cam"]["far"], 40)[None, :].repeat(n, 1)
         assert torch.equal(ret["z_vals"].cpu(), z)
         raw = orc.run_network(ro[..., None, :] + rd[..., None, :] * z[..., :, None])
         rgb, dep = orc.raw2outputs(raw, z)

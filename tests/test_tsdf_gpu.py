@@ -72,7 +72,12 @@ def _run_local(cuda, rf_lib, cam, lens, voxel, poses_frames, clamp=1.0, trunc=0.
     return n_touched_total
 
 
-def test_local_small_multi_frame(cuda, rf_lib):
+@pytest.mark.parametrize("far_plane", [False, True])
+def test_local_small_multi_frame(cuda, rf_lib, monkeypatch, far_plane):
+    """far_plane=True forces the far plane of the row clip (rf_tsdf_depth_max; normally only on volumes of >= 2^26 voxels):
+    the sweep then stops behind the farthest surface, and every output must still equal the reference kernel's bit for bit."""
+    from remixfusion_b200 import abi
+    monkeypatch.setattr(abi, "FAR_PLANE_MIN_VOXELS", 0 if far_plane else 1 << 62)
     cam = T.small_cam(4)
     bound = [[-3, 3], [-3, 3], [-2, 2]]
     rng = np.random.default_rng(1)
@@ -85,8 +90,11 @@ def test_local_small_multi_frame(cuda, rf_lib):
     _run_local(cuda, rf_lib, cam, (3, 3, 2), 0.05, frames)
 
 
-def test_local_cfg1_256cube(cuda, rf_lib):
+@pytest.mark.parametrize("far_plane", [False, True])
+def test_local_cfg1_256cube(cuda, rf_lib, monkeypatch, far_plane):
     """BASELINE config 1: one 640x480 frame into a 256^3 volume (voxel 6/256)."""
+    from remixfusion_b200 import abi
+    monkeypatch.setattr(abi, "FAR_PLANE_MIN_VOXELS", 0 if far_plane else 1 << 62)
     cam = synth.CFG1_CAM
     K, c2w, depth, rgb = T.frame(cam, [[-3, 3], [-3, 3], [-3, 3]], [0.2, 0.1, 0.3], [2.5, 1.0, 0.2])
     nt = _run_local(cuda, rf_lib, cam, (3, 3, 3), 6.0 / 256, [(K, c2w, depth, rgb)])
@@ -159,7 +167,14 @@ def test_global_replica_200(cuda, rf_lib):
     assert n > 100000
 
 
-def test_global_small_random_poses(cuda, rf_lib):
+@pytest.mark.parametrize("far_plane", [False, True])
+def test_global_small_random_poses(cuda, rf_lib, monkeypatch, far_plane):
+    from remixfusion_b200 import abi
+    monkeypatch.setattr(abi, "FAR_PLANE_MIN_VOXELS", 0 if far_plane else 1 << 62)
+    _global_small_random_poses(cuda, rf_lib)
+
+
+def _global_small_random_poses(cuda, rf_lib):
     cam = T.small_cam(4)
     bound = [[-2.0, 2.5], [-1.5, 2.0], [-1.0, 1.7]]
     rng = np.random.default_rng(11)
