@@ -83,6 +83,45 @@ __device__ void load_weights(unsigned char* w, const Weights& wt, int nthreads) 
     }
 }
 
+// Forward-only layout: the hi and lo parts of a weight matrix form ONE B operand of twice the rows ([hi rows | lo rows] inside
+// every 8-column chunk).  A k-step is then two MMAs instead of three:  A_hi x [W_hi | W_lo]  (N = 2 rows: columns [0, rows) hold
+// hi*hi, columns [rows, 2 rows) hi*lo)  and  A_lo x W_hi  (N = rows, same start address: the hi rows come first in a chunk);
+// the epilogue adds the two column blocks.  Same three products as the bf16x3 scheme, 2/3 of the A-operand reads.
+template <int HID>
+struct WLC {
+    static constexpr int HC = HID / 8;
+    static constexpr int o_w0 = 0, o_w1 = o_w0 + kXCh * 2 * HID * 16, o_w2 = o_w1 + HC * 32 * 16, o_w3 = o_w2 + 10 * 2 * HID * 16;
+    static constexpr int total = o_w3 + HC * 32 * 16;
+};
+__device__ __forceinline__ void store_split_cat(unsigned char* w, int rows, int r, int kx, float v) {
+    __nv_bfloat16 h, l; split_bf16(v, h, l);
+    const uint32_t col = (uint32_t)(kx & 7) * 2u;
+    *reinterpret_cast<__nv_bfloat16*>(w + chunk_off(2 * rows, r, kx >> 3) + col) = h;
+    *reinterpret_cast<__nv_bfloat16*>(w + chunk_off(2 * rows, rows + r, kx >> 3) + col) = l;
+}
+template <int HID>
+__device__ void load_weights_cat(unsigned char* w, const Weights& wt, int nthreads) {
+    using L = WLC<HID>;
+    constexpr int in1 = 81;
+    for (int i = threadIdx.x; i < HID * kKX; i += nthreads) {
+        int j = i / kKX, kx = i - j * kKX;
+        float v = 0.f;
+        if (kx < 32) v = wt.w_sdf0[j * in1 + hash_col_to_feature(kx)];
+        else if (kx < 80) v = wt.w_sdf0[j * in1 + kx];
+        else if (kx == 80 + kTailTsdf) v = wt.w_sdf0[j * in1 + 80];
+        store_split_cat(w + L::o_w0, HID, j, kx, v);
+    }
+    for (int i = threadIdx.x; i < 16 * HID; i += nthreads) {
+        int r = i / HID, j = i - r * HID;
+        store_split_cat(w + L::o_w1, 16, r, j, wt.w_sdf1[r * HID + j]);
+        store_split_cat(w + L::o_w3, 16, r, j, (r < 3) ? wt.w_col1[r * HID + j] : 0.f);
+    }
+    for (int i = threadIdx.x; i < HID * 80; i += nthreads) {
+        int j = i / 80, kx = i - j * 80;
+        store_split_cat(w + L::o_w2, HID, j, kx, (kx < kIn2) ? wt.w_col0[j * kIn2 + kx] : 0.f);
+    }
+}
+
 __device__ __forceinline__ void grp_sync(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
 
 __device__ __forceinline__ void grp_wait(uint64_t* bar, uint32_t& phase) {
@@ -240,13 +279,39 @@ __device__ __forceinline__ void prefetch_tile(const float* __restrict__ feat, lo
 // data-dependent columns).  TMEM columns of a group: accumulator [0,HID) (H, then O/rgb aliased on [0,16)),
 // hash hi/lo 16+16, tail hi/lo 16+16, hidden hi/lo HID/2 + HID/2.
 // ------------------------------------------------------------------------------------------------------------
-template <int HID>
+template <int HID, bool CAT = false>
 struct FwdL {
     static constexpr int c_blob_hi = 0, c_blob_lo = 6, chunks = 12;     // shared memory per group: OneBlob hi / lo
     static constexpr int bytes = chunks * kChunkB;
-    static constexpr int t_acc = 0, t_hash_hi = HID, t_hash_lo = HID + 16, t_tail_hi = HID + 32, t_tail_lo = HID + 48,
-                         t_h_hi = HID + 64, t_h_lo = HID + 64 + HID / 2, tcols = 2 * HID + 64;
+    // CAT (concatenated hi / lo weights, see WLC): the accumulator is 2 HID wide; at hidden 32 the hidden operand aliases its
+    // upper half (written only after both halves have been read back), at hidden 64 it has its own columns
+    static constexpr int AW = CAT ? 2 * HID : HID;
+    static constexpr int t_acc = 0, t_hash_hi = AW, t_hash_lo = AW + 16, t_tail_hi = AW + 32, t_tail_lo = AW + 48,
+                         t_h_hi = (CAT && HID == 32) ? HID : AW + 64, t_h_lo = t_h_hi + HID / 2,
+                         tcols = (CAT && HID == 32) ? AW + 64 : AW + 64 + HID;
 };
+
+// CAT k-steps: A from TMEM (hi at ah, lo at al) or from shared memory; B = concatenated weights at `b` (WLC), `rows` per part
+template <int NKS>
+__device__ __forceinline__ void mma_ts_cat(uint32_t d, uint32_t ah, uint32_t al, uint32_t b, int rows, uint32_t id2n, uint32_t idn, uint32_t& acc) {
+    uint64_t db = smem_desc(b, 2 * rows * 16, 128);
+#pragma unroll
+    for (int s = 0; s < NKS; ++s) {
+        mma_bf16_ts(d, ah + 8 * s, db, id2n, acc); acc = 1;
+        mma_bf16_ts(d, al + 8 * s, db, idn, 1);
+        db = desc_advance(db, 2 * 2 * rows * 16);
+    }
+}
+template <int NKS>
+__device__ __forceinline__ void mma_kk_cat(uint32_t d, uint32_t ah, uint32_t al, uint32_t b, int rows, uint32_t id2n, uint32_t idn, uint32_t& acc) {
+    uint64_t dah = smem_desc(ah, kChunkB, 128), dal = smem_desc(al, kChunkB, 128), db = smem_desc(b, 2 * rows * 16, 128);
+#pragma unroll
+    for (int s = 0; s < NKS; ++s) {
+        mma_bf16(d, dah, db, id2n, acc); acc = 1;
+        mma_bf16(d, dal, db, idn, 1);
+        dah = desc_advance(dah, 2 * kChunkB); dal = desc_advance(dal, 2 * kChunkB); db = desc_advance(db, 2 * 2 * rows * 16);
+    }
+}
 
 // A from TMEM (hi at column ah, lo at column al, 8 columns per k-step); B = weights K-major
 template <int NKS>
@@ -283,13 +348,28 @@ __device__ __forceinline__ void relu_to_tmem(uint32_t tacc, uint32_t th, uint32_
     }
 }
 
-template <int HID, int G>
+// CAT: hidden pre-activation = columns [0, HID) + columns [HID, 2 HID) of the accumulator
+template <int HID>
+__device__ __forceinline__ void relu_cat_to_tmem(uint32_t tacc, uint32_t th, uint32_t tl) {
+#pragma unroll
+    for (int q = 0; q < HID / 32; ++q) {
+        float v[32], u[32];
+        tmem_ld32(tacc + 32 * q, v);
+        tmem_ld32(tacc + HID + 32 * q, u);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + u[i], 0.f);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tstage8(th, tl, 4 * q + c, v + 8 * c);
+    }
+}
+
+template <int HID, int G, bool CAT>
 __global__ void __launch_bounds__(G * 128, 1) mlp_fwd_tc_kernel(RayK k, Weights wts, const float* __restrict__ feat, long long P,
                                                                 int variant, float* __restrict__ raw) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint64_t bars[G];
     __shared__ uint32_t tmem_base_s;
-    using W = WL<HID>; using A = FwdL<HID>;
+    using W = WL<HID>; using WC = WLC<HID>; using A = FwdL<HID, CAT>;
     constexpr int HC = HID / 8;
     constexpr uint32_t TCOLS = (G * A::tcols <= 128) ? 128 : (G * A::tcols <= 256) ? 256 : 512;
     static_assert(G * A::tcols <= 512, "TMEM columns");
@@ -298,7 +378,7 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_fwd_tc_kernel(RayK k, Weights 
     unsigned char* act = smem + g * A::bytes;
     if (warp == 0) tmem_alloc(&tmem_base_s, TCOLS);
     if (tid == 0) { for (int i = 0; i < G; ++i) mbar_init(&bars[i], 1); fence_mbar_init(); }
-    load_weights<HID>(wsm, wts, G * 128);
+    if (CAT) load_weights_cat<HID>(wsm, wts, G * 128); else load_weights<HID>(wsm, wts, G * 128);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -311,6 +391,8 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_fwd_tc_kernel(RayK k, Weights 
     const uint32_t w0h = smem_u32(wsm + W::o_w0h), w0l = smem_u32(wsm + W::o_w0l), w1h = smem_u32(wsm + W::o_w1h), w1l = smem_u32(wsm + W::o_w1l);
     const uint32_t w2h = smem_u32(wsm + W::o_w2h), w2l = smem_u32(wsm + W::o_w2l), w3h = smem_u32(wsm + W::o_w3h), w3l = smem_u32(wsm + W::o_w3l);
     constexpr uint32_t idH = idesc_bf16(HID, false, false), id16 = idesc_bf16(16, false, false);
+    constexpr uint32_t id2H = idesc_bf16(2 * HID, false, false), id32 = idesc_bf16(32, false, false);
+    const uint32_t c0 = smem_u32(wsm + WC::o_w0), c1 = smem_u32(wsm + WC::o_w1), c2 = smem_u32(wsm + WC::o_w2), c3 = smem_u32(wsm + WC::o_w3);   // CAT
 
     // Inputs are software-pipelined through their own registers: a tile's features and positions are dead once its X row
     // is staged, so the same registers are reloaded with the NEXT tile's inputs right away and those loads are in flight
@@ -350,24 +432,37 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_fwd_tc_kernel(RayK k, Weights 
         if (m == 0) {                                                                         // H1 = X1 W0^T
             fence_after_sync();
             uint32_t acc = 0;
-            mma_ts<2>(tb + A::t_acc, tb + A::t_hash_hi, tb + A::t_hash_lo, w0h, w0l, HID, idH, acc);
-            mma_kk<3>(tb + A::t_acc, smem_u32(blob_hi), smem_u32(blob_lo), w0h + kXBlob * HID * 16, w0l + kXBlob * HID * 16, HID, idH, acc);
-            mma_ts<2>(tb + A::t_acc, tb + A::t_tail_hi, tb + A::t_tail_lo, w0h + kXTail * HID * 16, w0l + kXTail * HID * 16, HID, idH, acc);
+            if (CAT) {
+                mma_ts_cat<2>(tb + A::t_acc, tb + A::t_hash_hi, tb + A::t_hash_lo, c0, HID, id2H, idH, acc);
+                mma_kk_cat<3>(tb + A::t_acc, smem_u32(blob_hi), smem_u32(blob_lo), c0 + kXBlob * 2 * HID * 16, HID, id2H, idH, acc);
+                mma_ts_cat<2>(tb + A::t_acc, tb + A::t_tail_hi, tb + A::t_tail_lo, c0 + kXTail * 2 * HID * 16, HID, id2H, idH, acc);
+            } else {
+                mma_ts<2>(tb + A::t_acc, tb + A::t_hash_hi, tb + A::t_hash_lo, w0h, w0l, HID, idH, acc);
+                mma_kk<3>(tb + A::t_acc, smem_u32(blob_hi), smem_u32(blob_lo), w0h + kXBlob * HID * 16, w0l + kXBlob * HID * 16, HID, idH, acc);
+                mma_ts<2>(tb + A::t_acc, tb + A::t_tail_hi, tb + A::t_tail_lo, w0h + kXTail * HID * 16, w0l + kXTail * HID * 16, HID, idH, acc);
+            }
             commit(bar);
         }
         grp_wait(bar, phase);
-        relu_to_tmem<HID>(tlane + A::t_acc, tlane + A::t_h_hi, tlane + A::t_h_lo);            // decoder.py:105-107
+        if (CAT) relu_cat_to_tmem<HID>(tlane + A::t_acc, tlane + A::t_h_hi, tlane + A::t_h_lo);
+        else relu_to_tmem<HID>(tlane + A::t_acc, tlane + A::t_h_hi, tlane + A::t_h_lo);       // decoder.py:105-107
         tmem_st_wait();
         fence_before_sync(); grp_sync(g);
         if (m == 0) {                                                                         // O = H1 W1^T
             fence_after_sync();
             uint32_t acc = 0;
-            mma_ts<HC / 2>(tb + A::t_acc, tb + A::t_h_hi, tb + A::t_h_lo, w1h, w1l, 16, id16, acc);
+            if (CAT) mma_ts_cat<HC / 2>(tb + A::t_acc, tb + A::t_h_hi, tb + A::t_h_lo, c1, 16, id32, id16, acc);
+            else mma_ts<HC / 2>(tb + A::t_acc, tb + A::t_h_hi, tb + A::t_h_lo, w1h, w1l, 16, id16, acc);
             commit(bar);
         }
         grp_wait(bar, phase);
         float o16[16];
-        tmem_ld16(tlane + A::t_acc, o16);
+        if (CAT) {
+            float o32[32];
+            tmem_ld32(tlane + A::t_acc, o32);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o16[i] = o32[i] + o32[16 + i];
+        } else tmem_ld16(tlane + A::t_acc, o16);
         const float sdf = o16[0] + t_add;                                                     // scene_rep.py:345
         {                                                                                     // geo15 into the tail
             float v0[8], v1[8];
@@ -384,22 +479,34 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_fwd_tc_kernel(RayK k, Weights 
         if (m == 0) {                                                                         // H2 = X2 W2^T
             fence_after_sync();
             uint32_t acc = 0;
-            mma_kk<3>(tb + A::t_acc, smem_u32(blob_hi), smem_u32(blob_lo), w2h, w2l, HID, idH, acc);
-            mma_ts<2>(tb + A::t_acc, tb + A::t_tail_hi, tb + A::t_tail_lo, w2h + 6 * HID * 16, w2l + 6 * HID * 16, HID, idH, acc);
+            if (CAT) {
+                mma_kk_cat<3>(tb + A::t_acc, smem_u32(blob_hi), smem_u32(blob_lo), c2, HID, id2H, idH, acc);
+                mma_ts_cat<2>(tb + A::t_acc, tb + A::t_tail_hi, tb + A::t_tail_lo, c2 + 6 * 2 * HID * 16, HID, id2H, idH, acc);
+            } else {
+                mma_kk<3>(tb + A::t_acc, smem_u32(blob_hi), smem_u32(blob_lo), w2h, w2l, HID, idH, acc);
+                mma_ts<2>(tb + A::t_acc, tb + A::t_tail_hi, tb + A::t_tail_lo, w2h + 6 * HID * 16, w2l + 6 * HID * 16, HID, idH, acc);
+            }
             commit(bar);
         }
         grp_wait(bar, phase);
-        relu_to_tmem<HID>(tlane + A::t_acc, tlane + A::t_h_hi, tlane + A::t_h_lo);            // decoder.py:49-51
+        if (CAT) relu_cat_to_tmem<HID>(tlane + A::t_acc, tlane + A::t_h_hi, tlane + A::t_h_lo);
+        else relu_to_tmem<HID>(tlane + A::t_acc, tlane + A::t_h_hi, tlane + A::t_h_lo);       // decoder.py:49-51
         tmem_st_wait();
         fence_before_sync(); grp_sync(g);
         if (m == 0) {                                                                         // rgb = H2 W3^T
             fence_after_sync();
             uint32_t acc = 0;
-            mma_ts<HC / 2>(tb + A::t_acc, tb + A::t_h_hi, tb + A::t_h_lo, w3h, w3l, 16, id16, acc);
+            if (CAT) mma_ts_cat<HC / 2>(tb + A::t_acc, tb + A::t_h_hi, tb + A::t_h_lo, c3, 16, id32, id16, acc);
+            else mma_ts<HC / 2>(tb + A::t_acc, tb + A::t_h_hi, tb + A::t_h_lo, w3h, w3l, 16, id16, acc);
             commit(bar);
         }
         grp_wait(bar, phase);
-        tmem_ld16(tlane + A::t_acc, o16);
+        if (CAT) {
+            float o32[32];
+            tmem_ld32(tlane + A::t_acc, o32);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) o16[i] = o32[i] + o32[16 + i];
+        } else tmem_ld16(tlane + A::t_acc, o16);
         if (live) reinterpret_cast<float4*>(raw)[p] = make_float4(o16[0] + gb.y, o16[1] + gb.z, o16[2] + gb.w, sdf);   // :344-345
         fence_before_sync();
     }
@@ -913,12 +1020,14 @@ __global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights
     if (warp == 0) tmem_dealloc(tmem_base_s, TCOLS);
 }
 
-template <int HID, int G> static size_t fwd_bytes() { return (size_t)G * FwdL<HID>::bytes + WL<HID>::total; }
+template <int HID, int G> static size_t fwd_bytes() { static_assert(WLC<HID>::total == WL<HID>::total, "weight layouts"); return (size_t)G * FwdL<HID>::bytes + WL<HID>::total; }
 template <int HID, int G> static size_t bwd_bytes() { return (size_t)G * BwdL<HID>::bytes + WL<HID>::total; }
 
 template <int HID, int G>
 static int launch_fwd_g(const RayK& k, const Weights& w, const float* feat, long long P, int variant, float* raw, cudaStream_t s) {
-    auto fn = mlp_fwd_tc_kernel<HID, G>;
+    // RF_FWD_CAT=0 selects the three-MMA k-steps (separate hi / lo weight operands); default: concatenated weights, two MMAs
+    static const bool cat = [] { const char* e = getenv("RF_FWD_CAT"); return e ? atoi(e) != 0 : true; }();
+    auto fn = cat ? mlp_fwd_tc_kernel<HID, G, true> : mlp_fwd_tc_kernel<HID, G, false>;
     size_t sm = fwd_bytes<HID, G>();
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return set_error((int)e, "cudaFuncSetAttribute(mlp_fwd_tc, %zu B): %s", sm, cudaGetErrorString(e));

@@ -375,6 +375,7 @@ class JointEncoding(nn.Module):
         rgb_map = torch.empty(n, 3, dtype=torch.float32, device=raw.device)
         depth_map = torch.empty(n, dtype=torch.float32, device=raw.device)
         cfg = self._ray_cfg()
+        cfg.n_range_d, cfg.n_samples_d = int(z.shape[1]), 0          # samples per ray as given (one group)
         abi.check(abi.lib().rf_ray_composite(C.byref(cfg), abi.dptr(raw), abi.dptr(z), C.c_int64(n), abi.dptr(rgb_map), abi.dptr(depth_map),
                                              abi.stream_ptr()), "rf_ray_composite")
         return rgb_map, depth_map
