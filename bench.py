@@ -408,6 +408,29 @@ def run_gpu(args, rank, world, local_rank):
     # ---- e2e: public API with HOST buffers, H2D/D2H inside the timed region ----------------------------------------
     e2e = run_e2e(args, cfg, K, frames, model, mvol, local, params, fg, dev, rank, world, group, per_frame_units, S)
 
+    # ---- the step's collectives timed on their own (events on the launching stream, max over ranks): what the N > 1 step adds ----
+    comm_ms = None
+    if world > 1:
+        def _t(fn, iters=10):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize(); dist.barrier()
+            a_, b_ = ev(), ev()
+            a_.record()
+            for _ in range(iters):
+                fn()
+            b_.record(); torch.cuda.synchronize()
+            t_ = torch.tensor([a_.elapsed_time(b_) / iters], dtype=torch.float64, device=dev)
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX, group=group)
+            return float(t_)
+        sizes_ = [4 * (rdist.slab(R, k, world)[1] - rdist.slab(R, k, world)[0]) * R * R for k in range(world)]
+        part_ = torch.zeros(8, dtype=torch.float64, device=dev)
+        comm_ms = {"frame_broadcast": _t(lambda: rdist.broadcast_frame(bc[0]["depth"], bc[0]["rgb"], 0, group)),
+                   "gbv_slab_all_gather": _t(lambda: rdist.gather_slabs(mvol.model.GBV.params, sizes_, group, out=full_gbv.params.data)),
+                   "loss_sums_all_reduce": _t(lambda: dist.all_reduce(part_, group=group)),
+                   "grad_all_reduce": _t(lambda: fg.allreduce(group)),
+                   "bytes": {"frame": int(16 * H * W), "gbv": int(16 * R ** 3), "grads": int(fg.flat.numel() * 4)}}
+
     # ---- the other BASELINE configurations (bench_workloads.py), every rank takes part --------------------------------
     extra_parts = {}
     if not args.no_extra:
@@ -498,6 +521,8 @@ def run_gpu(args, rank, world, local_rank):
         "clocks": clocks,
     }
     line["parts"].update(extra_parts)
+    if comm_ms is not None:
+        line["parts"]["collectives_ms"] = comm_ms
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(cfg, K, frames[0], H * W * S, args.cpu_rays)
     print(json.dumps(line), flush=True)

@@ -22,7 +22,7 @@ WANT = ['Grid Size', 'Block Size', 'gpu__time_duration.sum', 'dram__bytes_read.s
 
 
 def short(n):
-    return n.replace('void rf::<unnamed>::', '').replace('void rf::', '').replace('rf::', '').replace('void ', '').split('(')[0][:48]
+    return n.replace('unnamed>::', '').replace('void rf::', '').replace('rf::', '').replace('void ', '').split('(')[0][:48]
 
 
 def main(src, dst):

@@ -44,8 +44,8 @@ constexpr int kEncThreads = 160;        // 4 hash-quad roles + 1 GBV role, 32 (r
 
 // Forward.  ws: the workspace of ray_common.cuh.  POINTS: z_vals holds n already-normalised positions [n][3] (point queries,
 // model/scene_rep.py:212-310): n "rays" of one sample.
-template <bool POINTS>
-__global__ void __launch_bounds__(kEncThreads, 4) encode_walk4_kernel(const __grid_constant__ RayK k, const __grid_constant__ GridDev hg,
+template <bool POINTS, int MINB = 3>
+__global__ void __launch_bounds__(kEncThreads, MINB) encode_walk4_kernel(const __grid_constant__ RayK k, const __grid_constant__ GridDev hg,
                                                                    const __grid_constant__ GridDev gg, const float* __restrict__ hash_params,
                                                                    const float* __restrict__ gbv_params, const float* __restrict__ rays_o,
                                                                    const float* __restrict__ rays_d, const float* __restrict__ z_vals,
@@ -450,11 +450,14 @@ int launch_encode(const RayK& k, const GridDev& hg, const GridDev& gg, const rf_
     const int seg = walk_segment(k.n_rays, k.S);
     const long long units = k.n_rays * ((k.S + seg - 1) / seg);
     const size_t sm = 4 * (size_t)seg * 33 * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(encode_walk4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * kMaxS * 33 * sizeof(float)));
+    // resident blocks per SM the register allocation is tuned for (RF_ENC_MINB = 3 | 4 | 5: 136 / 96 / 80 registers per thread;
+    // measured on the bench frame: 5.50 / 6.12 / 9.77 ms — no spills beats occupancy, profiles/r2f_bench_minb3.json)
+    static const int minb = [] { const char* e = getenv("RF_ENC_MINB"); return e ? atoi(e) : 3; }();
+    auto fn = minb == 4 ? encode_walk4_kernel<false, 4> : minb == 5 ? encode_walk4_kernel<false, 5> : encode_walk4_kernel<false, 3>;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * kMaxS * 33 * sizeof(float)));
     if (e != cudaSuccess) return set_error((int)e, "cudaFuncSetAttribute(encode_walk4_kernel): %s", cudaGetErrorString(e));
     ProfScope ps(RF_PROF_ENCODE, s);
-    encode_walk4_kernel<false><<<(unsigned)((units + 31) / 32), kEncThreads, sm, s>>>(k, hg, gg, p->hash_params, p->gbv_params, rays_o, rays_d,
-                                                                                    z_vals, P, seg, feat);
+    fn<<<(unsigned)((units + 31) / 32), kEncThreads, sm, s>>>(k, hg, gg, p->hash_params, p->gbv_params, rays_o, rays_d, z_vals, P, seg, feat);
     RF_CHECK_LAUNCH("encode_walk4_kernel");
     return 0;
 }

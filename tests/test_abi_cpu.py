@@ -86,3 +86,42 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(abi, "LIB_PATH", "/nonexistent/librf_b200.so")
     with pytest.raises(abi.RfError):
         abi.lib()
+
+
+def test_mapvolume_rejects_mismatched_parameter_sizes():
+    """A z-slab object must own slab-sized parameter tensors and the unsharded one the full grids: a full-size model passed
+    together with a z_slab would be written at the wrong offset (checked at construction, no device needed)."""
+    import numpy as np
+    import pytest
+    import torch
+    from remixfusion_b200 import abi
+    from remixfusion_b200.global_volume import MapVolume
+    R = 16
+    cfg = {"globalV": {"base_resolution": R}, "mapping": {"bound": [[0, 1], [0, 1], [0, 1]]}, "training": {"c_trunc": 0.1}}
+
+    def model(nvox):
+        m = type("M", (), {})(); m.GBV = type("E", (), {})(); m.GBW = type("E", (), {})()
+        m.GBV.params = torch.zeros(4 * nvox); m.GBW.params = torch.zeros(nvox)
+        return m
+    K = np.eye(3)
+    MapVolume(cfg, model(R ** 3), K)                                     # full volume, exact size
+    MapVolume(cfg, model(R ** 3 + 8), K)                                 # tcnn pads to 8 entries
+    MapVolume(cfg, model(4 * R * R), K, z_slab=(4, 8))                   # slab-sized tensors with a slab
+    with pytest.raises(abi.RfError, match="z-slab"):
+        MapVolume(cfg, model(R ** 3), K, z_slab=(4, 8))                  # full-size model + slab: refused
+    with pytest.raises(abi.RfError, match="full volume"):
+        MapVolume(cfg, model(4 * R * R), K)                              # slab-sized tensors without a slab
+    with pytest.raises(abi.RfError, match="outside"):
+        MapVolume(cfg, model(4 * R * R), K, z_slab=(14, 18))
+
+
+def test_graphed_step_needs_eager_iterations():
+    import pytest
+    import torch
+    from remixfusion_b200 import abi
+    from remixfusion_b200.graph import GraphedMappingStep
+    from remixfusion_b200.optim import Adam
+    p = torch.nn.Parameter(torch.zeros(4))
+    opt = Adam([p], capturable=True)
+    with pytest.raises(abi.RfError, match="eager_steps"):
+        GraphedMappingStep(torch.nn.Linear(2, 2), opt, 16, lambda r: 0, eager_steps=0)
