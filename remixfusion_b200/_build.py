@@ -23,6 +23,11 @@ NVCC_FLAGS = [
 ]
 
 
+def _extra_defs():
+    """Debug-only -D flags (e.g. RF_NVCC_DEFS=-DRF_MLP_TRACE); part of the build digest."""
+    return os.environ.get("RF_NVCC_DEFS", "").split()
+
+
 def _sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
@@ -34,6 +39,7 @@ def _digest() -> str:
     for f in files:
         h.update(f.encode())
         h.update(open(f, "rb").read())
+    h.update(" ".join(_extra_defs()).encode())
     return h.hexdigest()
 
 
@@ -49,7 +55,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for src in _sources():
         obj = os.path.join(obj_dir, os.path.basename(src) + ".o")
         objs.append(obj)
-        cmd = ["nvcc"] + [f for f in NVCC_FLAGS if f != "-shared"] + ["-c", "-o", obj, src]
+        cmd = ["nvcc"] + [f for f in NVCC_FLAGS if f != "-shared"] + _extra_defs() + ["-c", "-o", obj, src]
         if verbose:
             print(" ".join(cmd))
         procs.append((cmd, subprocess.Popen(cmd)))

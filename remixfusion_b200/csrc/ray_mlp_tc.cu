@@ -50,6 +50,11 @@ struct WL {                                    // weight shared-memory layout (b
     static constexpr int o_w0h = 0, o_w0l = w0, o_w1h = 2 * w0, o_w1l = o_w1h + w1, o_w2h = o_w1l + w1, o_w2l = o_w2h + w2,
                          o_w3h = o_w2l + w2, o_w3l = o_w3h + w3;
     static constexpr int total = 2 * (w0 + w1 + w2 + w3);
+    // backward only: W21 = W2[:, geo] W1[geo, :]  ([HID rows j][HID columns i]), the colour net's view of the sdf net's hidden
+    // layer (geo = H1 W1[geo]^T feeds H2 without a nonlinearity in between, model/decoder.py:138-143)
+    static constexpr int w21 = HC * HID * 16;
+    static constexpr int o_w21h = total, o_w21l = total + w21;
+    static constexpr int total_bwd = total + 2 * w21;       // (the forward carries W21 too)
 };
 
 __device__ __forceinline__ void store_split(unsigned char* hi, unsigned char* lo, int rows, int r, int kx, float v) {
@@ -83,43 +88,18 @@ __device__ void load_weights(unsigned char* w, const Weights& wt, int nthreads) 
     }
 }
 
-// Forward-only layout: the hi and lo parts of a weight matrix form ONE B operand of twice the rows ([hi rows | lo rows] inside
-// every 8-column chunk).  A k-step is then two MMAs instead of three:  A_hi x [W_hi | W_lo]  (N = 2 rows: columns [0, rows) hold
-// hi*hi, columns [rows, 2 rows) hi*lo)  and  A_lo x W_hi  (N = rows, same start address: the hi rows come first in a chunk);
-// the epilogue adds the two column blocks.  Same three products as the bf16x3 scheme, 2/3 of the A-operand reads.
+// W21[j][i] = sum_g W2[j][48 + g] W1[1 + g][i] (fp32), stored like the other weights; w1s = W1[0][:] (the sdf row) as plain fp32
 template <int HID>
-struct WLC {
-    static constexpr int HC = HID / 8;
-    static constexpr int o_w0 = 0, o_w1 = o_w0 + kXCh * 2 * HID * 16, o_w2 = o_w1 + HC * 32 * 16, o_w3 = o_w2 + 10 * 2 * HID * 16;
-    static constexpr int total = o_w3 + HC * 32 * 16;
-};
-__device__ __forceinline__ void store_split_cat(unsigned char* w, int rows, int r, int kx, float v) {
-    __nv_bfloat16 h, l; split_bf16(v, h, l);
-    const uint32_t col = (uint32_t)(kx & 7) * 2u;
-    *reinterpret_cast<__nv_bfloat16*>(w + chunk_off(2 * rows, r, kx >> 3) + col) = h;
-    *reinterpret_cast<__nv_bfloat16*>(w + chunk_off(2 * rows, rows + r, kx >> 3) + col) = l;
-}
-template <int HID>
-__device__ void load_weights_cat(unsigned char* w, const Weights& wt, int nthreads) {
-    using L = WLC<HID>;
-    constexpr int in1 = 81;
-    for (int i = threadIdx.x; i < HID * kKX; i += nthreads) {
-        int j = i / kKX, kx = i - j * kKX;
+__device__ void load_w21(unsigned char* w, float* w1s, const Weights& wt, int nthreads) {
+    using L = WL<HID>;
+    for (int i = threadIdx.x; i < HID * HID; i += nthreads) {
+        const int j = i / HID, c = i - j * HID;
         float v = 0.f;
-        if (kx < 32) v = wt.w_sdf0[j * in1 + hash_col_to_feature(kx)];
-        else if (kx < 80) v = wt.w_sdf0[j * in1 + kx];
-        else if (kx == 80 + kTailTsdf) v = wt.w_sdf0[j * in1 + 80];
-        store_split_cat(w + L::o_w0, HID, j, kx, v);
+#pragma unroll
+        for (int g = 0; g < kGeo; ++g) v = fmaf(wt.w_col0[j * kIn2 + kBlob + g], wt.w_sdf1[(1 + g) * HID + c], v);
+        store_split(w + L::o_w21h, w + L::o_w21l, HID, j, c, v);
     }
-    for (int i = threadIdx.x; i < 16 * HID; i += nthreads) {
-        int r = i / HID, j = i - r * HID;
-        store_split_cat(w + L::o_w1, 16, r, j, wt.w_sdf1[r * HID + j]);
-        store_split_cat(w + L::o_w3, 16, r, j, (r < 3) ? wt.w_col1[r * HID + j] : 0.f);
-    }
-    for (int i = threadIdx.x; i < HID * 80; i += nthreads) {
-        int j = i / 80, kx = i - j * 80;
-        store_split_cat(w + L::o_w2, HID, j, kx, (kx < kIn2) ? wt.w_col0[j * kIn2 + kx] : 0.f);
-    }
+    for (int i = threadIdx.x; i < HID; i += nthreads) w1s[i] = wt.w_sdf1[i];
 }
 
 __device__ __forceinline__ void grp_sync(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
@@ -272,46 +252,23 @@ __device__ __forceinline__ void prefetch_tile(const float* __restrict__ feat, lo
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Forward.  The decoder kernels are bound by shared-memory bandwidth (tensor-core operand reads + staging stores), so
-// the forward keeps every A operand it can in TENSOR MEMORY: a thread writes its row of the hash features, of the
-// tail and of the hidden activations as bf16 pairs with tcgen05.st and the MMAs read them with the TS form
-// (tcgen05.mma [d], [a_tmem], b_desc).  Only the OneBlob block stays in shared memory (three scalars per coordinate at
-// data-dependent columns).  TMEM columns of a group: accumulator [0,HID) (H, then O/rgb aliased on [0,16)),
-// hash hi/lo 16+16, tail hi/lo 16+16, hidden hi/lo HID/2 + HID/2.
+// Forward.  The decoder kernels are bound by shared-memory bandwidth (tensor-core operand reads + staging stores) and by the
+// serial staging -> MMA -> read-back chain of a tile, so the forward keeps every A operand it can in TENSOR MEMORY (a thread
+// writes its row of the hash features, of the tail and of the hidden activations as bf16 pairs with tcgen05.st and the MMAs
+// read them with the TS form; only the OneBlob block stays in shared memory: three scalars per coordinate at data-dependent
+// columns) and runs THREE phases per tile instead of one per layer: the geo features are linear in H1 (model/decoder.py:138-143),
+// so the colour net's hidden layer is issued together with the sdf output, from H1 and W21 = W2[:, geo] W1[geo, :]:
+//   1  H1 = relu(X1 W0^T)      2  sdf = H1 W1[0]^T,  H2 = relu(X2' W2^T + H1 W21^T)      3  rgb = H2 W3^T
+// TMEM columns of a group: accumulator [0, HID), hash hi/lo 16+16 (the sdf result lands there in phase 2), tail hi/lo 16+16,
+// hidden hi/lo HID/2 + HID/2.
 // ------------------------------------------------------------------------------------------------------------
-template <int HID, bool CAT = false>
+template <int HID>
 struct FwdL {
     static constexpr int c_blob_hi = 0, c_blob_lo = 6, chunks = 12;     // shared memory per group: OneBlob hi / lo
     static constexpr int bytes = chunks * kChunkB;
-    // CAT (concatenated hi / lo weights, see WLC): the accumulator is 2 HID wide; at hidden 32 the hidden operand aliases its
-    // upper half (written only after both halves have been read back), at hidden 64 it has its own columns
-    static constexpr int AW = CAT ? 2 * HID : HID;
-    static constexpr int t_acc = 0, t_hash_hi = AW, t_hash_lo = AW + 16, t_tail_hi = AW + 32, t_tail_lo = AW + 48,
-                         t_h_hi = (CAT && HID == 32) ? HID : AW + 64, t_h_lo = t_h_hi + HID / 2,
-                         tcols = (CAT && HID == 32) ? AW + 64 : AW + 64 + HID;
+    static constexpr int t_acc = 0, t_hash_hi = HID, t_hash_lo = HID + 16, t_o = HID, t_tail_hi = HID + 32, t_tail_lo = HID + 48,
+                         t_h_hi = HID + 64, t_h_lo = t_h_hi + HID / 2, tcols = 2 * HID + 64;
 };
-
-// CAT k-steps: A from TMEM (hi at ah, lo at al) or from shared memory; B = concatenated weights at `b` (WLC), `rows` per part
-template <int NKS>
-__device__ __forceinline__ void mma_ts_cat(uint32_t d, uint32_t ah, uint32_t al, uint32_t b, int rows, uint32_t id2n, uint32_t idn, uint32_t& acc) {
-    uint64_t db = smem_desc(b, 2 * rows * 16, 128);
-#pragma unroll
-    for (int s = 0; s < NKS; ++s) {
-        mma_bf16_ts(d, ah + 8 * s, db, id2n, acc); acc = 1;
-        mma_bf16_ts(d, al + 8 * s, db, idn, 1);
-        db = desc_advance(db, 2 * 2 * rows * 16);
-    }
-}
-template <int NKS>
-__device__ __forceinline__ void mma_kk_cat(uint32_t d, uint32_t ah, uint32_t al, uint32_t b, int rows, uint32_t id2n, uint32_t idn, uint32_t& acc) {
-    uint64_t dah = smem_desc(ah, kChunkB, 128), dal = smem_desc(al, kChunkB, 128), db = smem_desc(b, 2 * rows * 16, 128);
-#pragma unroll
-    for (int s = 0; s < NKS; ++s) {
-        mma_bf16(d, dah, db, id2n, acc); acc = 1;
-        mma_bf16(d, dal, db, idn, 1);
-        dah = desc_advance(dah, 2 * kChunkB); dal = desc_advance(dal, 2 * kChunkB); db = desc_advance(db, 2 * 2 * rows * 16);
-    }
-}
 
 // A from TMEM (hi at column ah, lo at column al, 8 columns per k-step); B = weights K-major
 template <int NKS>
@@ -348,55 +305,44 @@ __device__ __forceinline__ void relu_to_tmem(uint32_t tacc, uint32_t th, uint32_
     }
 }
 
-// CAT: hidden pre-activation = columns [0, HID) + columns [HID, 2 HID) of the accumulator
-template <int HID>
-__device__ __forceinline__ void relu_cat_to_tmem(uint32_t tacc, uint32_t th, uint32_t tl) {
-#pragma unroll
-    for (int q = 0; q < HID / 32; ++q) {
-        float v[32], u[32];
-        tmem_ld32(tacc + 32 * q, v);
-        tmem_ld32(tacc + HID + 32 * q, u);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + u[i], 0.f);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tstage8(th, tl, 4 * q + c, v + 8 * c);
-    }
-}
-
-template <int HID, int G, bool CAT>
+template <int HID, int G>
 __global__ void __launch_bounds__(G * 128, 1) mlp_fwd_tc_kernel(RayK k, Weights wts, const float* __restrict__ feat, long long P,
                                                                 int variant, float* __restrict__ raw) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint64_t bars[G];
     __shared__ uint32_t tmem_base_s;
-    using W = WL<HID>; using WC = WLC<HID>; using A = FwdL<HID, CAT>;
+    __shared__ __align__(16) float w1s[HID];
+    using W = WL<HID>; using A = FwdL<HID>;
     constexpr int HC = HID / 8;
     constexpr uint32_t TCOLS = (G * A::tcols <= 128) ? 128 : (G * A::tcols <= 256) ? 256 : 512;
     static_assert(G * A::tcols <= 512, "TMEM columns");
-    const int tid = threadIdx.x, g = tid >> 7, m = tid & 127, warp = tid >> 5;
+    const int tid = threadIdx.x, m = tid & 127, warp = tid >> 5;
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);                  // warp-uniform for the compiler: MMA operands in uniform registers
+    const int g = warp_u >> 2;
+    const bool iwarp = (warp_u & 3) == 0;                                  // the group's MMA-issuing warp (uniform)
     unsigned char* wsm = smem + G * A::bytes;
     unsigned char* act = smem + g * A::bytes;
     if (warp == 0) tmem_alloc(&tmem_base_s, TCOLS);
     if (tid == 0) { for (int i = 0; i < G; ++i) mbar_init(&bars[i], 1); fence_mbar_init(); }
-    if (CAT) load_weights_cat<HID>(wsm, wts, G * 128); else load_weights<HID>(wsm, wts, G * 128);
+    load_weights<HID>(wsm, wts, G * 128);
+    load_w21<HID>(wsm, w1s, wts, G * 128);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-    const uint32_t tb = tmem_base_s + (uint32_t)g * A::tcols;              // group's columns (lane 0: MMA operand addresses)
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base_s, 0) + (uint32_t)g * A::tcols;   // group's columns (lane 0: MMA operand addresses)
     const uint32_t tlane = tb + ((uint32_t)((warp & 3) * 32) << 16);       // this thread's lane quadrant
     uint64_t* bar = &bars[g];
     uint32_t phase = 0;
     unsigned char *blob_hi = act + A::c_blob_hi * kChunkB, *blob_lo = act + A::c_blob_lo * kChunkB;
     const uint32_t w0h = smem_u32(wsm + W::o_w0h), w0l = smem_u32(wsm + W::o_w0l), w1h = smem_u32(wsm + W::o_w1h), w1l = smem_u32(wsm + W::o_w1l);
     const uint32_t w2h = smem_u32(wsm + W::o_w2h), w2l = smem_u32(wsm + W::o_w2l), w3h = smem_u32(wsm + W::o_w3h), w3l = smem_u32(wsm + W::o_w3l);
+    const uint32_t w21h = smem_u32(wsm + W::o_w21h), w21l = smem_u32(wsm + W::o_w21l);
     constexpr uint32_t idH = idesc_bf16(HID, false, false), id16 = idesc_bf16(16, false, false);
-    constexpr uint32_t id2H = idesc_bf16(2 * HID, false, false), id32 = idesc_bf16(32, false, false);
-    const uint32_t c0 = smem_u32(wsm + WC::o_w0), c1 = smem_u32(wsm + WC::o_w1), c2 = smem_u32(wsm + WC::o_w2), c3 = smem_u32(wsm + WC::o_w3);   // CAT
 
     // Inputs are software-pipelined through their own registers: a tile's features and positions are dead once its X row
     // is staged, so the same registers are reloaded with the NEXT tile's inputs right away and those loads are in flight
-    // during the four MMA phases (the first use of freshly loaded inputs was ~20 % of all stall samples).
+    // during the MMA phases (the first use of freshly loaded inputs was ~20 % of all stall samples).
     const long long tstep = (long long)gridDim.x * G;
     TilePos tp; tp.init(k.n_rays, k.S, ((long long)blockIdx.x * G + g) * kTile, tstep * kTile);
     TileIn t;
@@ -429,85 +375,50 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_fwd_tc_kernel(RayK k, Weights 
         load_tile(t, feat, P, tile + tstep, m);                                               // next tile's inputs (see above)
         tmem_st_wait();
         fence_async_smem(); fence_before_sync(); grp_sync(g);
-        if (m == 0) {                                                                         // H1 = X1 W0^T
+        if (iwarp && elect_one()) {                                                                         // 1: H1 = X1 W0^T
             fence_after_sync();
             uint32_t acc = 0;
-            if (CAT) {
-                mma_ts_cat<2>(tb + A::t_acc, tb + A::t_hash_hi, tb + A::t_hash_lo, c0, HID, id2H, idH, acc);
-                mma_kk_cat<3>(tb + A::t_acc, smem_u32(blob_hi), smem_u32(blob_lo), c0 + kXBlob * 2 * HID * 16, HID, id2H, idH, acc);
-                mma_ts_cat<2>(tb + A::t_acc, tb + A::t_tail_hi, tb + A::t_tail_lo, c0 + kXTail * 2 * HID * 16, HID, id2H, idH, acc);
-            } else {
-                mma_ts<2>(tb + A::t_acc, tb + A::t_hash_hi, tb + A::t_hash_lo, w0h, w0l, HID, idH, acc);
-                mma_kk<3>(tb + A::t_acc, smem_u32(blob_hi), smem_u32(blob_lo), w0h + kXBlob * HID * 16, w0l + kXBlob * HID * 16, HID, idH, acc);
-                mma_ts<2>(tb + A::t_acc, tb + A::t_tail_hi, tb + A::t_tail_lo, w0h + kXTail * HID * 16, w0l + kXTail * HID * 16, HID, idH, acc);
-            }
+            mma_ts<2>(tb + A::t_acc, tb + A::t_hash_hi, tb + A::t_hash_lo, w0h, w0l, HID, idH, acc);
+            mma_kk<3>(tb + A::t_acc, smem_u32(blob_hi), smem_u32(blob_lo), w0h + kXBlob * HID * 16, w0l + kXBlob * HID * 16, HID, idH, acc);
+            mma_ts<2>(tb + A::t_acc, tb + A::t_tail_hi, tb + A::t_tail_lo, w0h + kXTail * HID * 16, w0l + kXTail * HID * 16, HID, idH, acc);
             commit(bar);
         }
         grp_wait(bar, phase);
-        if (CAT) relu_cat_to_tmem<HID>(tlane + A::t_acc, tlane + A::t_h_hi, tlane + A::t_h_lo);
-        else relu_to_tmem<HID>(tlane + A::t_acc, tlane + A::t_h_hi, tlane + A::t_h_lo);       // decoder.py:105-107
+        relu_to_tmem<HID>(tlane + A::t_acc, tlane + A::t_h_hi, tlane + A::t_h_lo);            // decoder.py:105-107
         tmem_st_wait();
         fence_before_sync(); grp_sync(g);
-        if (m == 0) {                                                                         // O = H1 W1^T
+        if (iwarp && elect_one()) {                                                                         // 2: O = H1 W1^T (over the dead hash operand), H2 = X2' W2^T + H1 W21^T
             fence_after_sync();
             uint32_t acc = 0;
-            if (CAT) mma_ts_cat<HC / 2>(tb + A::t_acc, tb + A::t_h_hi, tb + A::t_h_lo, c1, 16, id32, id16, acc);
-            else mma_ts<HC / 2>(tb + A::t_acc, tb + A::t_h_hi, tb + A::t_h_lo, w1h, w1l, 16, id16, acc);
+            mma_ts<HC / 2>(tb + A::t_o, tb + A::t_h_hi, tb + A::t_h_lo, w1h, w1l, 16, id16, acc);
+            acc = 0;
+            mma_kk<3>(tb + A::t_acc, smem_u32(blob_hi), smem_u32(blob_lo), w2h, w2l, HID, idH, acc);
+            mma_ts<2>(tb + A::t_acc, tb + A::t_tail_hi, tb + A::t_tail_lo, w2h + 6 * HID * 16, w2l + 6 * HID * 16, HID, idH, acc);
+            mma_ts<HC / 2>(tb + A::t_acc, tb + A::t_h_hi, tb + A::t_h_lo, w21h, w21l, HID, idH, acc);
             commit(bar);
         }
         grp_wait(bar, phase);
-        float o16[16];
-        if (CAT) {
-            float o32[32];
-            tmem_ld32(tlane + A::t_acc, o32);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o16[i] = o32[i] + o32[16 + i];
-        } else tmem_ld16(tlane + A::t_acc, o16);
-        const float sdf = o16[0] + t_add;                                                     // scene_rep.py:345
-        {                                                                                     // geo15 into the tail
-            float v0[8], v1[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v0[i] = o16[1 + i];
-#pragma unroll
-            for (int i = 0; i < 7; ++i) v1[i] = o16[9 + i];
-            v1[7] = gb.y;
-            tstage8(tlane + A::t_tail_hi, tlane + A::t_tail_lo, 0, v0);
-            tstage8(tlane + A::t_tail_hi, tlane + A::t_tail_lo, 1, v1);
+        float sdf;
+        {
+            float o16[16];
+            tmem_ld16(tlane + A::t_o, o16);
+            sdf = o16[0] + t_add;                                                             // scene_rep.py:345
         }
+        relu_to_tmem<HID>(tlane + A::t_acc, tlane + A::t_h_hi, tlane + A::t_h_lo);            // decoder.py:49-51
         tmem_st_wait();
         fence_before_sync(); grp_sync(g);
-        if (m == 0) {                                                                         // H2 = X2 W2^T
+        if (iwarp && elect_one()) {                                                                         // 3: rgb = H2 W3^T
             fence_after_sync();
             uint32_t acc = 0;
-            if (CAT) {
-                mma_kk_cat<3>(tb + A::t_acc, smem_u32(blob_hi), smem_u32(blob_lo), c2, HID, id2H, idH, acc);
-                mma_ts_cat<2>(tb + A::t_acc, tb + A::t_tail_hi, tb + A::t_tail_lo, c2 + 6 * 2 * HID * 16, HID, id2H, idH, acc);
-            } else {
-                mma_kk<3>(tb + A::t_acc, smem_u32(blob_hi), smem_u32(blob_lo), w2h, w2l, HID, idH, acc);
-                mma_ts<2>(tb + A::t_acc, tb + A::t_tail_hi, tb + A::t_tail_lo, w2h + 6 * HID * 16, w2l + 6 * HID * 16, HID, idH, acc);
-            }
+            mma_ts<HC / 2>(tb + A::t_acc, tb + A::t_h_hi, tb + A::t_h_lo, w3h, w3l, 16, id16, acc);
             commit(bar);
         }
         grp_wait(bar, phase);
-        if (CAT) relu_cat_to_tmem<HID>(tlane + A::t_acc, tlane + A::t_h_hi, tlane + A::t_h_lo);
-        else relu_to_tmem<HID>(tlane + A::t_acc, tlane + A::t_h_hi, tlane + A::t_h_lo);       // decoder.py:49-51
-        tmem_st_wait();
-        fence_before_sync(); grp_sync(g);
-        if (m == 0) {                                                                         // rgb = H2 W3^T
-            fence_after_sync();
-            uint32_t acc = 0;
-            if (CAT) mma_ts_cat<HC / 2>(tb + A::t_acc, tb + A::t_h_hi, tb + A::t_h_lo, c3, 16, id32, id16, acc);
-            else mma_ts<HC / 2>(tb + A::t_acc, tb + A::t_h_hi, tb + A::t_h_lo, w3h, w3l, 16, id16, acc);
-            commit(bar);
+        {
+            float o16[16];
+            tmem_ld16(tlane + A::t_acc, o16);
+            if (live) reinterpret_cast<float4*>(raw)[p] = make_float4(o16[0] + gb.y, o16[1] + gb.z, o16[2] + gb.w, sdf);   // :344-345
         }
-        grp_wait(bar, phase);
-        if (CAT) {
-            float o32[32];
-            tmem_ld32(tlane + A::t_acc, o32);
-#pragma unroll
-            for (int i = 0; i < 3; ++i) o16[i] = o32[i] + o32[16 + i];
-        } else tmem_ld16(tlane + A::t_acc, o16);
-        if (live) reinterpret_cast<float4*>(raw)[p] = make_float4(o16[0] + gb.y, o16[1] + gb.z, o16[2] + gb.w, sdf);   // :344-345
         fence_before_sync();
     }
     fence_before_sync();
@@ -521,22 +432,39 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_fwd_tc_kernel(RayK k, Weights 
 template <int HID>
 struct BwdL {
     static constexpr int HC = HID / 8;
-    // group region (chunks): X hi [hash4|blob6|tail4] | X lo 14 | H1 hi,lo | H2 hi,lo | D hi 2 | D lo 2
+    // group region (chunks): X hi [hash4|blob6|tail4] | X lo 14 | H1 hi,lo | H2 hi,lo | D hi 1 | D lo 1
     static constexpr int c_x_hi = 0, c_x_lo = kXCh, c_h1_hi = 2 * kXCh, c_h1_lo = c_h1_hi + HC, c_h2_hi = c_h1_lo + HC, c_h2_lo = c_h2_hi + HC,
-                         c_d_hi = c_h2_lo + HC, c_d_lo = c_d_hi + 2;
-    static constexpr int chunks = c_d_lo + 2;
+                         c_d_hi = c_h2_lo + HC, c_d_lo = c_d_hi + 1;
+    static constexpr int chunks = c_d_lo + 1;
     static constexpr int bytes = chunks * kChunkB;
-    // TMEM columns of a group: weight-gradient accumulators (transposed: lane = input feature, column = output unit), work
-    // dW0^T, dW2^T: 2*HID columns each (hh + lh | hl); dW1^T, dW3^T: 32 columns each (x hi | x lo), rows hi then lo
-    static constexpr int t_w0 = 0, t_w2 = 2 * HID, t_w1 = 4 * HID, t_w3 = 4 * HID + 32, t_a = 4 * HID + 64, t_b = 5 * HID + 64;
+    // TMEM columns of a group.  Weight-gradient accumulators are transposed (lane = a row of the MN-major A window, column = a
+    // column of the MN-major B window):
+    //   t_w0 (112)  lanes [dH1 hi | dH1 lo | dH2 hi | dH2 lo] x 32 units (hidden 32; hidden 64: [dH1 hi | dH1 lo]), columns = X-order features
+    //   t_w2 (80)   hidden 64 only: lanes [dH2 hi | dH2 lo], columns = blob | tail
+    //   t_w3 (16)   lanes [H2 hi | H2 lo | ...], columns [dRGB hi 8 | dRGB lo 8]
+    //   t_m (2 HID) lanes [dH2 hi | dH2 lo | D hi 8 | D lo 8 | ...], columns [H1 hi | H1 lo]:  M21 = dH2^T H1 and (hidden 32) dsdf^T H1
+    //   t_w1 (16)   hidden 64 only: lanes [H1 hi | H1 lo], columns [dsdf hi 8 | dsdf lo 8]
+    //   t_a         the tile's working accumulator (HID columns; 64 in BA mode, over the slot), t_s the K-major operand slot [hi HID/2 | lo HID/2]
+    static constexpr int t_w0 = 0, t_w3 = 112, t_w2 = 128, t_w1 = 208,
+                         t_m = (HID == 32) ? 128 : 256, t_a = (HID == 32) ? 192 : 384, t_s = t_a + ((HID == 32) ? 32 : 64);
     static constexpr int tcols = (HID == 32) ? 256 : 512;
 };
 
 // ------------------------------------------------------------------------------------------------------------
-// Backward, two threads per tile row.  Same MMAs, layouts and TMEM map as mlp_bwd_tc_kernel; a group is 256 threads and
-// thread (m, h) handles half h of everything row m stages or reads back (hash levels 8h..8h+7, hidden units
-// [h HID/2, (h+1) HID/2), one of the two D chunks, ...), so the serial SIMT stretch between two tensor-core phases is
-// half as long and a CTA runs 16 warps (hidden 32) instead of 8.
+// Backward, two threads per tile row: a group is 256 threads and thread (m, h) handles half h of everything row m stages or
+// reads back (hidden units [h HID/2, (h+1) HID/2), ...), so the serial SIMT stretch between two tensor-core phases is half as
+// long and a CTA runs 16 warps (hidden 32).
+//
+// FIVE tensor-core phases per tile.  The geo features are linear in H1 (O = H1 W1^T, no activation, model/decoder.py:138-143), so
+// the colour net's hidden layer is computed from H1 directly with the combined matrix W21 = W2[:, geo] W1[geo, :], and its
+// gradient flows back the same way — neither O nor d geo is ever materialised:
+//   1  H1 = relu(X1 W0^T)
+//   2  H2 = relu(X2' W2^T + H1 W21^T)                       X2' = [blob | 0 x15 | gbv rgb]
+//   3  dH2 = (dRGB W3) . relu'                               dW3^T += H2^T dRGB
+//   4  dH1 = (dH2 W21 + dsdf W1[0]) . relu'                  M21 += dH2^T H1,  dW1[0] += dsdf^T H1   (hidden 64: dW2 += dH2^T X2')
+//   5  d hash = dH1 W0[:, hash]                              dW0 += dH1^T X1  (hidden 32: and dW2 += dH2^T X2' in the same MMAs)
+// When the accumulators are flushed, the gradients of the two factors of W21 come out of M21 (HID x HID, fp32):
+//   dW2[:, geo] = M21 W1[geo]^T,   dW1[geo] = W2[:, geo]^T M21.
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void grp_sync2(int g) { asm volatile("bar.sync %0, 256;" ::"r"(g + 1) : "memory"); }
 
@@ -576,12 +504,21 @@ __device__ __forceinline__ uint32_t relu_half(uint32_t taddr, unsigned char* hi,
     }
     return mk;
 }
+// (accumulator + a * w[.]) . mask -> chunks c0.. (shared memory and operand slot); w: NC fp32 values in shared memory (broadcast reads)
 template <int NC>
-__device__ __forceinline__ void masked_half(uint32_t taddr, unsigned char* hi, unsigned char* lo, int m, int c0, uint32_t mask, uint32_t th, uint32_t tl) {
+__device__ __forceinline__ void masked_half(uint32_t taddr, unsigned char* hi, unsigned char* lo, int m, int c0, uint32_t mask, uint32_t th, uint32_t tl,
+                                            float a = 0.f, const float* w = nullptr) {
 #pragma unroll
     for (int q = 0; q < NC / 16; ++q) {
         float v[16];
         tmem_ld16(taddr + 16 * q, v);
+        if (w) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+                const float4 ww = *reinterpret_cast<const float4*>(w + 16 * q + i);
+                v[i] = fmaf(a, ww.x, v[i]); v[i + 1] = fmaf(a, ww.y, v[i + 1]); v[i + 2] = fmaf(a, ww.z, v[i + 2]); v[i + 3] = fmaf(a, ww.w, v[i + 3]);
+            }
+        }
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = ((mask >> (16 * q + i)) & 1u) ? v[i] : 0.f;
         stage8_both(hi, lo, m, c0 + 2 * q, v, th, tl); stage8_both(hi, lo, m, c0 + 2 * q + 1, v + 8, th, tl);
@@ -608,14 +545,6 @@ __device__ __forceinline__ void load_half(TileHalf& t, const float* __restrict__
     }
 }
 
-// group-wide OR of a predicate over the 256 threads of a backward group (named-barrier reduction)
-__device__ __forceinline__ bool grp_any2(int g, bool pred) {
-    uint32_t r;
-    asm volatile("{\n .reg .pred p, q;\n setp.ne.u32 q, %2, 0;\n bar.red.or.pred p, %1, 256, q;\n selp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(r) : "r"(g + 1), "r"((uint32_t)pred) : "memory");
-    return r != 0;
-}
-
 // Input-layer weight gradients with the hidden-gradient block as the A operand (MN-major, M = 128 rows = 16 consecutive
 // chunks: [dH hi | dH lo] of one net at hidden 64, of both nets at hidden 32) and X as the B operand (MN-major, N = 8 per
 // chunk), first its hi part then its lo part into the SAME columns: D[row][f] += sum_m dH_part[m][row] (X_hi + X_lo)[m][f].
@@ -631,45 +560,86 @@ __device__ __forceinline__ void mma_wx(uint32_t d, uint32_t a, uint32_t bh, uint
     }
 }
 
-// Flush for the mma_wx layout.  Hidden 32: lanes = [dH1 hi | dH1 lo | dH2 hi | dH2 lo] x 32 units, columns = the 112 X-order
-// features (the colour net uses columns 32..97); the two threads of a lane split the columns.  Hidden 64: t_w0 holds the
-// sdf net (lanes = [hi | lo] x 64 units, 112 columns; thread h = 0), t_w2 the colour net (80 columns; thread h = 1).
+// Flush of the weight-gradient accumulators (layouts: BwdL).  `scratch`: HID * HID floats of the group's shared memory (the
+// H2 blocks, idle between tiles) for M21; every thread of the group calls this.
 template <int HID>
-__device__ __forceinline__ void flush_wgrads3(uint32_t tlane, const Grads& gr, int m, int h) {
+__device__ __forceinline__ void flush_wgrads3(uint32_t tlane, const Grads& gr, const Weights& wt, float* scratch, int g, int m, int h) {
     using A = BwdL<HID>;
     fence_after_sync();
-    const int j = m & (HID - 1);
-    const bool colour = (HID == 32) ? (m >= 64) : (h == 1);
-    float* gx = colour ? gr.g_w_col0 : gr.g_w_sdf0;
-    const int ld = colour ? kIn2 : 81;
-    const uint32_t tx = tlane + ((HID == 64 && h == 1) ? A::t_w2 : A::t_w0);
-    const int q0 = (HID == 32) ? (h ? 4 : 0) : 0;
-    const int q1 = (HID == 32) ? (h ? 7 : 4) : (h ? 5 : 7);
-    const int fshift = (HID == 32 && colour) ? -32 : 0;       // X-order column -> colour-net input (blob | tail)
+    {   // input layers: dW0 (sdf net) and dW2 (colour net) from the X products
+        const int j = m & (HID - 1);
+        const bool colour = (HID == 32) ? (m >= 64) : (h == 1);
+        float* gx = colour ? gr.g_w_col0 : gr.g_w_sdf0;
+        const int ld = colour ? kIn2 : 81;
+        const uint32_t tx = tlane + ((HID == 64 && h == 1) ? A::t_w2 : A::t_w0);
+        const int q0 = (HID == 32) ? (h ? 4 : 0) : 0;
+        const int q1 = (HID == 32) ? (h ? 7 : 4) : (h ? 5 : 7);
+        const int fshift = (HID == 32 && colour) ? -32 : 0;       // X-order column -> colour-net input (blob | tail)
 #pragma unroll 1
-    for (int q = q0; q < q1; ++q) {
-        float v[16];
-        tmem_ld16(tx + 16 * q, v);
-        if (!gx) continue;
+        for (int q = q0; q < q1; ++q) {
+            float v[16];
+            tmem_ld16(tx + 16 * q, v);
+            if (!gx) continue;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int f = 16 * q + i + fshift;
-            int c = -1;
-            if (colour) { if (f >= 0 && f < kIn2) c = f; }
-            else { if (f < 32) c = hash_col_to_feature(f); else if (f < 80) c = f; else if (f == 80 + kTailTsdf) c = 80; }
-            if (c >= 0) atomicAdd(gx + j * ld + c, v[i]);
+            for (int i = 0; i < 16; ++i) {
+                const int f = 16 * q + i + fshift;
+                int c = -1;
+                if (colour) { if (f >= 0 && f < kIn2 && (f < kBlob || f >= kBlob + kGeo)) c = f; }     // the geo columns come from M21 below
+                else { if (f < 32) c = hash_col_to_feature(f); else if (f < 80) c = f; else if (f == 80 + kTailTsdf) c = 80; }
+                if (c >= 0) atomicAdd(gx + j * ld + c, v[i]);
+            }
         }
     }
-    // H-based: rows [0,HID) = hi features (columns: x hi | x lo), rows [HID,2HID) = lo features (column block x hi)
-    float v32[32];
-    tmem_ld32(tlane + (h ? A::t_w3 : A::t_w1), v32);
-    float* gh = h ? gr.g_w_col1 : gr.g_w_sdf1;
-    const int rows = h ? 3 : 16;
-    if (gh && m < 2 * HID) {
-        const int jj = (m < HID) ? m : m - HID;
+    // the products below are [hi rows | lo rows] x [hi columns | lo columns]: value = hi.hi + hi.lo + lo.hi
+    const bool hi_lane = m < HID, lo_lane = m >= HID && m < 2 * HID;
+    const int jj = m & (HID - 1);
+    if (h == 1) {
+        float v[16];                                              // dW3[c][j], c < 3 (model/decoder.py:44-47)
+        tmem_ld16(tlane + A::t_w3, v);
+        if (gr.g_w_col1 && (hi_lane || lo_lane)) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) if (i < rows) atomicAdd(gh + i * HID + jj, (m < HID) ? v32[i] + v32[16 + i] : v32[i]);
+            for (int c = 0; c < 3; ++c) atomicAdd(gr.g_w_col1 + c * HID + jj, hi_lane ? v[c] + v[8 + c] : v[c]);
+        }
+        if constexpr (HID == 64) {                                // dW1[0][i] = dsdf^T H1
+            tmem_ld16(tlane + A::t_w1, v);
+            if (gr.g_w_sdf1 && (hi_lane || lo_lane)) atomicAdd(gr.g_w_sdf1 + jj, hi_lane ? v[0] + v[8] : v[0]);
+        }
     }
+    // M21[j][i] = sum over the samples of dH2[j] H1[i]
+    for (int i = (h * 128 + m); i < HID * HID; i += 256) scratch[i] = 0.f;
+    grp_sync2(g);
+    if (h == 0) {
+#pragma unroll 1
+        for (int q = 0; q < 2 * HID / 32; ++q) {
+            float v[32];
+            tmem_ld32(tlane + A::t_m + 32 * q, v);
+            const bool lo_cols = 32 * q >= HID;
+            if (hi_lane || (lo_lane && !lo_cols)) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) atomicAdd(scratch + jj * HID + ((32 * q + i) & (HID - 1)), v[i]);
+            }
+            if constexpr (HID == 32) {                            // lanes 64 / 72 = the hi / lo part of dsdf: dW1[0][i]
+                if (gr.g_w_sdf1 && (m == 64 || (m == 72 && !lo_cols))) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) atomicAdd(gr.g_w_sdf1 + i, v[i]);
+                }
+            }
+        }
+    }
+    grp_sync2(g);
+    for (int o = h * 128 + m; o < 2 * kGeo * HID; o += 256) {
+        float acc = 0.f;
+        if (o < kGeo * HID) {                                     // dW1[1 + gg][i] = sum_j W2[j][48 + gg] M21[j][i]
+            const int gg = o / HID, i = o - gg * HID;
+            for (int j = 0; j < HID; ++j) acc = fmaf(__ldg(wt.w_col0 + j * kIn2 + kBlob + gg), scratch[j * HID + i], acc);
+            if (gr.g_w_sdf1) atomicAdd(gr.g_w_sdf1 + (1 + gg) * HID + i, acc);
+        } else {                                                  // dW2[j][48 + gg] = sum_i M21[j][i] W1[1 + gg][i]
+            const int o2 = o - kGeo * HID, j = o2 / kGeo, gg = o2 - j * kGeo;
+            for (int i = 0; i < HID; ++i) acc = fmaf(scratch[j * HID + i], __ldg(wt.w_sdf1 + (1 + gg) * HID + i), acc);
+            if (gr.g_w_col0) atomicAdd(gr.g_w_col0 + j * kIn2 + kBlob + gg, acc);
+        }
+    }
+    grp_sync2(g);                                                 // scratch is operand memory again
 }
 
 // sum_k d blob_k / dx * g_k for the 16 bins of one coordinate (Appendix B7 derivative: d out_k / dx = pdf_k - pdf_{k+1} at the
@@ -701,37 +671,70 @@ __device__ __forceinline__ float oneblob_dot_grad(float x, const float (&g)[16])
 
 // BA: additionally writes, per sample, the gradient w.r.t. the GBV texel (dgb [P][4]) and the OneBlob part of the
 // gradient w.r.t. the normalised position (dxb [3][P]) for raygrad_walk_kernel: one more tensor-core phase per tile.
+// One flag per 128-row tile: does any of its rows (plane index q = s * N + r) lie below its ray's n_live?  A warp per tile.
+__global__ void __launch_bounds__(256) tile_live_kernel(long long n_rays, long long P, const int* __restrict__ n_live, unsigned char* __restrict__ flags) {
+    const long long tile = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (tile >= ws_tiles(P)) return;
+    const int lane = threadIdx.x & 31;
+    bool any = false;
+    const long long q0 = tile * kTile, s0 = q0 / n_rays;
+    long long r = q0 - s0 * n_rays + lane, s = s0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j, r += 32) {
+        while (r >= n_rays) { r -= n_rays; ++s; }
+        if (q0 + lane + 32 * j < P) any |= s < (long long)__ldg(n_live + r);
+    }
+    any = __any_sync(0xffffffffu, any);
+    if (lane == 0) flags[tile] = any ? 1 : 0;
+}
+
+// RF_MLP_TRACE (debug builds only: RF_NVCC_DEFS=-DRF_MLP_TRACE): the issuing thread of every group accumulates the clock cycles between
+// the marked points of its tile loop; rf_debug_mlp_trace() reads the sums (slot 31 = processed tiles).
+#ifdef RF_MLP_TRACE
+__device__ unsigned long long g_mlp_trace[32];
+#define TR(i) do { if (issuer) { const long long c_ = clock64(); tr_acc[i] += (unsigned long long)(c_ - tr_prev); tr_prev = c_; } } while (0)
+#else
+#define TR(i) do { } while (0)
+#endif
+
 template <int HID, int G, bool BA, bool TMAH>
 __global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights wts, const float* __restrict__ feat, long long P,
-                                                                 const float* __restrict__ d_raw_tot, const int* __restrict__ n_live,
+                                                                 const float* __restrict__ d_raw_tot, const unsigned char* __restrict__ tile_flags,
                                                                  float* __restrict__ dfeat, Grads gr, float* __restrict__ dgb, float* __restrict__ dxb) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint64_t bars[G], tma_bars[G];
     __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float w1s[HID];                                                  // W1[0][:], the sdf row (fp32)
     using W = WL<HID>; using A = BwdL<HID>;
     constexpr int HC = HID / 8, NH = HID / 2;
     constexpr uint32_t TCOLS = G * A::tcols;
-    // work columns: t_a as in BwdL; the 16-column results (O, d geo) alias the first columns of t_a at hidden 32 (its
-    // content is consumed by then), which frees HID columns for the operand slot: [hi HID/2 | lo HID/2] of the narrow
-    // operand the next GEMM reads K-major (H1, dRGB, dH2, dO, dH1 in turn)
-    constexpr uint32_t T_A = A::t_a, T_B = (HID == 32) ? A::t_a : A::t_b, T_S = (HID == 32) ? A::t_a + 32 : A::t_b + 16;
+    // T_A: working accumulator; T_S: [hi HID/2 | lo HID/2] of the narrow operand the next GEMM reads K-major (H1, dRGB, dH2, dH1 in turn)
+    constexpr uint32_t T_A = A::t_a, T_S = A::t_s;
     static_assert(T_S + HID <= A::tcols, "operand slot exceeds the group's TMEM columns");
-    const int tid = threadIdx.x, g = tid >> 8, m = tid & 127, h = (tid >> 7) & 1, warp = tid >> 5;
+    const int tid = threadIdx.x, m = tid & 127, h = (tid >> 7) & 1, warp = tid >> 5;
+    // Warp-uniform copies (shuffle broadcasts, the compiler's uniformity analysis understands them): everything an MMA operand is
+    // derived from — group index, shared-memory and TMEM bases, tile liveness — must be provably uniform, otherwise every
+    // tcgen05.mma is wrapped in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop over the active lanes (~80 cycles per MMA, measured
+    // with RF_MLP_TRACE: 41 % of a tile's time was MMA issue)
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+    const int g = warp_u >> 3;
     // weights sit after the group regions: the M = 128 MN-major reads of the narrow H / D operands run past their own
-    // chunks (rows of D that are never read back) and must stay inside the allocation
+    // chunks (rows of the accumulator that are never read back) and must stay inside the allocation
     unsigned char* wsm = smem + G * A::bytes;
     unsigned char* act = smem + g * A::bytes;
     if (warp == 0) tmem_alloc(&tmem_base_s, TCOLS);
     if (tid == 0) { for (int i = 0; i < G; ++i) { mbar_init(&bars[i], 1); mbar_init(&tma_bars[i], 1); } fence_mbar_init(); }
     load_weights<HID>(wsm, wts, G * 256);
+    load_w21<HID>(wsm, w1s, wts, G * 256);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-    const uint32_t tb = tmem_base_s + (uint32_t)g * A::tcols;
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base_s, 0) + (uint32_t)g * A::tcols;
     const uint32_t tlane = tb + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t ts_hi = tlane + T_S, ts_lo = tlane + T_S + NH;
-    const bool issuer = (tid & 255) == 0;
+    const bool iwarp = (warp_u & 7) == 0;                                                     // the group's MMA-issuing warp (uniform)
+    const bool issuer = iwarp && (tid & 31) == 0;                                             // bulk copies, trace
     uint64_t* bar = &bars[g];
     uint32_t phase = 0;
     unsigned char *x_hi = act + A::c_x_hi * kChunkB, *x_lo = act + A::c_x_lo * kChunkB;
@@ -740,27 +743,34 @@ __global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights
     unsigned char *d_hi = act + A::c_d_hi * kChunkB, *d_lo = act + A::c_d_lo * kChunkB;
     unsigned char *blob_hi = x_hi + kXBlob * kChunkB, *blob_lo = x_lo + kXBlob * kChunkB;
     unsigned char *tail_hi = x_hi + kXTail * kChunkB, *tail_lo = x_lo + kXTail * kChunkB;
-    const uint32_t w0h = smem_u32(wsm + W::o_w0h), w0l = smem_u32(wsm + W::o_w0l), w1h = smem_u32(wsm + W::o_w1h), w1l = smem_u32(wsm + W::o_w1l);
+    const uint32_t w0h = smem_u32(wsm + W::o_w0h), w0l = smem_u32(wsm + W::o_w0l);
     const uint32_t w2h = smem_u32(wsm + W::o_w2h), w2l = smem_u32(wsm + W::o_w2l), w3h = smem_u32(wsm + W::o_w3h), w3l = smem_u32(wsm + W::o_w3l);
+    const uint32_t w21h = smem_u32(wsm + W::o_w21h), w21l = smem_u32(wsm + W::o_w21l);
     const uint32_t xh = smem_u32(x_hi), xl = smem_u32(x_lo), h1h = smem_u32(h1_hi), h1l = smem_u32(h1_lo), h2h = smem_u32(h2_hi), h2l = smem_u32(h2_lo);
-    const uint32_t dh = smem_u32(d_hi), dl = smem_u32(d_lo);
-    constexpr uint32_t idH = idesc_bf16(HID, false, false), id16 = idesc_bf16(16, false, false);
+    const uint32_t dh = smem_u32(d_hi);
+    constexpr uint32_t idH = idesc_bf16(HID, false, false);
     constexpr uint32_t idH_bm = idesc_bf16(HID, false, true), id16_bm = idesc_bf16(16, false, true), id32_bm = idesc_bf16(32, false, true);
-    constexpr uint32_t idH_mm = idesc_bf16(HID, true, true), id2H_mm = idesc_bf16(2 * HID, true, true), id32_mm = idesc_bf16(32, true, true);
+    constexpr uint32_t id16_mm = idesc_bf16(16, true, true), id2H_mm = idesc_bf16(2 * HID, true, true);
     uint32_t wacc = 0;
     int since_flush = 0;
+#ifdef RF_MLP_TRACE
+    __shared__ unsigned long long tr_s[G][32];
+    unsigned long long* tr_acc = tr_s[g];
+    if ((tid & 255) < 32) tr_acc[tid & 255] = 0;
+    __syncthreads();
+    long long tr_prev = clock64();
+#endif
 
     uint64_t* tma_bar = &tma_bars[g];
-    uint32_t tma_phase = 0;                                                                   // tracked by the issuer only
+    uint32_t tma_phase = 0;
     const long long tstep = (long long)gridDim.x * G, n_tiles = ws_tiles(P);
     TilePos tp; tp.init(k.n_rays, k.S, ((long long)blockIdx.x * G + g) * kTile, tstep * kTile);
-    // a row is live if its sample index lies below its ray's n_live (composite_bwd_kernel): rows beyond carry an all-zero
-    // upstream gradient; a tile none of whose rows is live contributes nothing and is skipped as a whole
-    auto row_live = [&](const TilePos& pos, long long tile_) -> bool {
-        if (tile_ * kTile + m >= P) return false;
-        if (!n_live) return true;
-        long long ss, rr; pos.row(m, ss, rr);
-        return ss < (long long)__ldg(n_live + rr);
+    // A tile none of whose 128 rows carries an upstream gradient (rows beyond their ray's n_live, composite_bwd_kernel) contributes
+    // nothing and is skipped as a whole: tile_live_kernel has reduced n_live to one flag per tile, so the decision is one
+    // uniform byte load, issued two tiles ahead (no per-row loads, no vote barrier)
+    auto flag_of = [&](long long tile_) -> uint32_t {
+        if (tile_ >= n_tiles) return 0u;
+        return tile_flags ? (uint32_t)__ldg(tile_flags + tile_) : 1u;
     };
     // hash chunks of tile `tile_` -> chunks 0..3 of X hi / X lo: two bulk copies of 8 KB, completion on tma_bar
     auto fetch_hash = [&](long long tile_) {
@@ -774,41 +784,33 @@ __global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights
     long long tile = (long long)blockIdx.x * G + g;
     auto load_inputs = [&](const TilePos& pos, long long tile_) {                             // inputs of an alive tile
         load_half<BA, TMAH>(t, feat, P, tile_, m, h);
-        if (h) dr_next = (tile_ * kTile + m < P) ? __ldg(reinterpret_cast<const float4*>(d_raw_tot) + pos.raw_index(m)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        dr_next = (tile_ * kTile + m < P) ? __ldg(reinterpret_cast<const float4*>(d_raw_tot) + pos.raw_index(m)) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
-    // liveness is voted two tiles ahead (one group barrier per iteration): the tile after next is pulled towards L2 only if
-    // it will be processed, the next one has its inputs loaded / its hash chunks fetched while the current one is computed.
-    // The n_live value a vote needs is loaded one iteration before the vote, so the barrier never waits on memory.
+    // the next alive tile has its inputs loaded / its hash chunks fetched while the current one is computed, the one after it is
+    // pulled towards L2; flags are made warp-uniform for the compiler (see above)
     TilePos tn = tp; tn.next();
-    bool alive = (tile < n_tiles) && grp_any2(g, row_live(tp, tile));
-    bool alive_n = (tile + tstep < n_tiles) && grp_any2(g, row_live(tn, tile + tstep));
+    bool alive = __shfl_sync(0xffffffffu, flag_of(tile), 0) != 0;
+    bool alive_n = __shfl_sync(0xffffffffu, flag_of(tile + tstep), 0) != 0;
     if (alive) { if (TMAH && issuer) fetch_hash(tile); load_inputs(tp, tile); }
     if (alive_n && h == 0) prefetch_tile(feat, P, tile + tstep, m, true);
-    // (n_live of this row's ray, this row's sample index) of a tile: the row is live iff sample < n_live; the load is not consumed here
-    auto row_fetch = [&](const TilePos& pos, long long tile_, int& ss_out) -> int {
-        if (tile_ * kTile + m >= P) { ss_out = 1; return 0; }
-        if (!n_live) { ss_out = 0; return 1; }
-        long long ss, rr; pos.row(m, ss, rr);
-        ss_out = (int)ss;
-        return __ldg(n_live + rr);
-    };
     TilePos tnn = tn; tnn.next();
-    int ss_nn, nl_nn = row_fetch(tnn, tile + 2 * tstep, ss_nn);                               // for the next vote
+    uint32_t fl_nn = flag_of(tile + 2 * tstep);                                               // consumed one iteration later
     for (; tile < n_tiles; tile += tstep, tp = tn, tn = tnn, tnn.next()) {
         const long long q = tile * kTile + m;                                                 // plane index s * N + r
         const bool live = q < P;
         const long long tile_n = tile + tstep, tile_nn = tile_n + tstep;
-        const bool alive_nn = (tile_nn < n_tiles) && grp_any2(g, ss_nn < nl_nn);
-        { TilePos t3 = tnn; t3.next(); nl_nn = row_fetch(t3, tile_nn + tstep, ss_nn); }       // consumed by the next iteration's vote
+        const bool alive_nn = __shfl_sync(0xffffffffu, fl_nn, 0) != 0;
+        fl_nn = flag_of(tile_nn + tstep);
         if (alive_nn && h == 0) prefetch_tile(feat, P, tile_nn, m, true);
         const bool alive_cur = alive, alive_nx = alive_n;
         alive = alive_n; alive_n = alive_nn;                                                  // shifted for the next iteration
         if (!alive_cur) {                                                                     // nothing of this tile is needed
             if (alive_nx) { if (TMAH && issuer) fetch_hash(tile_n); load_inputs(tn, tile_n); }
+            TR(24);
             continue;
         }
-        const float4 dr = dr_next;                                                            // h = 1 only
-        const float gy = t.g.y;
+        TR(0);
+        const float4 dr = dr_next;
         const float xg1 = h ? t.xb : t.x0, xg2 = h ? t.g.x : t.xb;                            // BA: see load_half
         {                                                                                     // X row m, half h
             if (!TMAH) {                                                                      // ready operand chunks 2h, 2h + 1
@@ -827,7 +829,7 @@ __global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights
                 else { stage_zero(blob_hi, blob_lo, m, 4); stage_zero(blob_hi, blob_lo, m, 5); }
                 float t_add, cin, d0, d1;
                 tsdf_terms(k, 0, t.g.x, t_add, cin, d0, d1);
-                stage_zero(tail_hi, tail_lo, m, 0);
+                stage_zero(tail_hi, tail_lo, m, 0);                                           // the geo columns stay zero (W21 carries them)
                 float v1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, t.g.y};
                 float v2[8] = {t.g.z, t.g.w, cin, 0.f, 0.f, 0.f, 0.f, 0.f};
                 stage8(tail_hi, tail_lo, m, 1, v1);
@@ -836,51 +838,37 @@ __global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights
             }
         }
         if (alive_nx) load_inputs(tn, tile_n);                                                // next tile's inputs
+        TR(1);
         fence_async_smem(); fence_before_sync(); grp_sync2(g);
-        if (issuer) {                                                                         // H1 = X1 W0^T
-            if (TMAH) {                                                                       // this tile's hash chunks have landed
-                if (!mbar_wait(tma_bar, tma_phase)) __trap();
-                tma_phase ^= 1u;
-            }
+        TR(2);
+        if (TMAH && iwarp) {                                                                  // this tile's hash chunks have landed
+            if (!mbar_wait(tma_bar, tma_phase)) __trap();
+        }
+        if (TMAH) tma_phase ^= 1u;
+        TR(3);
+        if (iwarp && elect_one()) {                                                           // 1: H1 = X1 W0^T
             fence_after_sync();
             uint32_t acc = 0;
             mma_kk<kXCh / 2>(tb + T_A, xh, xl, w0h, w0l, HID, idH, acc);
             commit(bar);
         }
+        TR(4);
         grp_wait(bar, phase);
+        TR(5);
         const uint32_t mask1 = relu_half<NH>(tlane + T_A + NH * h, h1_hi, h1_lo, m, (HC / 2) * h, ts_hi, ts_lo);
+        TR(6);
         tmem_st_wait(); fence_async_smem(); fence_before_sync(); grp_sync2(g);
-        if (issuer) {                                                                         // O = H1 W1^T
-            fence_after_sync();
-            uint32_t acc = 0;
-            mma_ts<HC / 2>(tb + T_B, tb + T_S, tb + T_S + NH, w1h, w1l, 16, id16, acc);
-            commit(bar);
-        }
-        grp_wait(bar, phase);
-        {                                                                                     // geo -> tail chunk h
-            float o8[8];
-            if (h == 0) {
-                float o16[16];
-                tmem_ld16(tlane + T_B, o16);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) o8[i] = o16[1 + i];
-            } else {
-                float o16[16];
-                tmem_ld16(tlane + T_B, o16);
-#pragma unroll
-                for (int i = 0; i < 7; ++i) o8[i] = o16[9 + i];
-                o8[7] = gy;
-            }
-            stage8(tail_hi, tail_lo, m, h, o8);
-        }
-        fence_async_smem(); fence_before_sync(); grp_sync2(g);
-        if (issuer) {                                                                         // H2 = X2 W2^T
+        TR(7);
+        if (iwarp && elect_one()) {                                                                         // 2: H2 = X2' W2^T + H1 W21^T
             fence_after_sync();
             uint32_t acc = 0;
             mma_kk<5>(tb + T_A, xh + kXBlob * kChunkB, xl + kXBlob * kChunkB, w2h, w2l, HID, idH, acc);
+            mma_ts<HC / 2>(tb + T_A, tb + T_S, tb + T_S + NH, w21h, w21l, HID, idH, acc);
             commit(bar);
         }
+        TR(8);
         grp_wait(bar, phase);
+        TR(9);
         uint32_t mask2;
         {                                                                                     // H2 -> shared memory only (no GEMM reads it K-major)
             uint32_t mk = 0;
@@ -897,59 +885,53 @@ __global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights
         if (h) {                                                                              // dRGB (upstream of :344)
             float v0[8] = {dr.x, dr.y, dr.z, 0.f, 0.f, 0.f, 0.f, 0.f};
             stage8_both(d_hi, d_lo, m, 0, v0, ts_hi, ts_lo);
-        } else {
-            stage_zero(d_hi, d_lo, m, 1);
+        } else {                                                                              // K = 16: the upper 8 columns of the operand
             tmem_st4(ts_hi + 4, make_uint4(0, 0, 0, 0)); tmem_st4(ts_lo + 4, make_uint4(0, 0, 0, 0));
         }
+        TR(10);
         tmem_st_wait(); fence_async_smem(); fence_before_sync(); grp_sync2(g);
-        if (issuer) {
+        TR(11);
+        if (iwarp && elect_one()) {                                                                         // 3
             fence_after_sync();
             uint32_t acc = 0;
             mma_ts_m<1>(tb + T_A, tb + T_S, tb + T_S + NH, w3h, w3l, 16, idH_bm, acc);        // dH2pre = dRGB W3
             uint32_t a3 = wacc;
-            mma_mm1(tb + A::t_w3, h2h, dh, id32_mm, a3);                                      // dW3^T += H2^T dRGB
+            mma_mm1(tb + A::t_w3, h2h, dh, id16_mm, a3);                                      // dW3^T += H2^T dRGB
             commit(bar);
         }
+        TR(12);
         grp_wait(bar, phase);
+        TR(13);
         masked_half<NH>(tlane + T_A + NH * h, h2_hi, h2_lo, m, (HC / 2) * h, mask2, ts_hi, ts_lo);   // dH2 over H2
+        if (h) {                                                                              // D <- dsdf (its MMAs have completed)
+            float v0[8] = {dr.w, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            stage8(d_hi, d_lo, m, 0, v0);
+        }
+        TR(14);
         tmem_st_wait(); fence_async_smem(); fence_before_sync(); grp_sync2(g);
-        if (issuer) {
+        TR(15);
+        if (iwarp && elect_one()) {                                                                         // 4
             fence_after_sync();
             uint32_t acc = 0;
-            mma_ts_m<HC / 2>(tb + T_B, tb + T_S, tb + T_S + NH, w2h + 6 * HID * 16, w2l + 6 * HID * 16, HID, id16_bm, acc);   // d tail[0..15] = dH2 W2[:, 48..63]
-            if constexpr (HID == 64) {                                                        // dW2 += dH2^T X2 (hidden 32: with dW0 below)
+            mma_ts_m<HC / 2>(tb + T_A, tb + T_S, tb + T_S + NH, w21h, w21l, HID, idH_bm, acc);   // dH1pre = dH2 W21 (+ dsdf W1[0] in the epilogue)
+            uint32_t am = wacc;
+            mma_mm1(tb + A::t_m, h2h, h1h, id2H_mm, am);                                      // M21 += dH2^T H1 (hidden 32: rows 64.. = dsdf^T H1)
+            if constexpr (HID == 64) {
+                uint32_t a1 = wacc;
+                mma_mm1(tb + A::t_w1, h1h, dh, id16_mm, a1);                                  // dW1[0] += dsdf^T H1
                 uint32_t a2 = wacc;
-                mma_wx(tb + A::t_w2, h2h, xh + kXBlob * kChunkB, xl + kXBlob * kChunkB, idesc_bf16(80, true, true), a2);
+                mma_wx(tb + A::t_w2, h2h, xh + kXBlob * kChunkB, xl + kXBlob * kChunkB, idesc_bf16(80, true, true), a2);   // dW2 += dH2^T X2'
             }
             commit(bar);
         }
+        TR(16);
         grp_wait(bar, phase);
-        {                                                                                     // dO = [d sdf, d geo15], chunk 1 - h
-            float dg[16], v[8];
-            tmem_ld16(tlane + T_B, dg);
-            if (h) {
-                v[0] = dr.w;
-#pragma unroll
-                for (int i = 0; i < 7; ++i) v[1 + i] = dg[i];
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = dg[7 + i];
-            }
-            stage8_both(d_hi, d_lo, m, 1 - h, v, ts_hi, ts_lo);
-        }
+        TR(17);
+        masked_half<NH>(tlane + T_A + NH * h, h1_hi, h1_lo, m, (HC / 2) * h, mask1, ts_hi, ts_lo, dr.w, w1s + NH * h);   // dH1 over H1
+        TR(18);
         tmem_st_wait(); fence_async_smem(); fence_before_sync(); grp_sync2(g);
-        if (issuer) {
-            fence_after_sync();
-            uint32_t acc = 0;
-            mma_ts_m<1>(tb + T_A, tb + T_S, tb + T_S + NH, w1h, w1l, 16, idH_bm, acc);        // dH1pre = dO W1
-            uint32_t a1 = wacc;
-            mma_mm1(tb + A::t_w1, h1h, dh, id32_mm, a1);                                      // dW1^T += H1^T dO
-            commit(bar);
-        }
-        grp_wait(bar, phase);
-        masked_half<NH>(tlane + T_A + NH * h, h1_hi, h1_lo, m, (HC / 2) * h, mask1, ts_hi, ts_lo);   // dH1 over H1
-        tmem_st_wait(); fence_async_smem(); fence_before_sync(); grp_sync2(g);
-        if (issuer) {
+        TR(19);
+        if (iwarp && elect_one()) {                                                                         // 5
             fence_after_sync();
             uint32_t acc = 0;
             if constexpr (BA) {
@@ -966,7 +948,9 @@ __global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights
             commit(bar);
         }
         wacc = 1;
+        TR(20);
         grp_wait(bar, phase);
+        TR(21);
         // every MMA that reads this tile's X operand has completed: the next alive tile's hash chunks may land on it
         if (TMAH && issuer && alive_nx) fetch_hash(tile_n);
         {
@@ -985,8 +969,9 @@ __global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights
                 if (live) dxb[(long long)h * P + q] = oneblob_dot_grad(xg1, gb);
             }
             fence_before_sync(); grp_sync2(g);
-            if (issuer) {
-                // [blob(z) | tail 0..15] -> columns 0..31, tail 16..31 -> columns 32..47, from both nets
+            if (iwarp && elect_one()) {
+                // [blob(z) | tail 0..15] -> columns 0..31, tail 16..31 -> columns 32..47, from both nets (the geo columns of the
+                // tail are not inputs here: their part of the gradient went through W21)
                 fence_after_sync();
                 uint32_t acc = 0;
                 mma_km<HC / 2>(tb + T_A, h1h, h1l, w0h + 8 * HID * 16, w0l + 8 * HID * 16, HID, id32_bm, acc);
@@ -1011,23 +996,32 @@ __global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights
                 if (live) reinterpret_cast<float4*>(dgb)[q] = make_float4(tc[2] * dg_cin + dr.w * dg_add, ta[15] + dr.x, tc[0] + dr.y, tc[1] + dr.z);
             }
         }
-        if (++since_flush == kFlushTiles) { flush_wgrads3<HID>(tlane, gr, m, h); wacc = 0; since_flush = 0; }
+        TR(22);
+#ifdef RF_MLP_TRACE
+        if (issuer) tr_acc[31] += 1;
+#endif
+        if (++since_flush == kFlushTiles) {
+            fence_before_sync();
+            flush_wgrads3<HID>(tlane, gr, wts, reinterpret_cast<float*>(h2_hi), g, m, h); wacc = 0; since_flush = 0;
+        }
         fence_before_sync();
     }
-    if (wacc) flush_wgrads3<HID>(tlane, gr, m, h);
+    if (wacc) flush_wgrads3<HID>(tlane, gr, wts, reinterpret_cast<float*>(h2_hi), g, m, h);
+    TR(25);
+#ifdef RF_MLP_TRACE
+    if (issuer) for (int i = 0; i < 32; ++i) atomicAdd(&g_mlp_trace[i], tr_acc[i]);
+#endif
     fence_before_sync();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base_s, TCOLS);
 }
 
-template <int HID, int G> static size_t fwd_bytes() { static_assert(WLC<HID>::total == WL<HID>::total, "weight layouts"); return (size_t)G * FwdL<HID>::bytes + WL<HID>::total; }
-template <int HID, int G> static size_t bwd_bytes() { return (size_t)G * BwdL<HID>::bytes + WL<HID>::total; }
+template <int HID, int G> static size_t fwd_bytes() { return (size_t)G * FwdL<HID>::bytes + WL<HID>::total_bwd; }
+template <int HID, int G> static size_t bwd_bytes() { return (size_t)G * BwdL<HID>::bytes + WL<HID>::total_bwd; }
 
 template <int HID, int G>
 static int launch_fwd_g(const RayK& k, const Weights& w, const float* feat, long long P, int variant, float* raw, cudaStream_t s) {
-    // RF_FWD_CAT=0 selects the three-MMA k-steps (separate hi / lo weight operands); default: concatenated weights, two MMAs
-    static const bool cat = [] { const char* e = getenv("RF_FWD_CAT"); return e ? atoi(e) != 0 : true; }();
-    auto fn = cat ? mlp_fwd_tc_kernel<HID, G, true> : mlp_fwd_tc_kernel<HID, G, false>;
+    auto fn = mlp_fwd_tc_kernel<HID, G>;
     size_t sm = fwd_bytes<HID, G>();
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return set_error((int)e, "cudaFuncSetAttribute(mlp_fwd_tc, %zu B): %s", sm, cudaGetErrorString(e));
@@ -1039,8 +1033,8 @@ static int launch_fwd_g(const RayK& k, const Weights& w, const float* feat, long
     return 0;
 }
 template <int HID, int G>
-static int launch_bwd_g(const RayK& k, const Weights& w, const float* feat, long long P, const float* d_raw_tot, const int* n_live, float* dfeat,
-                        const Grads& gr, float* dgb, float* dxb, cudaStream_t s) {
+static int launch_bwd_g(const RayK& k, const Weights& w, const float* feat, long long P, const float* d_raw_tot, const int* n_live,
+                        unsigned char* tile_flags, float* dfeat, const Grads& gr, float* dgb, float* dxb, cudaStream_t s) {
     const bool ba = dgb != nullptr;
     // RF_BWD_HASH_TMA=0 moves the hash operand chunks through registers (LDG.128 -> STS.128) instead of TMA bulk copies
     static const bool tma = [] { const char* e = getenv("RF_BWD_HASH_TMA"); return e ? atoi(e) != 0 : true; }();
@@ -1052,12 +1046,25 @@ static int launch_bwd_g(const RayK& k, const Weights& w, const float* feat, long
     long long tiles = (P + kTile - 1) / kTile;
     int blocks = (int)std::min<long long>((tiles + G - 1) / G, (long long)num_sms());
     ProfScope ps(RF_PROF_MLP_BWD, s);
-    fn<<<blocks, G * 256, sm, s>>>(k, w, feat, P, d_raw_tot, n_live, dfeat, gr, dgb, dxb);
+    if (n_live) {
+        tile_live_kernel<<<(unsigned)((tiles * 32 + 255) / 256), 256, 0, s>>>(k.n_rays, P, n_live, tile_flags);
+        RF_CHECK_LAUNCH("tile_live_kernel");
+    }
+    fn<<<blocks, G * 256, sm, s>>>(k, w, feat, P, d_raw_tot, n_live ? tile_flags : nullptr, dfeat, gr, dgb, dxb);
     RF_CHECK_LAUNCH("mlp_bwd_tc2_kernel");
     return 0;
 }
 
 }  // namespace
+
+#ifdef RF_MLP_TRACE
+extern "C" int rf_debug_mlp_trace(unsigned long long* out, int reset) {
+    cudaDeviceSynchronize();
+    if (out) cudaMemcpyFromSymbol(out, g_mlp_trace, sizeof(unsigned long long) * 32);
+    if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(g_mlp_trace, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 int launch_encode(const RayK& k, const GridDev& hg, const GridDev& gg, const rf_ray_params* p, const float* rays_o, const float* rays_d,
                   const float* z_vals, long long P, float* feat, cudaStream_t s);
@@ -1088,7 +1095,7 @@ int launch_points_tc(RayK k, int hidden, const GridDev& hg, const GridDev& gg, c
 }
 
 // dfeat: 2L * P floats of scratch ([4 quads][P][8]), then (ray gradients only) 4P + 3P floats for the GBV-texel and OneBlob
-// gradients, then scatter_scratch_floats() floats for the table replicas
+// gradients, then scatter_scratch_floats() floats for the table replicas, then one byte per tile (liveness flags)
 int launch_bwd_tc(const RayK& k, int hidden, const GridDev& hg, const GridDev& gg, const rf_ray_params* p, long long P, const float* feat,
                   const float* d_raw_tot, const int* n_live, float* dfeat, const Grads& gr, float* g_rays_o, float* g_rays_d, cudaStream_t s) {
     Weights w{p->w_sdf0, p->w_sdf1, p->w_col0, p->w_col1};
@@ -1096,8 +1103,9 @@ int launch_bwd_tc(const RayK& k, int hidden, const GridDev& hg, const GridDev& g
     float* dgb = ba ? dfeat + 2ll * hg.n_levels * P : nullptr;
     float* dxb = ba ? dgb + 4 * P : nullptr;
     float* rep = ba ? dxb + ((3 * P + 3) & ~3ll) : dfeat + 2ll * hg.n_levels * P;     // replicas are float2 / float4 accessed
-    int rc = hidden == 64 ? launch_bwd_g<64, 1>(k, w, feat, P, d_raw_tot, n_live, dfeat, gr, dgb, dxb, s)
-                          : launch_bwd_g<32, 2>(k, w, feat, P, d_raw_tot, n_live, dfeat, gr, dgb, dxb, s);
+    unsigned char* tile_flags = reinterpret_cast<unsigned char*>(rep + scatter_scratch_floats(hg, k.n_rays));      // ws_tiles(P) bytes
+    int rc = hidden == 64 ? launch_bwd_g<64, 1>(k, w, feat, P, d_raw_tot, n_live, tile_flags, dfeat, gr, dgb, dxb, s)
+                          : launch_bwd_g<32, 2>(k, w, feat, P, d_raw_tot, n_live, tile_flags, dfeat, gr, dgb, dxb, s);
     if (rc) return rc;
     if (ba) return launch_scatter_raygrad(k, hg, gg, p, P, feat, dfeat, dgb, dxb, n_live, gr.g_hash, rep, g_rays_o, g_rays_d, s);
     if (gr.g_hash) rc = launch_scatter(k, hg, P, feat, dfeat, n_live, gr.g_hash, rep, nullptr, s);

@@ -828,7 +828,7 @@ extern "C" int64_t rf_ray_scratch_floats(const rf_ray_cfg* cfg, const rf_grid_de
     if (cfg->mlp_precision != 1 || !tc_supported(k, cfg->hidden)) return ray_grads ? 7 * P : 4 * P;
     GridDev hg = to_dev(hash);
     return (4 + 2 * hash->n_levels + (ray_grads ? 7 : 0)) * P + (ray_grads ? 4 : 0) + ((n_rays + 3) & ~(int64_t)3) +
-           (int64_t)scatter_scratch_floats(hg, (long long)n_rays);
+           (int64_t)scatter_scratch_floats(hg, (long long)n_rays) + (ws_tiles(P) + 3) / 4 + 4;      // + one byte per tile (liveness flags)
 }
 
 extern "C" int rf_point_query_forward(const rf_ray_cfg* cfg, const rf_grid_desc* hash, const rf_grid_desc* gbv, const rf_ray_params* p,

@@ -31,6 +31,14 @@ __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence
 // generic-proxy shared-memory writes -> visible to the async proxy (tensor core reads)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// One lane of a fully converged warp (elect.sync): ptxas recognises the pattern and issues the guarded tcgen05 instructions once,
+// from uniform registers, instead of wrapping each of them in a loop over the active lanes.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- mbarrier --------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
