@@ -605,24 +605,37 @@ __device__ __forceinline__ void flush_wgrads3(uint32_t tlane, const Grads& gr, c
             if (gr.g_w_sdf1 && (hi_lane || lo_lane)) atomicAdd(gr.g_w_sdf1 + jj, hi_lane ? v[0] + v[8] : v[0]);
         }
     }
-    // M21[j][i] = sum over the samples of dH2[j] H1[i]
-    for (int i = (h * 128 + m); i < HID * HID; i += 256) scratch[i] = 0.f;
-    grp_sync2(g);
-    if (h == 0) {
+    // M21[j][i] = sum over the samples of dH2[j] H1[i] -> scratch, in a fixed order (the hi lane of a unit writes hi.hi + hi.lo, its lo
+    // lane adds lo.hi after a barrier): no atomics, the result does not depend on thread timing
+    if (h == 0 && hi_lane) {                                      // warp-uniform: HID is a multiple of 32
 #pragma unroll 1
-        for (int q = 0; q < 2 * HID / 32; ++q) {
-            float v[32];
-            tmem_ld32(tlane + A::t_m + 32 * q, v);
-            const bool lo_cols = 32 * q >= HID;
-            if (hi_lane || (lo_lane && !lo_cols)) {
+        for (int q = 0; q < HID / 32; ++q) {
+            float u[32], v[32];
+            tmem_ld32(tlane + A::t_m + 32 * q, u);
+            tmem_ld32(tlane + A::t_m + HID + 32 * q, v);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) atomicAdd(scratch + jj * HID + ((32 * q + i) & (HID - 1)), v[i]);
-            }
-            if constexpr (HID == 32) {                            // lanes 64 / 72 = the hi / lo part of dsdf: dW1[0][i]
-                if (gr.g_w_sdf1 && (m == 64 || (m == 72 && !lo_cols))) {
+            for (int i = 0; i < 32; ++i) scratch[jj * HID + 32 * q + i] = u[i] + v[i];
+        }
+    }
+    grp_sync2(g);
+    if (h == 0 && lo_lane) {
+#pragma unroll 1
+        for (int q = 0; q < HID / 32; ++q) {
+            float u[32];
+            tmem_ld32(tlane + A::t_m + 32 * q, u);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) atomicAdd(gr.g_w_sdf1 + i, v[i]);
-                }
+            for (int i = 0; i < 32; ++i) scratch[jj * HID + 32 * q + i] += u[i];
+        }
+    }
+    if constexpr (HID == 32) {                                    // lanes 64 / 72 of t_m = the hi / lo part of dsdf: dW1[0][i] = dsdf^T H1
+        if (h == 0 && m >= 64 && m < 96) {
+            float u[32], v[32];
+            tmem_ld32(tlane + A::t_m, u);
+            tmem_ld32(tlane + A::t_m + 32, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float lo_part = __shfl_sync(0xffffffffu, u[i], 8);
+                if (m == 64 && gr.g_w_sdf1) atomicAdd(gr.g_w_sdf1 + i, (u[i] + v[i]) + lo_part);
             }
         }
     }
