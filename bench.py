@@ -273,8 +273,11 @@ def run_gpu(args, rank, world, local_rank):
         model.embed_res_fn.params.copy_((torch.rand_like(model.embed_res_fn.params) * 2 - 1) * 1e-2)
     model.train()
     params = [model.embed_res_fn.params] + list(model.decoder_res.fused_weights())
-    # several ranks: the gradients live in one flat buffer (views are the parameters' .grad) that is all-reduced in place
-    fg = rdist.FlatGrads(params) if world > 1 else None
+    # The optimiser step of the mapping loop closes every timed step (mp_slam/mapper.py:417-423; groups of mp_slam/slam.py:271-286):
+    # gradients and parameters live in two flat buffers; with several ranks the step is reduce-scatter -> fused Adam on the
+    # owned shard -> all-gather (remixfusion_b200.dist.ShardedAdam), on one GPU the fused Adam alone.  It also clears the gradients.
+    fg = rdist.ShardedAdam([{"params": params[1:], "weight_decay": 1e-6, "lr": 1e-2}, {"params": params[:1], "eps": 1e-15, "lr": 1e-2}],
+                           betas=(0.9, 0.99), group=group)
 
     R = cfg["globalV"]["base_resolution"]
     z_slab = rdist.slab(R, rank, world)
@@ -328,19 +331,13 @@ def run_gpu(args, rank, world, local_rank):
             sizes = [4 * (rdist.slab(R, k, world)[1] - rdist.slab(R, k, world)[0]) * R * R for k in range(world)]
             rdist.gather_slabs(mvol.model.GBV.params, sizes, group, out=full_gbv.params.data)
         if timed: e[2].record()
-        if fg is not None:
-            fg.zero()
-        else:
-            for p in params:
-                p.grad = None
         if timed and os.environ.get("RF_BENCH_DEBUG"):
             dbg = torch.cuda.Event(enable_timing=True); dbg.record(); e.append(dbg)
         ret = model.mapping(f["rays_o"], f["rays_d"], f["tgt_c"], f["tgt_d"])
         loss = configs.total_loss(cfg, ret)
         if timed: e[3].record()
         loss.backward()
-        if fg is not None:
-            fg.allreduce(group)
+        fg.step()
         if timed: e[4].record()
         return e, loss
 
@@ -428,8 +425,8 @@ def run_gpu(args, rank, world, local_rank):
         comm_ms = {"frame_broadcast": _t(lambda: rdist.broadcast_frame(bc[0]["depth"], bc[0]["rgb"], 0, group)),
                    "gbv_slab_all_gather": _t(lambda: rdist.gather_slabs(mvol.model.GBV.params, sizes_, group, out=full_gbv.params.data)),
                    "loss_sums_all_reduce": _t(lambda: dist.all_reduce(part_, group=group)),
-                   "grad_all_reduce": _t(lambda: fg.allreduce(group)),
-                   "bytes": {"frame": int(16 * H * W), "gbv": int(16 * R ** 3), "grads": int(fg.flat.numel() * 4)}}
+                   "grad_reduce_scatter_adam_all_gather": _t(lambda: fg.step()),
+                   "bytes": {"frame": int(16 * H * W), "gbv": int(16 * R ** 3), "grads": int(fg.gflat.numel() * 4)}}
 
     # ---- the other BASELINE configurations (bench_workloads.py), every rank takes part --------------------------------
     extra_parts = {}
@@ -516,8 +513,9 @@ def run_gpu(args, rank, world, local_rank):
         },
         "e2e": {"value": float(e2e_units[0]) / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"], "steps": e2e["steps"],
                 "ms_per_step": e2e_ms / e2e["steps"]},
-        # per step: 2 TSDF integrates, ray_z, encode walk, decoder fwd, composite fwd / bwd, decoder bwd, scatter walk, replica fold
-        "gpu_launches": 11 * args.steps,
+        # per step: 2 TSDF integrates, ray_z, encode walk, decoder fwd, composite fwd / bwd, tile liveness, decoder bwd, scatter walk,
+        # replica fold, fused Adam (one launch per parameter group segment: 2)
+        "gpu_launches": 13 * args.steps,
         "clocks": clocks,
     }
     line["parts"].update(extra_parts)
@@ -761,11 +759,6 @@ def run_e2e(args, cfg, K, frames, model, mvol, local, params, fg, dev, rank, wor
             R = cfg["globalV"]["base_resolution"]
             sizes = [4 * (rdist.slab(R, k, world)[1] - rdist.slab(R, k, world)[0]) * R * R for k in range(world)]
             rdist.gather_slabs(mvol.model.GBV.params, sizes, group, out=model.GBV.params.data)
-        if fg is not None:
-            fg.zero()
-        else:
-            for p in params:
-                p.grad = None
         (ro, rd, tc, td), ev = pre
         cur = torch.cuda.current_stream()
         cur.wait_event(ev)
@@ -774,8 +767,7 @@ def run_e2e(args, cfg, K, frames, model, mvol, local, params, fg, dev, rank, wor
         ret = model.mapping(ro, rd, tc, td)
         loss = configs.total_loss(cfg, ret)
         loss.backward()
-        if fg is not None:
-            fg.allreduce(group)
+        fg.step()                                                # the optimiser step (ShardedAdam of the resident loop)
         out = torch.stack([ret["rgb_res_loss"], ret["depth_res_loss"], ret["sdf_res_loss"], ret["fs_res_loss"]]).cpu()
         return out, nxt
 

@@ -292,12 +292,13 @@ def cfg5_part(dev, rank, world, group, n_keyframes=24, n_pool=4):
     keep = int(H * W * cfg["mapping"]["n_pixels"])
     store = KeyFrameDatabase(cfg, H, W, n_keyframes + 8, keep, dev)
     dec = [p for p in model.decoder_res.parameters()]
-    opt = Adam([{"params": dec, "weight_decay": 1e-6, "lr": cfg["mapping"]["lr_decoder"]},
-                {"params": [model.embed_res_fn.params], "eps": 1e-15, "lr": cfg["mapping"]["lr_embed_res"]}], betas=(0.9, 0.99),
-               capturable=(world == 1))
+    groups = [{"params": dec, "weight_decay": 1e-6, "lr": cfg["mapping"]["lr_decoder"]},
+              {"params": [model.embed_res_fn.params], "eps": 1e-15, "lr": cfg["mapping"]["lr_embed_res"]}]
     loss_fn = lambda r: configs.total_loss(cfg, r)
+    # one GPU: the whole iteration incl. the fused Adam is one CUDA graph; several ranks: reduce-scatter -> Adam on the owned shard
+    # -> all-gather (ShardedAdam), which also clears the gradients
+    opt = Adam(groups, betas=(0.9, 0.99), capturable=True) if world == 1 else rdist.ShardedAdam(groups, betas=(0.9, 0.99), group=group)
     graphed = GraphedMappingStep(model, opt, n_rays, loss_fn, eager_steps=2) if world == 1 else None
-    fg = rdist.FlatGrads([model.embed_res_fn.params] + dec) if world > 1 else None
 
     def rays_from_rows(rows, c2w_t):
         d = torch.sum(rows[:, None, :3] * c2w_t[:3, :3], -1)
@@ -310,12 +311,11 @@ def cfg5_part(dev, rank, world, group, n_keyframes=24, n_pool=4):
             return
         if ba:
             ro = ro.clone().requires_grad_(True); rd = rd.clone().requires_grad_(True)
-        if fg is not None:
-            fg.zero()
         loss_fn(model.mapping(ro, rd, tc, td, clamp=ba)).backward()
-        if fg is not None:
-            fg.allreduce(group)
-        opt.step(zero_grad=(fg is None))
+        if world == 1:
+            opt.step(zero_grad=True)
+        else:
+            opt.step()
 
     def keyframe_cycle(i):
         c2w, depth, rgb = pool[i % n_pool]
@@ -338,7 +338,7 @@ def cfg5_part(dev, rank, world, group, n_keyframes=24, n_pool=4):
     ms = _timed(keyframe_cycle, n_keyframes, world, dev, warm=3)
     iters = cfg["mapping"]["iters"] + cfg["mapping"]["BA_iters"]
     out = {"workload": f"uHumans2-shaped stream ({W}x{H}, {S} samples per ray, hash 16 x 2^21, GBV R = {R}): per keyframe integrate_kf + ray store + "
-                       f"{cfg['mapping']['iters']} mapping iterations (CUDA graph incl. fused Adam) + {cfg['mapping']['BA_iters']} BA iterations of {n_rays} rays",
+                       f"{cfg['mapping']['iters']} mapping iterations (one GPU: CUDA graph incl. fused Adam; several: reduce-scatter / Adam shard / all-gather) + {cfg['mapping']['BA_iters']} BA iterations of {n_rays} rays",
            "scaling": "weak", "keyframe_cycles_timed": n_keyframes, "ms_per_keyframe_cycle": ms, "keyframe_cycles_per_s": 1e3 / ms,
            "sequence_1000_frames_s": 200 * ms / 1e3, "ray_samples_per_s_fwd_bwd": world * iters * n_rays * S / (ms / 1e3),
            "iterations_per_cycle": iters, "rays_per_iteration_per_rank": n_rays}

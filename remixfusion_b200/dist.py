@@ -156,3 +156,89 @@ def gather_touched_box(full: torch.Tensor, local: torch.Tensor, R: int, z_slabs,
     dist.all_gather_into_tensor(stage.view(-1), piece.view(-1), group=group)
     full[:world * dz * R * R * channels].view(world, dz, R, R, channels)[:, :, lo[1]:hi[1], lo[0]:hi[0], :] = stage
     return full
+
+
+def _rf_adam_segment(p, g, m, v, hp, step):
+    """One fused Adam pass (rf_adam_step) over a contiguous fp32 CUDA segment; clears the gradient in the same pass."""
+    import ctypes as C
+    from . import abi
+    rc = abi.lib().rf_adam_step(abi.dptr(p), abi.dptr(g), abi.dptr(m), abi.dptr(v), C.c_int64(p.numel()), C.c_double(hp["lr"]),
+                                C.c_double(hp["betas"][0]), C.c_double(hp["betas"][1]), C.c_double(hp["eps"]),
+                                C.c_double(hp["weight_decay"]), C.c_int64(step), None, C.c_int(1), abi.stream_ptr())
+    abi.check(rc, "rf_adam_step")
+
+
+class ShardedAdam:
+    """The optimiser step of the mapping loop (mp_slam/mapper.py:417-423 over the groups of mp_slam/slam.py:271-286) for
+    replicated parameters and rank-sharded ray batches:  reduce-scatter of the gradients -> fused Adam on the owned 1/W of every
+    tensor -> all-gather of the updated parameters.  Same bytes on the wire as the all-reduce it replaces (a ring all-reduce IS
+    reduce-scatter + all-gather), but the Adam pass and its two moment buffers shrink by the world size.
+
+    Parameters and gradients are re-homed as views of two flat buffers (each tensor starts on a 16-byte boundary, the total is
+    padded to a multiple of 4 W floats): ``p.data`` / ``p.grad`` stay usable by the model and by autograd.  Element-wise, the
+    update is ``remixfusion_b200.optim.Adam``'s (torch's dense Adam); a shard that straddles two parameter groups is stepped
+    in one segment per group.  ``adam_fn`` replaces the CUDA kernel in the CPU tests of the host logic."""
+
+    def __init__(self, param_groups, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, group=None, adam_fn=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._adam = adam_fn or _rf_adam_segment
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        spans, off, first = [], 0, None                        # (param, start, numel, hyper-parameters)
+        for gdict in param_groups:
+            hp = {k: gdict.get(k, d) for k, d in defaults.items()}
+            for p in gdict["params"]:
+                if not p.requires_grad:
+                    continue
+                first = p if first is None else first
+                spans.append((p, off, p.numel(), hp))
+                off += (p.numel() + 3) & ~3
+        if first is None:
+            raise ValueError("ShardedAdam: no trainable parameter")
+        quantum = 4 * self.world
+        total = (off + quantum - 1) // quantum * quantum
+        self.pflat = torch.zeros(total, dtype=first.dtype, device=first.device)
+        self.gflat = torch.zeros(total, dtype=first.dtype, device=first.device)
+        for p, s, n, _ in spans:
+            self.pflat[s:s + n].copy_(p.data.reshape(-1))
+            p.data = self.pflat[s:s + n].view_as(p)
+            p.grad = self.gflat[s:s + n].view_as(p)
+        self.shard = total // self.world
+        self.lo = self.rank * self.shard
+        self.gshard = self.gflat[self.lo:self.lo + self.shard] if self.world == 1 else torch.zeros_like(self.gflat[:self.shard])
+        self.exp_avg = torch.zeros_like(self.gshard)
+        self.exp_avg_sq = torch.zeros_like(self.gshard)
+        self.segments = []                                     # (start inside the shard, numel, hyper-parameters)
+        for _, s, n, hp in spans:
+            a, b = max(s, self.lo), min(s + n, self.lo + self.shard)
+            if b > a:
+                self.segments.append((a - self.lo, b - a, hp))
+        self.steps = 0
+        self._rs = None
+        if self.world > 1:
+            try:                                               # gloo (the CPU tests) has no reduce-scatter: all-reduce and keep the shard
+                dist.reduce_scatter_tensor(torch.zeros_like(self.gshard), torch.zeros_like(self.gflat), group=group)
+                self._rs = True
+            except (RuntimeError, NotImplementedError):
+                self._rs = False
+
+    def zero_grad(self):
+        self.gflat.zero_()
+
+    @torch.no_grad()
+    def step(self):
+        """Gradients summed over the ranks, parameters stepped and replicated again, gradients cleared."""
+        if self.world > 1:
+            if self._rs:
+                dist.reduce_scatter_tensor(self.gshard, self.gflat, op=dist.ReduceOp.SUM, group=self.group)
+            else:
+                dist.all_reduce(self.gflat, op=dist.ReduceOp.SUM, group=self.group)
+                self.gshard.copy_(self.gflat[self.lo:self.lo + self.shard])
+        self.steps += 1
+        own = self.pflat[self.lo:self.lo + self.shard]
+        for a, n, hp in self.segments:
+            self._adam(own[a:a + n], self.gshard[a:a + n], self.exp_avg[a:a + n], self.exp_avg_sq[a:a + n], hp, self.steps)
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.pflat, own.clone() if not self._rs else own, group=self.group)
+            self.gflat.zero_()

@@ -110,3 +110,53 @@ def test_frustum_box_contains_every_projected_voxel():
         assert vis.sum() > 0
         for a in range(3):
             assert idx[:, a].min() >= lo[a] and idx[:, a].max() < hi[a], (a, lo, hi, idx[:, a].min(), idx[:, a].max())
+
+
+def _torch_adam_segment(p, g, m, v, hp, step):
+    """torch's dense Adam on a segment (stand-in for rf_adam_step in the CPU test of the sharding logic); clears g."""
+    b1, b2 = hp["betas"]
+    gg = g + hp["weight_decay"] * p if hp["weight_decay"] else g.clone()
+    m.lerp_(gg, 1 - b1)
+    v.mul_(b2).addcmul_(gg, gg, value=1 - b2)
+    bc1, bc2 = 1 - b1 ** step, 1 - b2 ** step
+    p.addcdiv_(m, v.sqrt() / (bc2 ** 0.5) + hp["eps"], value=-hp["lr"] / bc1)
+    g.zero_()
+
+
+def _sharded_adam_worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    rdist.init_from_env("gloo")
+    torch.manual_seed(1)                                         # replicated parameters
+    table = torch.nn.Parameter(torch.randn(1001)); w0 = torch.nn.Parameter(torch.randn(7, 5)); w1 = torch.nn.Parameter(torch.randn(3, 7))
+    ref = [torch.nn.Parameter(t.detach().clone()) for t in (table, w0, w1)]
+    groups = lambda ps: [{"params": [ps[1], ps[2]], "weight_decay": 1e-6, "lr": 1e-2}, {"params": [ps[0]], "eps": 1e-15, "lr": 1e-2}]
+    opt = rdist.ShardedAdam(groups([table, w0, w1]), betas=(0.9, 0.99), adam_fn=_torch_adam_segment)
+    ref_opt = torch.optim.Adam(groups(ref), betas=(0.9, 0.99))
+    ok = opt.world == world and table.grad._base is opt.gflat and table.data.untyped_storage().data_ptr() == opt.pflat.untyped_storage().data_ptr()
+    g = torch.Generator().manual_seed(7)
+    for it in range(4):
+        x = [torch.randn(world, *t.shape, generator=g) for t in (table, w0, w1)]      # every rank's loss weights (same stream on all ranks)
+        sum((p * xi[rank]).sum() for p, xi in zip((table, w0, w1), x)).backward()      # this rank's gradient
+        opt.step()
+        for r, xi in zip(ref, x):
+            r.grad = xi.sum(0)                                                          # the summed gradient, unsharded
+        ref_opt.step()
+        for a, b in zip((table, w0, w1), ref):
+            ok &= bool(torch.allclose(a.detach(), b.detach(), rtol=1e-6, atol=1e-7))
+        ok &= bool(float(opt.gflat.abs().sum()) == 0.0)
+    q.put((rank, ok, len(opt.segments)))
+    dist.destroy_process_group()
+
+
+def test_sharded_adam_world2_matches_unsharded():
+    """reduce-scatter -> Adam on the owned shard -> all-gather reproduces torch.optim.Adam on the summed gradients, with the
+    reference's two parameter groups (mp_slam/slam.py:271-286) and a shard boundary inside the hash table."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_sharded_adam_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in ps: p.start()
+    res = [q.get(timeout=120) for _ in ps]
+    for p in ps: p.join(timeout=60)
+    assert all(ok for _, ok, _ in res), res
+    assert sorted(n for _, _, n in res)[-1] >= 2, res              # some shard spans more than one tensor
