@@ -768,20 +768,43 @@ def run_e2e(args, cfg, K, frames, model, mvol, local, params, fg, dev, rank, wor
         loss = configs.total_loss(cfg, ret)
         loss.backward()
         fg.step()                                                # the optimiser step (ShardedAdam of the resident loop)
-        out = torch.stack([ret["rgb_res_loss"], ret["depth_res_loss"], ret["sdf_res_loss"], ret["fs_res_loss"]]).cpu()
-        return out, nxt
+        # the step's result goes to page-locked host memory; the host reads it one step later, so that it is already enqueueing
+        # the next step while this one runs (every step's losses are read inside the timed region, the last one before it ends)
+        slot = res_host[i % 2]
+        slot.copy_(torch.stack([ret["rgb_res_loss"], ret["depth_res_loss"], ret["sdf_res_loss"], ret["fs_res_loss"]]), non_blocking=True)
+        done = torch.cuda.Event(); done.record()
+        return (slot, done), nxt
 
-    n_steps = max(2, min(args.steps, 4))
+    def read_result(res):
+        slot, done = res
+        done.synchronize()
+        return float(slot.sum())
+
+    blocking_read = bool(os.environ.get("RF_E2E_BLOCKING_READ"))     # A/B switch: read every step's losses before enqueueing the next step
+
+    n_steps = max(2, min(args.steps, 8))
+    res_host = [torch.empty(4, dtype=torch.float32).pin_memory() for _ in range(2)]
     pre = prefetch(0)
-    _, pre = step(0, pre, True); _, pre = step(1, pre, False)
+    for w in range(3):                                     # warm-up: allocator blocks of two live steps, pinned staging, NCCL channels
+        r, pre = step(w, pre, w < 2)
+        read_result(r)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     pre = prefetch(0)                                      # the first step's inputs are copied inside the timed region too
+    prev = None
     for i in range(n_steps):
-        _, pre = step(i, pre, i + 1 < n_steps)
+        res, pre = step(i, pre, i + 1 < n_steps)
+        if blocking_read:
+            read_result(res)
+            continue
+        if prev is not None:
+            read_result(prev)
+        prev = res
+    if prev is not None:
+        read_result(prev)
     b.record(); torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

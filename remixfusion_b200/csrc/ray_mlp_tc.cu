@@ -3,13 +3,16 @@
 // Replaces ColorSDFNet.forward (model/decoder.py:132-146: SDFNet :59-110, ColorNet :6-53) and its autograd backward,
 // including the concatenations of JointEncoding.query_color_sdf (model/scene_rep.py:325-345), for 128-sample tiles:
 //
-//   forward   X1 = [hash32 | oneblob48 | tsdf]           H1 = relu(X1 W0^T)      O = H1 W1^T   (sdf, geo15)
+//   reference X1 = [hash32 | oneblob48 | tsdf]           H1 = relu(X1 W0^T)      O = H1 W1^T   (sdf, geo15)
 //             X2 = [oneblob48 | geo15 | gbv_rgb3]         H2 = relu(X2 W2^T)      rgb = H2 W3^T
 //             raw = (rgb + gbv_rgb, sdf + tsdf)                                   (:344-345)
-//   backward  recomputes the forward, then dH2 = (dRGB W3) . relu', dgeo = dH2 W2[:,geo], dO = [dsdf, dgeo],
-//             dH1 = (dO W1) . relu', dhash = dH1 W0[:,hash]; the four weight gradients X^T dH are accumulated in
-//             TMEM across the tiles a CTA processes and handed over with atomics every kFlushTiles tiles.
-//             BA mode additionally produces the gradients w.r.t. the OneBlob inputs and the GBV texel (ray gradients).
+//   here      the geo features are linear in H1, so they are never materialised: with W21 = W2[:, geo] W1[geo, :] (fp32, per CTA)
+//             H2 = relu([oneblob48 | gbv_rgb3] W2'^T + H1 W21^T),   sdf = H1 W1[0]^T
+//             — three tensor-core phases per tile forward, five backward (see the kernels), instead of one per layer and
+//             direction; the gradients of both factors of W21 come out of M21 = dH2^T H1 when the accumulators are flushed.
+//             The weight gradients are accumulated in TMEM across the tiles a CTA processes and handed over with atomics
+//             every kFlushTiles tiles.  BA mode additionally produces the gradients w.r.t. the OneBlob inputs and the GBV
+//             texel (ray gradients).
 //
 // Numerics: every GEMM is a bf16x3 product (a_hi b_hi + a_hi b_lo + a_lo b_hi, fp32 accumulation in TMEM), i.e.
 // ~2^-16 relative per product — the "rendered colour / depth and gradients within 1e-3" bar with two orders of margin;
@@ -17,14 +20,14 @@
 //
 // Structure: a CTA holds the decoder weights once (bf16 hi/lo, chunked no-swizzle layout of umma.cuh) and G
 // independent groups of 128 threads (forward) or 256 threads (backward: two threads per tile row, mlp_bwd_tc2_kernel).
-// A group owns one tile at a time: thread m stages row m of the operands, one elected thread issues the MMAs, everybody
-// waits on the group's mbarrier and reads its own TMEM lane.  Groups run out of phase, so one group's tensor-core latency is
+// A group owns one tile at a time: thread m stages row m of the operands, one elected thread (elect.sync, operands provably
+// warp-uniform: see mlp_bwd_tc2_kernel) issues the MMAs, everybody waits on the group's mbarrier and reads its own TMEM lane.  Groups run out of phase, so one group's tensor-core latency is
 // covered by another group's staging.  Inputs are what ray_encode.cu wrote (sample-major: a tile is 128 consecutive rays at
 // one sample index): the hash features arrive as READY bf16 hi / lo operand chunks, 16 KB per tile — the forward moves its row
 // of them straight into tensor memory, the backward's elected thread fetches the whole block into the X operand with two TMA
 // bulk copies (cp.async.bulk -> mbarrier) — plus the GBV features and positions (coalesced, streaming); no random access
 // happens here.  Only raw / d_raw ([N][S][4], the reference's layout) are strided.  The backward skips tiles none of whose
-// rows has a live upstream gradient (n_live, see ray_encode.cu).
+// rows has a live upstream gradient (one flag per tile, tile_live_kernel, from the per-ray n_live of composite_bwd_kernel).
 #include "ray_common.cuh"
 #include "umma.cuh"
 #include <stdlib.h>
@@ -35,17 +38,18 @@ namespace {
 using namespace umma;
 
 constexpr int kChunkB = 2048;                  // bytes of one 8-column chunk of a 128-row operand
-constexpr int kXBlob = 4, kXTail = 10, kXCh = 14;   // X-order chunks: hash 0-3 | oneblob 4-9 | tail 10-13
-constexpr int kTailTsdf = 18;                  // tail = [geo15 | gbv_rgb3 | tsdf | 0 x13]
-constexpr int kKX = kXCh * 8;                  // 112
+constexpr int kXBlob = 4, kXTail = 10, kXCh = 12;   // X-order chunks: hash 0-3 | oneblob 4-9 | tail 10-11
+constexpr int kTailTsdf = 3;                   // tail = [gbv_rgb3 | tsdf | 0 x12]: the geo features never appear as inputs (W21 below)
+constexpr int kKX = kXCh * 8;                  // 96
+constexpr int kK2 = kKX - 32;                  // colour-net input columns: oneblob 48 | tail 16
 constexpr int kFlushTiles = 256;               // weight-gradient accumulators are flushed every this many tiles
 
 template <int HID>
 struct WL {                                    // weight shared-memory layout (bytes); B operands, rows = out units
     static constexpr int HC = HID / 8;
-    static constexpr int w0 = kXCh * HID * 16; // W0 [HID rows][112]  (X-order columns)
+    static constexpr int w0 = kXCh * HID * 16; // W0 [HID rows][96]   (X-order columns)
     static constexpr int w1 = HC * 16 * 16;    // W1 [16 rows][HID]
-    static constexpr int w2 = 10 * HID * 16;   // W2 [HID rows][80]   (oneblob | tail)
+    static constexpr int w2 = 8 * HID * 16;    // W2 [HID rows][64]   (oneblob | tail)
     static constexpr int w3 = HC * 16 * 16;    // W3 [16 rows][HID]   (rows 3..15 zero)
     static constexpr int o_w0h = 0, o_w0l = w0, o_w1h = 2 * w0, o_w1l = o_w1h + w1, o_w2h = o_w1l + w1, o_w2l = o_w2h + w2,
                          o_w3h = o_w2l + w2, o_w3l = o_w3h + w3;
@@ -82,9 +86,12 @@ __device__ void load_weights(unsigned char* w, const Weights& wt, int nthreads) 
         store_split(w + L::o_w1h, w + L::o_w1l, 16, r, j, wt.w_sdf1[r * HID + j]);
         store_split(w + L::o_w3h, w + L::o_w3l, 16, r, j, (r < 3) ? wt.w_col1[r * HID + j] : 0.f);
     }
-    for (int i = threadIdx.x; i < HID * 80; i += nthreads) {
-        int j = i / 80, kx = i - j * 80;
-        store_split(w + L::o_w2h, w + L::o_w2l, HID, j, kx, (kx < kIn2) ? wt.w_col0[j * kIn2 + kx] : 0.f);
+    for (int i = threadIdx.x; i < HID * kK2; i += nthreads) {                  // colour net: blob | gbv rgb (its geo columns live in W21)
+        int j = i / kK2, kx = i - j * kK2;
+        float v = 0.f;
+        if (kx < kBlob) v = wt.w_col0[j * kIn2 + kx];
+        else if (kx < kBlob + 3) v = wt.w_col0[j * kIn2 + kGeo + kx];
+        store_split(w + L::o_w2h, w + L::o_w2l, HID, j, kx, v);
     }
 }
 
@@ -259,15 +266,17 @@ __device__ __forceinline__ void prefetch_tile(const float* __restrict__ feat, lo
 // columns) and runs THREE phases per tile instead of one per layer: the geo features are linear in H1 (model/decoder.py:138-143),
 // so the colour net's hidden layer is issued together with the sdf output, from H1 and W21 = W2[:, geo] W1[geo, :]:
 //   1  H1 = relu(X1 W0^T)      2  sdf = H1 W1[0]^T,  H2 = relu(X2' W2^T + H1 W21^T)      3  rgb = H2 W3^T
-// TMEM columns of a group: accumulator [0, HID), hash hi/lo 16+16 (the sdf result lands there in phase 2), tail hi/lo 16+16,
-// hidden hi/lo HID/2 + HID/2.
+// TMEM columns of a group: accumulator [0, HID) | hash hi/lo 16+16, later the hidden activations hi/lo HID/2 + HID/2 over the same
+// columns (the hash operand is dead once phase 1 has completed, H1 once phase 2 has) | tail hi/lo 8+8 | sdf result 16:
+// 96 columns at hidden 32 (four groups per SM; five fit but are slower, see launch_fwd_tc), 160 at hidden 64 (three).
 // ------------------------------------------------------------------------------------------------------------
 template <int HID>
 struct FwdL {
     static constexpr int c_blob_hi = 0, c_blob_lo = 6, chunks = 12;     // shared memory per group: OneBlob hi / lo
     static constexpr int bytes = chunks * kChunkB;
-    static constexpr int t_acc = 0, t_hash_hi = HID, t_hash_lo = HID + 16, t_o = HID, t_tail_hi = HID + 32, t_tail_lo = HID + 48,
-                         t_h_hi = HID + 64, t_h_lo = t_h_hi + HID / 2, tcols = 2 * HID + 64;
+    static constexpr int OPW = HID > 32 ? HID : 32;                     // operand block: hash (32 columns) or hidden (HID)
+    static constexpr int t_acc = 0, t_hash_hi = HID, t_hash_lo = HID + 16, t_h_hi = HID, t_h_lo = HID + HID / 2,
+                         t_tail_hi = HID + OPW, t_tail_lo = t_tail_hi + 8, t_o = t_tail_hi + 16, tcols = t_o + 16;
 };
 
 // A from TMEM (hi at column ah, lo at column al, 8 columns per k-step); B = weights K-major
@@ -295,13 +304,12 @@ __device__ __forceinline__ void tstage_zero(uint32_t th, uint32_t tl, int c) {
 template <int HID>
 __device__ __forceinline__ void relu_to_tmem(uint32_t tacc, uint32_t th, uint32_t tl) {
 #pragma unroll
-    for (int q = 0; q < HID / 32; ++q) {
-        float v[32];
-        tmem_ld32(tacc + 32 * q, v);
+    for (int q = 0; q < HID / 16; ++q) {                      // 16 columns at a time (register pressure)
+        float v[16];
+        tmem_ld16(tacc + 16 * q, v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tstage8(th, tl, 4 * q + c, v + 8 * c);
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+        tstage8(th, tl, 2 * q, v); tstage8(th, tl, 2 * q + 1, v + 8);
     }
 }
 
@@ -355,7 +363,7 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_fwd_tc_kernel(RayK k, Weights 
         const float4 gb = t.g;                                                                // GBV features of this tile
         float t_add, cin, d0, d1;
         tsdf_terms(k, variant, gb.x, t_add, cin, d0, d1);                                     // scene_rep.py:330-337 (:230-233, :292-294)
-        // X row: hash (ready bf16 hi / lo chunks) -> TMEM, OneBlob -> shared memory, tail = [0 x15 | gbv rgb | decoder tsdf input | 0] -> TMEM
+        // X row: hash (ready bf16 hi / lo chunks) -> TMEM, OneBlob -> shared memory, tail = [gbv rgb | decoder tsdf input | 0 x12] -> TMEM
 #pragma unroll
         for (int c = 0; c < 4; ++c) { tmem_st4(tlane + A::t_hash_hi + 4 * c, t.hh[c]); tmem_st4(tlane + A::t_hash_lo + 4 * c, t.hl[c]); }
         if (live) {
@@ -365,12 +373,9 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_fwd_tc_kernel(RayK k, Weights 
             for (int c = 0; c < 6; ++c) stage_zero(blob_hi, blob_lo, m, c);
         }
         {
-            float v1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, gb.y};
-            float v2[8] = {gb.z, gb.w, cin, 0.f, 0.f, 0.f, 0.f, 0.f};
-            tstage_zero(tlane + A::t_tail_hi, tlane + A::t_tail_lo, 0);
-            tstage8(tlane + A::t_tail_hi, tlane + A::t_tail_lo, 1, v1);
-            tstage8(tlane + A::t_tail_hi, tlane + A::t_tail_lo, 2, v2);
-            tstage_zero(tlane + A::t_tail_hi, tlane + A::t_tail_lo, 3);
+            float v1[8] = {gb.y, gb.z, gb.w, cin, 0.f, 0.f, 0.f, 0.f};
+            tstage8(tlane + A::t_tail_hi, tlane + A::t_tail_lo, 0, v1);
+            tstage_zero(tlane + A::t_tail_hi, tlane + A::t_tail_lo, 1);
         }
         load_tile(t, feat, P, tile + tstep, m);                                               // next tile's inputs (see above)
         tmem_st_wait();
@@ -380,20 +385,20 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_fwd_tc_kernel(RayK k, Weights 
             uint32_t acc = 0;
             mma_ts<2>(tb + A::t_acc, tb + A::t_hash_hi, tb + A::t_hash_lo, w0h, w0l, HID, idH, acc);
             mma_kk<3>(tb + A::t_acc, smem_u32(blob_hi), smem_u32(blob_lo), w0h + kXBlob * HID * 16, w0l + kXBlob * HID * 16, HID, idH, acc);
-            mma_ts<2>(tb + A::t_acc, tb + A::t_tail_hi, tb + A::t_tail_lo, w0h + kXTail * HID * 16, w0l + kXTail * HID * 16, HID, idH, acc);
+            mma_ts<1>(tb + A::t_acc, tb + A::t_tail_hi, tb + A::t_tail_lo, w0h + kXTail * HID * 16, w0l + kXTail * HID * 16, HID, idH, acc);
             commit(bar);
         }
         grp_wait(bar, phase);
         relu_to_tmem<HID>(tlane + A::t_acc, tlane + A::t_h_hi, tlane + A::t_h_lo);            // decoder.py:105-107
         tmem_st_wait();
         fence_before_sync(); grp_sync(g);
-        if (iwarp && elect_one()) {                                                                         // 2: O = H1 W1^T (over the dead hash operand), H2 = X2' W2^T + H1 W21^T
+        if (iwarp && elect_one()) {                                                                         // 2: O = H1 W1^T, H2 = X2' W2^T + H1 W21^T
             fence_after_sync();
             uint32_t acc = 0;
             mma_ts<HC / 2>(tb + A::t_o, tb + A::t_h_hi, tb + A::t_h_lo, w1h, w1l, 16, id16, acc);
             acc = 0;
             mma_kk<3>(tb + A::t_acc, smem_u32(blob_hi), smem_u32(blob_lo), w2h, w2l, HID, idH, acc);
-            mma_ts<2>(tb + A::t_acc, tb + A::t_tail_hi, tb + A::t_tail_lo, w2h + 6 * HID * 16, w2l + 6 * HID * 16, HID, idH, acc);
+            mma_ts<1>(tb + A::t_acc, tb + A::t_tail_hi, tb + A::t_tail_lo, w2h + 6 * HID * 16, w2l + 6 * HID * 16, HID, idH, acc);
             mma_ts<HC / 2>(tb + A::t_acc, tb + A::t_h_hi, tb + A::t_h_lo, w21h, w21l, HID, idH, acc);
             commit(bar);
         }
@@ -432,20 +437,20 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_fwd_tc_kernel(RayK k, Weights 
 template <int HID>
 struct BwdL {
     static constexpr int HC = HID / 8;
-    // group region (chunks): X hi [hash4|blob6|tail4] | X lo 14 | H1 hi,lo | H2 hi,lo | D hi 1 | D lo 1
+    // group region (chunks): X hi [hash4|blob6|tail2] | X lo 12 | H1 hi,lo | H2 hi,lo | D hi 1 | D lo 1
     static constexpr int c_x_hi = 0, c_x_lo = kXCh, c_h1_hi = 2 * kXCh, c_h1_lo = c_h1_hi + HC, c_h2_hi = c_h1_lo + HC, c_h2_lo = c_h2_hi + HC,
                          c_d_hi = c_h2_lo + HC, c_d_lo = c_d_hi + 1;
     static constexpr int chunks = c_d_lo + 1;
     static constexpr int bytes = chunks * kChunkB;
     // TMEM columns of a group.  Weight-gradient accumulators are transposed (lane = a row of the MN-major A window, column = a
     // column of the MN-major B window):
-    //   t_w0 (112)  lanes [dH1 hi | dH1 lo | dH2 hi | dH2 lo] x 32 units (hidden 32; hidden 64: [dH1 hi | dH1 lo]), columns = X-order features
-    //   t_w2 (80)   hidden 64 only: lanes [dH2 hi | dH2 lo], columns = blob | tail
+    //   t_w0 (96)   lanes [dH1 hi | dH1 lo | dH2 hi | dH2 lo] x 32 units (hidden 32; hidden 64: [dH1 hi | dH1 lo]), columns = X-order features
+    //   t_w2 (64)   hidden 64 only: lanes [dH2 hi | dH2 lo], columns = blob | tail
     //   t_w3 (16)   lanes [H2 hi | H2 lo | ...], columns [dRGB hi 8 | dRGB lo 8]
     //   t_m (2 HID) lanes [dH2 hi | dH2 lo | D hi 8 | D lo 8 | ...], columns [H1 hi | H1 lo]:  M21 = dH2^T H1 and (hidden 32) dsdf^T H1
     //   t_w1 (16)   hidden 64 only: lanes [H1 hi | H1 lo], columns [dsdf hi 8 | dsdf lo 8]
     //   t_a         the tile's working accumulator (HID columns; 64 in BA mode, over the slot), t_s the K-major operand slot [hi HID/2 | lo HID/2]
-    static constexpr int t_w0 = 0, t_w3 = 112, t_w2 = 128, t_w1 = 208,
+    static constexpr int t_w0 = 0, t_w3 = 96, t_w2 = 128, t_w1 = 208,
                          t_m = (HID == 32) ? 128 : 256, t_a = (HID == 32) ? 192 : 384, t_s = t_a + ((HID == 32) ? 32 : 64);
     static constexpr int tcols = (HID == 32) ? 256 : 512;
 };
@@ -572,8 +577,8 @@ __device__ __forceinline__ void flush_wgrads3(uint32_t tlane, const Grads& gr, c
         float* gx = colour ? gr.g_w_col0 : gr.g_w_sdf0;
         const int ld = colour ? kIn2 : 81;
         const uint32_t tx = tlane + ((HID == 64 && h == 1) ? A::t_w2 : A::t_w0);
-        const int q0 = (HID == 32) ? (h ? 4 : 0) : 0;
-        const int q1 = (HID == 32) ? (h ? 7 : 4) : (h ? 5 : 7);
+        const int q0 = (HID == 32) ? (h ? 3 : 0) : 0;
+        const int q1 = (HID == 32) ? (h ? 6 : 3) : (h ? 4 : 6);
         const int fshift = (HID == 32 && colour) ? -32 : 0;       // X-order column -> colour-net input (blob | tail)
 #pragma unroll 1
         for (int q = q0; q < q1; ++q) {
@@ -584,7 +589,7 @@ __device__ __forceinline__ void flush_wgrads3(uint32_t tlane, const Grads& gr, c
             for (int i = 0; i < 16; ++i) {
                 const int f = 16 * q + i + fshift;
                 int c = -1;
-                if (colour) { if (f >= 0 && f < kIn2 && (f < kBlob || f >= kBlob + kGeo)) c = f; }     // the geo columns come from M21 below
+                if (colour) { if (f >= 0 && f < kBlob) c = f; else if (f >= kBlob && f < kBlob + 3) c = f + kGeo; }     // (the geo columns come from M21 below)
                 else { if (f < 32) c = hash_col_to_feature(f); else if (f < 80) c = f; else if (f == 80 + kTailTsdf) c = 80; }
                 if (c >= 0) atomicAdd(gx + j * ld + c, v[i]);
             }
@@ -762,7 +767,7 @@ __global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights
     const uint32_t xh = smem_u32(x_hi), xl = smem_u32(x_lo), h1h = smem_u32(h1_hi), h1l = smem_u32(h1_lo), h2h = smem_u32(h2_hi), h2l = smem_u32(h2_lo);
     const uint32_t dh = smem_u32(d_hi);
     constexpr uint32_t idH = idesc_bf16(HID, false, false);
-    constexpr uint32_t idH_bm = idesc_bf16(HID, false, true), id16_bm = idesc_bf16(16, false, true), id32_bm = idesc_bf16(32, false, true);
+    constexpr uint32_t idH_bm = idesc_bf16(HID, false, true), id32_bm = idesc_bf16(32, false, true);
     constexpr uint32_t id16_mm = idesc_bf16(16, true, true), id2H_mm = idesc_bf16(2 * HID, true, true);
     uint32_t wacc = 0;
     int since_flush = 0;
@@ -842,12 +847,9 @@ __global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights
                 else { stage_zero(blob_hi, blob_lo, m, 4); stage_zero(blob_hi, blob_lo, m, 5); }
                 float t_add, cin, d0, d1;
                 tsdf_terms(k, 0, t.g.x, t_add, cin, d0, d1);
-                stage_zero(tail_hi, tail_lo, m, 0);                                           // the geo columns stay zero (W21 carries them)
-                float v1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, t.g.y};
-                float v2[8] = {t.g.z, t.g.w, cin, 0.f, 0.f, 0.f, 0.f, 0.f};
-                stage8(tail_hi, tail_lo, m, 1, v1);
-                stage8(tail_hi, tail_lo, m, 2, v2);
-                stage_zero(tail_hi, tail_lo, m, 3);
+                float v1[8] = {t.g.y, t.g.z, t.g.w, cin, 0.f, 0.f, 0.f, 0.f};                   // tail: gbv rgb | decoder tsdf input (the geo features: W21)
+                stage8(tail_hi, tail_lo, m, 0, v1);
+                stage_zero(tail_hi, tail_lo, m, 1);
             }
         }
         if (alive_nx) load_inputs(tn, tile_n);                                                // next tile's inputs
@@ -875,7 +877,7 @@ __global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights
         if (iwarp && elect_one()) {                                                                         // 2: H2 = X2' W2^T + H1 W21^T
             fence_after_sync();
             uint32_t acc = 0;
-            mma_kk<5>(tb + T_A, xh + kXBlob * kChunkB, xl + kXBlob * kChunkB, w2h, w2l, HID, idH, acc);
+            mma_kk<4>(tb + T_A, xh + kXBlob * kChunkB, xl + kXBlob * kChunkB, w2h, w2l, HID, idH, acc);
             mma_ts<HC / 2>(tb + T_A, tb + T_S, tb + T_S + NH, w21h, w21l, HID, idH, acc);
             commit(bar);
         }
@@ -933,7 +935,7 @@ __global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights
                 uint32_t a1 = wacc;
                 mma_mm1(tb + A::t_w1, h1h, dh, id16_mm, a1);                                  // dW1[0] += dsdf^T H1
                 uint32_t a2 = wacc;
-                mma_wx(tb + A::t_w2, h2h, xh + kXBlob * kChunkB, xl + kXBlob * kChunkB, idesc_bf16(80, true, true), a2);   // dW2 += dH2^T X2'
+                mma_wx(tb + A::t_w2, h2h, xh + kXBlob * kChunkB, xl + kXBlob * kChunkB, idesc_bf16(kK2, true, true), a2);   // dW2 += dH2^T X2'
             }
             commit(bar);
         }
@@ -957,7 +959,7 @@ __global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights
                 mma_ts_m<HC / 2>(tb + T_A, tb + T_S, tb + T_S + NH, w0h, w0l, HID, id32_bm, acc); // d hash = dH1 W0[:, 0..31]
             }
             uint32_t a0 = wacc;
-            mma_wx(tb + A::t_w0, h1h, xh, xl, idesc_bf16(112, true, true), a0);               // dW0 += dH1^T X1 (hidden 32: and dW2 += dH2^T X)
+            mma_wx(tb + A::t_w0, h1h, xh, xl, idesc_bf16(kKX, true, true), a0);               // dW0 += dH1^T X1 (hidden 32: and dW2 += dH2^T X)
             commit(bar);
         }
         wacc = 1;
@@ -983,15 +985,12 @@ __global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights
             }
             fence_before_sync(); grp_sync2(g);
             if (iwarp && elect_one()) {
-                // [blob(z) | tail 0..15] -> columns 0..31, tail 16..31 -> columns 32..47, from both nets (the geo columns of the
-                // tail are not inputs here: their part of the gradient went through W21)
+                // d [blob(z) | tail] -> columns 0..31, from both nets (the geo features are not inputs here: their part of the
+                // gradient went through W21)
                 fence_after_sync();
                 uint32_t acc = 0;
                 mma_km<HC / 2>(tb + T_A, h1h, h1l, w0h + 8 * HID * 16, w0l + 8 * HID * 16, HID, id32_bm, acc);
                 mma_km<HC / 2>(tb + T_A, h2h, h2l, w2h + 4 * HID * 16, w2l + 4 * HID * 16, HID, id32_bm, acc);
-                acc = 0;
-                mma_km<HC / 2>(tb + T_A + 32, h1h, h1l, w0h + 12 * HID * 16, w0l + 12 * HID * 16, HID, id16_bm, acc);
-                mma_km<HC / 2>(tb + T_A + 32, h2h, h2l, w2h + 8 * HID * 16, w2l + 8 * HID * 16, HID, id16_bm, acc);
                 commit(bar);
             }
             grp_wait(bar, phase);
@@ -1000,13 +999,12 @@ __global__ void __launch_bounds__(G * 256, 1) mlp_bwd_tc2_kernel(RayK k, Weights
                 tmem_ld16(tlane + T_A, gb);
                 if (live) dxb[2 * P + q] = oneblob_dot_grad(xg2, gb);
             } else {
-                float ta[16], tc[16];
-                tmem_ld16(tlane + T_A + 16, ta);                                              // tail 0..15: [geo15 | gbv r]
-                tmem_ld16(tlane + T_A + 32, tc);                                              // tail 16..31: [gbv g, b | decoder tsdf input | 0]
+                float ta[16];
+                tmem_ld16(tlane + T_A + 16, ta);                                              // d tail: [gbv r, g, b | decoder tsdf input | 0]
                 float t_add, cin, dg_add, dg_cin;
                 tsdf_terms(k, 0, xg2, t_add, cin, dg_add, dg_cin);
                 // GBV texel gradient: colour-net inputs + the residual adds (:344-345); tsdf through the decoder input and the add
-                if (live) reinterpret_cast<float4*>(dgb)[q] = make_float4(tc[2] * dg_cin + dr.w * dg_add, ta[15] + dr.x, tc[0] + dr.y, tc[1] + dr.z);
+                if (live) reinterpret_cast<float4*>(dgb)[q] = make_float4(ta[3] * dg_cin + dr.w * dg_add, ta[0] + dr.x, ta[1] + dr.y, ta[2] + dr.z);
             }
         }
         TR(22);
@@ -1094,7 +1092,9 @@ int launch_fwd_tc(const RayK& k, int hidden, const GridDev& hg, const GridDev& g
     int rc = launch_encode(k, hg, gg, p, rays_o, rays_d, z_vals, P, feat, s);
     if (rc) return rc;
     Weights w{p->w_sdf0, p->w_sdf1, p->w_col0, p->w_col1};
-    return hidden == 64 ? launch_fwd_g<64, 2>(k, w, feat, P, 0, raw, s) : launch_fwd_g<32, 4>(k, w, feat, P, 0, raw, s);
+    // groups per SM: hidden 64 -> 3 (TMEM 3 x 160 columns).  Hidden 32 would fit 5 (5 x 96 columns) but 640 threads cap the kernel at 96
+    // registers: measured 3.46 ms with 5 groups against 3.32 ms with 4 (bench config 2)
+    return hidden == 64 ? launch_fwd_g<64, 3>(k, w, feat, P, 0, raw, s) : launch_fwd_g<32, 4>(k, w, feat, P, 0, raw, s);
 }
 
 // point queries through the same kernels: n points = n rays of one sample; variant selects the tsdf handling
@@ -1104,7 +1104,7 @@ int launch_points_tc(RayK k, int hidden, const GridDev& hg, const GridDev& gg, c
     int rc = launch_encode_points(hg, gg, p, x, n, feat, s);
     if (rc) return rc;
     Weights w{p->w_sdf0, p->w_sdf1, p->w_col0, p->w_col1};
-    return hidden == 64 ? launch_fwd_g<64, 2>(k, w, feat, n, variant, raw, s) : launch_fwd_g<32, 4>(k, w, feat, n, variant, raw, s);
+    return hidden == 64 ? launch_fwd_g<64, 3>(k, w, feat, n, variant, raw, s) : launch_fwd_g<32, 4>(k, w, feat, n, variant, raw, s);
 }
 
 // dfeat: 2L * P floats of scratch ([4 quads][P][8]), then (ray gradients only) 4P + 3P floats for the GBV-texel and OneBlob
