@@ -105,6 +105,28 @@ int64_t rf_track_fitness_scratch_floats(int n_candidates, int H, int W, int leve
 int rf_track_cal_transform(const float* search_value, const float* search_count, const float* candidates, int n_candidates,
                            const float search_size[6], int count_search, float* out9, void* stream);
 
+/* rf_track_random_optimization replaces the 20-iteration search loop of `RO_tracker.random_optimization`
+ * (model/ROtracker.py:716-836) including `get_PST` (:467-493), `evaluate_tsdf` (:536-604), `cal_transform` (:606-714) and
+ * `update_PST` (:495-531): every iteration is four launches (fitness, fold, cal_transform, policy) on `stream` with the search
+ * state kept on the device, so nothing is read back between iterations (the reference reads 2 x n floats and uploads the search
+ * size every iteration).  `pst`: all candidate tables [.., 6] (device); for count_particle k = 0..19 the table starts at float
+ * offset pst_offset[k] and holds pst_n[k] candidates (the reference's tiff_index / PST_size), evaluated at pyramid level
+ * depth_level[k].  `state` (device, 64 floats, 16-byte aligned): in  [0,9) current_global_R, [9,12) current_global_T,
+ * [12,18) search_size, [18,24) previous_search_size, words 39.. = {count_particle 0, level_index 5, 0, 0, 0, 0, n, level,
+ * cand_off, chunks of k = 0} as rf_track_state_init fills them; out  the optimised R / T, the final search sizes, word 44 =
+ * success of iteration 0 (previous_frame_success), word 49 = bit mask of the successful iterations.
+ * search_value / search_count: max(pst_n) floats each; scratch: rf_track_random_optimization_scratch_floats() floats. */
+int rf_track_random_optimization(const float* tsdf_vol, const int vol_dim[3], const float vol_origin[3], float voxel_size,
+                                 const float* depth_vertex, const float* normal, int H, int W, const float K[9],
+                                 const float* pst, const int pst_offset[20], const int pst_n[20], const int depth_level[20],
+                                 int iters, int count_search, float scaling_coefficient, int fix_level_index, int iterative_scale,
+                                 float beta, float* state, float* search_value, float* search_count, float* scratch, void* stream);
+int64_t rf_track_random_optimization_scratch_floats(const int pst_n[20], const int depth_level[20], int H, int W);
+/* Host helper: fills the 64-word state image (host memory) for the first iteration. */
+int rf_track_state_init(float* state_host, const float R[9], const float T[3], const float search_size[6],
+                        const float previous_search_size[6], const int pst_offset[20], const int pst_n[20], const int depth_level[20],
+                        int H, int W);
+
 /* The per-pixel factor 1/sqrt(vx^2 + vy^2 + 1), vx = (px - cx)/fx, vy = (py - cy)/fy, of the projective SDF
  * (model/Volume.py:280-283, mp_slam/mapper.py:108-111).  It depends on the intrinsics only, so a caller computes it
  * once per camera and passes it to every integrate; the kernels then load it next to the depth instead of spending two

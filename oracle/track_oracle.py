@@ -148,3 +148,103 @@ def cal_transform(search_value, transform_candidate, search_size, count_search_m
     lens = 1 / np.sqrt(qww * qww + qxx * qxx + qyy * qyy + qzz * qzz)
     mean_transform[3] = qww * lens; mean_transform[4] = qxx * lens; mean_transform[5] = qyy * lens; mean_transform[6] = qzz * lens
     return True, float(mean_tsdf), mean_transform
+
+
+def update_PST(search_size, tsdf, mean_transform, min_scale=1e-3, scale=0.09):
+    """model/ROtracker.py:495-531, statement by statement; writes into `search_size` (float32[6]) in place.
+    Types as under the reference's numpy 1.21.6 (requirements.txt:6): a float32 scalar combined with a Python float or int gives
+    float64 there (before NEP 50), so every scalar below is float64 and only the stores into the float32 array narrow — made
+    explicit with float() so that the restatement does not depend on the NumPy version that runs it."""
+    tsdf = float(tsdf)
+    s_tx = abs(float(mean_transform[0])) + min_scale
+    s_ty = abs(float(mean_transform[1])) + min_scale
+    s_tz = abs(float(mean_transform[2])) + min_scale
+    s_qx = abs(float(mean_transform[4])) + min_scale
+    s_qy = abs(float(mean_transform[5])) + min_scale
+    s_qz = abs(float(mean_transform[6])) + min_scale
+    trans_norm = np.sqrt(s_tx**2 + s_ty**2 + s_tz**2 + s_qx**2 + s_qy**2 + s_qz**2)
+    normal_tx = s_tx / trans_norm; normal_ty = s_ty / trans_norm; normal_tz = s_tz / trans_norm
+    normal_qx = s_qx / trans_norm; normal_qy = s_qy / trans_norm; normal_qz = s_qz / trans_norm
+    search_size[3] = scale * tsdf * normal_qx + min_scale
+    search_size[4] = scale * tsdf * normal_qy + min_scale
+    search_size[5] = scale * tsdf * normal_qz + min_scale
+    search_size[0] = scale * tsdf * normal_tx + min_scale
+    search_size[1] = scale * tsdf * normal_ty + min_scale
+    search_size[2] = scale * tsdf * normal_tz + min_scale
+
+
+def random_optimization(tr, cur_id, cam_pose, depth_im, cam_intr, beta=0.9, inherit=False, seed_num=None):
+    """The search loop of model/ROtracker.py:716-836, statement by statement, driving a tracker object `tr` that offers the
+    reference's step methods (init_depth_vertex / init_normal / evaluate_tsdf / cal_transform / init_searchsize) and attributes
+    (tiff_index, depth_level, PST_size, ALL_PST, particle_iter_lens, fix_level_index, scaling_coefficient, iterative_scale).
+    Returns (pose 4x4, list of per-iteration success flags)."""
+    def get_PST(tiff_index):                                                             # :467-493
+        PST_class = tiff_index // 20
+        PST_class_num = tiff_index - PST_class * 20
+        PST_class_index = PST_class_num // 3
+        return tr.ALL_PST[PST_class][PST_class_index, ...]
+    tr.current_global_R = cam_pose[:3, :3].copy()
+    tr.current_global_T = cam_pose[:3, 3].copy()
+    if inherit is True and tr.previous_frame_success:
+        tr.search_size = tr.initialize_search_size
+    else:
+        tr.init_searchsize()
+    tr.init_depth_vertex(depth_im, cam_intr, seed_num=seed_num)
+    tr.init_normal()
+    previous_success = False
+    success = False
+    count_particle = 0
+    level_index = 5
+    flags = []
+    for i in range(tr.particle_iter_lens):
+        if not success:
+            count_particle = 0
+        PST_class = count_particle % 3
+        tr.transform_candidate = get_PST(tr.tiff_index[count_particle])
+        level = tr.depth_level[count_particle]
+        search_value, sv, sc = tr.evaluate_tsdf(cur_id, level, tr.PST_size[PST_class], cam_intr, level_index)
+        success, min_tsdf, mean_transform = tr.cal_transform(search_value)
+        flags.append(bool(success))
+        current_T_incremental = mean_transform[:3]
+        qw = mean_transform[3]; qx = mean_transform[4]; qy = mean_transform[5]; qz = mean_transform[6]
+        if success:
+            if count_particle < 19:
+                count_particle += 1
+            # float32 products and sums; `2 *` and `1 -` promote to float64 under numpy 1.21 (see update_PST), narrowed by dtype=
+            current_R_incremental = np.array([
+                [1 - 2 * float(qy*qy + qz*qz), 2 * float(qx*qy - qz*qw),     2 * float(qx*qz + qy*qw)],
+                [2 * float(qx*qy + qz*qw),     1 - 2 * float(qx*qx + qz*qz), 2 * float(qy*qz - qx*qw)],
+                [2 * float(qx*qz - qy*qw),     2 * float(qy*qz + qx*qw),     1 - 2 * float(qx*qx + qy*qy)]
+            ], dtype=np.float32)
+            tr.current_global_T += current_T_incremental
+            # np.matmul of two float32 3x3 matrices: written out (float32 products summed left to right) so that the result does
+            # not depend on the BLAS behind NumPy; any summation order differs from this one by at most an ulp per entry
+            A, B = current_R_incremental, np.asarray(tr.current_global_R, dtype=np.float32)
+            tr.current_global_R = np.array([[(A[r, 0] * B[0, c] + A[r, 1] * B[1, c]) + A[r, 2] * B[2, c] for c in range(3)] for r in range(3)],
+                                           dtype=np.float32)
+        if tr.fix_level_index:
+            level_index = 1
+        else:
+            level_index += 5
+        level_index = level_index % (tr.depth_level[count_particle])
+        update_PST(tr.search_size, min_tsdf, mean_transform, scale=tr.scaling_coefficient)
+        if previous_success and success:
+            for k in range(6):
+                tr.search_size[k] = beta * float(tr.search_size[k]) + (1 - beta) * float(tr.previous_search_size[k])
+        elif success:
+            if tr.iterative_scale:
+                previous_success = True
+            for k in range(6):
+                tr.previous_search_size[k] = tr.search_size[k]
+        if not success:
+            previous_success = False
+        if i == 0:
+            if success:
+                tr.initialize_search_size = tr.search_size
+                tr.previous_frame_success = True
+            else:
+                tr.previous_frame_success = False
+    cam_pose_iter = np.eye(4, dtype=np.float32)
+    cam_pose_iter[:3, :3] = tr.current_global_R
+    cam_pose_iter[:3, 3] = tr.current_global_T
+    return cam_pose_iter, flags

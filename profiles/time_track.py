@@ -48,3 +48,24 @@ for n, level, li in [(10240, 32, 5), (3072, 16, 10), (1024, 8, 1)]:
     L = abi.lib(); L.rf_profile_enable(1)
     s.evaluate_tsdf(0, level, n, K, li, as_numpy=False); buf = (C.c_float * 64)(); L.rf_profile_read(buf); L.rf_profile_enable(0)
     print(f"n={n} level={level}: product call {t_p:.1f} us (kernel {buf[14]*1e3:.1f} us), reference kernel {t_r:.1f} us, pairs {n*(H//level)*(W//level)/1e6:.1f} M")
+
+# ---- the whole search loop: host-driven (the reference's structure: 20 x [fitness, read-back, cal_transform, policy in NumPy]) vs
+# rf_track_random_optimization (20 iterations enqueued back to back, one read-back per frame); reference-sized PST tables
+import time
+from oracle import track_oracle as TO
+def pst(seed, sizes=(10240, 3072, 1024), tables=7):
+    g = np.random.default_rng(seed); out = []
+    for n_ in sizes:
+        a = np.clip(g.normal(0.0, 0.35, size=(tables, n_, 6)), -0.99, 0.99).astype(np.float32) * np.float32(0.57); a[:, 0, :] = 0.0; out.append(a)
+    return out
+ro = dict(init_size=0.02, scaling_coefficient=0.09, particle_iter_lens=20, PST_size=[10240, 3072, 1024], fix_level_index=False, count_search=200, iterative_scale=True)
+from remixfusion_b200.tracker import ROSearch
+a_dev = ROSearch(vol, H, W, 6.0, s.truncation, 3.0); a_dev.configure_search(ro, pst(1))
+a_host = ROSearch(vol, H, W, 6.0, s.truncation, 3.0); a_host.configure_search(ro, pst(1))
+def wall(fn, it=5):
+    fn(); torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(it): fn()
+    torch.cuda.synchronize(); return (time.perf_counter() - t0) / it * 1e3
+t_dev = wall(lambda: a_dev.random_optimization(0, c2w, None, depth, K, seed_num=5))
+t_host = wall(lambda: TO.random_optimization(a_host, 0, c2w, depth, K, seed_num=5))
+print(f"search loop per frame (20 iterations, wall clock incl. vertex / normal maps): device loop {t_dev:.2f} ms, host-driven loop {t_host:.2f} ms")

@@ -78,6 +78,7 @@ def lib() -> C.CDLL:
         _lib.rf_ray_scratch_floats.restype = C.c_int64
         _lib.rf_point_workspace_floats.restype = C.c_int64
         _lib.rf_track_fitness_scratch_floats.restype = C.c_int64
+        _lib.rf_track_random_optimization_scratch_floats.restype = C.c_int64
     return _lib
 
 

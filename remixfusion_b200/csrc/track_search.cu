@@ -81,31 +81,74 @@ __global__ void track_normal_kernel(const float4* __restrict__ vertex, int H, in
     normal[3 * i] = normal_x; normal[3 * i + 1] = normal_y; normal[3 * i + 2] = normal_z;
 }
 
+// Device-resident state of the search loop (rf_track_random_optimization): 64 32-bit words.  The host fills R, T, ss, prev_ss,
+// the loop kernels keep everything else; `n / level / cand_off / chunks` are the launch parameters of the NEXT fitness evaluation.
+struct TrackDevState {
+    float R[9], T[3];                     //  0..11  current_global_R / current_global_T
+    float ss[6], prev_ss[6], spare[6];    // 12..29  search_size, previous_search_size
+    float out9[9];                        // 30..38  cal_transform of the last iteration
+    int count_particle, level_index, success, previous_success, iter, prev_frame_success;   // 39..44
+    int n, level, cand_off, chunks;       // 45..48
+    int succ_mask, pad[14];               // 49      bit i = iteration i succeeded
+};
+static_assert(sizeof(TrackDevState) == 64 * 4, "TrackDevState layout");
+struct TrackPolicy {
+    int iters, count_search, fix_level_index, iterative_scale, n_sms, H, W;
+    float scaling, beta;
+    int pst_n[20], pst_off[20], depth_level[20];
+};
+
 struct FitArgs {
     const float* tsdf; int dx, dy, dz; int ox, oy, oz; float voxel;
     const float4* vertex; const float* normal; int H, W;
     TrackCam cam; TrackPose pose;
     const float* cand; int n; int level, level_index, ph, pw;               // ph x pw = sub-sampled pixel grid
     int chunks, pix_per_chunk;
+    const TrackDevState* st;                                                // device loop: pose, candidates and geometry come from here
 };
 
+__host__ __device__ inline int fit_chunks_of(int n, int pixels, int n_sms) {
+    const int cand_blocks = (n + 128 - 1) / 128;
+    int chunks = (16 * n_sms + cand_blocks - 1) / cand_blocks;
+    const int cap = (pixels + 31) / 32;
+    chunks = chunks < cap ? chunks : cap;
+    if (chunks < 1) chunks = 1;
+    return chunks < 512 ? chunks : 512;
+}
+
 // grid = (ceil(n / kCand), chunks); partial[(chunk * n + node) * 2 + {0,1}] = (sum, count) over the chunk's pixels
+// DEV: launched with the worst-case geometry of the search loop; candidate count, pyramid level, pose and search size are read from
+// the device state, and the pixel chunking is the one rf_track_fitness would have chosen (identical sums).
+template <bool DEV>
 __global__ void __launch_bounds__(kCand) track_fitness_kernel(FitArgs a, float* __restrict__ partial) {
     __shared__ float4 sv[kPixChunk];               // vertex rotated into the world frame (:211-213), gt tsdf
     __shared__ unsigned char sok[kPixChunk];       // pixel passes the validity tests (:182-203)
+    __shared__ float s_pose[18];                   // DEV: R, T, ss
+    if (DEV) {
+        const TrackDevState* st = a.st;
+        a.n = st->n; a.level = st->level; a.level_index = st->level_index; a.cand = a.cand + st->cand_off; a.chunks = st->chunks;
+        a.ph = a.H / a.level; a.pw = a.W / a.level;
+        const int pixels = a.ph * a.pw;
+        a.pix_per_chunk = max(1, (pixels + a.chunks - 1) / a.chunks);
+        if ((int)blockIdx.y >= a.chunks || (int)blockIdx.x * kCand >= a.n) return;       // block-uniform
+        if (threadIdx.x < 9) s_pose[threadIdx.x] = st->R[threadIdx.x];
+        else if (threadIdx.x < 12) s_pose[threadIdx.x] = st->T[threadIdx.x - 9];
+        else if (threadIdx.x < 18) s_pose[threadIdx.x] = st->ss[threadIdx.x - 12];
+        __syncthreads();
+    }
     const int node = blockIdx.x * kCand + threadIdx.x;
     const bool live = node < a.n;
-    const float* R = a.pose.R; const float* T = a.pose.T;
+    const float* R = DEV ? s_pose : a.pose.R; const float* T = DEV ? s_pose + 9 : a.pose.T; const float* SS = DEV ? s_pose + 12 : a.pose.ss;
     // candidate set-up (:215-222)
     float c0 = 0.f, c1 = 0.f, c2 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f, q0 = 1.f;
     if (live) {
         c0 = a.cand[node * 6 + 0]; c1 = a.cand[node * 6 + 1]; c2 = a.cand[node * 6 + 2];     // t = c * ss is contracted below
-        q1 = __fmul_rn(a.cand[node * 6 + 3], a.pose.ss[3]);
-        q2 = __fmul_rn(a.cand[node * 6 + 4], a.pose.ss[4]);
-        q3 = __fmul_rn(a.cand[node * 6 + 5], a.pose.ss[5]);
+        q1 = __fmul_rn(a.cand[node * 6 + 3], SS[3]);
+        q2 = __fmul_rn(a.cand[node * 6 + 4], SS[4]);
+        q3 = __fmul_rn(a.cand[node * 6 + 5], SS[5]);
         q0 = __fsqrt_rn(__fmaf_rn(-q3, q3, __fmaf_rn(-q2, q2, __fmaf_rn(-q1, q1, 1.0f))));   // :222
     }
-    const float ss0 = a.pose.ss[0], ss1 = a.pose.ss[1], ss2 = a.pose.ss[2];
+    const float ss0 = SS[0], ss1 = SS[1], ss2 = SS[2];
     float sum = 0.f, cnt = 0.f;
     const int im_h = a.ph * a.level, im_w = a.pw * a.level;                 // :171-172
     const int p_begin = blockIdx.y * a.pix_per_chunk, p_end = min(a.ph * a.pw, p_begin + a.pix_per_chunk);
@@ -170,7 +213,9 @@ __global__ void __launch_bounds__(kCand) track_fitness_kernel(FitArgs a, float* 
     }
 }
 
-__global__ void track_fold_kernel(const float* __restrict__ partial, int n, int chunks, float* __restrict__ value, float* __restrict__ count) {
+__global__ void track_fold_kernel(const float* __restrict__ partial, int n, int chunks, float* __restrict__ value, float* __restrict__ count,
+                                  const TrackDevState* __restrict__ st) {
+    if (st) { n = st->n; chunks = st->chunks; }
     const int node = blockIdx.x * blockDim.x + threadIdx.x;
     if (node >= n) return;
     float s = 0.f, c = 0.f;
@@ -189,7 +234,11 @@ __global__ void track_fold_kernel(const float* __restrict__ partial, int n, int 
 constexpr int kCalThreads = 1024;
 __global__ void __launch_bounds__(kCalThreads) track_cal_transform_kernel(const float* __restrict__ value, const float* __restrict__ count,
                                                                           const float* __restrict__ cand, int n, TrackPose pose, int count_search,
-                                                                          float* __restrict__ out) {
+                                                                          float* __restrict__ out, TrackDevState* __restrict__ st) {
+    if (st) {                                                                                // device loop: size, table, search size, output from the state
+        n = st->n; cand += st->cand_off; out = st->out9;
+        for (int i = 0; i < 6; ++i) pose.ss[i] = st->ss[i];
+    }
     __shared__ int s_cnt[kCalThreads];
     __shared__ double s_sum[9][32];
     const int t = threadIdx.x;
@@ -252,11 +301,64 @@ __global__ void __launch_bounds__(kCalThreads) track_cal_transform_kernel(const 
 
 // Pixel chunks per candidate block: enough blocks for ~16 per SM (the per-pair chain of five IEEE divisions and a
 // dependent gather needs many warps to hide), at least 32 pixels per chunk.
-static int fit_chunks(int n, int pixels) {
-    const int cand_blocks = (n + kCand - 1) / kCand;
-    int chunks = (16 * num_sms() + cand_blocks - 1) / cand_blocks;
-    chunks = std::max(1, std::min(chunks, (pixels + 31) / 32));
-    return std::min(chunks, 512);
+static int fit_chunks(int n, int pixels) { return fit_chunks_of(n, pixels, num_sms()); }
+
+// The search policy between two fitness evaluations (model/ROtracker.py:757-826: the body of random_optimization's loop after
+// cal_transform, and update_PST :495-531), one thread.  Scalars are combined in double and narrowed where the reference stores
+// into its float32 arrays.  It ends by setting up the next evaluation: the reset of count_particle at the top of the next
+// iteration (:758-759), the candidate table (:761-763 get_PST), the pyramid level (:764) and the pixel chunking.
+__global__ void track_policy_kernel(TrackDevState* __restrict__ st, TrackPolicy pol) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int i = st->iter;
+    const bool success = st->out9[0] > 0.5f;
+    const float min_tsdf = st->out9[1];
+    const float* mt = st->out9 + 2;                                    // tx ty tz qw qx qy qz
+    int cp = st->count_particle;
+    if (success) {                                                     // :776-787
+        if (cp < 19) cp += 1;
+        const float qw = mt[3], qx = mt[4], qy = mt[5], qz = mt[6];
+        // float32 products and sums, then `2 *` / `1 -` in double narrowed to float32: what the reference's numpy 1.21.6 computes
+        // (a float32 scalar times a Python int promotes to float64 there)
+        auto pp = [](float a, float b, float c, float d) { return __fadd_rn(__fmul_rn(a, b), __fmul_rn(c, d)); };
+        auto pm = [](float a, float b, float c, float d) { return __fsub_rn(__fmul_rn(a, b), __fmul_rn(c, d)); };
+        auto one_minus_2 = [](float v) { return (float)(1.0 - 2.0 * (double)v); };
+        const float Ri[9] = {one_minus_2(pp(qy, qy, qz, qz)), 2.f * pm(qx, qy, qz, qw), 2.f * pp(qx, qz, qy, qw),
+                             2.f * pp(qx, qy, qz, qw), one_minus_2(pp(qx, qx, qz, qz)), 2.f * pm(qy, qz, qx, qw),
+                             2.f * pm(qx, qz, qy, qw), 2.f * pp(qy, qz, qx, qw), one_minus_2(pp(qx, qx, qy, qy))};
+        for (int k = 0; k < 3; ++k) st->T[k] = __fadd_rn(st->T[k], mt[k]);
+        float Rn[9];
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c)
+                Rn[3 * r + c] = __fadd_rn(__fadd_rn(__fmul_rn(Ri[3 * r], st->R[c]), __fmul_rn(Ri[3 * r + 1], st->R[3 + c])), __fmul_rn(Ri[3 * r + 2], st->R[6 + c]));
+        for (int k = 0; k < 9; ++k) st->R[k] = Rn[k];
+        st->succ_mask |= 1 << i;
+    }
+    int li = pol.fix_level_index ? 1 : st->level_index + 5;            // :790-795
+    li = li % pol.depth_level[cp];
+    {   // update_PST (:495-531), min_scale = 1e-3, scale = scaling_coefficient
+        const double ms = 1e-3;
+        const double s_tx = fabs((double)mt[0]) + ms, s_ty = fabs((double)mt[1]) + ms, s_tz = fabs((double)mt[2]) + ms;
+        const double s_qx = fabs((double)mt[4]) + ms, s_qy = fabs((double)mt[5]) + ms, s_qz = fabs((double)mt[6]) + ms;
+        const double nrm = sqrt(s_tx * s_tx + s_ty * s_ty + s_tz * s_tz + s_qx * s_qx + s_qy * s_qy + s_qz * s_qz);
+        const double k = (double)pol.scaling * (double)min_tsdf;
+        st->ss[3] = (float)(k * (s_qx / nrm) + ms); st->ss[4] = (float)(k * (s_qy / nrm) + ms); st->ss[5] = (float)(k * (s_qz / nrm) + ms);
+        st->ss[0] = (float)(k * (s_tx / nrm) + ms); st->ss[1] = (float)(k * (s_ty / nrm) + ms); st->ss[2] = (float)(k * (s_tz / nrm) + ms);
+    }
+    int prev = st->previous_success;
+    if (prev && success) {                                             // :801-808
+        for (int k = 0; k < 6; ++k) st->ss[k] = (float)((double)pol.beta * (double)st->ss[k] + (1.0 - (double)pol.beta) * (double)st->prev_ss[k]);
+    } else if (success) {                                              // :810-819
+        if (pol.iterative_scale) prev = 1;
+        for (int k = 0; k < 6; ++k) st->prev_ss[k] = st->ss[k];
+    }
+    if (!success) prev = 0;                                            // :821-822
+    if (i == 0) st->prev_frame_success = success ? 1 : 0;              // :824-830 (initialize_search_size aliases search_size: the host mirrors that)
+    st->previous_success = prev; st->success = success ? 1 : 0; st->level_index = li; st->iter = i + 1;
+    // next evaluation (:758-764)
+    if (!success) cp = 0;
+    st->count_particle = cp;
+    st->n = pol.pst_n[cp]; st->cand_off = pol.pst_off[cp]; st->level = pol.depth_level[cp];
+    st->chunks = fit_chunks_of(st->n, (pol.H / st->level) * (pol.W / st->level), pol.n_sms);
 }
 
 }  // namespace
@@ -306,7 +408,7 @@ extern "C" int rf_track_fitness(const float* tsdf_vol, const int vol_dim[3], con
     for (int i = 0; i < 9; ++i) { a.cam.k[i] = K[i]; a.pose.R[i] = R[i]; }
     for (int i = 0; i < 3; ++i) a.pose.T[i] = T[i];
     for (int i = 0; i < 6; ++i) a.pose.ss[i] = search_size[i];
-    a.cand = candidates; a.n = n_candidates; a.level = level; a.level_index = level_index;
+    a.cand = candidates; a.n = n_candidates; a.level = level; a.level_index = level_index; a.st = nullptr;
     a.ph = H / level; a.pw = W / level;                                                    // host :587-588: int(im_h/level)
     const int pixels = a.ph * a.pw;
     a.chunks = fit_chunks(n_candidates, pixels);
@@ -314,10 +416,10 @@ extern "C" int rf_track_fitness(const float* tsdf_vol, const int vol_dim[3], con
     cudaStream_t s = (cudaStream_t)stream;
     {
         ProfScope ps(RF_PROF_TRACK_FITNESS, s);
-        track_fitness_kernel<<<dim3((n_candidates + kCand - 1) / kCand, a.chunks), kCand, 0, s>>>(a, scratch);
+        track_fitness_kernel<false><<<dim3((n_candidates + kCand - 1) / kCand, a.chunks), kCand, 0, s>>>(a, scratch);
     }
     RF_CHECK_LAUNCH("track_fitness_kernel");
-    track_fold_kernel<<<(n_candidates + 255) / 256, 256, 0, s>>>(scratch, n_candidates, a.chunks, search_value, search_count);
+    track_fold_kernel<<<(n_candidates + 255) / 256, 256, 0, s>>>(scratch, n_candidates, a.chunks, search_value, search_count, nullptr);
     RF_CHECK_LAUNCH("track_fold_kernel");
     return 0;
 }
@@ -328,7 +430,82 @@ extern "C" int rf_track_cal_transform(const float* search_value, const float* se
     RF_REQUIRE(n_candidates >= 1 && count_search >= 0, RF_E_RANGE, "rf_track_cal_transform: bad sizes");
     TrackPose pose; memset(&pose, 0, sizeof(pose));
     for (int i = 0; i < 6; ++i) pose.ss[i] = search_size[i];
-    track_cal_transform_kernel<<<1, kCalThreads, 0, (cudaStream_t)stream>>>(search_value, search_count, candidates, n_candidates, pose, count_search, out9);
+    track_cal_transform_kernel<<<1, kCalThreads, 0, (cudaStream_t)stream>>>(search_value, search_count, candidates, n_candidates, pose, count_search, out9, nullptr);
     RF_CHECK_LAUNCH("track_cal_transform_kernel");
+    return 0;
+}
+
+// ---- the whole search loop on the device (model/ROtracker.py:716-836 random_optimization) -------------------------------------
+static int ro_geometry(const int pst_n[20], const int depth_level[20], int H, int W, int& n_max, int& chunks_max) {
+    n_max = 0; chunks_max = 1;
+    for (int k = 0; k < 20; ++k) {
+        if (pst_n[k] <= 0 || depth_level[k] <= 0) return -1;
+        n_max = std::max(n_max, pst_n[k]);
+        chunks_max = std::max(chunks_max, fit_chunks(pst_n[k], (H / depth_level[k]) * (W / depth_level[k])));
+    }
+    return 0;
+}
+
+extern "C" int64_t rf_track_random_optimization_scratch_floats(const int pst_n[20], const int depth_level[20], int H, int W) {
+    int n_max, chunks_max;
+    if (!pst_n || !depth_level || ro_geometry(pst_n, depth_level, H, W, n_max, chunks_max)) return 0;
+    return 2ll * n_max * chunks_max;
+}
+
+extern "C" int rf_track_random_optimization(const float* tsdf_vol, const int vol_dim[3], const float vol_origin[3], float voxel_size,
+                                            const float* depth_vertex, const float* normal, int H, int W, const float K[9],
+                                            const float* pst, const int pst_offset[20], const int pst_n[20], const int depth_level[20],
+                                            int iters, int count_search, float scaling_coefficient, int fix_level_index,
+                                            int iterative_scale, float beta, float* state, float* search_value, float* search_count,
+                                            float* scratch, void* stream) {
+    RF_REQUIRE(tsdf_vol && vol_dim && vol_origin && depth_vertex && normal && K && pst && pst_offset && pst_n && depth_level && state &&
+               search_value && search_count && scratch, RF_E_NULL, "rf_track_random_optimization: NULL pointer");
+    RF_REQUIRE(iters >= 1 && iters <= 31 && count_search >= 0 && H > 0 && W > 0, RF_E_RANGE, "rf_track_random_optimization: bad sizes");
+    RF_REQUIRE((((uintptr_t)depth_vertex & 15) | ((uintptr_t)scratch & 7) | ((uintptr_t)state & 15)) == 0, RF_E_ALIGN,
+               "rf_track_random_optimization: depth_vertex / state 16-byte, scratch 8-byte alignment");
+    RF_REQUIRE((long long)vol_dim[0] * vol_dim[1] * vol_dim[2] < (1ll << 31), RF_E_RANGE, "rf_track_random_optimization: volume too large for the reference's int index");
+    int n_max, chunks_max;
+    RF_REQUIRE(ro_geometry(pst_n, depth_level, H, W, n_max, chunks_max) == 0, RF_E_RANGE, "rf_track_random_optimization: candidate counts and pyramid levels must be positive");
+    FitArgs a; memset(&a, 0, sizeof(a));
+    a.tsdf = tsdf_vol; a.dx = vol_dim[0]; a.dy = vol_dim[1]; a.dz = vol_dim[2];
+    a.ox = (int)vol_origin[0]; a.oy = (int)vol_origin[1]; a.oz = (int)vol_origin[2];
+    a.voxel = voxel_size;
+    a.vertex = reinterpret_cast<const float4*>(depth_vertex); a.normal = normal; a.H = H; a.W = W;
+    for (int i = 0; i < 9; ++i) a.cam.k[i] = K[i];
+    a.cand = pst;
+    TrackDevState* st = reinterpret_cast<TrackDevState*>(state);
+    a.st = st;
+    TrackPolicy pol; memset(&pol, 0, sizeof(pol));
+    pol.iters = iters; pol.count_search = count_search; pol.fix_level_index = fix_level_index; pol.iterative_scale = iterative_scale;
+    pol.n_sms = num_sms(); pol.H = H; pol.W = W; pol.scaling = scaling_coefficient; pol.beta = beta;
+    for (int k = 0; k < 20; ++k) { pol.pst_n[k] = pst_n[k]; pol.pst_off[k] = pst_offset[k]; pol.depth_level[k] = depth_level[k]; }
+    TrackPose none; memset(&none, 0, sizeof(none));
+    cudaStream_t s = (cudaStream_t)stream;
+    for (int i = 0; i < iters; ++i) {                        // 4 launches per iteration, nothing read back in between
+        track_fitness_kernel<true><<<dim3((n_max + kCand - 1) / kCand, chunks_max), kCand, 0, s>>>(a, scratch);
+        RF_CHECK_LAUNCH("track_fitness_kernel<dev>");
+        track_fold_kernel<<<(n_max + 255) / 256, 256, 0, s>>>(scratch, 0, 0, search_value, search_count, st);
+        RF_CHECK_LAUNCH("track_fold_kernel<dev>");
+        track_cal_transform_kernel<<<1, kCalThreads, 0, s>>>(search_value, search_count, pst, 1, none, count_search, nullptr, st);
+        RF_CHECK_LAUNCH("track_cal_transform_kernel<dev>");
+        track_policy_kernel<<<1, 32, 0, s>>>(st, pol);
+        RF_CHECK_LAUNCH("track_policy_kernel");
+    }
+    return 0;
+}
+
+extern "C" int rf_track_state_init(float* state_host, const float R[9], const float T[3], const float search_size[6],
+                                   const float previous_search_size[6], const int pst_offset[20], const int pst_n[20],
+                                   const int depth_level[20], int H, int W) {
+    RF_REQUIRE(state_host && R && T && search_size && previous_search_size && pst_offset && pst_n && depth_level, RF_E_NULL, "rf_track_state_init: NULL pointer");
+    RF_REQUIRE(pst_n[0] > 0 && depth_level[0] > 0 && H > 0 && W > 0, RF_E_RANGE, "rf_track_state_init: bad sizes");
+    TrackDevState st; memset(&st, 0, sizeof(st));
+    for (int i = 0; i < 9; ++i) st.R[i] = R[i];
+    for (int i = 0; i < 3; ++i) st.T[i] = T[i];
+    for (int i = 0; i < 6; ++i) { st.ss[i] = search_size[i]; st.prev_ss[i] = previous_search_size[i]; }
+    st.count_particle = 0; st.level_index = 5;                                   // model/ROtracker.py:752-755
+    st.n = pst_n[0]; st.level = depth_level[0]; st.cand_off = pst_offset[0];
+    st.chunks = fit_chunks(st.n, (H / st.level) * (W / st.level));
+    memcpy(state_host, &st, sizeof(st));
     return 0;
 }

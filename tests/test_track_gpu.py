@@ -151,3 +151,64 @@ def test_cal_transform_matches_host_loop(cuda, rf_lib, n, count_search, mode):
     assert ok == ok_ref and (mode != "none" or not ok)
     assert abs(min_tsdf - min_ref) <= 1e-6 * abs(min_ref) + 1e-9
     np.testing.assert_allclose(mt, mt_ref, rtol=2e-6, atol=1e-9)
+
+
+def _make_pst(seed, sizes=(2048, 1024, 1024), tables=7, zero_class=None):
+    """Synthetic particle tables (the reference loads them from .tiff files, absent offline): candidate 0 is the identity
+    (cal_transform compares everything with it), the others are Gaussian in the unit cube like the reference's PSTs."""
+    g = np.random.default_rng(seed)
+    out = []
+    for n in sizes:
+        a = np.clip(g.normal(0.0, 0.35, size=(tables, n, 6)), -0.99, 0.99).astype(np.float32) * np.float32(0.57)
+        a[:, 0, :] = 0.0
+        out.append(a)
+    if zero_class is not None:
+        out[zero_class][...] = 0.0          # every candidate of this class is the identity: no candidate beats candidate 0 -> failure branch
+    return out
+
+
+def _configured(scene, seed, zero_class=None):
+    from remixfusion_b200.tracker import ROSearch
+    s = ROSearch(scene["vol"], scene["H"], scene["W"], cut_dist=6.0, truncation=scene["cfg"]["volume"]["trunc"], sample_range=3.0)
+    ro = dict(init_size=0.02, scaling_coefficient=0.09, particle_iter_lens=20, PST_size=[2048, 1024, 1024], fix_level_index=False,
+              count_search=200, iterative_scale=True)
+    s.configure_search(ro, _make_pst(seed, zero_class=zero_class))
+    return s
+
+
+@pytest.mark.parametrize("offset,zero_class", [(0.0, None), (0.015, None), (0.01, 1)])
+def test_device_search_loop_matches_host_loop(scene, offset, zero_class):
+    """rf_track_random_optimization (20 iterations on the device, one read-back) against the reference's loop restated in
+    oracle/track_oracle.py driving the step methods (fitness + cal_transform kernels, policy in NumPy): same success sequence,
+    pose and search sizes to float32 rounding (the policy scalars are float64 on the device, mixed float32 / float64 in NumPy).
+    Two frames in a row with inherit=True exercise the state carried between frames; with the class-1 tables zeroed every second
+    evaluation fails (no candidate beats the identity), which exercises the reset / failure branches of the policy."""
+    from oracle import track_oracle as TO
+    dev, host = _configured(scene, 11, zero_class), _configured(scene, 11, zero_class)
+    pose0 = scene["c2w"].copy(); pose0[:3, 3] += np.float32(offset)                       # start off the true pose
+    for frame in range(2):
+        got = dev.random_optimization(frame, pose0, None, scene["depth"], scene["K"], beta=0.9, inherit=frame > 0, seed_num=77 + frame)
+        want, flags = TO.random_optimization(host, frame, pose0, scene["depth"], scene["K"], beta=0.9, inherit=frame > 0, seed_num=77 + frame)
+        mask = sum(1 << i for i, f in enumerate(flags) if f)
+        assert dev.success_mask == mask, (frame, bin(dev.success_mask), bin(mask))
+        assert any(flags) and (zero_class is None or not all(flags))
+        np.testing.assert_allclose(got, want, rtol=2e-5, atol=2e-6)
+        np.testing.assert_allclose(dev.search_size, host.search_size, rtol=1e-4, atol=1e-7)
+        np.testing.assert_allclose(dev.previous_search_size, host.previous_search_size, rtol=1e-4, atol=1e-7)
+        assert dev.previous_frame_success == host.previous_frame_success
+        pose0 = got.copy()
+
+
+def test_device_search_loop_argument_checks(scene):
+    import ctypes as C
+    from remixfusion_b200 import abi
+    s = _configured(scene, 3)
+    bad = (C.c_int * 20)(*([0] * 20))
+    assert abi.lib().rf_track_random_optimization_scratch_floats(bad, bad, scene["H"], scene["W"]) == 0
+    from remixfusion_b200.tracker import ROSearch
+    s2 = ROSearch(scene["vol"], scene["H"], scene["W"], 6.0, 0.1, 3.0)
+    with pytest.raises(abi.RfError, match="configure_search"):
+        s2.random_optimization(0, scene["c2w"], None, scene["depth"], scene["K"])
+    with pytest.raises(abi.RfError, match="multiple of 1024"):
+        s2.configure_search(dict(init_size=0.02, scaling_coefficient=0.09, particle_iter_lens=20, PST_size=[1000, 1024, 1024],
+                                 fix_level_index=False, count_search=200, iterative_scale=True), _make_pst(1, sizes=(1000, 1024, 1024)))
