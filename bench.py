@@ -733,37 +733,37 @@ def run_e2e(args, cfg, K, frames, model, mvol, local, params, fg, dev, rank, wor
         host.append(dict(c2w=c2w, depth=depth, rgb=rgb, rgb255=pin(np.floor(rgb * 255.0).astype(np.float32)),
                          rays_o=pin(rays_o), rays_d=pin(rays_d), tgt_c=pin(rgb.reshape(-1, 3)), tgt_d=pin(depth.reshape(-1, 1)),
                          rgb_t=pin(rgb), depth_t=pin(depth)))
-    h2d = 2 * (H * W * 4 + H * W * 12) + H * W * (12 + 12 + 12 + 4)
+    h2d = (H * W * 4 + 2 * H * W * 12) + H * W * (12 + 12 + 12 + 4)      # depth, colour x 255 (local volume), colour (GBV); rays, targets
     d2h = 4 * 4
 
-    # Ray inputs are staged the way a caller of the public API would: pinned host tensors copied with non_blocking=True on a
-    # copy stream, one step ahead, so that the 33 MB of rays / targets of step i+1 cross PCIe while step i computes.  Every
-    # step's copy is issued (and completes) inside the timed region; the TSDF frames go through moving_volume.integrate /
-    # integrate_kf as page-locked host tensors (one asynchronous H2D copy each inside the call; numpy arrays would be staged
-    # through the object's pinned ring first).
+    # Inputs are staged the way a caller of the public API would: pinned host tensors copied with non_blocking=True on a
+    # copy stream, one step ahead, so that the 59 MB of frame + rays / targets of step i+1 cross PCIe while step i computes.
+    # Every step's copies are issued (and complete) inside the timed region; moving_volume.integrate / integrate_kf /
+    # JointEncoding.mapping receive the device tensors (they accept host arrays too: those are staged through the objects'
+    # pinned rings on the compute stream).
     copy_stream = torch.cuda.Stream(device=dev)
 
     def prefetch(i):
         f = host[i % len(host)]
         with torch.cuda.stream(copy_stream):
-            t = tuple(f[k].to(dev, non_blocking=True) for k in ("rays_o", "rays_d", "tgt_c", "tgt_d"))
+            t = tuple(f[k].to(dev, non_blocking=True) for k in ("rays_o", "rays_d", "tgt_c", "tgt_d", "rgb255", "depth_t", "rgb_t"))
         ev = torch.cuda.Event(); ev.record(copy_stream)
         return t, ev
 
     def step(i, pre, more):
         f = host[i % len(host)]
         nxt = prefetch(i + 1) if more else None
-        local.integrate(f["rgb255"], f["depth_t"], K, f["c2w"], None, 1.0, 0.0)
-        mvol.integrate_kf({"rgb": f["rgb_t"], "depth": f["depth_t"]}, torch.from_numpy(f["c2w"]).float(), 1.0)
+        (ro, rd, tc, td, rgb255_d, depth_d, rgb_d), ev = pre
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev)
+        for t in (ro, rd, tc, td, rgb255_d, depth_d, rgb_d):
+            t.record_stream(cur)
+        local.integrate(rgb255_d, depth_d, K, f["c2w"], None, 1.0, 0.0)
+        mvol.integrate_kf({"rgb": rgb_d, "depth": depth_d}, torch.from_numpy(f["c2w"]).float(), 1.0)
         if world > 1:
             R = cfg["globalV"]["base_resolution"]
             sizes = [4 * (rdist.slab(R, k, world)[1] - rdist.slab(R, k, world)[0]) * R * R for k in range(world)]
             rdist.gather_slabs(mvol.model.GBV.params, sizes, group, out=model.GBV.params.data)
-        (ro, rd, tc, td), ev = pre
-        cur = torch.cuda.current_stream()
-        cur.wait_event(ev)
-        for t in (ro, rd, tc, td):
-            t.record_stream(cur)
         ret = model.mapping(ro, rd, tc, td)
         loss = configs.total_loss(cfg, ret)
         loss.backward()
@@ -771,7 +771,7 @@ def run_e2e(args, cfg, K, frames, model, mvol, local, params, fg, dev, rank, wor
         # the step's result goes to page-locked host memory; the host reads it one step later, so that it is already enqueueing
         # the next step while this one runs (every step's losses are read inside the timed region, the last one before it ends)
         slot = res_host[i % 2]
-        slot.copy_(torch.stack([ret["rgb_res_loss"], ret["depth_res_loss"], ret["sdf_res_loss"], ret["fs_res_loss"]]), non_blocking=True)
+        slot.copy_(torch.stack([ret["rgb_res_loss"], ret["depth_res_loss"], ret["sdf_res_loss"], ret["fs_res_loss"]]).detach(), non_blocking=True)
         done = torch.cuda.Event(); done.record()
         return (slot, done), nxt
 
