@@ -513,9 +513,9 @@ def run_gpu(args, rank, world, local_rank):
         },
         "e2e": {"value": float(e2e_units[0]) / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"], "steps": e2e["steps"],
                 "ms_per_step": e2e_ms / e2e["steps"]},
-        # per step: 2 TSDF integrates, ray_z, encode walk, decoder fwd, composite fwd / bwd, tile liveness, decoder bwd, scatter walk,
-        # replica fold, fused Adam (one launch per parameter group segment: 2)
-        "gpu_launches": 13 * args.steps,
+        # our kernels per step: 2 TSDF integrates, ray_z, encode walk, decoder fwd, composite fwd, loss finalisation, composite bwd,
+        # tile liveness, decoder bwd, scatter walk, replica fold, fused Adam x 2 (one launch per parameter-group segment)
+        "gpu_launches": 14 * args.steps,
         "clocks": clocks,
     }
     line["parts"].update(extra_parts)
