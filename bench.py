@@ -265,7 +265,8 @@ def run_gpu(args, rank, world, local_rank):
     group = dist.group.WORLD if world > 1 else None
 
     # frames: the TSDF frame is rank 0's (broadcast); each rank renders rays of its own frame
-    K, poses, frames = make_frames(cfg, N_POOL, first=17 * rank, stride=50)
+    # RF_BENCH_SAME_FRAMES=1 (diagnostic): every rank renders the SAME frames, which removes the per-step load imbalance between ranks
+    K, poses, frames = make_frames(cfg, N_POOL, first=0 if os.environ.get("RF_BENCH_SAME_FRAMES") else 17 * rank, stride=50)
     bb = torch.from_numpy(np.array(cfg["mapping"]["bound"])).to(torch.float64)
     torch.manual_seed(0)
     model = JointEncoding(cfg, bb, process_group=group, equal_shards=True).to(dev)      # every rank renders one full frame
