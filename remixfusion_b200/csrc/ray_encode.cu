@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(512 / LPT, LPT == 4 ? 4 : 2) scatter_walk4_ker
                                                                   const float* __restrict__ xn,
                                                                   const float* __restrict__ dfeat, const int* __restrict__ n_live,
                                                                   long long P, long long N, int S, int seg, float* __restrict__ g_hash,
-                                                                  float* __restrict__ g_rep, RayGradArgs rg) {
+                                                                  float* __restrict__ g_rep, RayGradArgs rg, int pair16) {
     extern __shared__ float sx[];                       // [3 (+1 BA)][seg][32]
     constexpr int NT = 512 / LPT;
     const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
@@ -266,8 +266,20 @@ __global__ void __launch_bounds__(512 / LPT, LPT == 4 ? 4 : 2) scatter_walk4_ker
                                                   : reinterpret_cast<float2*>(g_hash) + hg.offset[l];
                     unsigned idx[8];
                     cell_indices(hg, l, pc[j][0], pc[j][1], pc[j][2], idx);
+                    // The two corners of an x edge are neighbours in memory whenever the low corner's entry index is even: a dense
+                    // level has stride 1 in x, and on a hashed level x enters the index as x ^ (...) so x -> x + 1 flips only bit 0
+                    // for even x.  Such a pair is ONE 16-byte vector reduction (red.global.add.v4.f32) into one 32-byte sector
+                    // instead of two 8-byte ones: the kernel is bound by the L2 atomic unit, which counts sector operations.
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) atomicAdd(gtab + idx[c], acc[j][c]);
+                    for (int c = 0; c < 8; c += 2) {
+                        const unsigned i0 = idx[c], i1 = idx[c + 1];
+                        if (!BA && pair16 && (i0 ^ i1) == 1u) {           // (BA variant: register-bound, the extra selects cost more than they save: 9.1 vs 8.9 ms)
+                            const float2 a = (i0 < i1) ? acc[j][c] : acc[j][c + 1], b = (i0 < i1) ? acc[j][c + 1] : acc[j][c];
+                            atomicAdd(reinterpret_cast<float4*>(gtab + (i0 & ~1u)), make_float4(a.x, a.y, b.x, b.y));
+                        } else {
+                            atomicAdd(gtab + i0, acc[j][c]); atomicAdd(gtab + i1, acc[j][c + 1]);
+                        }
+                    }
                 }
 #pragma unroll
                 for (int c = 0; c < 8; ++c) acc[j][c] = make_float2(0.f, 0.f);
@@ -477,17 +489,22 @@ int launch_scatter(const RayK& k, const GridDev& hg, long long P, const float* f
     const long long units = k.n_rays * ((k.S + seg - 1) / seg);
     const unsigned gx = (unsigned)((units + 31) / 32);
     RayGradArgs none{};
+    // 16-byte vector reductions for neighbouring corner pairs need every level's table (caller's or replica) to start on a 16-byte
+    // boundary: even float2 offsets on 16-byte aligned buffers (the ABI only promises 8 bytes for g_hash); RF_SCATTER_PAIR16=0 disables
+    static const bool pair_env = [] { const char* e = getenv("RF_SCATTER_PAIR16"); return e ? atoi(e) != 0 : true; }();
+    int pair16 = pair_env && ((((uintptr_t)g_hash) | ((uintptr_t)g_rep)) & 15) == 0;
+    for (int l = 0; l < hg.n_levels; ++l) pair16 = pair16 && (hg.offset[l] % 2 == 0) && (hg.size[l] % 2 == 0) && (rep.base[l] % 2 == 0);
     {
         ProfScope ps(RF_PROF_SCATTER, s);
         cudaError_t e;
         if (rg) {
             const size_t sm = 4 * (size_t)seg * 32 * sizeof(float);
             e = cudaFuncSetAttribute(scatter_walk4_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * kMaxS * 32 * sizeof(float)));
-            if (e == cudaSuccess) scatter_walk4_kernel<2, true><<<gx, 256, sm, s>>>(hg, rep, xn, dfeat, n_live, P, k.n_rays, k.S, seg, g_hash, g_rep, *rg);
+            if (e == cudaSuccess) scatter_walk4_kernel<2, true><<<gx, 256, sm, s>>>(hg, rep, xn, dfeat, n_live, P, k.n_rays, k.S, seg, g_hash, g_rep, *rg, pair16);
         } else {
             const size_t sm = 3 * (size_t)seg * 32 * sizeof(float);
             e = cudaFuncSetAttribute(scatter_walk4_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * kMaxS * 32 * sizeof(float)));
-            if (e == cudaSuccess) scatter_walk4_kernel<4, false><<<gx, 128, sm, s>>>(hg, rep, xn, dfeat, n_live, P, k.n_rays, k.S, seg, g_hash, g_rep, none);
+            if (e == cudaSuccess) scatter_walk4_kernel<4, false><<<gx, 128, sm, s>>>(hg, rep, xn, dfeat, n_live, P, k.n_rays, k.S, seg, g_hash, g_rep, none, pair16);
         }
         if (e != cudaSuccess) return set_error((int)e, "cudaFuncSetAttribute(scatter_walk4_kernel): %s", cudaGetErrorString(e));
     }
