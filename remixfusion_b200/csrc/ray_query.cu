@@ -42,15 +42,19 @@ __global__ void ray_z_kernel(RayK k, const float* __restrict__ target_d, const f
     for (int i = lane; i < nA; i += 32) za[i] = (d <= 0.f) ? tAnf[i] : __fadd_rn(tA[i], d);      // :422-424
     __syncwarp();
     if (nB > 0) {                                                                                 // :426-428 (cat + sort)
+        // both lists are ascending (linspace; linspace + d), so the rank of an element in the other list is a binary search: the merged
+        // position is the same as with the linear counts (#{tB < v} for the near-surface samples, #{za <= v} for the uniform ones)
         for (int i = lane; i < nA; i += 32) {
-            float v = za[i]; int c = 0;
-            for (int j = 0; j < nB; ++j) c += (tB[j] < v) ? 1 : 0;
-            zs[i + c] = v;
+            const float v = za[i];
+            int lo = 0, hi = nB;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (tB[mid] < v) lo = mid + 1; else hi = mid; }
+            zs[i + lo] = v;
         }
         for (int j = lane; j < nB; j += 32) {
-            float v = tB[j]; int c = 0;
-            for (int i = 0; i < nA; ++i) c += (za[i] <= v) ? 1 : 0;
-            zs[j + c] = v;
+            const float v = tB[j];
+            int lo = 0, hi = nA;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (za[mid] <= v) lo = mid + 1; else hi = mid; }
+            zs[j + lo] = v;
         }
     } else {
         for (int i = lane; i < nA; i += 32) zs[i] = za[i];
