@@ -299,6 +299,7 @@ def cfg5_part(dev, rank, world, group, n_keyframes=24, n_pool=4):
     # -> all-gather (ShardedAdam), which also clears the gradients
     opt = Adam(groups, betas=(0.9, 0.99), capturable=True) if world == 1 else rdist.ShardedAdam(groups, betas=(0.9, 0.99), group=group)
     graphed = GraphedMappingStep(model, opt, n_rays, loss_fn, eager_steps=2) if world == 1 else None
+    graphed_ba = GraphedMappingStep(model, opt, n_rays, loss_fn, eager_steps=2, ray_grads=True) if world == 1 else None
 
     def rays_from_rows(rows, c2w_t):
         d = torch.sum(rows[:, None, :3] * c2w_t[:3, :3], -1)
@@ -306,8 +307,8 @@ def cfg5_part(dev, rank, world, group, n_keyframes=24, n_pool=4):
 
     def iteration(rows, c2w_t, ba):
         ro, rd, tc, td = rays_from_rows(rows, c2w_t)
-        if graphed is not None and not ba:
-            graphed(ro, rd, tc, td)
+        if graphed is not None:
+            (graphed_ba if ba else graphed)(ro, rd, tc, td)
             return
         if ba:
             ro = ro.clone().requires_grad_(True); rd = rd.clone().requires_grad_(True)
@@ -338,10 +339,10 @@ def cfg5_part(dev, rank, world, group, n_keyframes=24, n_pool=4):
     ms = _timed(keyframe_cycle, n_keyframes, world, dev, warm=3)
     iters = cfg["mapping"]["iters"] + cfg["mapping"]["BA_iters"]
     out = {"workload": f"uHumans2-shaped stream ({W}x{H}, {S} samples per ray, hash 16 x 2^21, GBV R = {R}): per keyframe integrate_kf + ray store + "
-                       f"{cfg['mapping']['iters']} mapping iterations (one GPU: CUDA graph incl. fused Adam; several: reduce-scatter / Adam shard / all-gather) + {cfg['mapping']['BA_iters']} BA iterations of {n_rays} rays",
+                       f"{cfg['mapping']['iters']} mapping iterations + {cfg['mapping']['BA_iters']} BA iterations of {n_rays} rays (one GPU: every iteration is one CUDA graph incl. the fused Adam; several: eager, reduce-scatter / Adam shard / all-gather)",
            "scaling": "weak", "keyframe_cycles_timed": n_keyframes, "ms_per_keyframe_cycle": ms, "keyframe_cycles_per_s": 1e3 / ms,
            "sequence_1000_frames_s": 200 * ms / 1e3, "ray_samples_per_s_fwd_bwd": world * iters * n_rays * S / (ms / 1e3),
            "iterations_per_cycle": iters, "rays_per_iteration_per_rank": n_rays}
-    del model, store, graphed, opt
+    del model, store, graphed, graphed_ba, opt
     torch.cuda.empty_cache()
     return out

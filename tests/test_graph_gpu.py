@@ -105,3 +105,28 @@ def test_smoothness_matches_oracle_and_is_capturable(cuda, rf_lib):
         loss, _ = step(ro, rd, tc, td)
         losses.append(float(loss))
     assert step.graph is not None and all(np.isfinite(losses))
+
+
+def test_graphed_ba_iteration_matches_eager(cuda, rf_lib):
+    """ray_grads=True: the captured bundle-adjustment iteration (clamp=True, gradients w.r.t. the ray origins / directions handed
+    back with the loss) against the eager one on the same batches: same losses, ray gradients to 1e-3 of their scale."""
+    n = 2048
+    cfg_e, m_e, opt_e = _make(cuda, False)
+    cfg_g, m_g, opt_g = _make(cuda, True)
+    step = GraphedMappingStep(m_g, opt_g, n, lambda r: configs.total_loss(cfg_g, r), eager_steps=2, ray_grads=True)
+    g = torch.Generator().manual_seed(1)
+    b = torch.tensor(cfg_e["mapping"]["bound"])
+    for it in range(6):
+        ro = (b[:, 0] + (0.3 + 0.4 * torch.rand(n, 3, generator=g)) * (b[:, 1] - b[:, 0])).to(cuda)
+        rd = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1).to(cuda)
+        tc = torch.rand(n, 3, generator=g).to(cuda); td = (0.3 + 2.5 * torch.rand(n, 1, generator=g)).to(cuda)
+        ro_e = ro.clone().requires_grad_(True); rd_e = rd.clone().requires_grad_(True)
+        loss_e = configs.total_loss(cfg_e, m_e.mapping(ro_e, rd_e, tc, td, clamp=True))
+        loss_e.backward()
+        opt_e.step(zero_grad=True)
+        loss_g, out = step(ro, rd, tc, td)
+        assert abs(float(loss_g) - float(loss_e.detach())) <= 1e-4 * abs(float(loss_e.detach())), (it, float(loss_g), float(loss_e.detach()))
+        for got, want in ((out["g_rays_o"], ro_e.grad), (out["g_rays_d"], rd_e.grad)):
+            scale = float(want.abs().max())
+            assert scale > 0 and float((got - want).abs().max()) <= 1e-3 * scale, (it, float((got - want).abs().max()), scale)
+    assert step.graph is not None
