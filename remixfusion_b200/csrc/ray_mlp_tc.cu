@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(G * 128, 1) mlp_fwd_tc_kernel(RayK k, Weights 
 #pragma unroll
         for (int c = 0; c < 4; ++c) { tmem_st4(tlane + A::t_hash_hi + 4 * c, t.hh[c]); tmem_st4(tlane + A::t_hash_lo + 4 * c, t.hl[c]); }
         if (live) {
-#pragma unroll 1
+#pragma unroll
             for (int a = 0; a < 3; ++a) stage_oneblob(t.x[a], blob_hi, blob_lo, m, 2 * a);
         } else {
             for (int c = 0; c < 6; ++c) stage_zero(blob_hi, blob_lo, m, c);
