@@ -232,12 +232,16 @@ __global__ void track_fold_kernel(const float* __restrict__ partial, int n, int 
 // double (the reference accumulates float32 products into Python floats) and folded in a fixed order.
 // out[0] = success (0 / 1), out[1] = min_tsdf, out[2..8] = mean_transform (tx, ty, tz, qw, qx, qy, qz).
 constexpr int kCalThreads = 1024;
-__global__ void __launch_bounds__(kCalThreads) track_cal_transform_kernel(const float* __restrict__ value, const float* __restrict__ count,
+__global__ void __launch_bounds__(kCalThreads, 1) track_cal_transform_kernel(const float* __restrict__ value, const float* __restrict__ count,
                                                                           const float* __restrict__ cand, int n, TrackPose pose, int count_search,
                                                                           float* __restrict__ out, TrackDevState* __restrict__ st) {
+    float ss[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) ss[i] = pose.ss[i];
     if (st) {                                                                                // device loop: size, table, search size, output from the state
         n = st->n; cand += st->cand_off; out = st->out9;
-        for (int i = 0; i < 6; ++i) pose.ss[i] = st->ss[i];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) ss[i] = st->ss[i];
     }
     __shared__ int s_cnt[kCalThreads];
     __shared__ double s_sum[9][32];
@@ -267,7 +271,7 @@ __global__ void __launch_bounds__(kCalThreads) track_cal_transform_kernel(const 
         const float* c = cand + (size_t)j * 6;
         a[0] += (double)__fmul_rn(c[0], weight); a[1] += (double)__fmul_rn(c[1], weight); a[2] += (double)__fmul_rn(c[2], weight);   // :649-654
         a[3] += (double)__fmul_rn(c[3], weight); a[4] += (double)__fmul_rn(c[4], weight); a[5] += (double)__fmul_rn(c[5], weight);
-        const float qx = __fmul_rn(c[3], pose.ss[3]), qy = __fmul_rn(c[4], pose.ss[4]), qz = __fmul_rn(c[5], pose.ss[5]);           // :657-659
+        const float qx = __fmul_rn(c[3], ss[3]), qy = __fmul_rn(c[4], ss[4]), qz = __fmul_rn(c[5], ss[5]);           // :657-659
         const float qw = __fsqrt_rn(__fadd_rn(__fadd_rn(__fadd_rn(1.0f, -__fmul_rn(qx, qx)), -__fmul_rn(qy, qy)), -__fmul_rn(qz, qz)));   // :670
         a[6] += (double)__fmul_rn(qw, weight); a[7] += (double)weight; a[8] += (double)__fmul_rn(cur_fit, weight);                 // :671-673
     }
@@ -280,7 +284,11 @@ __global__ void __launch_bounds__(kCalThreads) track_cal_transform_kernel(const 
     __syncthreads();
     if (t == 0) {
         double r[9];
-        for (int k = 0; k < 9; ++k) { double v = 0; for (int w = 0; w < kCalThreads / 32; ++w) v += s_sum[k][w]; r[k] = v; }
+#pragma unroll 1
+        for (int w = 0; w < kCalThreads / 32; ++w) {           // (not unrolled: 288 hoisted loads spilled 1.8 KB per thread)
+#pragma unroll
+            for (int k = 0; k < 9; ++k) r[k] = (w == 0 ? 0.0 : r[k]) + s_sum[k][w];
+        }
         if (total <= 0) {                                                                    // :681-684
             out[0] = 0.f; out[1] = origin;
             for (int k = 2; k < 9; ++k) out[k] = 0.f;
@@ -288,11 +296,11 @@ __global__ void __launch_bounds__(kCalThreads) track_cal_transform_kernel(const 
             const double sw = r[7];
             out[0] = 1.f;
             out[1] = (float)(r[8] / sw);                                                     // :687, :712
-            out[2] = (float)((r[0] / sw) * (double)pose.ss[0]);                              // :688-690
-            out[3] = (float)((r[1] / sw) * (double)pose.ss[1]);
-            out[4] = (float)((r[2] / sw) * (double)pose.ss[2]);
-            const double qww = r[6] / sw, qxx = (r[3] / sw) * (double)pose.ss[3], qyy = (r[4] / sw) * (double)pose.ss[4],
-                         qzz = (r[5] / sw) * (double)pose.ss[5];                              // :691-694
+            out[2] = (float)((r[0] / sw) * (double)ss[0]);                              // :688-690
+            out[3] = (float)((r[1] / sw) * (double)ss[1]);
+            out[4] = (float)((r[2] / sw) * (double)ss[2]);
+            const double qww = r[6] / sw, qxx = (r[3] / sw) * (double)ss[3], qyy = (r[4] / sw) * (double)ss[4],
+                         qzz = (r[5] / sw) * (double)ss[5];                              // :691-694
             const double lens = 1.0 / sqrt(qww * qww + qxx * qxx + qyy * qyy + qzz * qzz);   // :701
             out[5] = (float)(qww * lens); out[6] = (float)(qxx * lens); out[7] = (float)(qyy * lens); out[8] = (float)(qzz * lens);
         }
