@@ -513,7 +513,8 @@ def run_gpu(args, rank, world, local_rank):
             "ray_fwd_bwd_gather_form": gather_form(P, kern),
         },
         "e2e": {"value": float(e2e_units[0]) / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"], "steps": e2e["steps"],
-                "ms_per_step": e2e_ms / e2e["steps"]},
+                "ms_per_step": e2e_ms / e2e["steps"], "h2d_gbs_measured": e2e["h2d_gbs"],
+                "inputs": "per step: colour + depth frame and the pose from pinned host memory; rays, 0..255 colour and targets derived on the device"},
         # our kernels per step: 2 TSDF integrates, ray_z, encode walk, decoder fwd, composite fwd, loss finalisation, composite bwd,
         # tile liveness, decoder bwd, scatter walk, replica fold, fused Adam x 2 (one launch per parameter-group segment)
         "gpu_launches": 14 * args.steps,
@@ -730,41 +731,43 @@ def run_e2e(args, cfg, K, frames, model, mvol, local, params, fg, dev, rank, wor
     import torch.distributed as dist
     from remixfusion_b200 import dist as rdist
     cam = cfg["cam"]; H, W = cam["H"], cam["W"]
-    dirs = synth.camera_dirs(K, H, W).reshape(-1, 3)
+    # Per-pixel camera directions are a constant of the camera: resident on the device, uploaded once (the reference keeps
+    # `batch['direction']` per frame but it never changes).  Per step the host supplies what a frame IS: colour, depth and the pose;
+    # the rays (mp_slam/mapper.py: rays_o = c2w[:3, -1], rays_d = sum(dirs[..., None, :] * c2w[:3, :3], -1)), the 0..255 colour of the
+    # local volume and the ray targets (views of the same frame) are derived on the device inside the timed region.
+    dirs_dev = torch.from_numpy(synth.camera_dirs(K, H, W).reshape(-1, 3).astype(np.float32)).to(dev)
     host = []
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     for c2w, depth, rgb in frames:
-        c2w32 = c2w.astype(np.float32)
-        rays_d = (dirs[:, None, :] * c2w32[None, :3, :3]).sum(-1).astype(np.float32)
-        rays_o = np.broadcast_to(c2w32[:3, 3], rays_d.shape).copy()
-        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-        host.append(dict(c2w=c2w, depth=depth, rgb=rgb, rgb255=pin(np.floor(rgb * 255.0).astype(np.float32)),
-                         rays_o=pin(rays_o), rays_d=pin(rays_d), tgt_c=pin(rgb.reshape(-1, 3)), tgt_d=pin(depth.reshape(-1, 1)),
-                         rgb_t=pin(rgb), depth_t=pin(depth)))
-    h2d = (H * W * 4 + 2 * H * W * 12) + H * W * (12 + 12 + 12 + 4)      # depth, colour x 255 (local volume), colour (GBV); rays, targets
+        host.append(dict(c2w=c2w, rgb_t=pin(rgb), depth_t=pin(depth), c2w_t=pin(c2w.astype(np.float32))))
+    h2d = H * W * 4 + H * W * 12 + 64                      # depth, colour, pose
     d2h = 4 * 4
 
     # Inputs are staged the way a caller of the public API would: pinned host tensors copied with non_blocking=True on a
-    # copy stream, one step ahead, so that the 59 MB of frame + rays / targets of step i+1 cross PCIe while step i computes.
-    # Every step's copies are issued (and complete) inside the timed region; moving_volume.integrate / integrate_kf /
-    # JointEncoding.mapping receive the device tensors (they accept host arrays too: those are staged through the objects'
-    # pinned rings on the compute stream).
+    # copy stream, one step ahead, so that the frame of step i+1 crosses PCIe while step i computes.  Every step's copies are
+    # issued (and complete) inside the timed region; moving_volume.integrate / integrate_kf / JointEncoding.mapping receive the
+    # device tensors (they accept host arrays too: those are staged through the objects' pinned rings on the compute stream).
     copy_stream = torch.cuda.Stream(device=dev)
 
     def prefetch(i):
         f = host[i % len(host)]
         with torch.cuda.stream(copy_stream):
-            t = tuple(f[k].to(dev, non_blocking=True) for k in ("rays_o", "rays_d", "tgt_c", "tgt_d", "rgb255", "depth_t", "rgb_t"))
+            t = tuple(f[k].to(dev, non_blocking=True) for k in ("rgb_t", "depth_t", "c2w_t"))
         ev = torch.cuda.Event(); ev.record(copy_stream)
         return t, ev
 
     def step(i, pre, more):
         f = host[i % len(host)]
         nxt = prefetch(i + 1) if more else None
-        (ro, rd, tc, td, rgb255_d, depth_d, rgb_d), ev = pre
+        (rgb_d, depth_d, c2w_d), ev = pre
         cur = torch.cuda.current_stream()
         cur.wait_event(ev)
-        for t in (ro, rd, tc, td, rgb255_d, depth_d, rgb_d):
+        for t in (rgb_d, depth_d, c2w_d):
             t.record_stream(cur)
+        rgb255_d = torch.floor(rgb_d * 255.0)
+        rd = torch.sum(dirs_dev[:, None, :] * c2w_d[None, :3, :3], -1)
+        ro = c2w_d[None, :3, 3].expand(rd.shape).contiguous()
+        tc = rgb_d.reshape(-1, 3); td = depth_d.reshape(-1, 1)
         local.integrate(rgb255_d, depth_d, K, f["c2w"], None, 1.0, 0.0)
         mvol.integrate_kf({"rgb": rgb_d, "depth": depth_d}, torch.from_numpy(f["c2w"]).float(), 1.0)
         if world > 1:
@@ -791,6 +794,12 @@ def run_e2e(args, cfg, K, frames, model, mvol, local, params, fg, dev, rank, wor
 
     n_steps = max(2, min(args.steps, 8))
     res_host = [torch.empty(4, dtype=torch.float32).pin_memory() for _ in range(2)]
+    # diagnostic: the host->device rate this box delivers for one frame (pinned, copy stream, nothing else running)
+    prefetch(0); torch.cuda.synchronize()
+    ca, cb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ca.record(copy_stream); _keep = prefetch(0); cb.record(copy_stream); torch.cuda.synchronize()
+    h2d_gbs = h2d / (ca.elapsed_time(cb) * 1e-3) / 1e9
+    del _keep
     pre = prefetch(0)
     for w in range(3):                                     # warm-up: allocator blocks of two live steps, pinned staging, NCCL channels
         r, pre = step(w, pre, w < 2)
@@ -819,7 +828,7 @@ def run_e2e(args, cfg, K, frames, model, mvol, local, params, fg, dev, rank, wor
     for i in range(n_steps):
         tl, tg = per_frame_units[i % N_POOL]
         units += tl + tg + H * W * S
-    return {"ms": a.elapsed_time(b), "steps": n_steps, "units": units, "h2d": h2d, "d2h": d2h}
+    return {"ms": a.elapsed_time(b), "steps": n_steps, "units": units, "h2d": h2d, "d2h": d2h, "h2d_gbs": h2d_gbs}
 
 
 def cpu_baseline(cfg, K, frame, full_samples, n_rays=65536):

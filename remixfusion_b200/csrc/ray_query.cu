@@ -171,24 +171,34 @@ __global__ void __launch_bounds__(kTile) sample_fwd_kernel(RayK k, GridDev hg, G
 // Composite (sdf2weights + raw2outputs, model/scene_rep.py:107-127,156-179) and the loss partial sums
 // (model/scene_rep.py:493-517, model/utils.py:170-256).  One warp per ray.
 // ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float sigmoidf_(float a) { return 1.0f / (1.0f + expf(-a)); }
+// sigmoid(a) and the unnormalised rendering weight sigmoid(a) sigmoid(-a) (model/scene_rep.py:116) = t / (1 + t)^2 with
+// t = exp(-|a|): one exponential (ex2.approx) and one reciprocal (rcp.approx; 1 + t lies in [1, 2]) instead of two IEEE
+// divisions and two expf per sample — the composite kernels were bound by exactly that instruction stream.  Relative error of
+// both results <= 4e-7 (parity bar of the rendered outputs: 2e-4).
+__device__ __forceinline__ void sdf_weight(float a, float& sg, float& e) {
+    const float t = __expf(-fabsf(a));
+    float inv;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(1.0f + t));
+    const float ti = t * inv;
+    sg = (a >= 0.f) ? inv : ti;
+    e = ti * inv;
+}
 
-struct RayState { int first; float zthr; float denom; };
+struct RayState { int first; float zthr; float denom; float inv_denom; };
 
 // A ray's samples in registers: lane l holds samples l, l + 32, ... (S <= kMaxS = 128: at most four), with the
 // unnormalised weight e = sigmoid(s / trunc) sigmoid(-s / trunc) (model/scene_rep.py:116) computed once.
-constexpr int kPerLane = kMaxS / 32;
-struct RaySamples { float4 v[kPerLane]; float z[kPerLane]; float sg[kPerLane]; float e[kPerLane]; };
+// The kernels are instantiated per NPL = ceil(S / 32) (1..4), so that a 59-sample ray keeps two samples per lane in registers, not four.
+template <int NPL> struct RaySamples { float4 v[NPL]; float z[NPL]; float sg[NPL]; float e[NPL]; };
 
-__device__ __forceinline__ void load_ray(const RayK& k, const float4* __restrict__ raw_r, const float* __restrict__ z_r, int lane, RaySamples& rs) {
+template <int NPL>
+__device__ __forceinline__ void load_ray(const RayK& k, float inv_trunc, const float4* __restrict__ raw_r, const float* __restrict__ z_r, int lane, RaySamples<NPL>& rs) {
 #pragma unroll
-    for (int i = 0; i < kPerLane; ++i) {
+    for (int i = 0; i < NPL; ++i) {
         const int s = lane + 32 * i;
         if (s < k.S) {
             rs.v[i] = raw_r[s]; rs.z[i] = z_r[s];
-            const float a = __fdiv_rn(rs.v[i].w, k.trunc);
-            rs.sg[i] = sigmoidf_(a);
-            rs.e[i] = rs.sg[i] * sigmoidf_(-a);
+            sdf_weight(rs.v[i].w * inv_trunc, rs.sg[i], rs.e[i]);
         } else {
             rs.v[i] = make_float4(0.f, 0.f, 0.f, 0.f); rs.z[i] = 0.f; rs.sg[i] = 0.f; rs.e[i] = 0.f;
         }
@@ -196,32 +206,35 @@ __device__ __forceinline__ void load_ray(const RayK& k, const float4* __restrict
 }
 
 // first sign change (argmax of the 0/1 mask => 0 if none), truncation threshold, normaliser (:119-127)
+template <int NPL>
 __device__ __forceinline__ RayState ray_state(const RayK& k, const float4* __restrict__ raw_r, const float* __restrict__ z_r, int lane,
-                                              const RaySamples& rs) {
+                                              const RaySamples<NPL>& rs) {
     const int S = k.S;
     int first = 0x7fffffff;
 #pragma unroll
-    for (int i = 0; i < kPerLane; ++i) {
+    for (int i = 0; i < NPL; ++i) {
         const int s = lane + 32 * i;
         if (s < S - 1 && first == 0x7fffffff && raw_r[s + 1].w * rs.v[i].w < 0.f) first = s;
     }
-    for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+    first = __reduce_min_sync(0xffffffffu, first);
     if (first == 0x7fffffff) first = 0;
     RayState st; st.first = first;
     st.zthr = __fadd_rn(z_r[first], k.sc_trunc);
     float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < kPerLane; ++i) {
+    for (int i = 0; i < NPL; ++i) {
         const int s = lane + 32 * i;
         if (s < S) sum += (rs.z[i] < st.zthr) ? rs.e[i] : 0.f;
     }
     st.denom = warp_sum(sum) + 1e-8f;
+    st.inv_denom = __frcp_rn(st.denom);              // w = e / denom as one reciprocal per ray (<= 1 ulp from the quotient)
     return st;
 }
 
 // Warp per ray, four rays per block; the seven loss partial sums (double) are added per block.  (A persistent variant with
 // one set of atomics per block of many rays was slower: 91 registers, 1.02 vs 0.91 ms — the atomics are not the bound.)
-__global__ void __launch_bounds__(128) composite_fwd_kernel(RayK k, const float* __restrict__ raw, const float* __restrict__ z_vals,
+template <int NPL>
+__global__ void __launch_bounds__(128, NPL == 4 ? 10 : 12) composite_fwd_kernel(RayK k, const float* __restrict__ raw, const float* __restrict__ z_vals,
                                                             const float* __restrict__ target_d, const float* __restrict__ target_rgb,
                                                             float* __restrict__ rgb_map, float* __restrict__ depth_map, double* __restrict__ partials) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -231,18 +244,18 @@ __global__ void __launch_bounds__(128) composite_fwd_kernel(RayK k, const float*
     if (r < k.n_rays) {
         const float4* raw_r = reinterpret_cast<const float4*>(raw) + r * S;
         const float* z_r = z_vals + r * S;
-        RaySamples rs; load_ray(k, raw_r, z_r, lane, rs);
+        RaySamples<NPL> rs; load_ray(k, __frcp_rn(k.trunc), raw_r, z_r, lane, rs);
         RayState st = ray_state(k, raw_r, z_r, lane, rs);
         float c0 = 0.f, c1 = 0.f, c2 = 0.f, dm = 0.f;
         float d = partials ? target_d[r] : 0.f;
         bool valid = (d > 0.f) && (d < k.depth_trunc);
         float fs = 0.f, sd = 0.f; int nf = 0, ns = 0;
 #pragma unroll
-        for (int i = 0; i < kPerLane; ++i) {
+        for (int i = 0; i < NPL; ++i) {
             if (lane + 32 * i >= S) continue;
             const float4 v = rs.v[i]; const float z = rs.z[i];
             float w = (z < st.zthr) ? rs.e[i] : 0.f;
-            w = w / st.denom;
+            w = w * st.inv_denom;
             c0 = fmaf(w, v.x, c0); c1 = fmaf(w, v.y, c1); c2 = fmaf(w, v.z, c2); dm = fmaf(w, z, dm);
             if (partials) {
                 bool front = z < __fsub_rn(d, k.sc_trunc), back = z > __fadd_rn(d, k.sc_trunc);
@@ -255,7 +268,7 @@ __global__ void __launch_bounds__(128) composite_fwd_kernel(RayK k, const float*
         c0 = warp_sum(c0); c1 = warp_sum(c1); c2 = warp_sum(c2); dm = warp_sum(dm);
         if (lane == 0) { rgb_map[3 * r] = c0; rgb_map[3 * r + 1] = c1; rgb_map[3 * r + 2] = c2; depth_map[r] = dm; }
         if (partials) {
-            fs = warp_sum(fs); sd = warp_sum(sd); nf = warp_sum(nf); ns = warp_sum(ns);
+            fs = warp_sum(fs); sd = warp_sum(sd); nf = __reduce_add_sync(0xffffffffu, nf); ns = __reduce_add_sync(0xffffffffu, ns);
             if (lane == 0) {
                 float wgt = (k.rgb_all_ones || valid) ? 1.f : 0.f;
                 float e0 = c0 * wgt - target_rgb[3 * r] * wgt, e1 = c1 * wgt - target_rgb[3 * r + 1] * wgt, e2 = c2 * wgt - target_rgb[3 * r + 2] * wgt;
@@ -279,7 +292,8 @@ __global__ void __launch_bounds__(128) composite_fwd_kernel(RayK k, const float*
 // Backward of composite + losses: writes the total gradient w.r.t. raw [N,S,4] into d_raw_out.
 // Upstream: d_rgb_map [N,3], d_depth_map [N], d_raw [N,S,4] (each may be NULL) and loss_grads (device float[4]:
 // d/d rgb_loss, depth_loss, sdf_loss, fs_loss; may be NULL) with the forward's `partials`.
-__global__ void __launch_bounds__(128) composite_bwd_kernel(RayK k, const float* __restrict__ raw, const float* __restrict__ z_vals,
+template <int NPL>
+__global__ void __launch_bounds__(128, NPL == 4 ? 7 : 8) composite_bwd_kernel(RayK k, const float* __restrict__ raw, const float* __restrict__ z_vals,
                                                             const float* __restrict__ rgb_map, const float* __restrict__ depth_map,
                                                             const float* __restrict__ target_d, const float* __restrict__ target_rgb,
                                                             const float* __restrict__ d_rgb_map, const float* __restrict__ d_depth_map,
@@ -292,7 +306,8 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(RayK k, const float*
     const int S = k.S;
     const float4* raw_r = reinterpret_cast<const float4*>(raw) + r * S;
     const float* z_r = z_vals + r * S;
-    RaySamples rs; load_ray(k, raw_r, z_r, lane, rs);
+    const float inv_trunc = __frcp_rn(k.trunc);
+    RaySamples<NPL> rs; load_ray(k, inv_trunc, raw_r, z_r, lane, rs);
     RayState st = ray_state(k, raw_r, z_r, lane, rs);
     float G0 = 0.f, G1 = 0.f, G2 = 0.f, GD = 0.f;
     if (d_rgb_map) { G0 = d_rgb_map[3 * r]; G1 = d_rgb_map[3 * r + 1]; G2 = d_rgb_map[3 * r + 2]; }
@@ -317,10 +332,10 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(RayK k, const float*
     // pass 1: dot = sum_j dw_j * w_j
     float dot = 0.f;
 #pragma unroll
-    for (int i = 0; i < kPerLane; ++i) {
+    for (int i = 0; i < NPL; ++i) {
         if (lane + 32 * i >= S) continue;
         const float4 v = rs.v[i]; const float z = rs.z[i];
-        float w = ((z < st.zthr) ? rs.e[i] : 0.f) / st.denom;
+        float w = ((z < st.zthr) ? rs.e[i] : 0.f) * st.inv_denom;
         float dw = G0 * v.x + G1 * v.y + G2 * v.z + GD * z;
         dot = fmaf(dw, w, dot);
     }
@@ -329,18 +344,18 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(RayK k, const float*
     int last_nz = 0;
     const float4* up_r = d_raw ? reinterpret_cast<const float4*>(d_raw) + r * S : nullptr;
 #pragma unroll
-    for (int i = 0; i < kPerLane; ++i) {
+    for (int i = 0; i < NPL; ++i) {
         const int s = lane + 32 * i;
         if (s >= S) continue;
         const float4 v = rs.v[i]; const float z = rs.z[i];
         float sg = rs.sg[i];
         float e = (z < st.zthr) ? rs.e[i] : 0.f;
-        float w = e / st.denom;
+        float w = e * st.inv_denom;
         float dw = G0 * v.x + G1 * v.y + G2 * v.z + GD * z;
-        float de = (dw - dot) / st.denom;
+        float de = (dw - dot) * st.inv_denom;
         float4 o;
         o.x = w * G0; o.y = w * G1; o.z = w * G2;
-        o.w = de * e * (1.0f - 2.0f * sg) / k.trunc;
+        o.w = de * e * (1.0f - 2.0f * sg) * inv_trunc;
         if (loss_grads) {
             bool front = z < __fsub_rn(d, k.sc_trunc), back = z > __fadd_rn(d, k.sc_trunc);
             bool sm = !front && !back && (d > 0.f);
@@ -355,9 +370,35 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(RayK k, const float*
     // weight (scene_rep.py:124) and no loss term (utils.py:170-198), so the tail of most rays is exactly zero and the
     // decoder backward / table scatter skip it.
     if (n_live) {
-        for (int o = 16; o > 0; o >>= 1) last_nz = max(last_nz, __shfl_xor_sync(0xffffffffu, last_nz, o));
+        last_nz = __reduce_max_sync(0xffffffffu, last_nz);
         if (lane == 0) n_live[r] = last_nz;
     }
+}
+
+// one instantiation per number of samples a lane holds (S <= kMaxS = 128)
+static void launch_composite_fwd(const RayK& k, const float* raw, const float* z_vals, const float* target_d, const float* target_rgb,
+                                 float* rgb_map, float* depth_map, double* partials, cudaStream_t s) {
+    const unsigned grid = (unsigned)((k.n_rays + 3) / 4);
+    switch ((k.S + 31) / 32) {
+        case 1: composite_fwd_kernel<1><<<grid, 128, 0, s>>>(k, raw, z_vals, target_d, target_rgb, rgb_map, depth_map, partials); break;
+        case 2: composite_fwd_kernel<2><<<grid, 128, 0, s>>>(k, raw, z_vals, target_d, target_rgb, rgb_map, depth_map, partials); break;
+        case 3: composite_fwd_kernel<3><<<grid, 128, 0, s>>>(k, raw, z_vals, target_d, target_rgb, rgb_map, depth_map, partials); break;
+        default: composite_fwd_kernel<4><<<grid, 128, 0, s>>>(k, raw, z_vals, target_d, target_rgb, rgb_map, depth_map, partials); break;
+    }
+}
+static void launch_composite_bwd(const RayK& k, const float* raw, const float* z_vals, const float* rgb_map, const float* depth_map,
+                                 const float* target_d, const float* target_rgb, const float* d_rgb_map, const float* d_depth_map,
+                                 const float* d_raw, const float* loss_grads, const double* partials, float* d_raw_out, int* n_live, cudaStream_t s) {
+    const unsigned grid = (unsigned)((k.n_rays + 3) / 4);
+#define RF_CBWD(N) composite_bwd_kernel<N><<<grid, 128, 0, s>>>(k, raw, z_vals, rgb_map, depth_map, target_d, target_rgb, d_rgb_map, d_depth_map, \
+                                                                d_raw, loss_grads, partials, d_raw_out, n_live)
+    switch ((k.S + 31) / 32) {
+        case 1: RF_CBWD(1); break;
+        case 2: RF_CBWD(2); break;
+        case 3: RF_CBWD(3); break;
+        default: RF_CBWD(4); break;
+    }
+#undef RF_CBWD
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -727,7 +768,7 @@ extern "C" int rf_ray_composite(const rf_ray_cfg* cfg, const float* raw, const f
     k.sc_trunc = (float)((double)cfg->sc_factor * (double)cfg->trunc);
     cudaStream_t s = (cudaStream_t)stream;
     ProfScope ps(RF_PROF_COMPOSITE_FWD, s);
-    composite_fwd_kernel<<<(unsigned)((n_rays + 3) / 4), 128, 0, s>>>(k, raw, z_vals, nullptr, nullptr, rgb_map, depth_map, nullptr);
+    launch_composite_fwd(k, raw, z_vals, nullptr, nullptr, rgb_map, depth_map, nullptr, s);
     RF_CHECK_LAUNCH("composite_fwd_kernel");
     return 0;
 }
@@ -764,7 +805,7 @@ extern "C" int rf_ray_query_forward(const rf_ray_cfg* cfg, const rf_grid_desc* h
     if (rc) return rc;
     {
         ProfScope ps(RF_PROF_COMPOSITE_FWD, s);
-        composite_fwd_kernel<<<(unsigned)((n_rays + 3) / 4), 128, 0, s>>>(k, raw, z_vals, target_d, target_rgb, rgb_map, depth_map, loss_partials);
+        launch_composite_fwd(k, raw, z_vals, target_d, target_rgb, rgb_map, depth_map, loss_partials, s);
     }
     RF_CHECK_LAUNCH("composite_fwd_kernel");
     return 0;
@@ -792,8 +833,8 @@ extern "C" int rf_ray_query_backward(const rf_ray_cfg* cfg, const rf_grid_desc* 
     float* d_pts = scratch + 4 * P;             // [P,3] (BA mode, fp32 SIMT path only)
     {
         ProfScope ps(RF_PROF_COMPOSITE_BWD, s);
-        composite_bwd_kernel<<<(unsigned)((n_rays + 3) / 4), 128, 0, s>>>(k, raw, z_vals, rgb_map, depth_map, target_d, target_rgb,
-                                                                           d_rgb_map, d_depth_map, d_raw, loss_grads, loss_partials, d_raw_tot, n_live);
+        launch_composite_bwd(k, raw, z_vals, rgb_map, depth_map, target_d, target_rgb, d_rgb_map, d_depth_map, d_raw, loss_grads, loss_partials,
+                             d_raw_tot, n_live, s);
     }
     RF_CHECK_LAUNCH("composite_bwd_kernel");
     Grads gr{g->g_hash, g->g_w_sdf0, g->g_w_sdf1, g->g_w_col0, g->g_w_col1};
