@@ -121,6 +121,33 @@ def test_local_no_clamp_and_deintegrate(cuda, rf_lib):
     _run_local(cuda, rf_lib, cam, (3, 3, 2), 0.05, [(K, c2w, depth, rgb)] * 3, clamp=0.0)
 
 
+def _special_frame(cam):
+    """Axis-aligned camera at the origin, piecewise-constant depth with holes, colour with exactly black regions."""
+    H, W = cam["H"], cam["W"]
+    K = synth.intrinsics(cam["fx"], cam["fy"], cam["cx"], cam["cy"])
+    c2w = np.eye(4)
+    depth = np.full((H, W), 1.5, np.float32)
+    depth[:, W // 2:] = 1.0
+    depth[: H // 8] = 0.0
+    rgb = np.zeros((H, W, 3), np.float32)                      # left third black: every colour numerator is exactly 0
+    rgb[:, W // 3: 2 * W // 3] = [0.0, 0.5, 1.0]               # one channel 0
+    rgb[:, 2 * W // 3:] = np.random.default_rng(3).random((H, W - 2 * W // 3, 3)).astype(np.float32)
+    return K, c2w, depth, rgb
+
+
+def test_division_special_operands(cuda, rf_lib):
+    """The kernels take their IEEE quotients from a shared reciprocal when every operand lies within 2^+-40 and fall back to
+    div.rn otherwise (csrc/tsdf_integrate.cu: div_fast / div_ok).  This frame drives the fall-backs: voxel coordinates that are
+    exact binary fractions put X = 0 and Y = 0 exactly on two planes of voxels, black pixels make the colour numerators exactly
+    0 on the first and on the repeated integrations; results must still equal the reference kernel's bit for bit."""
+    cam = T.small_cam(4)
+    fr = _special_frame(cam)
+    nt = _run_local(cuda, rf_lib, cam, (2, 2, 2), 0.0625, [fr] * 3, trunc=0.125)
+    assert nt > 5000
+    n = _run_global(cuda, rf_lib, cam, 64, [[-2.0, 2.0], [-2.0, 2.0], [-2.0, 2.0]], [fr] * 3, trunc=0.125)
+    assert n > 1000
+
+
 def _run_global(cuda, rf_lib, cam, R, bound, frames, trunc=0.1, obs=1.0):
     cfg = {"globalV": {"base_resolution": R}, "mapping": {"bound": bound}, "training": {"c_trunc": trunc}}
     model = _Model(R, cuda)
