@@ -12,6 +12,7 @@ tiny-cuda-nn and no CPU fallback.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -30,6 +31,27 @@ def batchify(fn, chunk=1024 * 64):
     def ret(inputs):
         return torch.cat([fn(inputs[i:i + chunk]) for i in range(0, inputs.shape[0], chunk)], 0)
     return ret
+
+
+def _chunk_rays(cfg, hdesc, n, S, dev):
+    """Rays per launch.  The tensor-core path keeps 160 B of feature planes per sample between forward and backward and the
+    backward needs about as much scratch; when that does not fit into the free device memory the batch is processed in
+    chunks of rays (the backward then recomputes each chunk's planes).  RF_RAY_CHUNK forces a chunk size (tests)."""
+    forced = int(os.environ.get("RF_RAY_CHUNK", "0"))
+    if forced > 0:
+        return max(128, forced // 128 * 128)
+    if dev.type != "cuda" or n * S < (1 << 26) or torch.cuda.is_current_stream_capturing():
+        return n
+    L = abi.lib()
+    probe = 1 << 16
+    per_ray = 4.0 * (int(L.rf_ray_workspace_floats(C.byref(cfg), C.byref(hdesc), C.c_int64(probe))) +
+                     int(L.rf_ray_scratch_floats(C.byref(cfg), C.byref(hdesc), C.c_int64(probe), C.c_int(1)))) / probe
+    free, _ = torch.cuda.mem_get_info(dev)
+    free += torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)          # blocks the caching allocator can reuse
+    budget = 0.6 * free
+    if per_ray * n <= budget:
+        return n
+    return max(128, int(budget / per_ray) // 128 * 128)
 
 
 class _RayQueryFn(torch.autograd.Function):
@@ -61,14 +83,21 @@ class _RayQueryFn(torch.autograd.Function):
                 dist.all_reduce(cnt, group=group)
                 n_total = int(cnt.item())
         cfg.n_rays_total = n_total
-        nws = int(abi.lib().rf_ray_workspace_floats(C.byref(cfg), C.byref(hdesc), C.c_int64(n)))
-        # feature planes of the tensor-core path: written by the forward, re-read by the backward
+        chunk = _chunk_rays(cfg, hdesc, n, S, dev)
+        nws = int(abi.lib().rf_ray_workspace_floats(C.byref(cfg), C.byref(hdesc), C.c_int64(min(n, chunk))))
+        # feature planes of the tensor-core path: written by the forward, re-read by the backward (one chunk of rays at a time
+        # when the whole batch's planes do not fit: the backward then recomputes them chunk by chunk)
         ws = torch.empty(nws, dtype=torch.float32, device=dev) if nws > 0 else None
-        rc = abi.lib().rf_ray_query_forward(C.byref(cfg), C.byref(hdesc), C.byref(gdesc), C.byref(p), abi.dptr(ro), abi.dptr(rd),
-                                            abi.dptr(td), abi.dptr(tc), abi.dptr(z_vals), C.c_int64(n), abi.dptr(raw),
-                                            abi.dptr(rgb_map), abi.dptr(depth_map), abi.dptr(partials), abi.dptr(ws),
-                                            abi.stream_ptr())
-        abi.check(rc, "rf_ray_query_forward")
+        sl = lambda t, a, b: None if t is None else t[a:b]
+        for a in range(0, max(n, 1), max(chunk, 1)):
+            b = min(n, a + chunk)
+            rc = abi.lib().rf_ray_query_forward(C.byref(cfg), C.byref(hdesc), C.byref(gdesc), C.byref(p), abi.dptr(ro[a:b]), abi.dptr(rd[a:b]),
+                                                abi.dptr(sl(td, a, b)), abi.dptr(sl(tc, a, b)), abi.dptr(z_vals[a:b]), C.c_int64(b - a), abi.dptr(raw[a:b]),
+                                                abi.dptr(rgb_map[a:b]), abi.dptr(depth_map[a:b]), abi.dptr(partials), abi.dptr(ws),
+                                                abi.stream_ptr())
+            abi.check(rc, "rf_ray_query_forward")
+        if chunk < n:
+            ws = None                                            # holds the last chunk only
         losses = torch.zeros(4, dtype=torch.float32, device=dev)
         if with_losses:
             if group is not None:
@@ -80,6 +109,7 @@ class _RayQueryFn(torch.autograd.Function):
                                                      abi.stream_ptr()), "rf_ray_loss_finalize")
         ctx.meta = meta
         ctx.n_total = n_total
+        ctx.chunk = chunk
         ctx.ws = ws if any(ctx.needs_input_grad) else None
         ctx.save_for_backward(ro, rd, hash_params, w_sdf0, w_sdf1, w_col0, w_col1, gbv_params, z_vals, td, tc, raw,
                               rgb_map, depth_map, partials)
@@ -101,23 +131,37 @@ class _RayQueryFn(torch.autograd.Function):
         ba = need[0] or need[1]
         g_o = torch.empty_like(ro) if ba else None
         g_d = torch.empty_like(rd) if ba else None
-        nsc = int(abi.lib().rf_ray_scratch_floats(C.byref(cfg), C.byref(hdesc), C.c_int64(n), C.c_int(1 if ba else 0)))
+        chunk = min(ctx.chunk, n) if n > 0 else 0
+        nsc = int(abi.lib().rf_ray_scratch_floats(C.byref(cfg), C.byref(hdesc), C.c_int64(chunk), C.c_int(1 if ba else 0)))
         scratch = torch.empty(nsc, dtype=torch.float32, device=dev)
-        grads = abi.RayGrads(abi.dptr(g_hash), abi.dptr(g_w[0]), abi.dptr(g_w[1]), abi.dptr(g_w[2]), abi.dptr(g_w[3]),
-                             abi.dptr(g_o), abi.dptr(g_d))
         p = abi.RayParams(abi.dptr(hash_params.detach()), abi.dptr(gbv_params.detach()), abi.dptr(w_sdf0.detach()),
                           abi.dptr(w_sdf1.detach()), abi.dptr(w_col0.detach()), abi.dptr(w_col1.detach()))
         use_loss = d_losses is not None and partials is not None
         # contiguous fp32 copies of the upstream gradients must stay referenced until the kernels are enqueued: a temporary
         # dropped right after dptr() hands its block back to the caching allocator, and the next temporary may reuse it
         up = [f32(d_rgb_map), f32(d_depth_map), f32(d_raw), f32(d_losses) if use_loss else None]
-        rc = abi.lib().rf_ray_query_backward(
-            C.byref(cfg), C.byref(hdesc), C.byref(gdesc), C.byref(p), abi.dptr(ro), abi.dptr(rd), abi.dptr(td), abi.dptr(tc),
-            C.c_int64(n), abi.dptr(z_vals), abi.dptr(raw), abi.dptr(rgb_map), abi.dptr(depth_map),
-            abi.dptr(up[0]), abi.dptr(up[1]), abi.dptr(up[2]),
-            abi.dptr(up[3]), abi.dptr(partials if use_loss else None),
-            C.byref(grads), abi.dptr(ctx.ws), abi.dptr(scratch), abi.stream_ptr())
-        abi.check(rc, "rf_ray_query_backward")
+        ws = ctx.ws
+        if chunk < n:                                            # the planes are recomputed chunk by chunk (see forward)
+            nws = int(abi.lib().rf_ray_workspace_floats(C.byref(cfg), C.byref(hdesc), C.c_int64(chunk)))
+            ws = torch.empty(nws, dtype=torch.float32, device=dev) if nws > 0 else None
+        sl = lambda t, a, b: None if t is None else t[a:b]
+        for a in range(0, max(n, 1), max(chunk, 1)):
+            b = min(n, a + chunk)
+            if chunk < n:
+                # raw / rgb_map / depth_map come out bit-identical to the first pass; no loss sums this time (partials = NULL)
+                rc = abi.lib().rf_ray_query_forward(C.byref(cfg), C.byref(hdesc), C.byref(gdesc), C.byref(p), abi.dptr(ro[a:b]), abi.dptr(rd[a:b]),
+                                                    abi.dptr(None), abi.dptr(None), abi.dptr(z_vals[a:b]), C.c_int64(b - a), abi.dptr(raw[a:b]),
+                                                    abi.dptr(rgb_map[a:b]), abi.dptr(depth_map[a:b]), abi.dptr(None), abi.dptr(ws), abi.stream_ptr())
+                abi.check(rc, "rf_ray_query_forward (recompute)")
+            grads = abi.RayGrads(abi.dptr(g_hash), abi.dptr(g_w[0]), abi.dptr(g_w[1]), abi.dptr(g_w[2]), abi.dptr(g_w[3]),
+                                 abi.dptr(sl(g_o, a, b)), abi.dptr(sl(g_d, a, b)))
+            rc = abi.lib().rf_ray_query_backward(
+                C.byref(cfg), C.byref(hdesc), C.byref(gdesc), C.byref(p), abi.dptr(ro[a:b]), abi.dptr(rd[a:b]), abi.dptr(sl(td, a, b)), abi.dptr(sl(tc, a, b)),
+                C.c_int64(b - a), abi.dptr(z_vals[a:b]), abi.dptr(raw[a:b]), abi.dptr(rgb_map[a:b]), abi.dptr(depth_map[a:b]),
+                abi.dptr(sl(up[0], a, b)), abi.dptr(sl(up[1], a, b)), abi.dptr(sl(up[2], a, b)),
+                abi.dptr(up[3]), abi.dptr(partials if use_loss else None),
+                C.byref(grads), abi.dptr(ws), abi.dptr(scratch), abi.stream_ptr())
+            abi.check(rc, "rf_ray_query_backward")
         return (g_o if need[0] else None, g_d if need[1] else None, g_hash, g_w[0], g_w[1], g_w[2], g_w[3],
                 None, None, None, None, None)
 

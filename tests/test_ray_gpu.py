@@ -108,6 +108,41 @@ def test_mapping_matches_reference_golden(cuda, rf_lib, name, clamp, ray_grads, 
 
 
 @pytest.mark.parametrize("prec", PRECISIONS)
+def test_chunked_batch_equals_whole_batch(cuda, rf_lib, monkeypatch, prec):
+    """A batch whose feature planes would not fit is processed in chunks of rays, the backward recomputing each chunk's planes
+    (scene_rep._chunk_rays; forced here through RF_RAY_CHUNK).  Losses are batch-global means, so every chunk's backward must see
+    the whole batch's sums: outputs bit-identical, losses and gradients equal up to the summation order of the atomics."""
+    def run(chunk):
+        if chunk:
+            monkeypatch.setenv("RF_RAY_CHUNK", str(chunk))
+        else:
+            monkeypatch.delenv("RF_RAY_CHUNK", raising=False)
+        cfg, m = _model_from_golden("B", cuda, prec=prec)
+        m.train()
+        rng = np.random.default_rng(7)                            # the 96 golden rays six times over, directions jittered
+        rep = lambda a: np.concatenate([a] * 6, 0)
+        d = rep(G["in_rays_d"]); d = (d + 0.02 * rng.standard_normal(d.shape)).astype(np.float32)
+        ro = torch.from_numpy(rep(G["in_rays_o"])).to(cuda).requires_grad_(True)
+        rd = torch.from_numpy(d).to(cuda).requires_grad_(True)
+        tc = torch.from_numpy(rep(G["in_target_rgb"])).to(cuda); td = torch.from_numpy(rep(G["in_target_d"])).to(cuda)
+        ret = m.mapping(ro, rd, tc, td, clamp=True, u=torch.from_numpy(rng.random((d.shape[0], G["B_u"].shape[1])).astype(np.float32)))
+        _total(cfg, ret).backward()
+        s, c = m.decoder_res.sdf_net.model, m.decoder_res.color_net.model
+        out = {k: ret[k].detach().cpu().numpy() for k in ("rgb_res", "depth_res", "rgb_res_loss", "depth_res_loss", "sdf_res_loss", "fs_res_loss")}
+        out.update(g_hash=m.embed_res_fn.params.grad.cpu().numpy(), g_w_sdf0=s[0].weight.grad.cpu().numpy(), g_w_col1=c[2].weight.grad.cpu().numpy(),
+                   g_o=ro.grad.cpu().numpy(), g_d=rd.grad.cpu().numpy())
+        return out, ro.shape[0]
+    whole, n = run(0)
+    assert n == 576
+    parts, _ = run(128)                                          # five chunks, the last one ragged (64 rays)
+    for k in ("rgb_res", "depth_res"):
+        assert np.array_equal(whole[k], parts[k]), k
+    for k in whole:
+        scale = float(np.abs(whole[k]).max()) + 1e-30
+        np.testing.assert_allclose(parts[k], whole[k], rtol=2e-5, atol=2e-6 * scale, err_msg=k)
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
 def test_eval_render_matches_reference_golden(cuda, rf_lib, prec):
     cfg, m = _model_from_golden("C", cuda, prec=prec)
     m.eval()
