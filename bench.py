@@ -613,7 +613,10 @@ def time_kernels(model, cfg, f, dev, params):
         return a.elapsed_time(b) / iters
 
     vol = moving_volume(cfg, None, f["c2w"], device=dev)
-    out["tsdf_local_ms"] = timeit(lambda: vol.integrate_packed(f["depth"], f["packed"], Kmat, f["c2w"], None, 1.0, 0.0))
+    # launch durations of the two integrate kernels: events the library records around the launch (the host call around a 30-60 us
+    # kernel is Python-bound, so events around the call would time the host)
+    from bench_workloads import _kernel_ms
+    out["tsdf_local_ms"] = _kernel_ms(lambda i: vol.integrate_packed(f["depth"], f["packed"], Kmat, f["c2w"], None, 1.0, 0.0), 0, iters=5, warm=1)
     tl, tb = vol.count_touched(f["depth"], Kmat, f["c2w"])
     out.update(touched_local=tl, band_local=tb, swept_local=int(np.prod(vol.vol_dim)))
     # N2: re-centring of the moving volume by one metre along x (ping-pong arrays: 12 B read + 12 B written per voxel)
@@ -633,7 +636,7 @@ def time_kernels(model, cfg, f, dev, params):
     gv = MapVolume(cfg, m2, Kmat); gv.init_mapvolume()
     pose = torch.from_numpy(f["c2w"]).float()
     out["touched_global"] = gv.count_touched(f["depth"], pose)
-    out["tsdf_global_ms"] = timeit(lambda: gv.integrate_kf({"rgb": f["rgb"], "depth": f["depth"]}, pose, 1.0))
+    out["tsdf_global_ms"] = _kernel_ms(lambda i: gv.integrate_kf({"rgb": f["rgb"], "depth": f["depth"]}, pose, 1.0), 1, iters=5, warm=1)
     del gv, m2
     # ray kernels through the C-ABI directly
     n = H * W
