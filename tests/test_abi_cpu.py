@@ -125,3 +125,16 @@ def test_graphed_step_needs_eager_iterations():
     opt = Adam([p], capturable=True)
     with pytest.raises(abi.RfError, match="eager_steps"):
         GraphedMappingStep(torch.nn.Linear(2, 2), opt, 16, lambda r: 0, eager_steps=0)
+
+
+def test_ray_chunk_policy(monkeypatch):
+    """scene_rep._chunk_rays: the whole batch unless the planes cannot fit; RF_RAY_CHUNK forces a multiple of 128 (one decoder tile)."""
+    import torch
+    from remixfusion_b200 import scene_rep
+    cpu = torch.device("cpu")
+    monkeypatch.delenv("RF_RAY_CHUNK", raising=False)
+    assert scene_rep._chunk_rays(None, None, 1000, 59, cpu) == 1000
+    monkeypatch.setenv("RF_RAY_CHUNK", "300")
+    assert scene_rep._chunk_rays(None, None, 1000, 59, cpu) == 256
+    monkeypatch.setenv("RF_RAY_CHUNK", "5")
+    assert scene_rep._chunk_rays(None, None, 1000, 59, cpu) == 128
