@@ -156,3 +156,31 @@ def test_level_scale_rounding_sensitivity_on_the_bench_table():
     print(f"2-ulp level scales: cell flips {worst_flip:.2e} of (position, level) pairs, feature change {worst_feat:.2e} of the feature scale")
     assert worst_flip < 1e-4, worst_flip
     assert worst_feat < 1e-3, worst_feat
+
+
+def test_fast_sdf_weight_formula_error_bound():
+    """csrc/ray_query.cu: sdf_weight computes sigmoid(a) sigmoid(-a) (model/scene_rep.py:116) as t / (1 + t)^2 with t = exp(-|a|) from
+    ex2.approx (2 ulp, argument rounded once) and rcp.approx (1 ulp).  A float32 model of that evaluation with the approximations'
+    worst-case errors injected stays within the bound the kernel's comment states (8e-7 + 6e-8 |a|, relative), against the float64
+    value of the reference formula."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    a = np.concatenate([rng.uniform(-30, 30, 400000), rng.normal(0, 2, 400000)]).astype(np.float32)
+    a64 = a.astype(np.float64)
+    truth = 1.0 / (1.0 + np.exp(-a64)) / (1.0 + np.exp(a64))
+    sig_truth = 1.0 / (1.0 + np.exp(-a64))
+    bound = 8e-7 + 6e-8 * np.abs(a64)
+    for d_t in (-2, 0, 2):
+        for d_r in (-1, 0, 1):
+            arg = (-np.abs(a) * np.float32(1.4426950408889634)).astype(np.float32)          # x * log2(e), rounded once
+            t = np.exp2(arg.astype(np.float64)).astype(np.float32)
+            t = (t.view(np.int32) + d_t).view(np.float32)                                   # ex2.approx: 2 ulp
+            inv = (np.float32(1.0) / (np.float32(1.0) + t)).astype(np.float32)
+            inv = (inv.view(np.int32) + d_r).view(np.float32)                               # rcp.approx: 1 ulp
+            ti = (t * inv).astype(np.float32)
+            e = (ti * inv).astype(np.float32)
+            sg = np.where(a >= 0, inv, ti)
+            rel_e = np.abs(e.astype(np.float64) - truth) / truth
+            rel_s = np.abs(sg.astype(np.float64) - sig_truth) / sig_truth
+            assert np.all(rel_e <= bound), (d_t, d_r, float(np.max(rel_e - bound)))
+            assert np.all(rel_s <= bound), (d_t, d_r, float(np.max(rel_s - bound)))
